@@ -1,0 +1,145 @@
+/* libsbn254 -- B200-native (sm_100a) backend for the Hyrax commit / opening hot path of
+ * Antiparadox/Spartan-BN254.  Flat C ABI: plain pointers and sizes, opaque handles, no unwinding.
+ *
+ * The reference has no FFI of its own (100% Rust); each entry point below replaces one Rust call
+ * site, cited as file:line under the reference tree.  INTEGRATION.md shows the `extern "C"` shim a
+ * maintainer adds on the Rust side.
+ *
+ * Data layout (identical to ark-ff / ark-ec in-memory values, so the shim passes slices as-is):
+ *   sbn_fr   Fr element, 4 x u64 little-endian limbs, MONTGOMERY form (reference scalar.rs:15)
+ *   sbn_g1a  affine G1 point, x then y, each 4 x u64 LE limbs Montgomery Fq; the identity is
+ *            carried out-of-band by an `inf` byte array (1 = identity, coordinates then ignored
+ *            on input and written as zero on output)  (reference group.rs:20, commitments.rs:24)
+ *
+ * Return value: 0 on success, negative sbn_status on error; sbn_strerror() names it.  Preconditions
+ * the reference enforces with assert!/panic (hyrax.rs:258,290,295; commitments.rs:134,146;
+ * bullet.rs:42-47) come back as SBN_ERR_SHAPE -- the shim turns non-zero into panic!.
+ * There is no CPU fallback: without a usable CUDA device every call fails with SBN_ERR_CUDA.
+ *
+ * Threading: a context serialises its own calls with an internal mutex (reference call sites are
+ * single threaded except rayon fan-out inside commit_inner, which this library replaces wholesale).
+ */
+#ifndef SBN254_H
+#define SBN254_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } sbn_fr;
+typedef struct { uint64_t x[4], y[4]; } sbn_g1a;
+
+typedef struct sbn_ctx sbn_ctx;        /* one CUDA device + streams + workspace            */
+typedef struct sbn_bases sbn_bases;    /* generator set resident in HBM with window tables */
+typedef struct sbn_bullet sbn_bullet;  /* device-resident state of one bullet reduction    */
+typedef struct sbn_sumcheck sbn_sumcheck;
+
+typedef enum {
+    SBN_OK = 0,
+    SBN_ERR_ARG = -1,      /* null pointer / bad handle                */
+    SBN_ERR_SHAPE = -2,    /* size precondition of the reference broken */
+    SBN_ERR_CUDA = -3,     /* CUDA runtime error (see sbn_last_cuda_error) */
+    SBN_ERR_OOM = -4,
+    SBN_ERR_UNSUPPORTED = -5
+} sbn_status;
+
+const char* sbn_strerror(int status);
+const char* sbn_last_cuda_error(const sbn_ctx* ctx);   /* text of the last CUDA failure, "" if none */
+int sbn_version(void);                                  /* 100 * major + minor */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int sbn_ctx_create(int device, sbn_ctx** out);
+int sbn_ctx_destroy(sbn_ctx* ctx);
+int sbn_ctx_synchronize(sbn_ctx* ctx);
+/* Tunables: "chunk_rows" (rows per pipeline stage), "window_bits" (0 = auto). */
+int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
+/* Counters since creation / last reset: kernels launched by this library, bytes copied H2D / D2H. */
+int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
+/* Device time (ms, CUDA events on the library's compute stream) of the kernels of the last
+ * sbn_hyrax_commit* call, per stage: [0] digit decomposition + bucket sort, [1] bucket accumulation,
+ * [2] bucket reduction, [3] affine normalisation; and the number of launches per stage. */
+int sbn_ctx_last_commit_profile(sbn_ctx* ctx, float ms[4], int launches[4]);
+
+/* pinned host memory for callers that want overlapped copies (optional) */
+int sbn_host_alloc(void** out, size_t bytes);
+int sbn_host_free(void* p);
+
+/* ---- generators: MultiCommitGens kept resident (commitments.rs:17-27, G_affine + h_affine) ---- */
+/* Uploads n affine generators G and the blinding generator h, and precomputes the fixed-base window
+ * tables 2^(k*c) * G_j used by every later commit.  inf may be NULL (no identity among the bases). */
+int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* h,
+                     sbn_bases** out);
+int sbn_bases_destroy(sbn_bases* bases);
+size_t sbn_bases_len(const sbn_bases* bases);                 /* n (without h) */
+int sbn_bases_window_bits(const sbn_bases* bases);
+
+/* ---- a7/a9: DensePolynomial::commit_inner (hyrax.rs:253-281), R1CSProof::commit_poly
+ *      (r1csproof.rs:210-237).  C_i = sum_j Z[i*R_size + j] * G_j + blinds[i] * h  for i < L_size.
+ * Requires R_size == sbn_bases_len(bases) (commitments.rs:146 assert).  blinds NULL = zeros
+ * (hyrax.rs:301-305).  Outputs are AFFINE (what append_to_transcript needs, hyrax.rs:44-52). */
+int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size_t L_size, size_t R_size,
+                     const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);
+/* Same with every buffer already in device memory of ctx's device (Z, blinds, C_out, inf_out are
+ * device pointers); runs asynchronously on `stream` (a cudaStream_t, 0 = the context's stream). */
+int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* bases, const void* dZ, size_t L_size, size_t R_size,
+                            const void* dblinds, void* dC_out, void* dinf_out, void* stream);
+
+/* ---- a6: GroupElement::msm_affine / vartime_multiscalar_mul (group.rs:143-175).
+ * One variable-base MSM over caller-supplied points.  The reference swallows a length mismatch into
+ * the identity (`unwrap_or_default`); here the caller passes one n, so that case cannot arise. */
+int sbn_msm(sbn_ctx* ctx, const sbn_g1a* points, const uint8_t* inf, const sbn_fr* scalars, size_t n,
+            sbn_g1a* out, uint8_t* inf_out);
+/* a5: <[Scalar] as Commitments>::commit (commitments.rs:144-154) against resident bases:
+ * sum_j s[j] G_j + blind * h, n == sbn_bases_len. */
+int sbn_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* scalars, size_t n, const sbn_fr* blind,
+               sbn_g1a* out, uint8_t* inf_out);
+
+/* ---- batched fixed-point scalar multiplication: out[i] = s[i] * P  (group.rs:121,130 generator() *
+ *      scalar for generator derivation; commitments.rs:64-76 MultiCommitGens::scale) */
+int sbn_g1_scalar_mul_batch(sbn_ctx* ctx, const sbn_g1a* P, const sbn_fr* s, size_t n, sbn_g1a* out, uint8_t* inf_out);
+/* out[i] = s * P[i] */
+int sbn_g1_scale_points(sbn_ctx* ctx, const sbn_g1a* P, const uint8_t* inf, size_t n, const sbn_fr* s,
+                        sbn_g1a* out, uint8_t* inf_out);
+
+/* ---- a11: DensePolynomial::bound (hyrax.rs:311-324): LZ[i] = sum_j L[j] * Z[j*R_size + i] */
+int sbn_bound(sbn_ctx* ctx, const sbn_fr* Z, const sbn_fr* L, size_t L_size, size_t R_size, sbn_fr* LZ_out);
+
+/* ---- a14: BulletReductionProof::prove (nizk/bullet.rs:24-126) with G, a, b resident on device.
+ * The Fiat-Shamir transcript stays on the host: each round returns (L, R), the caller appends them,
+ * draws u and hands it back.
+ *   begin : uploads a, b (n scalars each), uses bases' G[0..n) and h as H; computes
+ *           Gamma = MSM(a,G) + <a,b> Q + blind H                              (bullet.rs:57-59)
+ *   round : L = MSM(a_L,G_R) + c_L Q + blind_L H, R = MSM(a_R,G_L) + c_R Q + blind_R H (bullet.rs:70-76)
+ *   fold  : G <- u^-1 G_L + u G_R, a <- u a_L + u^-1 a_R, b <- u^-1 b_L + u b_R       (bullet.rs:85-102)
+ *   end   : a_hat, b_hat, g_hat                                                 (bullet.rs:110-112) */
+int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* a, const sbn_fr* b,
+                     size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf, sbn_bullet** out);
+int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn_fr* blind_R,
+                     sbn_g1a* L_out, uint8_t* L_inf, sbn_g1a* R_out, uint8_t* R_inf);
+int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_inv);
+int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_g1a* g_hat, uint8_t* g_hat_inf);
+int sbn_bullet_destroy(sbn_bullet* st);
+
+/* ---- a16: R1CS-sat sumcheck round (sumcheck.rs:501-530 evaluation, :551-554 + hyrax.rs:195-203 bind).
+ * Four tables (tau, Az, Bz, Cz) of `len` scalars stay on device across rounds. */
+int sbn_sumcheck_begin(sbn_ctx* ctx, const sbn_fr* tau, const sbn_fr* Az, const sbn_fr* Bz, const sbn_fr* Cz,
+                       size_t len, sbn_sumcheck** out);
+int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2, sbn_fr* e3);
+int sbn_sumcheck_bind(sbn_sumcheck* st, const sbn_fr* r);
+int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]);   /* the four length-1 tables */
+int sbn_sumcheck_destroy(sbn_sumcheck* st);
+
+/* ---- utilities used by tests / harnesses */
+int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
+int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
+/* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for
+ * kind 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE (counted as 2 results), 3 = Montgomery Fq
+ * multiplications per second (not x264). */
+int sbn_microbench(sbn_ctx* ctx, int kind, double* per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+// BN254 G1 (y^2 = x^3 + 3) point arithmetic in extended Jacobian "XYZZ" coordinates
+// (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2), all coordinates Montgomery Fq.
+//
+// Bucket accumulation meets P+P and P+(-P) constantly with the reference's generators (about two
+// thirds of MultiCommitGens::new outputs are the same point G -- reference group.rs:110-132 falls
+// through to Scalar::one()), so every addition here handles doubling / cancellation / identity
+// explicitly instead of assuming distinct inputs.
+#pragma once
+#include "fp.cuh"
+
+namespace sbn {
+
+struct Affine {   // 64 B, layout of sbn_g1a in include/sbn254.h; (0,0) encodes the identity
+    Fq x, y;
+    SBN_HD bool is_identity() const { return x.is_zero() && y.is_zero(); }
+    static SBN_HD Affine identity() { Affine a; a.x = Fq::zero(); a.y = Fq::zero(); return a; }
+};
+
+struct XYZZ {     // 128 B; ZZ == 0 encodes the identity
+    Fq X, Y, ZZ, ZZZ;
+    SBN_HD bool is_identity() const { return ZZ.is_zero(); }
+    static SBN_HD XYZZ identity() {
+        XYZZ r; r.X = Fq::zero(); r.Y = Fq::zero(); r.ZZ = Fq::zero(); r.ZZZ = Fq::zero(); return r;
+    }
+    static SBN_HD XYZZ from_affine(const Affine& a) {
+        XYZZ r;
+        if (a.is_identity()) return identity();
+        r.X = a.x; r.Y = a.y; r.ZZ = Fq::one(); r.ZZZ = Fq::one();
+        return r;
+    }
+};
+
+// 2 * (x, y) for an affine input (mdbl-2008-s-1, a = 0)
+SBN_HD XYZZ xyzz_dbl_affine(const Affine& p) {
+    XYZZ r;
+    Fq U = fp_dbl(p.y);
+    Fq V = fp_sqr(U);
+    Fq W = fp_mul(U, V);
+    Fq S = fp_mul(p.x, V);
+    Fq xx = fp_sqr(p.x);
+    Fq M = fp_add(fp_dbl(xx), xx);
+    r.X = fp_sub(fp_sqr(M), fp_dbl(S));
+    r.Y = fp_sub(fp_mul(M, fp_sub(S, r.X)), fp_mul(W, p.y));
+    r.ZZ = V;
+    r.ZZZ = W;
+    return r;
+}
+
+// 2 * P (dbl-2008-s-1, a = 0).  y == 0 cannot happen on a prime-order curve.
+SBN_HD XYZZ xyzz_dbl(const XYZZ& p) {
+    if (p.is_identity()) return p;
+    XYZZ r;
+    Fq U = fp_dbl(p.Y);
+    Fq V = fp_sqr(U);
+    Fq W = fp_mul(U, V);
+    Fq S = fp_mul(p.X, V);
+    Fq xx = fp_sqr(p.X);
+    Fq M = fp_add(fp_dbl(xx), xx);
+    r.X = fp_sub(fp_sqr(M), fp_dbl(S));
+    r.Y = fp_sub(fp_mul(M, fp_sub(S, r.X)), fp_mul(W, p.Y));
+    r.ZZ = fp_mul(V, p.ZZ);
+    r.ZZZ = fp_mul(W, p.ZZZ);
+    return r;
+}
+
+// acc += q  (mixed addition madd-2008-s: 8M + 2S), q affine and not the identity
+SBN_HD void xyzz_add_mixed(XYZZ& acc, const Affine& q) {
+    if (acc.is_identity()) { acc.X = q.x; acc.Y = q.y; acc.ZZ = Fq::one(); acc.ZZZ = Fq::one(); return; }
+    Fq U2 = fp_mul(q.x, acc.ZZ);
+    Fq S2 = fp_mul(q.y, acc.ZZZ);
+    Fq P = fp_sub(U2, acc.X);
+    Fq R = fp_sub(S2, acc.Y);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl_affine(q);   // same point
+        else acc = XYZZ::identity();                  // opposite points
+        return;
+    }
+    Fq PP = fp_sqr(P);
+    Fq PPP = fp_mul(P, PP);
+    Fq Q = fp_mul(acc.X, PP);
+    Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
+    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(acc.Y, PPP));
+    acc.X = X3;
+    acc.Y = Y3;
+    acc.ZZ = fp_mul(acc.ZZ, PP);
+    acc.ZZZ = fp_mul(acc.ZZZ, PPP);
+}
+
+// acc += q  (add-2008-s: 12M + 2S)
+SBN_HD void xyzz_add(XYZZ& acc, const XYZZ& q) {
+    if (q.is_identity()) return;
+    if (acc.is_identity()) { acc = q; return; }
+    Fq U1 = fp_mul(acc.X, q.ZZ);
+    Fq U2 = fp_mul(q.X, acc.ZZ);
+    Fq S1 = fp_mul(acc.Y, q.ZZZ);
+    Fq S2 = fp_mul(q.Y, acc.ZZZ);
+    Fq P = fp_sub(U2, U1);
+    Fq R = fp_sub(S2, S1);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl(acc);
+        else acc = XYZZ::identity();
+        return;
+    }
+    Fq PP = fp_sqr(P);
+    Fq PPP = fp_mul(P, PP);
+    Fq Q = fp_mul(U1, PP);
+    Fq X3 = fp_sub(fp_sub(fp_sqr(R), PPP), fp_dbl(Q));
+    Fq Y3 = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(S1, PPP));
+    acc.X = X3;
+    acc.Y = Y3;
+    acc.ZZ = fp_mul(fp_mul(acc.ZZ, q.ZZ), PP);
+    acc.ZZZ = fp_mul(fp_mul(acc.ZZZ, q.ZZZ), PPP);
+}
+
+SBN_HD Affine affine_neg(const Affine& a) {
+    Affine r;
+    r.x = a.x;
+    r.y = a.y.is_zero() ? a.y : fp_neg(a.y);   // keeps (0,0) as the identity encoding
+    return r;
+}
+
+// XYZZ -> affine with one field inversion: I = 1/(ZZ*ZZZ)  =>  1/ZZ = ZZZ * I,  1/ZZZ = ZZ * I.
+SBN_HD Affine xyzz_to_affine(const XYZZ& p) {
+    if (p.is_identity()) return Affine::identity();
+    Fq I = fp_inv(fp_mul(p.ZZ, p.ZZZ));
+    Affine r;
+    r.x = fp_mul(p.X, fp_mul(p.ZZZ, I));
+    r.y = fp_mul(p.Y, fp_mul(p.ZZ, I));
+    return r;
+}
+
+}  // namespace sbn

@@ -1,0 +1,304 @@
+// BN254 prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256).
+//
+// The multiply is a word-serial (CIOS) Montgomery product built from 32x32->64 multiply-adds
+// (`mad.lo.cc.u32` / `madc.hi.cc.u32` pairs, which ptxas fuses into IMAD.WIDE.U32[.X] carry chains).
+// Two interleaved accumulators hold the even- and odd-limb partial products so that every 64-bit
+// product lands on an aligned limb pair and each accumulator is a single unbroken carry chain.
+//
+// Layout in memory matches ark-ff's Fp256<MontBackend> (4 x u64 little-endian limbs == 8 x u32 LE
+// limbs), i.e. what `Scalar(pub Fr)` (reference scalar.rs:15) and G1Affine coordinates hold.
+//
+// Every function is __host__ __device__: on the host the PTX carry-flag primitives are emulated with
+// a thread-local carry bit so the exact same algorithm is unit-tested on CPU (tests/host_fp_test.cu)
+// before it ever reaches a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SBN_HD __host__ __device__ __forceinline__
+#define SBN_D __device__ __forceinline__
+#else
+#define SBN_HD inline
+#define SBN_D inline
+#endif
+
+namespace sbn {
+
+// ------------------------------------------------------------------------------------------------
+// carry-flag primitives
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+SBN_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBN_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+SBN_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+SBN_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+SBN_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+SBN_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+SBN_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+// host emulation of the PTX condition-code register
+inline uint32_t& cc_flag() { static thread_local uint32_t cc = 0; return cc; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cc_flag(); cc_flag() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cc_flag(); return (uint32_t)t; }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; cc_flag() = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cc_flag(); cc_flag() = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cc_flag(); return (uint32_t)t; }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_lo(a, b), c); }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_lo(a, b), c); }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return addc(mul_hi(a, b), c); }
+#endif
+// NOTE: PTX sub.cc sets CC.CF to the *borrow*; subc consumes it as a borrow -- the emulation matches.
+
+// ------------------------------------------------------------------------------------------------
+// field parameters (as constexpr functions so unrolled loops fold them into IMAD immediates)
+// ------------------------------------------------------------------------------------------------
+struct FqParams {   // base field of BN254 (coordinates of G1)
+    static SBN_HD constexpr uint32_t P(int i) {
+        constexpr uint32_t v[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static SBN_HD constexpr uint32_t R1(int i) {  // 2^256 mod p
+        constexpr uint32_t v[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    static SBN_HD constexpr uint32_t R2(int i) {  // 2^512 mod p
+        constexpr uint32_t v[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return v[i];
+    }
+    static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32
+};
+struct FrParams {   // scalar field of BN254
+    static SBN_HD constexpr uint32_t P(int i) {
+        constexpr uint32_t v[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return v[i];
+    }
+    static SBN_HD constexpr uint32_t R1(int i) {
+        constexpr uint32_t v[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return v[i];
+    }
+    static SBN_HD constexpr uint32_t R2(int i) {
+        constexpr uint32_t v[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return v[i];
+    }
+    static constexpr uint32_t INV = 0xefffffffu;
+};
+
+// ------------------------------------------------------------------------------------------------
+// field element
+// ------------------------------------------------------------------------------------------------
+template <class F>
+struct Fp {
+    uint32_t l[8];
+
+    static SBN_HD Fp zero() { Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = 0;
+        return r; }
+    static SBN_HD Fp one() { Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = F::R1(i);
+        return r; }
+    SBN_HD bool is_zero() const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t |= l[i];
+        return t == 0;
+    }
+    SBN_HD bool operator==(const Fp& o) const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t |= l[i] ^ o.l[i];
+        return t == 0;
+    }
+    SBN_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+};
+
+// r = a - p if a >= p else a   (a < 2p)
+template <class F>
+SBN_HD void fp_reduce_once(Fp<F>& a) {
+    uint32_t t[8];
+    t[0] = sub_cc(a.l[0], F::P(0));
+#pragma unroll
+    for (int i = 1; i < 8; i++) t[i] = subc_cc(a.l[i], F::P(i));
+    uint32_t borrow = subc(0u, 0u);  // 0 - 0 - CF -> 0xffffffff when a < p
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.l[i] = borrow ? a.l[i] : t[i];
+}
+
+template <class F>
+SBN_HD Fp<F> fp_add(const Fp<F>& a, const Fp<F>& b) {
+    Fp<F> r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    r.l[7] = addc(a.l[7], b.l[7]);   // a,b < p < 2^254: no carry out of limb 7
+    fp_reduce_once(r);
+    return r;
+}
+
+template <class F>
+SBN_HD Fp<F> fp_sub(const Fp<F>& a, const Fp<F>& b) {
+    Fp<F> r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = subc(0u, 0u);   // all-ones when a < b
+    r.l[0] = add_cc(r.l[0], F::P(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < 7; i++) r.l[i] = addc_cc(r.l[i], F::P(i) & borrow);
+    r.l[7] = addc(r.l[7], F::P(7) & borrow);
+    return r;
+}
+
+template <class F>
+SBN_HD Fp<F> fp_neg(const Fp<F>& a) {
+    return fp_sub(Fp<F>::zero(), a);
+}
+
+template <class F>
+SBN_HD Fp<F> fp_dbl(const Fp<F>& a) { return fp_add(a, a); }
+
+// ------------------------------------------------------------------------------------------------
+// Montgomery multiplication.  Requires a < 2p; b may be any 256-bit value.  Returns a*b/R mod p, < p.
+//
+// Invariant between word iterations: T = E + O * 2^32 with E = sum e[k] 2^(32k), O = sum o[k] 2^(32k).
+// Products of even-indexed limbs of `a` (and p) go to E, odd-indexed ones to O, so each 64-bit
+// product is added to an aligned (lo, hi) limb pair.  After the reduction step e[0] == 0 and the
+// division by 2^32 is a role swap: E' = O + e[1],  O' = E >> 64.
+// Bound: T < a + p <= 3p < 2^256 after every iteration, so neither accumulator overflows.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+SBN_HD Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
+    uint32_t e[8], o[8];
+
+    // ---- i = 0: E = a_even * b0, O = a_odd * b0
+    {
+        const uint32_t bi = b.l[0];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            e[j] = mul_lo(a.l[j], bi);
+            e[j + 1] = mul_hi(a.l[j], bi);
+            o[j] = mul_lo(a.l[j + 1], bi);
+            o[j + 1] = mul_hi(a.l[j + 1], bi);
+        }
+        const uint32_t m = mul_lo(e[0], F::INV);
+        // O += p_odd * m
+        o[0] = mad_lo_cc(F::P(1), m, o[0]);
+        o[1] = madc_hi_cc(F::P(1), m, o[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            o[j] = madc_lo_cc(F::P(j + 1), m, o[j]);
+            o[j + 1] = madc_hi_cc(F::P(j + 1), m, o[j + 1]);
+        }
+        // E += p_even * m ; carry out -> o[7]
+        e[0] = mad_lo_cc(F::P(0), m, e[0]);
+        e[1] = madc_hi_cc(F::P(0), m, e[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            e[j] = madc_lo_cc(F::P(j), m, e[j]);
+            e[j + 1] = madc_hi_cc(F::P(j), m, e[j + 1]);
+        }
+        o[7] = addc(o[7], 0u);
+    }
+
+    // ---- i = 1..7.  `x` is the accumulator that becomes the new E (old O); `y` becomes the new O.
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+        const uint32_t bi = b.l[i];
+        uint32_t* x = (i & 1) ? o : e;   // new even-aligned accumulator
+        uint32_t* y = (i & 1) ? e : o;   // new odd-aligned accumulator (holds old E, to be shifted by 64 bits)
+
+        x[0] = add_cc(x[0], y[1]);                       // E' = O + e[1]; carry joins O' at weight 2^32
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {                 // O' = (E >> 64) + a_odd * bi + carry
+            y[j] = madc_lo_cc(a.l[j + 1], bi, y[j + 2]);
+            y[j + 1] = madc_hi_cc(a.l[j + 1], bi, y[j + 3]);
+        }
+        y[6] = madc_lo_cc(a.l[7], bi, 0u);
+        y[7] = madc_hi(a.l[7], bi, 0u);
+
+        x[0] = mad_lo_cc(a.l[0], bi, x[0]);              // E' += a_even * bi
+        x[1] = madc_hi_cc(a.l[0], bi, x[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            x[j] = madc_lo_cc(a.l[j], bi, x[j]);
+            x[j + 1] = madc_hi_cc(a.l[j], bi, x[j + 1]);
+        }
+        y[7] = addc(y[7], 0u);
+
+        const uint32_t m = mul_lo(x[0], F::INV);
+        y[0] = mad_lo_cc(F::P(1), m, y[0]);              // O' += p_odd * m
+        y[1] = madc_hi_cc(F::P(1), m, y[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            y[j] = madc_lo_cc(F::P(j + 1), m, y[j]);
+            y[j + 1] = madc_hi_cc(F::P(j + 1), m, y[j + 1]);
+        }
+        x[0] = mad_lo_cc(F::P(0), m, x[0]);              // E' += p_even * m  (x[0] becomes 0)
+        x[1] = madc_hi_cc(F::P(0), m, x[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            x[j] = madc_lo_cc(F::P(j), m, x[j]);
+            x[j + 1] = madc_hi_cc(F::P(j), m, x[j + 1]);
+        }
+        y[7] = addc(y[7], 0u);
+    }
+
+    // after i = 7 (odd): E lives in `o`, O lives in `e`.  result = (E >> 32) + O
+    Fp<F> r;
+    r.l[0] = add_cc(e[0], o[1]);
+#pragma unroll
+    for (int k = 1; k < 7; k++) r.l[k] = addc_cc(e[k], o[k + 1]);
+    r.l[7] = addc(e[7], 0u);
+    fp_reduce_once(r);
+    return r;
+}
+
+template <class F>
+SBN_HD Fp<F> fp_sqr(const Fp<F>& a) { return fp_mul(a, a); }
+
+// Montgomery -> canonical: a * 1 / R
+template <class F>
+SBN_HD Fp<F> fp_from_mont(const Fp<F>& a) {
+    Fp<F> one = Fp<F>::zero();
+    one.l[0] = 1;
+    return fp_mul(a, one);
+}
+// canonical (any 256-bit value) -> Montgomery: v * R2 / R
+template <class F>
+SBN_HD Fp<F> fp_to_mont(const Fp<F>& v) {
+    Fp<F> r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r2.l[i] = F::R2(i);
+    return fp_mul(r2, v);
+}
+
+// a^(p-2) by square-and-multiply over the constant exponent (variable time in nothing secret)
+template <class F>
+SBN_HD Fp<F> fp_inv(const Fp<F>& a) {
+    Fp<F> acc = Fp<F>::one();
+    // exponent p - 2, MSB first
+    for (int i = 7; i >= 0; i--) {
+        uint32_t w = F::P(i);
+        if (i == 0) w -= 2;  // low limb of both moduli is >= 2, no borrow
+        for (int b = 31; b >= 0; b--) {
+            acc = fp_sqr(acc);
+            if ((w >> b) & 1) acc = fp_mul(acc, a);
+        }
+    }
+    return acc;
+}
+
+typedef Fp<FqParams> Fq;
+typedef Fp<FrParams> Fr;
+
+}  // namespace sbn

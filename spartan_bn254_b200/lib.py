@@ -1,0 +1,247 @@
+"""ctypes binding of the libsbn254 C ABI (include/sbn254.h).  numpy arrays carry the ABI layouts:
+scalars uint64[n,4] (Montgomery Fr), points uint64[n,8] (affine Montgomery x|y) + uint8[n] inf."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libsbn254.so")
+
+EXPORTS = [
+    "sbn_strerror", "sbn_last_cuda_error", "sbn_version",
+    "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
+    "sbn_ctx_last_commit_profile", "sbn_host_alloc", "sbn_host_free",
+    "sbn_bases_create", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits",
+    "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
+    "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
+    "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
+    "sbn_sumcheck_begin", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
+    "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+]
+
+
+class SbnError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        self.status = status
+        super().__init__(f"{what}: status {status}" + (f" ({detail})" if detail else ""))
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsbn254.so; raises (never falls back) when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SbnError(-3, "libsbn254.so missing",
+                       f"build it with `python -m spartan_bn254_b200.build` (expected at {LIB_PATH})")
+    lib = C.CDLL(LIB_PATH)
+    lib.sbn_strerror.restype = C.c_char_p
+    lib.sbn_last_cuda_error.restype = C.c_char_p
+    lib.sbn_last_cuda_error.argtypes = [C.c_void_p]
+    lib.sbn_bases_len.restype = C.c_size_t
+    lib.sbn_bases_len.argtypes = [C.c_void_p]
+    lib.sbn_bases_window_bits.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, cols)
+
+
+class Context:
+    """sbn_ctx: one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.sbn_ctx_create(C.c_int(device), C.byref(h))
+        if st != 0:
+            raise SbnError(st, "sbn_ctx_create", self.lib.sbn_strerror(st).decode() +
+                           " -- a CUDA device is required, there is no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def _check(self, st, what):
+        if st != 0:
+            detail = self.lib.sbn_strerror(st).decode()
+            cuda = self.lib.sbn_last_cuda_error(self.h).decode()
+            raise SbnError(st, what, detail + (": " + cuda if cuda and st in (-3, -4) else ""))
+
+    def close(self):
+        if self.h:
+            self.lib.sbn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set(self, key, value):
+        self._check(self.lib.sbn_ctx_set(self.h, key.encode(), C.c_long(value)), "sbn_ctx_set")
+
+    def synchronize(self):
+        self._check(self.lib.sbn_ctx_synchronize(self.h), "sbn_ctx_synchronize")
+
+    def counters(self, reset=False):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.sbn_ctx_counters(self.h, C.byref(a), C.byref(b), C.byref(c), C.c_int(int(reset))),
+                    "sbn_ctx_counters")
+        return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    def last_commit_profile(self):
+        ms = (C.c_float * 4)()
+        n = (C.c_int * 4)()
+        self._check(self.lib.sbn_ctx_last_commit_profile(self.h, ms, n), "sbn_ctx_last_commit_profile")
+        names = ["sort", "accumulate", "reduce", "normalize"]
+        return {names[i]: dict(ms=float(ms[i]), launches=int(n[i])) for i in range(4)}
+
+    # ---- generators
+    def bases(self, G, h, G_inf=None):
+        return Bases(self, G, h, G_inf)
+
+    # ---- a7: DensePolynomial::commit_inner
+    def hyrax_commit(self, bases, Z, L_size, R_size, blinds=None):
+        Z = _u64(Z, 4)
+        if Z.shape[0] != L_size * R_size:
+            raise SbnError(-2, "sbn_hyrax_commit", "len(Z) != L_size * R_size")
+        bl = None if blinds is None else _u64(blinds, 4)
+        if bl is not None and bl.shape[0] != L_size:
+            raise SbnError(-2, "sbn_hyrax_commit", "len(blinds) != L_size")
+        out = np.zeros((L_size, 8), dtype=np.uint64)
+        inf = np.zeros(L_size, dtype=np.uint8)
+        st = self.lib.sbn_hyrax_commit(self.h, bases.h, _ptr(Z), C.c_size_t(L_size), C.c_size_t(R_size), _ptr(bl),
+                                       _ptr(out), _ptr(inf))
+        self._check(st, "sbn_hyrax_commit")
+        return out, inf
+
+    def hyrax_commit_raw(self, bases, Z_ptr, L_size, R_size, blinds_ptr, out_ptr, inf_ptr):
+        """Host-pointer call without numpy marshalling (bench e2e: pinned buffers)."""
+        st = self.lib.sbn_hyrax_commit(self.h, bases.h, C.c_void_p(Z_ptr), C.c_size_t(L_size), C.c_size_t(R_size),
+                                       C.c_void_p(blinds_ptr) if blinds_ptr else None, C.c_void_p(out_ptr),
+                                       C.c_void_p(inf_ptr))
+        self._check(st, "sbn_hyrax_commit")
+
+    def hyrax_commit_device(self, bases, dZ_ptr, L_size, R_size, dblinds_ptr, dC_ptr, dinf_ptr, stream=0):
+        st = self.lib.sbn_hyrax_commit_device(self.h, bases.h, C.c_void_p(dZ_ptr), C.c_size_t(L_size),
+                                              C.c_size_t(R_size), C.c_void_p(dblinds_ptr) if dblinds_ptr else None,
+                                              C.c_void_p(dC_ptr), C.c_void_p(dinf_ptr) if dinf_ptr else None,
+                                              C.c_void_p(stream) if stream else None)
+        self._check(st, "sbn_hyrax_commit_device")
+
+    # ---- a6 / a5
+    def msm(self, points, inf, scalars):
+        points = _u64(points, 8)
+        scalars = _u64(scalars, 4)
+        n = points.shape[0]
+        if scalars.shape[0] != n:
+            # group.rs:156,173 `.unwrap_or_default()`: a length mismatch yields the identity
+            return np.zeros(8, dtype=np.uint64), 1
+        infa = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros(8, dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        st = self.lib.sbn_msm(self.h, _ptr(points), _ptr(infa), _ptr(scalars), C.c_size_t(n), _ptr(out), _ptr(oinf))
+        self._check(st, "sbn_msm")
+        return out, int(oinf[0])
+
+    def commit(self, bases, scalars, blind):
+        scalars = _u64(scalars, 4)
+        out = np.zeros(8, dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        st = self.lib.sbn_commit(self.h, bases.h, _ptr(scalars), C.c_size_t(scalars.shape[0]),
+                                 _ptr(_u64(blind, 4)), _ptr(out), _ptr(oinf))
+        self._check(st, "sbn_commit")
+        return out, int(oinf[0])
+
+    def scalar_mul_batch(self, P, scalars):
+        scalars = _u64(scalars, 4)
+        n = scalars.shape[0]
+        out = np.zeros((n, 8), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        st = self.lib.sbn_g1_scalar_mul_batch(self.h, _ptr(_u64(P, 8)), _ptr(scalars), C.c_size_t(n), _ptr(out), _ptr(inf))
+        self._check(st, "sbn_g1_scalar_mul_batch")
+        return out, inf
+
+    def scale_points(self, P, inf, s):
+        P = _u64(P, 8)
+        n = P.shape[0]
+        infa = None if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros((n, 8), dtype=np.uint64)
+        oinf = np.zeros(n, dtype=np.uint8)
+        st = self.lib.sbn_g1_scale_points(self.h, _ptr(P), _ptr(infa), C.c_size_t(n), _ptr(_u64(s, 4)), _ptr(out), _ptr(oinf))
+        self._check(st, "sbn_g1_scale_points")
+        return out, oinf
+
+    # ---- a11
+    def bound(self, Z, Lvec, L_size, R_size):
+        Z = _u64(Z, 4)
+        Lvec = _u64(Lvec, 4)
+        if Z.shape[0] != L_size * R_size or Lvec.shape[0] != L_size:
+            raise SbnError(-2, "sbn_bound", "shape mismatch")
+        out = np.zeros((R_size, 4), dtype=np.uint64)
+        st = self.lib.sbn_bound(self.h, _ptr(Z), _ptr(Lvec), C.c_size_t(L_size), C.c_size_t(R_size), _ptr(out))
+        self._check(st, "sbn_bound")
+        return out
+
+    # ---- utilities
+    def fr_from_canonical(self, canon):
+        canon = _u64(canon, 4)
+        out = np.zeros_like(canon)
+        self._check(self.lib.sbn_fr_from_canonical(self.h, _ptr(canon), C.c_size_t(canon.shape[0]), _ptr(out)),
+                    "sbn_fr_from_canonical")
+        return out
+
+    def fr_to_canonical(self, mont):
+        mont = _u64(mont, 4)
+        out = np.zeros_like(mont)
+        self._check(self.lib.sbn_fr_to_canonical(self.h, _ptr(mont), C.c_size_t(mont.shape[0]), _ptr(out)),
+                    "sbn_fr_to_canonical")
+        return out
+
+    def microbench(self, kind):
+        v = C.c_double()
+        self._check(self.lib.sbn_microbench(self.h, C.c_int(kind), C.byref(v)), "sbn_microbench")
+        return v.value
+
+
+class Bases:
+    """sbn_bases: a MultiCommitGens (G[0..n) + h) resident in HBM with its window tables."""
+
+    def __init__(self, ctx, G, h, G_inf=None):
+        self.ctx = ctx
+        G = _u64(G, 8)
+        h = _u64(h, 8)
+        infa = None if G_inf is None else np.ascontiguousarray(G_inf, dtype=np.uint8)
+        hd = C.c_void_p()
+        st = ctx.lib.sbn_bases_create(ctx.h, _ptr(G), _ptr(infa), C.c_size_t(G.shape[0]), _ptr(h), C.byref(hd))
+        ctx._check(st, "sbn_bases_create")
+        self.h = hd
+        self.n = G.shape[0]
+
+    @property
+    def window_bits(self):
+        return self.ctx.lib.sbn_bases_window_bits(self.h)
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_bases_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
