@@ -178,44 +178,18 @@ SBN_HD Fp<F> fp_dbl(const Fp<F>& a) { return fp_add(a, a); }
 // ------------------------------------------------------------------------------------------------
 template <class F>
 SBN_HD Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
+    // Both accumulators start at zero and every word iteration (including the first) has the same
+    // shape: with a special-cased first iteration ptxas splits the a*b_i products into
+    // IMAD + IMAD.HI + IADD3 instead of IMAD.WIDE.U32.X (IMAD.HI is half rate on sm_100).
     uint32_t e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { e[i] = 0; o[i] = 0; }
 
-    // ---- i = 0: E = a_even * b0, O = a_odd * b0
-    {
-        const uint32_t bi = b.l[0];
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-            e[j] = mul_lo(a.l[j], bi);
-            e[j + 1] = mul_hi(a.l[j], bi);
-            o[j] = mul_lo(a.l[j + 1], bi);
-            o[j + 1] = mul_hi(a.l[j + 1], bi);
-        }
-        const uint32_t m = mul_lo(e[0], F::INV);
-        // O += p_odd * m
-        o[0] = mad_lo_cc(F::P(1), m, o[0]);
-        o[1] = madc_hi_cc(F::P(1), m, o[1]);
-#pragma unroll
-        for (int j = 2; j < 8; j += 2) {
-            o[j] = madc_lo_cc(F::P(j + 1), m, o[j]);
-            o[j + 1] = madc_hi_cc(F::P(j + 1), m, o[j + 1]);
-        }
-        // E += p_even * m ; carry out -> o[7]
-        e[0] = mad_lo_cc(F::P(0), m, e[0]);
-        e[1] = madc_hi_cc(F::P(0), m, e[1]);
-#pragma unroll
-        for (int j = 2; j < 8; j += 2) {
-            e[j] = madc_lo_cc(F::P(j), m, e[j]);
-            e[j + 1] = madc_hi_cc(F::P(j), m, e[j + 1]);
-        }
-        o[7] = addc(o[7], 0u);
-    }
-
-    // ---- i = 1..7.  `x` is the accumulator that becomes the new E (old O); `y` becomes the new O.
-#pragma unroll
-    for (int i = 1; i < 8; i++) {
+    for (int i = 0; i < 8; i++) {
         const uint32_t bi = b.l[i];
-        uint32_t* x = (i & 1) ? o : e;   // new even-aligned accumulator
-        uint32_t* y = (i & 1) ? e : o;   // new odd-aligned accumulator (holds old E, to be shifted by 64 bits)
+        uint32_t* x = (i & 1) ? o : e;   // even-aligned accumulator of this iteration (old O)
+        uint32_t* y = (i & 1) ? e : o;   // odd-aligned accumulator (old E, shifted down by 64 bits)
 
         x[0] = add_cc(x[0], y[1]);                       // E' = O + e[1]; carry joins O' at weight 2^32
 #pragma unroll
@@ -224,7 +198,7 @@ SBN_HD Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
             y[j + 1] = madc_hi_cc(a.l[j + 1], bi, y[j + 3]);
         }
         y[6] = madc_lo_cc(a.l[7], bi, 0u);
-        y[7] = madc_hi(a.l[7], bi, 0u);
+        y[7] = madc_hi_cc(a.l[7], bi, 0u);               // (no carry out: T < 3p; .cc form lets ptxas fuse the pair)
 
         x[0] = mad_lo_cc(a.l[0], bi, x[0]);              // E' += a_even * bi
         x[1] = madc_hi_cc(a.l[0], bi, x[1]);

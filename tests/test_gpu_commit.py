@@ -1,0 +1,193 @@
+"""GPU parity tests (run on a B200 with -m gpu): the CUDA Hyrax commit, called through the C ABI, must be
+bit-exact (affine x, y, infinity flag) against the CPU oracle and the committed golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "hyrax_golden.json")))
+
+
+def h2i(s):
+    return int(s, 16)
+
+
+def test_generators_match_reference_rule(ctx, orc):
+    """MultiCommitGens::new (commitments.rs:31-62): SHAKE256 / SHA3-256 rule + GPU scalar muls."""
+    from spartan_bn254_b200.hyrax import MultiCommitGens, DotProductProofGens
+    for label in (b"gens_r1cs_sat", b"gens_r1cs_eval", b"test"):
+        gens = MultiCommitGens.new(40, label, ctx)
+        G, h = orc.multi_commit_gens(label, 40)
+        assert np.array_equal(gens.G, G) and np.array_equal(gens.h, h)
+    g = GOLD["generators"]["gens_r1cs_eval"]
+    gens = MultiCommitGens.new(16, b"gens_r1cs_eval", ctx)
+    got = orc.points_to_ints(gens.G[:6], [0] * 6)
+    assert got == [(h2i(p[0]), h2i(p[1])) for p in g["points"]]
+    # DotProductProofGens::new(n) = MultiCommitGens::new(n+1).split_at(n)  (nizk/mod.rs:412-415)
+    d = DotProductProofGens(8, b"gens_r1cs_eval", ctx)
+    Gn, hh, G1 = orc.dotproduct_gens(b"gens_r1cs_eval", 8)
+    assert np.array_equal(d.gens_n.G, Gn) and np.array_equal(d.gens_n.h, hh)
+    assert np.array_equal(d.gens_1.G[0], G1) and np.array_equal(d.gens_1.h, hh)
+
+
+def test_commit_golden_vector(ctx, orc):
+    from spartan_bn254_b200.hyrax import DensePolynomial, PolyCommitmentGens
+    g = GOLD["hyrax_commit_4x8"]
+    gens = PolyCommitmentGens(5, g["label"].encode(), ctx)
+    Z = orc.to_mont([h2i(z) for z in g["Z"]])
+    bl = orc.to_mont([h2i(b) for b in g["blinds"]])
+    comm, _ = DensePolynomial(Z).commit(gens, bl)
+    exp = [None if p is None else (h2i(p[0]), h2i(p[1])) for p in g["C"]]
+    assert orc.points_to_ints(comm.C, comm.inf) == exp
+    assert [c.hex() for c in comm.compressed()] == g["C_compressed"]
+    assert comm.inf[3] == 1
+
+
+SHAPES = [
+    # (ell, gens kind, blinds, scalars)
+    (2, "ref", True, "uniform"),
+    (7, "ref", False, "uniform"),
+    (12, "ref", True, "uniform"),        # cfg0 witness: 64 x 64, random blinds (r1csproof.rs:210-237)
+    (15, "ref", False, "derefs"),        # cfg0 derefs: 128 x 256, zero blinds, last quarter of rows zero
+    (16, "ref", False, "derefs"),        # 256 x 256
+    (13, "distinct", True, "uniform"),
+    (14, "ref", False, "small"),         # comb_ops-like small scalars
+]
+
+
+@pytest.mark.parametrize("ell,gens_kind,use_blinds,kind", SHAPES)
+def test_commit_matches_oracle(ctx, orc, ell, gens_kind, use_blinds, kind):
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import DensePolynomial, PolyCommitmentGens, MultiCommitGens, compute_factored_lens
+    l, r = compute_factored_lens(ell)
+    L, R = 1 << l, 1 << r
+    if gens_kind == "ref":
+        gens = PolyCommitmentGens(ell, b"gens_r1cs_eval", ctx)
+    else:
+        G, h = synth.distinct_generators(ctx, R)
+        gens = PolyCommitmentGens.__new__(PolyCommitmentGens)
+        gens.gens = type("D", (), {})()
+        gens.gens.gens_n = MultiCommitGens(G, h, ctx)
+    if kind == "uniform":
+        Z = synth.uniform_scalars(1, L * R)
+    elif kind == "derefs":
+        Z = synth.derefs_scalars(ell)
+    else:
+        Z = ctx.fr_from_canonical(synth.small_scalars_canonical(8, L * R))
+    blinds = synth.uniform_scalars(4, L) if use_blinds else None
+    comm, _ = DensePolynomial(Z).commit(gens, blinds)
+    gn = gens.gens.gens_n
+    C, inf = orc.hyrax_commit(gn.G, gn.h, Z, L, R, blinds)
+    assert np.array_equal(comm.inf, inf)
+    assert np.array_equal(comm.C, C)
+    if kind == "derefs":
+        assert comm.inf[3 * L // 4:].all() and not comm.inf[: 3 * L // 4].any()
+
+
+def test_commit_adversarial_rows(ctx, orc):
+    """Inputs the reference never tests: all-zero rows, scalar 0 / 1 / r-1, rows that
+    cancel to the identity through duplicate generators, a blind that cancels the row."""
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import MultiCommitGens
+    R = 32
+    gens = MultiCommitGens.new(R, b"gens_r1cs_eval", ctx)      # contains many copies of G
+    sc, kinds = orc.gen_scalars(b"gens_r1cs_eval", R)
+    ones = [i for i in range(R) if kinds[i] == 2]
+    assert len(ones) >= 4
+    rmod = h2i(GOLD["constants"]["r"])
+    L = 8
+    Z = [[0] * R for _ in range(L)]
+    Z[1][0] = 1
+    Z[2][ones[0]] = 5; Z[2][ones[1]] = rmod - 5            # 5G - 5G = identity
+    Z[3] = [rmod - 1] * R
+    Z[4][ones[0]] = 7; Z[4][ones[1]] = 7; Z[4][ones[2]] = 7  # same base three times (P + P paths)
+    Z[5] = [1] * R
+    Z[6][3] = 123456789
+    Zm = orc.to_mont([v for row in Z for v in row])
+    blinds = [0] * L
+    blinds[6] = 42
+    bm = orc.to_mont(blinds)
+    C, inf = ctx.hyrax_commit(gens.device_bases(), Zm, L, R, bm)
+    Co, info = orc.hyrax_commit(gens.G, gens.h, Zm, L, R, bm)
+    assert np.array_equal(inf, info) and np.array_equal(C, Co)
+    assert inf[0] == 1 and inf[2] == 1
+
+
+def test_commit_chunking_and_window_override(ctx, orc):
+    """Results do not depend on the pipeline chunk size or the window width."""
+    from spartan_bn254_b200 import Context, synth
+    L, R = 64, 128
+    G, h = synth.distinct_generators(ctx, R)
+    Z = synth.uniform_scalars(2, L * R)
+    bl = synth.uniform_scalars(3, L)
+    Co, info = orc.hyrax_commit(G, h, Z, L, R, bl)
+    for chunk, c in ((7, 0), (64, 5), (1000, 9), (16, 12)):
+        c2 = Context(0)
+        c2.set("chunk_rows", chunk)
+        c2.set("window_bits", c)
+        b = c2.bases(G, h)
+        if c:
+            assert b.window_bits == c
+        C, inf = c2.hyrax_commit(b, Z, L, R, bl)
+        assert np.array_equal(C, Co) and np.array_equal(inf, info), (chunk, c)
+        b.close()
+        c2.close()
+
+
+def test_shape_errors(ctx):
+    """Reference preconditions (commitments.rs:146, hyrax.rs:258) surface as SBN_ERR_SHAPE / AssertionError."""
+    from spartan_bn254_b200 import SbnError, synth
+    from spartan_bn254_b200.hyrax import DensePolynomial, MultiCommitGens
+    G, h = synth.distinct_generators(ctx, 16)
+    gens = MultiCommitGens(G, h, ctx)
+    Z = synth.uniform_scalars(1, 64)
+    with pytest.raises(SbnError) as e:
+        ctx.hyrax_commit(gens.device_bases(), Z, 8, 8, None)       # R_size != gens.n
+    assert e.value.status == -2
+    with pytest.raises(AssertionError):
+        DensePolynomial(Z).commit_inner(np.zeros((8, 4), dtype=np.uint64), gens)
+
+
+def test_full_size_linearity_property(ctx):
+    """cfg1 size (1024 x 1024): commit(Z1 + Z2) == commit(Z1) + commit(Z2) row by row, checked with the
+    GPU's own point addition through a 2-term MSM, plus the oracle on a sample of rows."""
+    import oracle as orc
+    from spartan_bn254_b200 import synth
+    L = R = 1024
+    G, h = synth.distinct_generators(ctx, R)
+    bases = ctx.bases(G, h)
+    Z1 = synth.uniform_scalars(21, L * R)
+    Z2 = synth.uniform_scalars(22, L * R)
+    C1, i1 = ctx.hyrax_commit(bases, Z1, L, R, None)
+    C2, i2 = ctx.hyrax_commit(bases, Z2, L, R, None)
+    assert not i1.any() and not i2.any()
+    rows = np.arange(0, L, 64)
+    Zs = Z1.reshape(L, R, 4)[rows].reshape(-1, 4)
+    Co, info = orc.hyrax_commit(G, h, Zs, len(rows), R, None, threads=0)
+    assert np.array_equal(C1[rows], Co)
+    # linearity through the oracle's point addition on the sampled rows
+    Zsum = synth.reduce_mod_r(_add256(Z1.reshape(L, R, 4)[rows].reshape(-1, 4), Z2.reshape(L, R, 4)[rows].reshape(-1, 4)))
+    Csum, isum = ctx.hyrax_commit(bases, np.tile(Zsum, (L // len(rows), 1)), L, R, None)
+    for k, rrow in enumerate(rows):
+        o = np.zeros(8, dtype=np.uint64)
+        oi = np.zeros(1, dtype=np.uint8)
+        orc.lib().orc_g1_add_affine(C1[rrow].ctypes.data, 0, C2[rrow].ctypes.data, 0, o.ctypes.data, oi.ctypes.data)
+        assert np.array_equal(o, Csum[k]) and oi[0] == 0
+
+
+def _add256(a, b):
+    """limb-wise 256-bit add of uint64[n,4] arrays, both < r < 2^254 (no overflow out of limb 3)."""
+    out = np.zeros_like(a)
+    carry = np.zeros(a.shape[0], dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for k in range(4):
+            t = a[:, k] + b[:, k]
+            c1 = (t < a[:, k]).astype(np.uint64)
+            t2 = t + carry
+            c2 = (t2 < t).astype(np.uint64)
+            out[:, k] = t2
+            carry = c1 | c2
+    return out
