@@ -7,7 +7,7 @@
 //
 //   K1+K2  k_sort_row      per row: Montgomery Fr -> canonical, signed c-bit digits, counting sort of
 //                          (window, base) entries by bucket in shared memory, buckets ranked by size
-//   K3     k_accumulate    one thread per (row, bucket): XYZZ mixed additions of table points
+//   K3     k_accumulate    one thread per (row, task <= cap entries of a bucket): XYZZ mixed additions
 //   K4a    k_reduce        per row: sum_b (b+1) * S_b by chunked running sums + shared-memory tree
 //   K4b    k_normalize     XYZZ -> affine (one Fq inversion per row)
 //
@@ -80,8 +80,8 @@ __global__ void k_build_tables(const Affine* __restrict__ bases, const uint8_t* 
     store_affine(table + j, p);
     XYZZ acc = XYZZ::from_affine(p);
     for (int k = 1; k < W; k++) {
-        for (int d = 0; d < c; d++) acc = xyzz_dbl(acc);
-        p = xyzz_to_affine(acc);
+        for (int d = 0; d < c; d++) acc = xyzz_dbl<MulCall>(acc);
+        p = xyzz_to_affine<MulCall>(acc);
         store_affine(table + (size_t)k * n1 + j, p);
         acc = XYZZ::from_affine(p);
     }
@@ -113,20 +113,32 @@ __device__ __forceinline__ void for_each_digit(const Fr& canon, Fn&& f) {
 
 static constexpr int kSortThreads = 256;
 static constexpr int kRankBins = 256;
+static constexpr int kMaxTaskCap = 255;
 
-// entries[row * E + ...] : bucket-sorted list of (k * n1 + j) | (negative << 31)
-// starts [row * (NB + 1) + b] : first entry of bucket b (starts[NB] = total)
-// order  [row * NB + rank]   : bucket ids by decreasing size
+// A task is a run of at most `cap` bucket-sorted entries of one bucket: the unit of work of one
+// accumulation thread.  Buckets fuller than `cap` (the top window of a 254-bit scalar only has a few
+// distinct digits; derefs-style inputs repeat scalars) are split so no thread owns a long tail.
+struct Task {
+    uint32_t start;      // first entry (row-relative)
+    uint32_t len_slot;   // len << 24 | slot   (slot = position of the partial sum, bucket-ordered)
+};
+
+__host__ __device__ inline size_t msm_max_tasks(size_t E, int nb, int cap) { return E / cap + nb + 1; }
+
+// entries[row * E + ...]        : bucket-sorted list of (k * n1 + j) | (negative << 31)
+// tstart [row * (NB + 1) + b]   : first task slot of bucket b (tstart[NB] = number of tasks of the row)
+// tasks  [row * max_tasks + rank]: tasks by decreasing length
 template <int C>
 __global__ void __launch_bounds__(kSortThreads)
-k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int scalars_are_mont,
-           uint32_t E, uint32_t* __restrict__ entries, uint32_t* __restrict__ starts, uint16_t* __restrict__ order) {
+k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int scalars_are_mont, int cap,
+           uint32_t E, uint32_t max_tasks, uint32_t* __restrict__ entries, uint32_t* __restrict__ tstart,
+           Task* __restrict__ tasks) {
     constexpr int NB = 1 << (C - 1);
     constexpr int PER = (NB + kSortThreads - 1) / kSortThreads;   // buckets per thread in the scans
     __shared__ uint32_t counts[NB];
     __shared__ uint32_t cursor[NB];
     __shared__ uint32_t rank_hist[kRankBins];
-    __shared__ uint32_t warp_sums[kSortThreads / 32];
+    __shared__ uint32_t warp_sums[2][kSortThreads / 32];
 
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
@@ -154,41 +166,49 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
     }
     __syncthreads();
 
-    // exclusive scan of counts -> cursor, starts
-    uint32_t local[PER];
-    uint32_t sum = 0;
+    // exclusive scans over buckets: entry offsets (-> cursor) and task slots (-> tstart)
+    uint32_t loc_e[PER], loc_t[PER];
+    uint32_t sum_e = 0, sum_t = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         int b = tid * PER + i;
         uint32_t v = (b < NB) ? counts[b] : 0;
-        local[i] = sum;
-        sum += v;
+        loc_e[i] = sum_e;
+        loc_t[i] = sum_t;
+        sum_e += v;
+        sum_t += (v + cap - 1) / cap;
     }
-    uint32_t incl = sum;
+    uint32_t inc_e = sum_e, inc_t = sum_t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((tid & 31) >= o) incl += t;
+        uint32_t te = __shfl_up_sync(0xffffffffu, inc_e, o);
+        uint32_t tt = __shfl_up_sync(0xffffffffu, inc_t, o);
+        if ((tid & 31) >= o) { inc_e += te; inc_t += tt; }
     }
-    if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+    if ((tid & 31) == 31) { warp_sums[0][tid >> 5] = inc_e; warp_sums[1][tid >> 5] = inc_t; }
     __syncthreads();
-    uint32_t base = 0;
-    for (int w = 0; w < (tid >> 5); w++) base += warp_sums[w];
-    base += incl - sum;
-    uint32_t* srow = starts + (size_t)row * (NB + 1);
+    uint32_t base_e = inc_e - sum_e, base_t = inc_t - sum_t;
+    for (int w = 0; w < (tid >> 5); w++) { base_e += warp_sums[0][w]; base_t += warp_sums[1][w]; }
+    uint32_t* trow = tstart + (size_t)row * (NB + 1);
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         int b = tid * PER + i;
         if (b < NB) {
-            cursor[b] = base + local[i];
-            srow[b] = base + local[i];
-            atomicAdd(&rank_hist[min(counts[b], (uint32_t)(kRankBins - 1))], 1u);
+            cursor[b] = base_e + loc_e[i];
+            trow[b] = base_t + loc_t[i];
+            // task-length histogram: (nt - 1) full tasks + one remainder
+            uint32_t n = counts[b];
+            if (n) {
+                uint32_t nt = (n + cap - 1) / cap;
+                if (nt > 1) atomicAdd(&rank_hist[cap], nt - 1);
+                atomicAdd(&rank_hist[n - (nt - 1) * cap], 1u);
+            }
         }
     }
-    if (tid == kSortThreads - 1) srow[NB] = base + sum;
+    if (tid == kSortThreads - 1) trow[NB] = base_t + sum_t;
     __syncthreads();
 
-    // bucket ranking by decreasing size (counting sort on the clamped size)
+    // rank tasks by decreasing length (exact counting sort, len <= cap <= 255)
     uint32_t rank_base = 0;
     if (tid < kRankBins) {
         for (int v = tid + 1; v < kRankBins; v++) rank_base += rank_hist[v];
@@ -196,11 +216,25 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
     __syncthreads();
     if (tid < kRankBins) rank_hist[tid] = rank_base;
     __syncthreads();
-    uint16_t* orow = order + (size_t)row * NB;
-    for (int b = tid; b < NB; b += kSortThreads) {
-        uint32_t pos = atomicAdd(&rank_hist[min(counts[b], (uint32_t)(kRankBins - 1))], 1u);
-        orow[pos] = (uint16_t)b;
+    Task* krow = tasks + (size_t)row * max_tasks;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        int b = tid * PER + i;
+        if (b >= NB) continue;
+        uint32_t n = counts[b];
+        uint32_t start = cursor[b];          // not yet advanced: pass 2 starts after the next barrier
+        uint32_t slot = base_t + loc_t[i];
+        while (n) {
+            uint32_t len = n < (uint32_t)cap ? n : (uint32_t)cap;
+            uint32_t pos = atomicAdd(&rank_hist[len], 1u);
+            Task t;
+            t.start = start;
+            t.len_slot = (len << 24) | slot;
+            krow[pos] = t;
+            start += len; slot++; n -= len;
+        }
     }
+    __syncthreads();
 
     // pass 2: scatter
     uint32_t* erow = entries + (size_t)row * E;
@@ -216,56 +250,55 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
 
 // ---------------------------------------------------------------------------------------------
 // K3: bucket accumulation.  Thread gid -> (rank = gid / rows, row = gid % rows): a warp holds the
-// same size-rank of 32 different rows (near-identical trip counts), and the grid walks ranks from
-// the fullest buckets to the emptiest (longest-processing-time-first).
+// same length-rank of 32 different rows (near-identical trip counts), and the grid walks ranks from
+// the longest tasks to the shortest (longest-processing-time-first).
 // ---------------------------------------------------------------------------------------------
 static constexpr int kAccThreads = 128;
 
 __global__ void __launch_bounds__(kAccThreads)
 k_accumulate(const Affine* __restrict__ table, const uint32_t* __restrict__ entries,
-             const uint32_t* __restrict__ starts, const uint16_t* __restrict__ order,
-             XYZZ* __restrict__ buckets, int rows, int nb, uint32_t E) {
+             const uint32_t* __restrict__ tstart, const Task* __restrict__ tasks,
+             XYZZ* __restrict__ partials, int rows, int nb, uint32_t E, uint32_t max_tasks) {
     const size_t gid = (size_t)blockIdx.x * kAccThreads + threadIdx.x;
-    if (gid >= (size_t)rows * nb) return;
-    const int rank = (int)(gid / rows);
+    if (gid >= (size_t)rows * max_tasks) return;
+    const uint32_t rank = (uint32_t)(gid / rows);
     const int row = (int)(gid % rows);
-    const int b = order[(size_t)row * nb + rank];
-    const uint32_t* srow = starts + (size_t)row * (nb + 1);
-    uint32_t i = srow[b];
-    const uint32_t end = srow[b + 1];
-    const uint32_t* erow = entries + (size_t)row * E;
+    if (rank >= tstart[(size_t)row * (nb + 1) + nb]) return;
+    const Task t = tasks[(size_t)row * max_tasks + rank];
+    const uint32_t* e = entries + (size_t)row * E + t.start;
+    const uint32_t len = t.len_slot >> 24;
 
     XYZZ acc = XYZZ::identity();
-    for (; i < end; i++) {
-        const uint32_t v = __ldg(erow + i);
+    for (uint32_t i = 0; i < len; i++) {
+        const uint32_t v = __ldg(e + i);
         Affine p = load_affine(table + (v & 0x7fffffffu));
         if (p.is_identity()) continue;
         if (v >> 31) p.y = fp_neg(p.y);
         xyzz_add_mixed(acc, p);
     }
-    store_xyzz(buckets + (size_t)row * nb + b, acc);
+    store_xyzz(partials + (size_t)row * max_tasks + (t.len_slot & 0xffffffu), acc);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4a: per-row bucket reduction  T = sum_b (b + 1) * S_b
-// TPR threads per row, each owns m = nb / TPR consecutive buckets: running sums give
-// tot = sum (b - lo + 1) S_b and run = sum S_b; the thread contributes tot + lo * run; contributions
-// are combined by a shared-memory tree.
+// K4a: per-row bucket reduction  T = sum_b (b + 1) * S_b,  S_b = sum of the bucket's task partials.
+//
+// T equals the sum of all suffix sums  Suf_j = sum_{b >= j} S_b.  TPR threads per row each own m
+// consecutive buckets: a sequential pass gives the thread's local suffix sums (their total `tot`) and
+// its bucket total A_t.  An inclusive suffix scan of A_t across the threads (shared memory,
+// Kogge-Stone) gives I_t = sum_{u >= t} A_u; every bucket of thread t is short of I_{t+1}, so
+//     T = sum_t tot_t + m * sum_{t >= 1} I_t .
+// Control flow is uniform (no per-thread scalar multiplication) and the XYZZ addition is a single
+// out-of-line function, so the kernel stays small.
 // ---------------------------------------------------------------------------------------------
 static constexpr int kRedThreads = 128;
 
-__device__ __forceinline__ XYZZ xyzz_small_mul(const XYZZ& p, uint32_t k) {
-    XYZZ r = XYZZ::identity();
-    if (k == 0) return r;
-    for (int bit = 31 - __clz(k); bit >= 0; bit--) {
-        r = xyzz_dbl(r);
-        if ((k >> bit) & 1) xyzz_add(r, p);
-    }
-    return r;
-}
+// One out-of-line copy of the full addition with its 14 products inlined (instruction-level
+// parallelism between independent products matters at the 3-4 warps per scheduler this kernel runs at).
+__device__ __noinline__ void xyzz_add_call(XYZZ* acc, const XYZZ* q) { xyzz_add<MulInline, MulCall>(*acc, *q); }
 
 __global__ void __launch_bounds__(kRedThreads)
-k_reduce(const XYZZ* __restrict__ buckets, int rows, int nb, int tpr, XYZZ* __restrict__ row_totals) {
+k_reduce(const XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, int rows, int nb, int tpr,
+         uint32_t max_tasks, XYZZ* __restrict__ row_totals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XYZZ* sm = reinterpret_cast<XYZZ*>(smem_raw);
     const int rows_per_block = kRedThreads / tpr;
@@ -275,30 +308,43 @@ k_reduce(const XYZZ* __restrict__ buckets, int rows, int nb, int tpr, XYZZ* __re
     const int m = nb / tpr;
     const bool active = row < rows;
 
-    XYZZ tot = XYZZ::identity();
+    XYZZ tot = XYZZ::identity();   // sum of the local suffix sums
+    XYZZ run = XYZZ::identity();   // A_t, then I_t
     if (active) {
-        const XYZZ* brow = buckets + (size_t)row * nb;
+        const XYZZ* prow = partials + (size_t)row * max_tasks;
+        const uint32_t* trow = tstart + (size_t)row * (nb + 1);
         const int lo = t * m;
-        XYZZ run = XYZZ::identity();
+        uint32_t hi_slot = trow[lo + m];
         for (int b = lo + m - 1; b >= lo; b--) {
-            XYZZ s = load_xyzz(brow + b);
-            xyzz_add(run, s);
-            xyzz_add(tot, run);
-        }
-        if (lo) {
-            XYZZ w = xyzz_small_mul(run, (uint32_t)lo);
-            xyzz_add(tot, w);
+            const uint32_t lo_slot = trow[b];
+            for (uint32_t s = lo_slot; s < hi_slot; s++) {
+                XYZZ part = load_xyzz(prow + s);
+                xyzz_add_call(&run, &part);
+            }
+            hi_slot = lo_slot;
+            xyzz_add_call(&tot, &run);
         }
     }
-    // tree over the tpr threads of each row
+    // inclusive suffix scan of A_t over the tpr threads of the row
+    for (int off = 1; off < tpr; off <<= 1) {
+        sm[threadIdx.x] = run;
+        __syncthreads();
+        XYZZ v = (t + off < tpr) ? sm[threadIdx.x + off] : XYZZ::identity();
+        __syncthreads();
+        xyzz_add_call(&run, &v);
+    }
+    // V_t = tot_t + (t >= 1 ? m * I_t : 0)
+    if (t >= 1) {
+        for (int k = 1; k < m; k <<= 1) run = xyzz_dbl<MulCall>(run);
+        xyzz_add_call(&tot, &run);
+    }
+    // tree sum of V_t
     for (int stride = tpr >> 1; stride >= 1; stride >>= 1) {
+        sm[threadIdx.x] = tot;
         __syncthreads();
-        if (t >= stride && t < 2 * stride) sm[threadIdx.x] = tot;
+        XYZZ o = (t < stride) ? sm[threadIdx.x + stride] : XYZZ::identity();
         __syncthreads();
-        if (t < stride) {
-            XYZZ o = sm[threadIdx.x + stride];
-            xyzz_add(tot, o);
-        }
+        xyzz_add_call(&tot, &o);
     }
     if (active && t == 0) store_xyzz(row_totals + row, tot);
 }
@@ -310,7 +356,7 @@ __global__ void k_normalize(const XYZZ* __restrict__ in, int n, Affine* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     XYZZ p = load_xyzz(in + i);
-    Affine a = xyzz_to_affine(p);
+    Affine a = xyzz_to_affine<MulCall>(p);
     store_affine(out + i, a);
     if (inf) inf[i] = p.is_identity() ? 1 : 0;
 }
@@ -333,12 +379,12 @@ __global__ void k_scalar_mul(const Affine* __restrict__ P, const uint8_t* __rest
             uint32_t word = k.l[w];
             if (!started && word == 0) continue;
             for (int bit = 31; bit >= 0; bit--) {
-                if (started) acc = xyzz_dbl(acc);
-                if ((word >> bit) & 1) { xyzz_add_mixed(acc, p); started = true; }
+                if (started) acc = xyzz_dbl<MulCall>(acc);
+                if ((word >> bit) & 1) { xyzz_add_mixed<MulCall>(acc, p); started = true; }
             }
         }
     }
-    Affine a = xyzz_to_affine(acc);
+    Affine a = xyzz_to_affine<MulCall>(acc);
     store_affine(out + i, a);
     if (inf) inf[i] = acc.is_identity() ? 1 : 0;
 }

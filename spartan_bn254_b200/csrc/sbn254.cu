@@ -36,9 +36,17 @@ struct sbn_ctx {
     std::string last_error;
     long chunk_rows = 512;
     long window_bits = 0;
+    long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
+    long reduce_m = 16;     // buckets per reduction thread
     uint64_t launches = 0, h2d = 0, d2h = 0;
     // grow-only workspaces
-    DevBuf entries, starts, order, buckets, totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    struct Slot {          // one in-flight chunk of rows: private workspace + stream
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf entries, tstart, tasks, partials;
+    } slots[2];
+    cudaEvent_t fork = nullptr;
+    DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
     // last-commit profile
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[4] = {0, 0, 0, 0};
@@ -71,8 +79,7 @@ struct sbn_bases {
 static int ensure(sbn_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return SBN_OK;
     if (b.p) {
-        SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-        SBN_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
+        SBN_CUDA(ctx, cudaDeviceSynchronize());
         SBN_CUDA(ctx, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -110,8 +117,14 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
     sbn_ctx* ctx = new (std::nothrow) sbn_ctx();
     if (!ctx) return SBN_ERR_OOM;
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& sl : ctx->slots)
+        ok = ok && cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         delete ctx;
         return SBN_ERR_CUDA;
     }
@@ -124,9 +137,16 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
-    for (DevBuf* b : {&ctx->entries, &ctx->starts, &ctx->order, &ctx->buckets, &ctx->totals, &ctx->dZ, &ctx->dblinds,
-                      &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1, &ctx->scratch2})
+    for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
+                      &ctx->scratch2})
         release(*b);
+    for (auto& sl : ctx->slots) {
+        cudaStreamSynchronize(sl.stream);
+        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials}) release(*b);
+        cudaStreamDestroy(sl.stream);
+        cudaEventDestroy(sl.done);
+    }
+    cudaEventDestroy(ctx->fork);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
@@ -149,6 +169,12 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "chunk_rows")) {
         if (value < 1) return SBN_ERR_ARG;
         ctx->chunk_rows = value;
+    } else if (!strcmp(key, "task_cap")) {
+        if (value < 0 || value > kMaxTaskCap) return SBN_ERR_ARG;
+        ctx->task_cap = value;
+    } else if (!strcmp(key, "reduce_m")) {
+        if (value < 1 || (value & (value - 1))) return SBN_ERR_ARG;
+        ctx->reduce_m = value;
     } else if (!strcmp(key, "window_bits")) {
         if (value != 0 && (value < kMinWindowBits || value > kMaxWindowBits)) return SBN_ERR_ARG;
         ctx->window_bits = value;
@@ -197,6 +223,10 @@ static int choose_window(size_t n1) {
     }
     return best;
 }
+
+// Natural buckets (Poisson around the mean occupancy) stay whole; only genuinely heavy ones -- the top
+// window of a 254-bit scalar has few distinct digits, derefs-style inputs repeat scalars -- are split.
+static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b);
 
 // ------------------------------------------------------------------------------------------------
 // bases
@@ -272,6 +302,13 @@ extern "C" int sbn_bases_window_bits(const sbn_bases* b) { return b ? b->c : 0; 
 // ------------------------------------------------------------------------------------------------
 // commit pipeline
 // ------------------------------------------------------------------------------------------------
+static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b) {
+    if (ctx->task_cap) return (int)ctx->task_cap;
+    double mean = double(b->W) * b->n1 / b->nb;
+    int cap = (int)(2.5 * mean + 0.5);
+    return std::max(32, std::min(kMaxTaskCap, cap));
+}
+
 static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
     while (ctx->ev_pool.size() <= idx) {
         cudaEvent_t e;
@@ -282,15 +319,15 @@ static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
 }
 
 template <int C>
-static void launch_sort(const Fr* Z, const Fr* blinds, int R, uint32_t E, uint32_t* entries, uint32_t* starts,
-                        uint16_t* order, int rows, cudaStream_t s) {
-    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, 1, E, entries, starts, order);
+static void launch_sort(const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks, uint32_t* entries,
+                        uint32_t* tstart, Task* tasks, int rows, cudaStream_t s) {
+    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, 1, cap, E, max_tasks, entries, tstart, tasks);
 }
 
-static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, uint32_t E, uint32_t* entries, uint32_t* starts,
-                         uint16_t* order, int rows, cudaStream_t s) {
+static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks,
+                         uint32_t* entries, uint32_t* tstart, Task* tasks, int rows, cudaStream_t s) {
     switch (c) {
-#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, E, entries, starts, order, rows, s); return SBN_OK;
+#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, cap, E, max_tasks, entries, tstart, tasks, rows, s); return SBN_OK;
         SBN_CASE(4) SBN_CASE(5) SBN_CASE(6) SBN_CASE(7) SBN_CASE(8) SBN_CASE(9) SBN_CASE(10) SBN_CASE(11)
         SBN_CASE(12) SBN_CASE(13)
 #undef SBN_CASE
@@ -298,32 +335,34 @@ static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, uint32_t E
     }
 }
 
-// Runs the four stages for rows [row0, row0 + rows) on `stream`; dZ points at row 0 of the chunk.
-static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ_chunk, const Fr* dblinds_chunk, int rows, int R,
-                        XYZZ* totals_chunk, cudaStream_t stream, size_t& ev_idx, std::vector<int>* ev_stage) {
+// Runs the first three stages for `rows` rows in pipeline slot `sl`; dZ_chunk points at the chunk's first row.
+static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const Fr* dZ_chunk, const Fr* dblinds_chunk,
+                        int rows, int R, XYZZ* totals_chunk, size_t& ev_idx, std::vector<int>& ev_stage) {
     const uint32_t E = (uint32_t)b->W * (uint32_t)b->n1;
-    uint32_t* entries = (uint32_t*)ctx->entries.p;
-    uint32_t* starts = (uint32_t*)ctx->starts.p;
-    uint16_t* order = (uint16_t*)ctx->order.p;
-    XYZZ* buckets = (XYZZ*)ctx->buckets.p;
+    const int cap = task_cap_for(ctx, b);
+    const uint32_t max_tasks = (uint32_t)msm_max_tasks(E, b->nb, cap);
+    uint32_t* entries = (uint32_t*)sl.entries.p;
+    uint32_t* tstart = (uint32_t*)sl.tstart.p;
+    Task* tasks = (Task*)sl.tasks.p;
+    XYZZ* partials = (XYZZ*)sl.partials.p;
+    cudaStream_t stream = sl.stream;
     auto mark = [&](int stage) {
-        if (!ev_stage) return;
         cudaEvent_t e = get_event(ctx, ev_idx++);
         if (e) cudaEventRecord(e, stream);
-        ev_stage->push_back(stage);
+        ev_stage.push_back(stage);
     };
     mark(-1);
-    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, E, entries, starts, order, rows, stream));
+    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, cap, E, max_tasks, entries, tstart, tasks, rows, stream));
     mark(0);
-    const size_t threads = (size_t)rows * b->nb;
+    const size_t threads = (size_t)rows * max_tasks;
     k_accumulate<<<(unsigned)((threads + kAccThreads - 1) / kAccThreads), kAccThreads, 0, stream>>>(
-        b->table, entries, starts, order, buckets, rows, b->nb, E);
+        b->table, entries, tstart, tasks, partials, rows, b->nb, E, max_tasks);
     mark(1);
-    int m = std::min(32, b->nb);
+    int m = std::min((int)ctx->reduce_m, b->nb);
     int tpr = std::min(kRedThreads, b->nb / m);
     int rows_per_block = kRedThreads / tpr;
     k_reduce<<<(rows + rows_per_block - 1) / rows_per_block, kRedThreads, kRedThreads * sizeof(XYZZ), stream>>>(
-        buckets, rows, b->nb, tpr, totals_chunk);
+        partials, tstart, rows, b->nb, tpr, max_tasks, totals_chunk);
     mark(2);
     ctx->launches += 3;
     SBN_CUDA(ctx, cudaGetLastError());
@@ -332,10 +371,16 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ_chunk, co
 
 static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chunk, size_t L) {
     const size_t E = (size_t)b->W * b->n1;
-    SBN_TRY(ensure(ctx, ctx->entries, chunk * E * sizeof(uint32_t)));
-    SBN_TRY(ensure(ctx, ctx->starts, chunk * (b->nb + 1) * sizeof(uint32_t)));
-    SBN_TRY(ensure(ctx, ctx->order, chunk * b->nb * sizeof(uint16_t)));
-    SBN_TRY(ensure(ctx, ctx->buckets, chunk * b->nb * sizeof(XYZZ)));
+    const size_t max_tasks = msm_max_tasks(E, b->nb, task_cap_for(ctx, b));
+    if (max_tasks >= (1u << 24)) return SBN_ERR_SHAPE;
+    const size_t nslots = L > chunk ? 2 : 1;
+    for (size_t i = 0; i < nslots; i++) {
+        auto& sl = ctx->slots[i];
+        SBN_TRY(ensure(ctx, sl.entries, chunk * E * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.tstart, chunk * (b->nb + 1) * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.tasks, chunk * max_tasks * sizeof(Task)));
+        SBN_TRY(ensure(ctx, sl.partials, chunk * max_tasks * sizeof(XYZZ)));
+    }
     SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
     return SBN_OK;
 }
@@ -360,6 +405,56 @@ static int check_commit_shape(const sbn_bases* b, size_t L, size_t R) {
     return SBN_OK;
 }
 
+// The pipeline shared by both entry points.  Chunks of rows alternate between two slots (streams with
+// private workspaces) so one chunk's latency-bound reduction overlaps the next chunk's accumulation; when
+// `host_Z` is given each chunk's H2D copy is issued on the copy stream and handed over by an event.
+// `main` is the stream the caller's inputs are ordered on and on which the normalisation runs.
+static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
+                      const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage) {
+    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    const size_t nchunks = (L + chunk - 1) / chunk;
+    XYZZ* totals = (XYZZ*)ctx->totals.p;
+    size_t ev_idx = 0;
+    const size_t handoff_base = 4 * nchunks + 8;    // copy->compute events live after the profiling events
+    SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
+    const size_t nslots = nchunks > 1 ? 2 : 1;
+    for (size_t i = 0; i < nslots; i++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->fork, 0));
+    if (host_Z) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
+    for (size_t ci = 0, row0 = 0; row0 < L; row0 += chunk, ci++) {
+        auto& sl = ctx->slots[ci % nslots];
+        int rows = (int)std::min(chunk, L - row0);
+        if (host_Z) {
+            SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0 * R), host_Z + row0 * R, (size_t)rows * R * sizeof(Fr),
+                                          cudaMemcpyHostToDevice, ctx->copy));
+            ctx->h2d += (size_t)rows * R * sizeof(Fr);
+            cudaEvent_t copied = get_event(ctx, handoff_base + ci);
+            if (!copied) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
+            SBN_CUDA(ctx, cudaEventRecord(copied, ctx->copy));
+            SBN_CUDA(ctx, cudaStreamWaitEvent(sl.stream, copied, 0));
+        }
+        SBN_TRY(commit_chunk(ctx, b, sl, dZ + row0 * R, dblinds ? dblinds + row0 : nullptr, rows, (int)R, totals + row0,
+                             ev_idx, ev_stage));
+    }
+    for (size_t i = 0; i < nslots; i++) {
+        SBN_CUDA(ctx, cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream));
+        SBN_CUDA(ctx, cudaStreamWaitEvent(main, ctx->slots[i].done, 0));
+    }
+    {
+        cudaEvent_t e = get_event(ctx, ev_idx++);
+        if (e) cudaEventRecord(e, main);
+        ev_stage.push_back(-1);
+    }
+    k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, main>>>(totals, (int)L, dC, dinf);
+    ctx->launches++;
+    {
+        cudaEvent_t e = get_event(ctx, ev_idx++);
+        if (e) cudaEventRecord(e, main);
+        ev_stage.push_back(3);
+    }
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
 extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const void* dZ, size_t L, size_t R,
                                        const void* dblinds, void* dC_out, void* dinf_out, void* stream_) {
     if (!ctx || !b || !dZ || !dC_out || b->ctx != ctx) return SBN_ERR_ARG;
@@ -369,28 +464,9 @@ extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const v
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->compute;
     const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
-    size_t ev_idx = 0;
     std::vector<int> ev_stage;
-    XYZZ* totals = (XYZZ*)ctx->totals.p;
-    for (size_t row0 = 0; row0 < L; row0 += chunk) {
-        int rows = (int)std::min(chunk, L - row0);
-        const Fr* z = (const Fr*)dZ + row0 * R;
-        const Fr* bl = dblinds ? (const Fr*)dblinds + row0 : nullptr;
-        SBN_TRY(commit_chunk(ctx, b, z, bl, rows, (int)R, totals + row0, stream, ev_idx, &ev_stage));
-    }
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, stream);
-        ev_stage.push_back(-1);
-    }
-    k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, stream>>>(totals, (int)L, (Affine*)dC_out, (uint8_t*)dinf_out);
-    ctx->launches++;
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, stream);
-        ev_stage.push_back(3);
-    }
-    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(run_commit(ctx, b, (const Fr*)dZ, nullptr, L, R, (const Fr*)dblinds, (Affine*)dC_out, (uint8_t*)dinf_out,
+                       stream, ev_stage));
     if (!stream_) {   // context stream: resolve the stage timings now
         SBN_CUDA(ctx, cudaStreamSynchronize(stream));
         collect_profile(ctx, ev_stage);
@@ -411,48 +487,16 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
     SBN_TRY(ensure(ctx, ctx->dZ, L * R * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
     SBN_TRY(ensure(ctx, ctx->dinf, L));
-    if (blinds) SBN_TRY(ensure(ctx, ctx->dblinds, L * sizeof(Fr)));
-    Fr* dZ = (Fr*)ctx->dZ.p;
-    Fr* dbl = blinds ? (Fr*)ctx->dblinds.p : nullptr;
-    XYZZ* totals = (XYZZ*)ctx->totals.p;
-
-    // the copy stream must not overwrite dZ while an earlier call's kernels still read it
-    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    Fr* dbl = nullptr;
     if (blinds) {
-        SBN_CUDA(ctx, cudaMemcpyAsync(dbl, blinds, L * sizeof(Fr), cudaMemcpyHostToDevice, ctx->copy));
+        SBN_TRY(ensure(ctx, ctx->dblinds, L * sizeof(Fr)));
+        dbl = (Fr*)ctx->dblinds.p;
+        SBN_CUDA(ctx, cudaMemcpyAsync(dbl, blinds, L * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute));
         ctx->h2d += L * sizeof(Fr);
     }
-    size_t ev_idx = 0;
     std::vector<int> ev_stage;
-    std::vector<cudaEvent_t> copied;
-    size_t nchunks = (L + chunk - 1) / chunk;
-    // events for copy->compute hand-off live after the profiling events in the pool
-    size_t handoff_base = 4 * nchunks + 8;
-    for (size_t ci = 0, row0 = 0; row0 < L; row0 += chunk, ci++) {
-        int rows = (int)std::min(chunk, L - row0);
-        SBN_CUDA(ctx, cudaMemcpyAsync(dZ + row0 * R, (const Fr*)Z + row0 * R, (size_t)rows * R * sizeof(Fr),
-                                      cudaMemcpyHostToDevice, ctx->copy));
-        ctx->h2d += (size_t)rows * R * sizeof(Fr);
-        cudaEvent_t done = get_event(ctx, handoff_base + ci);
-        if (!done) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
-        SBN_CUDA(ctx, cudaEventRecord(done, ctx->copy));
-        SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, done, 0));
-        SBN_TRY(commit_chunk(ctx, b, dZ + row0 * R, dbl ? dbl + row0 : nullptr, rows, (int)R, totals + row0,
-                             ctx->compute, ev_idx, &ev_stage));
-    }
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, ctx->compute);
-        ev_stage.push_back(-1);
-    }
-    k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, ctx->compute>>>(totals, (int)L, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p);
-    ctx->launches++;
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, ctx->compute);
-        ev_stage.push_back(3);
-    }
-    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(run_commit(ctx, b, (const Fr*)ctx->dZ.p, (const Fr*)Z, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p,
+                       ctx->compute, ev_stage));
     SBN_CUDA(ctx, cudaMemcpyAsync(C_out, ctx->dC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, ctx->compute));
     SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, ctx->dinf.p, L, cudaMemcpyDeviceToHost, ctx->compute));
     ctx->d2h += L * sizeof(Affine) + L;
