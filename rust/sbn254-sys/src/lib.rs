@@ -1,0 +1,105 @@
+//! Thin FFI crate over `include/sbn254.h`.  NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no
+//! Rust toolchain and no crates.io access; this is the source a maintainer of Spartan-BN254 drops in.
+//!
+//! Layout contract: `ark_bn254::Fr` / `Fq` are `Fp256<MontBackend<_, 4>>` whose only field is
+//! `BigInt<4>([u64; 4])` in Montgomery form, so a `&[Scalar]` (newtype over `Fr`, reference scalar.rs:15)
+//! is passed as `*const SbnFr` without conversion.  `G1Affine { x, y, infinity }` is not `repr(C)`, so
+//! generators are marshalled field by field ONCE per generator set (see `Bases::new`).
+#![allow(non_camel_case_types)]
+use ark_bn254::{Fq, Fr, G1Affine};
+use ark_ff::{BigInt, PrimeField};
+use std::os::raw::{c_char, c_int, c_long, c_void};
+
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct SbnFr { pub l: [u64; 4] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct SbnG1a { pub x: [u64; 4], pub y: [u64; 4] }
+#[repr(C)] pub struct sbn_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_bases { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_bullet { _p: [u8; 0] }
+
+extern "C" {
+    pub fn sbn_strerror(status: c_int) -> *const c_char;
+    pub fn sbn_ctx_create(device: c_int, out: *mut *mut sbn_ctx) -> c_int;
+    pub fn sbn_ctx_destroy(ctx: *mut sbn_ctx) -> c_int;
+    pub fn sbn_ctx_set(ctx: *mut sbn_ctx, key: *const c_char, value: c_long) -> c_int;
+    pub fn sbn_bases_create(ctx: *mut sbn_ctx, g: *const SbnG1a, g_inf: *const u8, n: usize, h: *const SbnG1a,
+                            out: *mut *mut sbn_bases) -> c_int;
+    pub fn sbn_bases_destroy(b: *mut sbn_bases) -> c_int;
+    pub fn sbn_hyrax_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, z: *const SbnFr, l_size: usize, r_size: usize,
+                            blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_msm(ctx: *mut sbn_ctx, pts: *const SbnG1a, inf: *const u8, s: *const SbnFr, n: usize,
+                   out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, s: *const SbnFr, n: usize, blind: *const SbnFr,
+                      out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_bound(ctx: *mut sbn_ctx, z: *const SbnFr, l: *const SbnFr, l_size: usize, r_size: usize,
+                     lz_out: *mut SbnFr) -> c_int;
+    pub fn sbn_bullet_begin(ctx: *mut sbn_ctx, b: *const sbn_bases, q: *const SbnG1a, a: *const SbnFr, bv: *const SbnFr,
+                            n: usize, blind: *const SbnFr, gamma: *mut SbnG1a, gamma_inf: *mut u8,
+                            out: *mut *mut sbn_bullet) -> c_int;
+    pub fn sbn_bullet_round(st: *mut sbn_bullet, blind_l: *const SbnFr, blind_r: *const SbnFr, l_out: *mut SbnG1a,
+                            l_inf: *mut u8, r_out: *mut SbnG1a, r_inf: *mut u8) -> c_int;
+    pub fn sbn_bullet_fold(st: *mut sbn_bullet, u: *const SbnFr, u_inv: *const SbnFr) -> c_int;
+    pub fn sbn_bullet_end(st: *mut sbn_bullet, a_hat: *mut SbnFr, b_hat: *mut SbnFr, g_hat: *mut SbnG1a,
+                          g_hat_inf: *mut u8) -> c_int;
+    pub fn sbn_bullet_destroy(st: *mut sbn_bullet) -> c_int;
+}
+
+fn check(status: c_int, what: &str) {
+    // The reference's preconditions are assert!/panic (hyrax.rs:258,290,295; commitments.rs:146): keep that.
+    if status != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(sbn_strerror(status)) }.to_string_lossy().into_owned();
+        panic!("{what}: libsbn254 status {status} ({msg})");
+    }
+}
+
+#[inline] fn fq_limbs(v: &Fq) -> [u64; 4] { (v.0).0 }          // Montgomery limbs as stored by ark-ff
+#[inline] fn fq_from_limbs(l: [u64; 4]) -> Fq { ark_ff::Fp(BigInt(l), core::marker::PhantomData) }
+
+pub fn to_abi(p: &G1Affine) -> (SbnG1a, u8) {
+    if p.infinity { (SbnG1a::default(), 1) } else { (SbnG1a { x: fq_limbs(&p.x), y: fq_limbs(&p.y) }, 0) }
+}
+pub fn from_abi(p: &SbnG1a, inf: u8) -> G1Affine {
+    if inf != 0 { G1Affine::identity() } else { G1Affine::new_unchecked(fq_from_limbs(p.x), fq_from_limbs(p.y)) }
+}
+
+pub struct Context(pub *mut sbn_ctx);
+unsafe impl Send for Context {}
+unsafe impl Sync for Context {}            // the library serialises calls per context
+impl Context {
+    pub fn new(device: i32) -> Self { let mut h = std::ptr::null_mut(); check(unsafe { sbn_ctx_create(device, &mut h) }, "sbn_ctx_create"); Context(h) }
+}
+impl Drop for Context { fn drop(&mut self) { unsafe { sbn_ctx_destroy(self.0) }; } }
+
+/// A `MultiCommitGens` resident on the GPU (upload once per generator set; commitments.rs:17-27).
+pub struct Bases { pub h: *mut sbn_bases, pub n: usize }
+unsafe impl Send for Bases {}
+unsafe impl Sync for Bases {}
+impl Bases {
+    pub fn new(ctx: &Context, g_affine: &[G1Affine], h_affine: &G1Affine) -> Self {
+        let (pts, inf): (Vec<_>, Vec<_>) = g_affine.iter().map(to_abi).unzip();
+        let (h, _) = to_abi(h_affine);
+        let mut out = std::ptr::null_mut();
+        check(unsafe { sbn_bases_create(ctx.0, pts.as_ptr(), inf.as_ptr(), pts.len(), &h, &mut out) }, "sbn_bases_create");
+        Bases { h: out, n: pts.len() }
+    }
+}
+impl Drop for Bases { fn drop(&mut self) { unsafe { sbn_bases_destroy(self.h) }; } }
+
+/// Drop-in body of `DensePolynomial::commit_inner` (hyrax.rs:253-281): `z` is the row-major evaluation
+/// vector, `blinds.len()` = L_size.  `Fr` slices are passed as-is (Montgomery limbs).
+pub fn hyrax_commit(ctx: &Context, bases: &Bases, z: &[Fr], blinds: &[Fr]) -> Vec<G1Affine> {
+    let l_size = blinds.len();
+    let r_size = z.len() / l_size;
+    assert_eq!(l_size * r_size, z.len());
+    let mut c = vec![SbnG1a::default(); l_size];
+    let mut inf = vec![0u8; l_size];
+    let zero_blinds = blinds.iter().all(|b| b.is_zero_vartime());
+    let bp = if zero_blinds { std::ptr::null() } else { blinds.as_ptr() as *const SbnFr };
+    check(unsafe { sbn_hyrax_commit(ctx.0, bases.h, z.as_ptr() as *const SbnFr, l_size, r_size, bp, c.as_mut_ptr(), inf.as_mut_ptr()) },
+          "sbn_hyrax_commit");
+    c.iter().zip(inf.iter()).map(|(p, i)| from_abi(p, *i)).collect()
+}
+
+trait IsZeroVartime { fn is_zero_vartime(&self) -> bool; }
+impl IsZeroVartime for Fr { fn is_zero_vartime(&self) -> bool { self.into_bigint().0 == [0u64; 4] } }
+
+#[allow(dead_code)] fn _unused(_: *mut c_void) {}
