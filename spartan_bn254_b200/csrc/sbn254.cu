@@ -410,7 +410,8 @@ static int check_commit_shape(const sbn_bases* b, size_t L, size_t R) {
 // `host_Z` is given each chunk's H2D copy is issued on the copy stream and handed over by an event.
 // `main` is the stream the caller's inputs are ordered on and on which the normalisation runs.
 static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
-                      const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage) {
+                      const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
+                      bool normalize = true) {
     const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
     const size_t nchunks = (L + chunk - 1) / chunk;
     XYZZ* totals = (XYZZ*)ctx->totals.p;
@@ -439,6 +440,7 @@ static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
         SBN_CUDA(ctx, cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream));
         SBN_CUDA(ctx, cudaStreamWaitEvent(main, ctx->slots[i].done, 0));
     }
+    if (!normalize) return SBN_OK;     // caller consumes the XYZZ row totals in ctx->totals
     {
         cudaEvent_t e = get_event(ctx, ev_idx++);
         if (e) cudaEventRecord(e, main);
@@ -626,18 +628,353 @@ extern "C" int sbn_microbench(sbn_ctx* ctx, int kind, double* per_second) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// not yet implemented entry points
+// a6 / a5: single MSMs
 // ------------------------------------------------------------------------------------------------
-extern "C" int sbn_msm(sbn_ctx*, const sbn_g1a*, const uint8_t*, const sbn_fr*, size_t, sbn_g1a*, uint8_t*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_commit(sbn_ctx*, const sbn_bases*, const sbn_fr*, size_t, const sbn_fr*, sbn_g1a*, uint8_t*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bound(sbn_ctx*, const sbn_fr*, const sbn_fr*, size_t, size_t, sbn_fr*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bullet_begin(sbn_ctx*, const sbn_bases*, const sbn_g1a*, const sbn_fr*, const sbn_fr*, size_t, const sbn_fr*, sbn_g1a*, uint8_t*, sbn_bullet**) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bullet_round(sbn_bullet*, const sbn_fr*, const sbn_fr*, sbn_g1a*, uint8_t*, sbn_g1a*, uint8_t*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bullet_fold(sbn_bullet*, const sbn_fr*, const sbn_fr*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bullet_end(sbn_bullet*, sbn_fr*, sbn_fr*, sbn_g1a*, uint8_t*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_bullet_destroy(sbn_bullet*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_sumcheck_begin(sbn_ctx*, const sbn_fr*, const sbn_fr*, const sbn_fr*, const sbn_fr*, size_t, sbn_sumcheck**) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_sumcheck_round_eval(sbn_sumcheck*, sbn_fr*, sbn_fr*, sbn_fr*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_sumcheck_bind(sbn_sumcheck*, const sbn_fr*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_sumcheck_end(sbn_sumcheck*, sbn_fr*) { return SBN_ERR_UNSUPPORTED; }
-extern "C" int sbn_sumcheck_destroy(sbn_sumcheck*) { return SBN_ERR_UNSUPPORTED; }
+extern "C" int sbn_msm(sbn_ctx* ctx, const sbn_g1a* points, const uint8_t* inf, const sbn_fr* scalars, size_t n,
+                       sbn_g1a* out, uint8_t* inf_out) {
+    if (!ctx || !out || !inf_out || (n && (!points || !scalars))) return SBN_ERR_ARG;
+    if (n > (1u << 26)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {   // empty sum = identity
+        memset(out, 0, sizeof(*out));
+        *inf_out = 1;
+        return SBN_OK;
+    }
+    cudaStream_t st = ctx->compute;
+    SBN_TRY(upload(ctx, ctx->scratch0, points, n * sizeof(Affine)));
+    SBN_TRY(upload(ctx, ctx->scratch1, scalars, n * sizeof(Fr)));
+    const uint8_t* dinf_in = nullptr;
+    if (inf) {
+        SBN_TRY(upload(ctx, ctx->scratch2, inf, n));
+        dinf_in = (const uint8_t*)ctx->scratch2.p;
+    }
+    const unsigned blocks = (unsigned)((n + kSmallThreads - 1) / kSmallThreads);
+    SBN_TRY(ensure(ctx, ctx->totals, (blocks + 1) * sizeof(XYZZ)));
+    SBN_TRY(ensure(ctx, ctx->dC, sizeof(Affine)));
+    SBN_TRY(ensure(ctx, ctx->dinf, 1));
+    XYZZ* part = (XYZZ*)ctx->totals.p;
+    k_msm_naive<<<dim3(blocks, 1), kSmallThreads, 0, st>>>((const Affine*)ctx->scratch0.p, dinf_in, 0,
+                                                           (const Fr*)ctx->scratch1.p, 0, (int)n, 1, part);
+    k_points_sum<<<1, kSmallThreads, 0, st>>>(part, (int)blocks, part + blocks, 1);
+    k_combine<<<1, 1, 0, st>>>(part + blocks, 1, 1, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p);
+    ctx->launches += 3;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, ctx->dC.p, sizeof(Affine)));
+    SBN_TRY(download(ctx, inf_out, ctx->dinf.p, 1));
+    SBN_CUDA(ctx, cudaStreamSynchronize(st));
+    return SBN_OK;
+}
+
+extern "C" int sbn_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* scalars, size_t n, const sbn_fr* blind,
+                          sbn_g1a* out, uint8_t* inf_out) {
+    if (!bases) return SBN_ERR_ARG;
+    return sbn_hyrax_commit(ctx, bases, scalars, 1, n, blind, out, inf_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a11: bound
+// ------------------------------------------------------------------------------------------------
+static int bound_device(sbn_ctx* ctx, const Fr* dZ, const Fr* dL, size_t L, size_t R, Fr* dout, cudaStream_t st) {
+    const unsigned bx = (unsigned)((R + 127) / 128);
+    unsigned slices = (unsigned)std::max<size_t>(1, std::min<size_t>(L, 1184 / std::max(1u, bx)));
+    const int rows_per_slice = (int)((L + slices - 1) / slices);
+    slices = (unsigned)((L + rows_per_slice - 1) / rows_per_slice);
+    SBN_TRY(ensure(ctx, ctx->scratch2, (size_t)slices * R * sizeof(Fr)));
+    k_bound_partial<<<dim3(bx, slices), 128, 0, st>>>(dZ, dL, (int)L, (int)R, rows_per_slice, (Fr*)ctx->scratch2.p);
+    k_fr_colsum<<<bx, 128, 0, st>>>((const Fr*)ctx->scratch2.p, (int)slices, (int)R, dout);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
+extern "C" int sbn_bound(sbn_ctx* ctx, const sbn_fr* Z, const sbn_fr* Lv, size_t L, size_t R, sbn_fr* LZ_out) {
+    if (!ctx || !Z || !Lv || !LZ_out) return SBN_ERR_ARG;
+    if (L == 0 || R == 0 || L > (1u << 24) || R > (1u << 24)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_TRY(upload(ctx, ctx->dZ, Z, L * R * sizeof(Fr)));
+    SBN_TRY(upload(ctx, ctx->scratch0, Lv, L * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, R * sizeof(Fr)));
+    SBN_TRY(bound_device(ctx, (const Fr*)ctx->dZ.p, (const Fr*)ctx->scratch0.p, L, R, (Fr*)ctx->scratch1.p, ctx->compute));
+    SBN_TRY(download(ctx, LZ_out, ctx->scratch1.p, R * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a14: bullet reduction with device-resident G, a, b
+// ------------------------------------------------------------------------------------------------
+struct sbn_bullet {
+    sbn_ctx* ctx = nullptr;
+    size_t n = 0;
+    Affine* G = nullptr;
+    uint8_t* Ginf = nullptr;
+    Fr *a = nullptr, *b = nullptr;
+    Affine* QH = nullptr;       // [Q, H, Q, H]
+    Fr* scal = nullptr;         // [c_L, blind_L, c_R, blind_R] + [u, u_inv]
+    XYZZ* partial = nullptr;    // 2 x blocks
+    XYZZ* terms = nullptr;      // 2 groups x 3
+    Fr* frpart = nullptr;       // 2 x blocks
+    Affine* outp = nullptr;     // 2
+    uint8_t* outinf = nullptr;  // 2
+    unsigned max_blocks = 0;
+};
+
+static void bullet_free(sbn_bullet* st) {
+    for (void* p : {(void*)st->G, (void*)st->Ginf, (void*)st->a, (void*)st->b, (void*)st->QH, (void*)st->scal,
+                    (void*)st->partial, (void*)st->terms, (void*)st->frpart, (void*)st->outp, (void*)st->outinf})
+        if (p) cudaFree(p);
+    delete st;
+}
+
+extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* a, const sbn_fr* b,
+                                size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf, sbn_bullet** out) {
+    if (!ctx || !bases || !Q || !a || !b || !blind || !Gamma_out || !Gamma_inf || !out || bases->ctx != ctx) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (n == 0 || (n & (n - 1)) || n != bases->n) return SBN_ERR_SHAPE;   // bullet.rs:42-47
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    sbn_bullet* st = new (std::nothrow) sbn_bullet();
+    if (!st) return SBN_ERR_OOM;
+    st->ctx = ctx;
+    st->n = n;
+    st->max_blocks = (unsigned)((n / 2 + kSmallThreads - 1) / kSmallThreads) + 1;
+    const unsigned dot_blocks = 64;
+    bool ok = cudaMalloc(&st->G, n * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->Ginf, n) == cudaSuccess &&
+              cudaMalloc(&st->a, n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->b, n * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->QH, 4 * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->scal, 6 * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
+              cudaMalloc(&st->terms, 6 * sizeof(XYZZ)) == cudaSuccess &&
+              cudaMalloc(&st->frpart, 2 * (dot_blocks + 1) * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->outp, 2 * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->outinf, 2) == cudaSuccess;
+    if (!ok) { bullet_free(st); ctx->last_error = "sbn_bullet_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
+    auto fail = [&](int code) { bullet_free(st); return code; };
+#define BCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(SBN_ERR_CUDA); } } while (0)
+    // G <- the resident generators (window 0 of the tables), H = h
+    BCUDA(cudaMemcpyAsync(st->G, bases->table, n * sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+    BCUDA(cudaMemsetAsync(st->Ginf, 0, n, s));
+    BCUDA(cudaMemcpyAsync(st->a, a, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    BCUDA(cudaMemcpyAsync(st->b, b, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    for (int k = 0; k < 2; k++) {
+        BCUDA(cudaMemcpyAsync(st->QH + 2 * k, Q, sizeof(Affine), cudaMemcpyHostToDevice, s));
+        BCUDA(cudaMemcpyAsync(st->QH + 2 * k + 1, bases->table + n, sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+    }
+    BCUDA(cudaMemcpyAsync(st->scal + 1, blind, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ctx->h2d += 2 * n * sizeof(Fr) + sizeof(Affine) + sizeof(Fr);
+    // Gamma = MSM(a, G) + blind * H  (one row through the table pipeline) + <a, b> * Q   (bullet.rs:57-59)
+    int rc = ensure_commit_workspace(ctx, bases, 1, 1);
+    if (rc != SBN_OK) return fail(rc);
+    std::vector<int> ev_stage;
+    rc = run_commit(ctx, bases, st->a, nullptr, 1, n, st->scal + 1, nullptr, nullptr, s, ev_stage, false);
+    if (rc != SBN_OK) return fail(rc);
+    k_fr_dot<<<dim3(dot_blocks, 1), kDotThreads, 0, s>>>(st->a, 0, st->b, 0, (int)n, st->frpart);
+    k_fr_sum<<<1, kDotThreads, 0, s>>>(st->frpart, (int)dot_blocks, st->scal, 1);
+    k_scalar_mul_terms<<<1, 32, 0, s>>>(st->QH, st->scal, 1, st->terms + 1, 1, 0);
+    BCUDA(cudaMemcpyAsync(st->terms, ctx->totals.p, sizeof(XYZZ), cudaMemcpyDeviceToDevice, s));
+    k_combine<<<1, 1, 0, s>>>(st->terms, 1, 2, st->outp, st->outinf);
+    ctx->launches += 4;
+    BCUDA(cudaGetLastError());
+    BCUDA(cudaMemcpyAsync(Gamma_out, st->outp, sizeof(Affine), cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaMemcpyAsync(Gamma_inf, st->outinf, 1, cudaMemcpyDeviceToHost, s));
+    BCUDA(cudaStreamSynchronize(s));
+    ctx->d2h += sizeof(Affine) + 1;
+    *out = st;
+    return SBN_OK;
+}
+
+extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn_fr* blind_R, sbn_g1a* L_out, uint8_t* L_inf,
+                                sbn_g1a* R_out, uint8_t* R_inf) {
+    if (!st || !blind_L || !blind_R || !L_out || !L_inf || !R_out || !R_inf) return SBN_ERR_ARG;
+    if (st->n < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const long n2 = (long)(st->n / 2);
+    const unsigned blocks = (unsigned)((n2 + kSmallThreads - 1) / kSmallThreads);
+    const unsigned dot_blocks = (unsigned)std::min<long>(64, (n2 + kDotThreads - 1) / kDotThreads);
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 1, blind_L, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 3, blind_R, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    // set 0: L = <a_L, G_R>, set 1: R = <a_R, G_L>                                        (bullet.rs:75-76)
+    k_msm_naive<<<dim3(blocks, 2), kSmallThreads, 0, s>>>(st->G + n2, st->Ginf + n2, -n2, st->a, n2, (int)n2, 1, st->partial);
+    k_points_sum<<<2, kSmallThreads, 0, s>>>(st->partial, (int)blocks, st->terms, 3);
+    // set 0: c_L = <a_L, b_R>, set 1: c_R = <a_R, b_L>                                     (bullet.rs:70-71)
+    k_fr_dot<<<dim3(dot_blocks, 2), kDotThreads, 0, s>>>(st->a, n2, st->b + n2, -n2, (int)n2, st->frpart);
+    k_fr_sum<<<2, kDotThreads, 0, s>>>(st->frpart, (int)dot_blocks, st->scal, 2);
+    // terms: [L_msm, c_L Q, blind_L H, R_msm, c_R Q, blind_R H]
+    k_scalar_mul_terms<<<4, 32, 0, s>>>(st->QH, st->scal, 4, st->terms + 1, 3, 2);
+    k_combine<<<1, 2, 0, s>>>(st->terms, 2, 3, st->outp, st->outinf);
+    ctx->launches += 6;
+    SBN_CUDA(ctx, cudaGetLastError());
+    sbn_g1a pts[2];
+    uint8_t infs[2];
+    SBN_CUDA(ctx, cudaMemcpyAsync(pts, st->outp, 2 * sizeof(Affine), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(infs, st->outinf, 2, cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->h2d += 2 * sizeof(Fr);
+    ctx->d2h += 2 * sizeof(Affine) + 2;
+    *L_out = pts[0]; *L_inf = infs[0];
+    *R_out = pts[1]; *R_inf = infs[1];
+    return SBN_OK;
+}
+
+extern "C" int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_inv) {
+    if (!st || !u || !u_inv) return SBN_ERR_ARG;
+    if (st->n < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const int n2 = (int)(st->n / 2);
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 4, u, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 5, u_inv, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    k_fold_points<<<(n2 + kSmallThreads - 1) / kSmallThreads, kSmallThreads, 0, s>>>(st->G, st->Ginf, n2, st->scal + 4);
+    k_fold_scalars<<<(n2 + 127) / 128, 128, 0, s>>>(st->a, st->b, n2, st->scal + 4);
+    ctx->launches += 2;
+    ctx->h2d += 2 * sizeof(Fr);
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    st->n = n2;
+    return SBN_OK;
+}
+
+extern "C" int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_g1a* g_hat, uint8_t* g_hat_inf) {
+    if (!st || !a_hat || !b_hat || !g_hat || !g_hat_inf) return SBN_ERR_ARG;
+    if (st->n != 1) return SBN_ERR_SHAPE;                      // bullet.rs:110-112 asserts
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    SBN_CUDA(ctx, cudaMemcpyAsync(a_hat, st->a, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(b_hat, st->b, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat, st->G, sizeof(Affine), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat_inf, st->Ginf, 1, cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += 2 * sizeof(Fr) + sizeof(Affine) + 1;
+    if (*g_hat_inf) memset(g_hat, 0, sizeof(*g_hat));
+    return SBN_OK;
+}
+
+extern "C" int sbn_bullet_destroy(sbn_bullet* st) {
+    if (!st) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(st->ctx->mu);
+        cudaSetDevice(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->compute);
+    }
+    bullet_free(st);
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a16: sumcheck rounds with the four tables resident
+// ------------------------------------------------------------------------------------------------
+struct sbn_sumcheck {
+    sbn_ctx* ctx = nullptr;
+    size_t len = 0;
+    Fr* T[4] = {nullptr, nullptr, nullptr, nullptr};
+    Fr* partial = nullptr;   // 3 x blocks
+    Fr* out = nullptr;       // 3 evals + r
+    unsigned blocks = 0;
+};
+
+static void sumcheck_free(sbn_sumcheck* st) {
+    for (Fr* t : st->T) if (t) cudaFree(t);
+    if (st->partial) cudaFree(st->partial);
+    if (st->out) cudaFree(st->out);
+    delete st;
+}
+
+extern "C" int sbn_sumcheck_begin(sbn_ctx* ctx, const sbn_fr* tau, const sbn_fr* Az, const sbn_fr* Bz, const sbn_fr* Cz,
+                                  size_t len, sbn_sumcheck** out) {
+    if (!ctx || !tau || !Az || !Bz || !Cz || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (len < 1 || (len & (len - 1)) || len > (1u << 28)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    sbn_sumcheck* st = new (std::nothrow) sbn_sumcheck();
+    if (!st) return SBN_ERR_OOM;
+    st->ctx = ctx;
+    st->len = len;
+    st->blocks = 592;
+    const sbn_fr* src[4] = {tau, Az, Bz, Cz};
+    bool ok = cudaMalloc(&st->partial, 3 * st->blocks * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->out, 4 * sizeof(Fr)) == cudaSuccess;
+    for (int k = 0; k < 4 && ok; k++) ok = cudaMalloc(&st->T[k], len * sizeof(Fr)) == cudaSuccess;
+    if (!ok) { sumcheck_free(st); ctx->last_error = "sbn_sumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
+    for (int k = 0; k < 4; k++) {
+        if (cudaMemcpyAsync(st->T[k], src[k], len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess) {
+            sumcheck_free(st);
+            ctx->last_error = "sbn_sumcheck_begin: upload failed";
+            return SBN_ERR_CUDA;
+        }
+    }
+    ctx->h2d += 4 * len * sizeof(Fr);
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    *out = st;
+    return SBN_OK;
+}
+
+extern "C" int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2, sbn_fr* e3) {
+    if (!st || !e0 || !e2 || !e3) return SBN_ERR_ARG;
+    if (st->len < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const int half = (int)(st->len / 2);
+    const unsigned blocks = (unsigned)std::min<size_t>(st->blocks, (half + kDotThreads - 1) / kDotThreads);
+    k_sumcheck_eval<<<blocks, kDotThreads, 0, s>>>(st->T[0], st->T[1], st->T[2], st->T[3], half, st->partial);
+    k_fr_sum<<<3, kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    sbn_fr host[3];
+    SBN_CUDA(ctx, cudaMemcpyAsync(host, st->out, 3 * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += 3 * sizeof(Fr);
+    *e0 = host[0]; *e2 = host[1]; *e3 = host[2];
+    return SBN_OK;
+}
+
+extern "C" int sbn_sumcheck_bind(sbn_sumcheck* st, const sbn_fr* r) {
+    if (!st || !r) return SBN_ERR_ARG;
+    if (st->len < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const int half = (int)(st->len / 2);
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->out + 3, r, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    k_bind_top<<<(half + 127) / 128, 128, 0, s>>>(st->T[0], st->T[1], st->T[2], st->T[3], half, st->out + 3);
+    ctx->launches += 1;
+    ctx->h2d += sizeof(Fr);
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    st->len = half;
+    return SBN_OK;
+}
+
+extern "C" int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]) {
+    if (!st || !finals) return SBN_ERR_ARG;
+    if (st->len != 1) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int k = 0; k < 4; k++)
+        SBN_CUDA(ctx, cudaMemcpyAsync(&finals[k], st->T[k], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->d2h += 4 * sizeof(Fr);
+    return SBN_OK;
+}
+
+extern "C" int sbn_sumcheck_destroy(sbn_sumcheck* st) {
+    if (!st) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(st->ctx->mu);
+        cudaSetDevice(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->compute);
+    }
+    sumcheck_free(st);
+    return SBN_OK;
+}

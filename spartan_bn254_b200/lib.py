@@ -196,6 +196,14 @@ class Context:
         self._check(st, "sbn_bound")
         return out
 
+    # ---- a14: bullet reduction (state on device, transcript on host)
+    def bullet_begin(self, bases, Q, a, b, blind):
+        return BulletState(self, bases, Q, a, b, blind)
+
+    # ---- a16: sumcheck rounds
+    def sumcheck_begin(self, tau, Az, Bz, Cz):
+        return SumcheckState(self, tau, Az, Bz, Cz)
+
     # ---- utilities
     def fr_from_canonical(self, canon):
         canon = _u64(canon, 4)
@@ -238,6 +246,97 @@ class Bases:
     def close(self):
         if self.h and self.ctx.h:
             self.ctx.lib.sbn_bases_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BulletState:
+    """sbn_bullet: G, a, b of BulletReductionProof::prove (nizk/bullet.rs:24-126) resident on the GPU."""
+
+    def __init__(self, ctx, bases, Q, a, b, blind):
+        self.ctx = ctx
+        a = _u64(a, 4)
+        b = _u64(b, 4)
+        if a.shape[0] != b.shape[0]:
+            raise SbnError(-2, "sbn_bullet_begin", "len(a) != len(b)")      # bullet.rs:42-43
+        self.n = a.shape[0]
+        self.Gamma = np.zeros(8, dtype=np.uint64)
+        ginf = np.zeros(1, dtype=np.uint8)
+        h = C.c_void_p()
+        st = ctx.lib.sbn_bullet_begin(ctx.h, bases.h, _ptr(_u64(Q, 8)), _ptr(a), _ptr(b), C.c_size_t(self.n),
+                                      _ptr(_u64(blind, 4)), _ptr(self.Gamma), _ptr(ginf), C.byref(h))
+        ctx._check(st, "sbn_bullet_begin")
+        self.Gamma_inf = int(ginf[0])
+        self.h = h
+
+    def round(self, blind_L, blind_R):
+        L = np.zeros(8, dtype=np.uint64); Li = np.zeros(1, dtype=np.uint8)
+        R = np.zeros(8, dtype=np.uint64); Ri = np.zeros(1, dtype=np.uint8)
+        st = self.ctx.lib.sbn_bullet_round(self.h, _ptr(_u64(blind_L, 4)), _ptr(_u64(blind_R, 4)), _ptr(L), _ptr(Li),
+                                           _ptr(R), _ptr(Ri))
+        self.ctx._check(st, "sbn_bullet_round")
+        return (L, int(Li[0])), (R, int(Ri[0]))
+
+    def fold(self, u, u_inv):
+        self.ctx._check(self.ctx.lib.sbn_bullet_fold(self.h, _ptr(_u64(u, 4)), _ptr(_u64(u_inv, 4))), "sbn_bullet_fold")
+        self.n //= 2
+
+    def end(self):
+        a = np.zeros(4, dtype=np.uint64); b = np.zeros(4, dtype=np.uint64)
+        g = np.zeros(8, dtype=np.uint64); gi = np.zeros(1, dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.sbn_bullet_end(self.h, _ptr(a), _ptr(b), _ptr(g), _ptr(gi)), "sbn_bullet_end")
+        return a, b, g, int(gi[0])
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_bullet_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SumcheckState:
+    """sbn_sumcheck: the four tables of the R1CS-sat cubic sumcheck (sumcheck.rs:465-649) on the GPU."""
+
+    def __init__(self, ctx, tau, Az, Bz, Cz):
+        self.ctx = ctx
+        t = [_u64(x, 4) for x in (tau, Az, Bz, Cz)]
+        self.len = t[0].shape[0]
+        if any(x.shape[0] != self.len for x in t):
+            raise SbnError(-2, "sbn_sumcheck_begin", "table lengths differ")
+        h = C.c_void_p()
+        st = ctx.lib.sbn_sumcheck_begin(ctx.h, _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), _ptr(t[3]), C.c_size_t(self.len),
+                                        C.byref(h))
+        ctx._check(st, "sbn_sumcheck_begin")
+        self.h = h
+
+    def round_eval(self):
+        e = [np.zeros(4, dtype=np.uint64) for _ in range(3)]
+        self.ctx._check(self.ctx.lib.sbn_sumcheck_round_eval(self.h, _ptr(e[0]), _ptr(e[1]), _ptr(e[2])),
+                        "sbn_sumcheck_round_eval")
+        return e
+
+    def bind(self, r):
+        self.ctx._check(self.ctx.lib.sbn_sumcheck_bind(self.h, _ptr(_u64(r, 4))), "sbn_sumcheck_bind")
+        self.len //= 2
+
+    def end(self):
+        f = np.zeros((4, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_sumcheck_end(self.h, _ptr(f)), "sbn_sumcheck_end")
+        return f
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_sumcheck_destroy(self.h)
         self.h = None
 
     def __del__(self):
