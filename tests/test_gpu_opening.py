@@ -168,3 +168,18 @@ def test_sumcheck_rounds_match_oracle(ctx, orc, lg):
     for k in range(4):
         assert np.array_equal(fin[k], cur[k][0])
     st.close()
+
+
+def test_cpp_host_mirror(orc, tmp_path):
+    """The C++ host mirror of the reference interface (compiled-language host side above the C ABI)."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "host_mirror_test")
+    libdir = os.path.join(root, "spartan_bn254_b200", "_lib")
+    odir = os.path.join(root, "oracle", "_build")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "host", "host_mirror_test.cpp"),
+                           "-L" + libdir, "-lsbn254", "-L" + odir, "-loracle", "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir,
+                           "-pthread"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host mirror: ok" in out.stdout
