@@ -54,7 +54,8 @@ int sbn_ctx_create(int device, sbn_ctx** out);
 int sbn_ctx_destroy(sbn_ctx* ctx);
 int sbn_ctx_synchronize(sbn_ctx* ctx);
 /* Tunables: "chunk_rows" (rows per pipeline stage), "window_bits" (0 = auto, applies to bases created
- * afterwards), "task_cap" (max entries one accumulation thread sums; fuller buckets are split). */
+ * afterwards), "task_cap" (max entries one accumulation thread sums; fuller buckets are split; 0 = auto), "reduce_m"
+ * (buckets per reduction thread). */
 int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
 /* Counters since creation / last reset: kernels launched by this library, bytes copied H2D / D2H. */
 int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
@@ -136,7 +137,7 @@ int sbn_sumcheck_destroy(sbn_sumcheck* st);
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
 int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
 /* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for
- * kind 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE (counted as 2 results), 3 = Montgomery Fq
+ * kind 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE (a 64-bit result counted as 2), 3 = Montgomery Fq
  * multiplications per second (not x264). */
 int sbn_microbench(sbn_ctx* ctx, int kind, double* per_second);
 

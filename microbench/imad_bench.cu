@@ -19,6 +19,59 @@ __global__ void k_wide(uint32_t* out, uint32_t seed) {
     uint32_t r = 0; for (int i = 0; i < 8; i++) r ^= (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);
     if (r == 0x12345678u) out[0] = r;
 }
+// kind 0b: IMAD.WIDE whose multiplicand evolves (cannot be hoisted): w = lo(w) * b + w
+__global__ void k_wide_dep(uint32_t* out, uint32_t seed) {
+    uint64_t w[8]; uint32_t b = seed | 1;
+    for (int i = 0; i < 8; i++) w[i] = (threadIdx.x * 2654435761u + i) | 1;
+    for (int it = 0; it < ITERS; it++)
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[i]), "r"(b));
+    uint32_t r = 0; for (int i = 0; i < 8; i++) r ^= (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);
+    if (r == 0x12345678u) out[0] = r;
+}
+// kind 0c: mul.wide (no addend) with evolving multiplicand, results xor-folded on the ALU pipe
+__global__ void k_mulwide_dep(uint32_t* out, uint32_t seed) {
+    uint32_t a[8]; uint32_t b = seed | 1;
+    for (int i = 0; i < 8; i++) a[i] = (threadIdx.x * 2654435761u + i) | 1;
+    for (int it = 0; it < ITERS; it++)
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) { uint64_t w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(a[i]), "r"(b)); a[i] = (uint32_t)w ^ (uint32_t)(w >> 32); }
+    uint32_t r = 0; for (int i = 0; i < 8; i++) r ^= a[i];
+    if (r == 0x12345678u) out[0] = r;
+}
+// FP64 pipe: independent DFMA chains (round-toward-zero, as in double-precision big-integer multiplication)
+__global__ void k_dfma(uint32_t* out, uint32_t seed) {
+    double a[8], b = 1.0 + seed * 1e-9, c = 0.5;
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1.25 + i;
+    for (int it = 0; it < ITERS; it++)
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __fma_rz(a[i], b, c);
+    double r = 0; for (int i = 0; i < 8; i++) r += a[i];
+    if (r == 1234.5) out[0] = 1;
+}
+// DFMA and IMAD.WIDE carry chains interleaved in one instruction stream: do the two pipes overlap?
+__global__ void k_dfma_imad(uint32_t* out, uint32_t seed) {
+    double a[8], b = 1.0 + seed * 1e-9, c = 0.5;
+    uint32_t acc[8], m[8], bi = seed | 1;
+    for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 1.25 + i; m[i] = threadIdx.x * 2654435761u + i; acc[i] = m[i]; }
+    for (int it = 0; it < ITERS; it++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = __fma_rz(a[i], b, c);
+            acc[0] = mad_lo_cc(m[0], bi, acc[0]); acc[1] = madc_hi_cc(m[0], bi, acc[1]);
+#pragma unroll
+            for (int j = 2; j < 8; j += 2) { acc[j] = madc_lo_cc(m[j], bi, acc[j]); acc[j + 1] = madc_hi_cc(m[j], bi, acc[j + 1]); }
+        }
+    double r = 0; for (int i = 0; i < 8; i++) r += a[i] + acc[i];
+    if (r == 1234.5) out[0] = 1;
+}
 // kind 1: carry chains of 4 wide products (8 limbs): acc += a_even * b, NCH independent accumulators
 template <int NCH>
 __global__ void k_chain(uint32_t* out, uint32_t seed) {
@@ -86,8 +139,12 @@ static double run(const char* name, K launch, double ops_per_thread, int threads
 
 int main() {
     uint32_t* d; cudaMalloc(&d, 4096);
-    for (int threads : {128, 256, 512}) {
-        run("imad.wide (no carry)", [&](int b, int t) { k_wide<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
+    for (int threads : {128, 256}) {
+        run("64-bit add pairs (product hoisted by ptxas)", [&](int b, int t) { k_wide<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
+        run("imad.wide acc, evolving operand", [&](int b, int t) { k_wide_dep<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
+        run("mul.wide + xor, evolving operand", [&](int b, int t) { k_mulwide_dep<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
+        run("dfma.rz (fp64 pipe)", [&](int b, int t) { k_dfma<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
+        run("dfma.rz x8 + 4 wide-carry (per dfma)", [&](int b, int t) { k_dfma_imad<<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
         run("wide carry chain x1 (products)", [&](int b, int t) { k_chain<1><<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
         run("wide carry chain x2 (products)", [&](int b, int t) { k_chain<2><<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);
         run("wide carry chain x4 (products)", [&](int b, int t) { k_chain<4><<<b, t>>>(d, 1); }, 32.0 * ITERS, threads);

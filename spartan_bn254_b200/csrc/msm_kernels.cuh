@@ -432,7 +432,7 @@ __global__ void k_microbench(uint32_t* out, int iters, uint32_t seed) {
 #pragma unroll
             for (int u = 0; u < 4; u++)
 #pragma unroll
-                for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b));
+                for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((uint32_t)w[i]), "r"(b));
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) a[i] ^= (uint32_t)w[i] ^ (uint32_t)(w[i] >> 32);

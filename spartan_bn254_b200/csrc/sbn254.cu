@@ -355,8 +355,8 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, con
     SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, cap, E, max_tasks, entries, tstart, tasks, rows, stream));
     mark(0);
     const size_t threads = (size_t)rows * max_tasks;
-    k_accumulate<<<(unsigned)((threads + kAccThreads - 1) / kAccThreads), kAccThreads, 0, stream>>>(
-        b->table, entries, tstart, tasks, partials, rows, b->nb, E, max_tasks);
+    const unsigned acc_blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
+    k_accumulate<<<acc_blocks, kAccThreads, 0, stream>>>(b->table, entries, tstart, tasks, partials, rows, b->nb, E, max_tasks);
     mark(1);
     int m = std::min((int)ctx->reduce_m, b->nb);
     int tpr = std::min(kRedThreads, b->nb / m);
