@@ -843,3 +843,215 @@ void orc_transcript_challenge_scalar(orc_transcript* t, const uint8_t* label, si
     fp_mul(FR, &b, &r2, &b);
     fp_add(FR, &a, &b, out);
 }
+
+/* ------------------------------------------------------------------ Hyrax opening proof with transcripts */
+static void t_append(orc_transcript* t, const char* label, const uint8_t* msg, size_t n) {
+    orc_transcript_append(t, (const uint8_t*)label, strlen(label), msg, n);
+}
+static void t_protocol(orc_transcript* t, const char* name) { t_append(t, "protocol-name", (const uint8_t*)name, strlen(name)); } /* transcript.rs:38-40 */
+static void t_scalar(orc_transcript* t, const char* label, const ofp* s) { /* transcript.rs:42-44 + scalar.rs:75-84 */
+    uint64_t c[4];
+    uint8_t b[32];
+    fp_to_canon(FR, s, c);
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 8; j++) b[8 * i + j] = (uint8_t)(c[i] >> (8 * j));
+    t_append(t, label, b, 32);
+}
+static void t_point(orc_transcript* t, const char* label, const og1a* p, uint8_t inf) { /* transcript.rs:102-108 */
+    uint8_t b[32];
+    orc_g1_compress(p, inf, b);
+    t_append(t, label, b, 32);
+}
+static void t_challenge(orc_transcript* t, const char* label, ofp* out) {
+    orc_transcript_challenge_scalar(t, (const uint8_t*)label, strlen(label), out);
+}
+static void j_commit2(const og1a* g, const ofp* s, const og1a* h, const ofp* blind, og1j* out) { /* s*g + blind*h */
+    og1j t;
+    j_mul_fr(g, 0, s, out);
+    j_mul_fr(h, 0, blind, &t);
+    j_add(out, &t, out);
+}
+
+void orc_poly_eval_prove(const ofp* Z, size_t ell, const ofp* blinds, const ofp* r, const ofp* Zr, const ofp* blind_Zr,
+                         const og1a* G, const og1a* h, const og1a* G1, orc_transcript* tr, orc_transcript* tape,
+                         orc_eval_proof* proof, og1a* C_Zr_prime, uint8_t* C_Zr_prime_inf) {
+    t_protocol(tr, "polynomial evaluation proof");                       /* hyrax.rs:75 */
+    const size_t lv = ell / 2, rv = ell - lv, L_size = (size_t)1 << lv, n = (size_t)1 << rv;
+    ofp* Lv = (ofp*)malloc(sizeof(ofp) * L_size);
+    ofp* Rv = (ofp*)malloc(sizeof(ofp) * n);
+    orc_eq_evals(r, lv, Lv);
+    orc_eq_evals(r + lv, rv, Rv);
+    ofp* LZ = (ofp*)malloc(sizeof(ofp) * n);
+    orc_bound(Z, Lv, L_size, n, 0, LZ);                                   /* hyrax.rs:100 */
+    ofp LZ_blind, zero, t1, t2;
+    memset(&zero, 0, sizeof zero);
+    LZ_blind = zero;
+    if (blinds) for (size_t i = 0; i < L_size; i++) { fp_mul(FR, &blinds[i], &Lv[i], &t1); fp_add(FR, &LZ_blind, &t1, &LZ_blind); }
+    const ofp* blind_y = blind_Zr ? blind_Zr : &zero;
+
+    /* DotProductProofLog::prove (nizk/mod.rs:439-522) */
+    t_protocol(tr, "dot product proof (log)");
+    size_t lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    ofp d, r_delta, r_beta, bl1[ORC_MAX_LG], bl2[ORC_MAX_LG];
+    t_challenge(tape, "d", &d);
+    t_challenge(tape, "r_delta", &r_delta);
+    t_challenge(tape, "r_delta", &r_beta);                                 /* sic: same label, mod.rs:459 */
+    for (size_t i = 0; i < lg; i++) t_challenge(tape, "blinds_vec_1", &bl1[i]);
+    for (size_t i = 0; i < lg; i++) t_challenge(tape, "blinds_vec_2", &bl2[i]);
+
+    og1j acc, tj;
+    og1a Cx, Cy;
+    uint8_t Cx_inf, Cy_inf;
+    j_msm_affine_pts(G, NULL, LZ, n, &acc);                               /* Cx = x.commit(blind_x, gens_n) */
+    j_mul_fr(h, 0, &LZ_blind, &tj); j_add(&acc, &tj, &acc);
+    j_to_affine(&acc, &Cx, &Cx_inf);
+    t_point(tr, "Cx", &Cx, Cx_inf);
+    j_commit2(G1, Zr, h, blind_y, &acc);                                   /* Cy = y.commit(blind_y, gens_1) */
+    j_to_affine(&acc, &Cy, &Cy_inf);
+    t_point(tr, "Cy", &Cy, Cy_inf);
+    for (size_t i = 0; i < n; i++) t_scalar(tr, "a", &Rv[i]);             /* a_vec.append_to_transcript(b"a") */
+    ofp rr;
+    t_challenge(tr, "r", &rr);
+    og1a Q; uint8_t Q_inf;                                                 /* gens_1.scale(r).G[0] */
+    orc_g1_scalar_mul(G1, 0, &rr, &Q, &Q_inf);
+    ofp blind_Gamma;
+    fp_mul(FR, &rr, blind_y, &t1);
+    fp_add(FR, &LZ_blind, &t1, &blind_Gamma);
+
+    /* BulletReductionProof::prove (bullet.rs:24-126), challenges from the transcript */
+    og1a* Gc = (og1a*)malloc(sizeof(og1a) * n);
+    uint8_t* Ginf = (uint8_t*)calloc(n, 1);
+    ofp* a = (ofp*)malloc(sizeof(ofp) * n);
+    ofp* b = (ofp*)malloc(sizeof(ofp) * n);
+    memcpy(Gc, G, sizeof(og1a) * n); memcpy(a, LZ, sizeof(ofp) * n); memcpy(b, Rv, sizeof(ofp) * n);
+    proof->lg_n = lg;
+    ofp rhat = blind_Gamma;
+    size_t m = n;
+    for (size_t round = 0; round < lg; round++) {
+        m /= 2;
+        ofp cL, cR;
+        fr_dot(a, b + m, m, &cL);
+        fr_dot(a + m, b, m, &cR);
+        j_msm_affine_pts(Gc + m, Ginf + m, a, m, &acc);
+        j_mul_fr(&Q, Q_inf, &cL, &tj); j_add(&acc, &tj, &acc);
+        j_mul_fr(h, 0, &bl1[round], &tj); j_add(&acc, &tj, &acc);
+        j_to_affine(&acc, &proof->L[round], &proof->L_inf[round]);
+        j_msm_affine_pts(Gc, Ginf, a + m, m, &acc);
+        j_mul_fr(&Q, Q_inf, &cR, &tj); j_add(&acc, &tj, &acc);
+        j_mul_fr(h, 0, &bl2[round], &tj); j_add(&acc, &tj, &acc);
+        j_to_affine(&acc, &proof->R[round], &proof->R_inf[round]);
+        t_point(tr, "L", &proof->L[round], proof->L_inf[round]);
+        t_point(tr, "R", &proof->R[round], proof->R_inf[round]);
+        ofp u, ui, uu, uiui;
+        t_challenge(tr, "u", &u);
+        fp_inv(FR, &u, &ui);
+        fold_ctx fc = {Gc, Ginf, m, &u, &ui};
+        parallel_for((long)m, 8, 0, fold_body, &fc);
+        for (size_t i = 0; i < m; i++) {
+            fp_mul(FR, &u, &a[i], &t1); fp_mul(FR, &ui, &a[m + i], &t2); fp_add(FR, &t1, &t2, &a[i]);
+            fp_mul(FR, &ui, &b[i], &t1); fp_mul(FR, &u, &b[m + i], &t2); fp_add(FR, &t1, &t2, &b[i]);
+        }
+        fp_mul(FR, &u, &u, &uu); fp_mul(FR, &ui, &ui, &uiui);
+        fp_mul(FR, &uu, &bl1[round], &t1); fp_mul(FR, &uiui, &bl2[round], &t2);
+        fp_add(FR, &rhat, &t1, &rhat); fp_add(FR, &rhat, &t2, &rhat);
+    }
+    ofp x_hat = a[0], a_hat = b[0], y_hat;
+    og1a g_hat = Gc[0]; uint8_t g_hat_inf = Ginf[0];
+    fp_mul(FR, &x_hat, &a_hat, &y_hat);
+    /* delta = d.commit(r_delta, (g_hat, h)); beta = d.commit(r_beta, gens_1_scaled)   (mod.rs:497-505) */
+    j_mul_fr(&g_hat, g_hat_inf, &d, &acc); j_mul_fr(h, 0, &r_delta, &tj); j_add(&acc, &tj, &acc);
+    j_to_affine(&acc, &proof->delta, &proof->delta_inf);
+    t_point(tr, "delta", &proof->delta, proof->delta_inf);
+    j_mul_fr(&Q, Q_inf, &d, &acc); j_mul_fr(h, 0, &r_beta, &tj); j_add(&acc, &tj, &acc);
+    j_to_affine(&acc, &proof->beta, &proof->beta_inf);
+    t_point(tr, "beta", &proof->beta, proof->beta_inf);
+    ofp c;
+    t_challenge(tr, "c", &c);
+    fp_mul(FR, &c, &y_hat, &t1); fp_add(FR, &d, &t1, &proof->z1);          /* z1 = d + c*y_hat */
+    fp_mul(FR, &c, &rhat, &t1); fp_add(FR, &t1, &r_beta, &t1);            /* z2 = a_hat*(c*rhat + r_beta) + r_delta */
+    fp_mul(FR, &a_hat, &t1, &t1); fp_add(FR, &t1, &r_delta, &proof->z2);
+    *C_Zr_prime = Cy; *C_Zr_prime_inf = Cy_inf;
+    free(Lv); free(Rv); free(LZ); free(Gc); free(Ginf); free(a); free(b);
+}
+
+int orc_poly_eval_verify(const orc_eval_proof* proof, size_t ell, const ofp* r, const og1a* C_Zr, uint8_t C_Zr_inf,
+                         const og1a* comm, const uint8_t* comm_inf, const og1a* G, const og1a* h, const og1a* G1,
+                         orc_transcript* tr) {
+    t_protocol(tr, "polynomial evaluation proof");                       /* hyrax.rs:126 */
+    const size_t lv = ell / 2, rv = ell - lv, L_size = (size_t)1 << lv, n = (size_t)1 << rv;
+    ofp* Lv = (ofp*)malloc(sizeof(ofp) * L_size);
+    ofp* Rv = (ofp*)malloc(sizeof(ofp) * n);
+    orc_eq_evals(r, lv, Lv);
+    orc_eq_evals(r + lv, rv, Rv);
+    og1j C_LZ;                                                            /* hyrax.rs:133 */
+    j_msm_affine_pts(comm, comm_inf, Lv, L_size, &C_LZ);
+    og1a Cx; uint8_t Cx_inf;
+    j_to_affine(&C_LZ, &Cx, &Cx_inf);
+    /* DotProductProofLog::verify (mod.rs:525-567) */
+    t_protocol(tr, "dot product proof (log)");
+    t_point(tr, "Cx", &Cx, Cx_inf);
+    t_point(tr, "Cy", C_Zr, C_Zr_inf);
+    for (size_t i = 0; i < n; i++) t_scalar(tr, "a", &Rv[i]);
+    ofp rr;
+    t_challenge(tr, "r", &rr);
+    og1a Q; uint8_t Q_inf;
+    orc_g1_scalar_mul(G1, 0, &rr, &Q, &Q_inf);
+    og1j Gamma, tj;                                                       /* Gamma = Cx + r*Cy */
+    j_mul_fr(C_Zr, C_Zr_inf, &rr, &Gamma);
+    j_add(&Gamma, &C_LZ, &Gamma);
+    /* BulletReductionProof::verify (bullet.rs:130-173) */
+    const size_t lg = proof->lg_n;
+    int ok = (((size_t)1 << lg) == n);
+    ofp u[ORC_MAX_LG], ui[ORC_MAX_LG], usq[ORC_MAX_LG], uisq[ORC_MAX_LG];
+    for (size_t i = 0; i < lg && ok; i++) {
+        t_point(tr, "L", &proof->L[i], proof->L_inf[i]);
+        t_point(tr, "R", &proof->R[i], proof->R_inf[i]);
+        t_challenge(tr, "u", &u[i]);
+        fp_inv(FR, &u[i], &ui[i]);
+        fp_mul(FR, &u[i], &u[i], &usq[i]);
+        fp_inv(FR, &usq[i], &uisq[i]);
+    }
+    ofp* s = (ofp*)malloc(sizeof(ofp) * n);
+    for (size_t i = 0; i < n && ok; i++) {                                /* compute_s */
+        fp_one(FR, &s[i]);
+        for (size_t j = 0; j < lg; j++) fp_mul(FR, &s[i], ((i >> j) & 1) ? &u[lg - 1 - j] : &ui[lg - 1 - j], &s[i]);
+    }
+    int result = 0;
+    if (ok) {
+        og1j g_hat, Gamma_hat, lhs, rhs, t2;
+        ofp a_hat, t1;
+        j_msm_affine_pts(G, NULL, s, n, &g_hat);
+        fr_dot(s, Rv, n, &a_hat);
+        j_msm_affine_pts(proof->L, proof->L_inf, usq, lg, &Gamma_hat);
+        j_msm_affine_pts(proof->R, proof->R_inf, uisq, lg, &tj);
+        j_add(&Gamma_hat, &Gamma, &Gamma_hat);
+        j_add(&Gamma_hat, &tj, &Gamma_hat);
+        t_point(tr, "delta", &proof->delta, proof->delta_inf);
+        t_point(tr, "beta", &proof->beta, proof->beta_inf);
+        ofp c;
+        t_challenge(tr, "c", &c);
+        /* lhs = (c*Gamma_hat + beta)*a_hat + delta ; rhs = z1*(g_hat + a_hat*Q) + z2*h */
+        og1a tmp; uint8_t tmp_inf; og1j bj, dj;
+        j_to_affine(&Gamma_hat, &tmp, &tmp_inf);
+        j_mul_fr(&tmp, tmp_inf, &c, &lhs);
+        j_from_affine(&proof->beta, proof->beta_inf, &bj);
+        j_add(&lhs, &bj, &lhs);
+        j_to_affine(&lhs, &tmp, &tmp_inf);
+        j_mul_fr(&tmp, tmp_inf, &a_hat, &lhs);
+        j_from_affine(&proof->delta, proof->delta_inf, &dj);
+        j_add(&lhs, &dj, &lhs);
+        j_mul_fr(&Q, Q_inf, &a_hat, &t2);
+        j_add(&t2, &g_hat, &t2);
+        j_to_affine(&t2, &tmp, &tmp_inf);
+        j_mul_fr(&tmp, tmp_inf, &proof->z1, &rhs);
+        j_mul_fr(h, 0, &proof->z2, &t2);
+        j_add(&rhs, &t2, &rhs);
+        og1a la, ra; uint8_t li, ri;
+        j_to_affine(&lhs, &la, &li);
+        j_to_affine(&rhs, &ra, &ri);
+        result = (li == ri) && (li || (fp_eq(&la.x, &ra.x) && fp_eq(&la.y, &ra.y)));
+        (void)t1;
+    }
+    free(Lv); free(Rv); free(s);
+    return result;
+}

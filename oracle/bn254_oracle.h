@@ -75,6 +75,28 @@ void orc_transcript_append(orc_transcript* t, const uint8_t* label, size_t llen,
 void orc_transcript_challenge(orc_transcript* t, const uint8_t* label, size_t llen, uint8_t* out, size_t outlen);
 void orc_transcript_challenge_scalar(orc_transcript* t, const uint8_t* label, size_t llen, ofp* out_mont);
 
+
+/* Hyrax opening proof (hyrax.rs:65-151 PolyEvalProof, nizk/mod.rs:418-567 DotProductProofLog,
+ * nizk/bullet.rs BulletReductionProof) with Merlin transcripts.  The random tape is a transcript the caller
+ * seeds (the reference seeds it from OsRng, random.rs:15-23). */
+#define ORC_MAX_LG 32
+typedef struct {
+    size_t lg_n;
+    og1a L[ORC_MAX_LG], R[ORC_MAX_LG];
+    uint8_t L_inf[ORC_MAX_LG], R_inf[ORC_MAX_LG];
+    og1a delta, beta;
+    uint8_t delta_inf, beta_inf;
+    ofp z1, z2;
+} orc_eval_proof;
+/* gens: G[n] + h (gens_n) and G1 = gens_1.G[0]; n = 2^(ell - ell/2).  blinds may be NULL (zeros), blind_Zr may be NULL. */
+void orc_poly_eval_prove(const ofp* Z, size_t ell, const ofp* blinds, const ofp* r, const ofp* Zr, const ofp* blind_Zr,
+                         const og1a* G, const og1a* h, const og1a* G1, orc_transcript* transcript, orc_transcript* tape,
+                         orc_eval_proof* proof, og1a* C_Zr_prime, uint8_t* C_Zr_prime_inf);
+/* returns 1 when the proof verifies (hyrax.rs:118-137) */
+int orc_poly_eval_verify(const orc_eval_proof* proof, size_t ell, const ofp* r, const og1a* C_Zr, uint8_t C_Zr_inf,
+                         const og1a* comm, const uint8_t* comm_inf, const og1a* G, const og1a* h, const og1a* G1,
+                         orc_transcript* transcript);
+
 #ifdef __cplusplus
 }
 #endif

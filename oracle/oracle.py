@@ -229,3 +229,67 @@ class Transcript:
         out = np.zeros(4, dtype=np.uint64)
         lib().orc_transcript_challenge_scalar(C.byref(self.t), label, C.c_size_t(len(label)), _p(out))
         return out
+
+
+class EvalProof(C.Structure):
+    """orc_eval_proof: PolyEvalProof { DotProductProofLog { bullet L/R, delta, beta, z1, z2 } }."""
+    _fields_ = [("lg_n", C.c_size_t), ("L", (C.c_uint64 * 8) * 32), ("R", (C.c_uint64 * 8) * 32),
+                ("L_inf", C.c_uint8 * 32), ("R_inf", C.c_uint8 * 32), ("delta", C.c_uint64 * 8), ("beta", C.c_uint64 * 8),
+                ("delta_inf", C.c_uint8), ("beta_inf", C.c_uint8), ("z1", C.c_uint64 * 4), ("z2", C.c_uint64 * 4)]
+
+    def to_dict(self):
+        lg = self.lg_n
+        return dict(L=[(np.array(self.L[i], dtype=np.uint64), int(self.L_inf[i])) for i in range(lg)],
+                    R=[(np.array(self.R[i], dtype=np.uint64), int(self.R_inf[i])) for i in range(lg)],
+                    delta=(np.array(self.delta, dtype=np.uint64), int(self.delta_inf)),
+                    beta=(np.array(self.beta, dtype=np.uint64), int(self.beta_inf)),
+                    z1=np.array(self.z1, dtype=np.uint64), z2=np.array(self.z2, dtype=np.uint64))
+
+    @staticmethod
+    def from_dict(d):
+        p = EvalProof()
+        p.lg_n = len(d["L"])
+        for i, ((l, li), (r, ri)) in enumerate(zip(d["L"], d["R"])):
+            for k in range(8):
+                p.L[i][k] = int(l[k]); p.R[i][k] = int(r[k])
+            p.L_inf[i] = li; p.R_inf[i] = ri
+        for k in range(8):
+            p.delta[k] = int(d["delta"][0][k]); p.beta[k] = int(d["beta"][0][k])
+        p.delta_inf = d["delta"][1]; p.beta_inf = d["beta"][1]
+        for k in range(4):
+            p.z1[k] = int(d["z1"][k]); p.z2[k] = int(d["z2"][k])
+        return p
+
+
+def poly_eval_prove(Z, ell, blinds, r, Zr, blind_Zr, G, h, G1, transcript, tape):
+    """PolyEvalProof::prove (hyrax.rs:65-116) on the CPU; returns (EvalProof, C_Zr', inf)."""
+    Z = _u64(Z).reshape(-1, 4)
+    proof = EvalProof()
+    Cz = np.zeros(8, dtype=np.uint64); Czi = np.zeros(1, dtype=np.uint8)
+    b = None if blinds is None else _u64(blinds).reshape(-1, 4)
+    bz = None if blind_Zr is None else _u64(blind_Zr)
+    lib().orc_poly_eval_prove(_p(Z), C.c_size_t(ell), _p(b), _p(_u64(r).reshape(-1, 4)), _p(_u64(Zr)), _p(bz),
+                              _p(_u64(G).reshape(-1, 8)), _p(_u64(h)), _p(_u64(G1)), C.byref(transcript.t),
+                              C.byref(tape.t), C.byref(proof), _p(Cz), _p(Czi))
+    return proof, Cz, int(Czi[0])
+
+
+def poly_eval_verify(proof, ell, r, C_Zr, C_Zr_inf, comm, comm_inf, G, h, G1, transcript):
+    """PolyEvalProof::verify (hyrax.rs:118-137) on the CPU; True when the proof verifies."""
+    comm = _u64(comm).reshape(-1, 8)
+    ci = np.ascontiguousarray(comm_inf, dtype=np.uint8)
+    return bool(lib().orc_poly_eval_verify(C.byref(proof), C.c_size_t(ell), _p(_u64(r).reshape(-1, 4)), _p(_u64(C_Zr)),
+                                           C.c_uint8(C_Zr_inf), _p(comm), _p(ci), _p(_u64(G).reshape(-1, 8)), _p(_u64(h)),
+                                           _p(_u64(G1)), C.byref(transcript.t)))
+
+
+def evaluate(Z, r):
+    """DensePolynomial::evaluate (hyrax.rs:217-222): <Z, eq(r)>."""
+    Z = _u64(Z).reshape(-1, 4)
+    chis = eq_evals(r)
+    acc = 0
+    zs, cs = from_mont(Z), from_mont(chis)
+    R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    for a, b in zip(zs, cs):
+        acc = (acc + a * b) % R_MOD
+    return to_mont([acc])[0]

@@ -124,21 +124,24 @@ struct Task {
 };
 
 __host__ __device__ inline size_t msm_max_tasks(size_t E, int nb, int cap) { return E / cap + nb + 1; }
+__host__ __device__ inline size_t msm_max_heavy(size_t E, int cap) { return E / cap + 1; }   // buckets with > cap entries
 
 // entries[row * E + ...]        : bucket-sorted list of (k * n1 + j) | (negative << 31)
 // tstart [row * (NB + 1) + b]   : first task slot of bucket b (tstart[NB] = number of tasks of the row)
 // tasks  [row * max_tasks + rank]: tasks by decreasing length
+// heavy  [row * (max_heavy + 1)] : number of split buckets of the row, followed by their ids
 template <int C>
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int scalars_are_mont, int cap,
-           uint32_t E, uint32_t max_tasks, uint32_t* __restrict__ entries, uint32_t* __restrict__ tstart,
-           Task* __restrict__ tasks) {
+           uint32_t E, uint32_t max_tasks, uint32_t max_heavy, uint32_t* __restrict__ entries,
+           uint32_t* __restrict__ tstart, Task* __restrict__ tasks, uint32_t* __restrict__ heavy) {
     constexpr int NB = 1 << (C - 1);
     constexpr int PER = (NB + kSortThreads - 1) / kSortThreads;   // buckets per thread in the scans
     __shared__ uint32_t counts[NB];
     __shared__ uint32_t cursor[NB];
     __shared__ uint32_t rank_hist[kRankBins];
     __shared__ uint32_t warp_sums[2][kSortThreads / 32];
+    __shared__ uint32_t heavy_n;
 
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
@@ -147,6 +150,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
 
     for (int b = tid; b < NB; b += kSortThreads) counts[b] = 0;
     if (tid < kRankBins) rank_hist[tid] = 0;
+    if (tid == 0) heavy_n = 0;
     __syncthreads();
 
     auto load_scalar = [&](int j, Fr& s) -> bool {
@@ -224,6 +228,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
         uint32_t n = counts[b];
         uint32_t start = cursor[b];          // not yet advanced: pass 2 starts after the next barrier
         uint32_t slot = base_t + loc_t[i];
+        if (n > (uint32_t)cap) heavy[(size_t)row * (max_heavy + 1) + 1 + atomicAdd(&heavy_n, 1u)] = (uint32_t)b;
         while (n) {
             uint32_t len = n < (uint32_t)cap ? n : (uint32_t)cap;
             uint32_t pos = atomicAdd(&rank_hist[len], 1u);
@@ -235,6 +240,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
         }
     }
     __syncthreads();
+    if (tid == 0) heavy[(size_t)row * (max_heavy + 1)] = heavy_n;
 
     // pass 2: scatter
     uint32_t* erow = entries + (size_t)row * E;
@@ -280,7 +286,7 @@ k_accumulate(const Affine* __restrict__ table, const uint32_t* __restrict__ entr
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4a: per-row bucket reduction  T = sum_b (b + 1) * S_b,  S_b = sum of the bucket's task partials.
+// K4a: per-row bucket reduction  T = sum_b (b + 1) * S_b,  S_b = the bucket's (folded) partial sum.
 //
 // T equals the sum of all suffix sums  Suf_j = sum_{b >= j} S_b.  TPR threads per row each own m
 // consecutive buckets: a sequential pass gives the thread's local suffix sums (their total `tot`) and
@@ -295,6 +301,45 @@ static constexpr int kRedThreads = 128;
 // One out-of-line copy of the full addition with its 14 products inlined (instruction-level
 // parallelism between independent products matters at the 3-4 warps per scheduler this kernel runs at).
 __device__ __noinline__ void xyzz_add_call(XYZZ* acc, const XYZZ* q) { xyzz_add<MulInline, MulCall>(*acc, *q); }
+
+// Split buckets: one warp per (row, heavy bucket) folds the bucket's task partials into its first slot
+// (lanes take partials strided by 32, then a shared-memory tree), so the reduction below reads exactly
+// one partial per bucket.  Persistent grid: warps stride over the rows.
+static constexpr int kHeavyThreads = 128;
+
+__global__ void __launch_bounds__(kHeavyThreads)
+k_combine_heavy(XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy,
+                int rows, int nb, uint32_t max_tasks, uint32_t max_heavy) {
+    __shared__ XYZZ sm[kHeavyThreads];
+    const int lane = threadIdx.x & 31;
+    XYZZ* wsm = sm + (threadIdx.x & ~31);
+    const int warp = (blockIdx.x * kHeavyThreads + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * kHeavyThreads) >> 5;
+    for (int row = warp; row < rows; row += nwarps) {
+        const uint32_t* hrow = heavy + (size_t)row * (max_heavy + 1);
+        const uint32_t nh = hrow[0];
+        const uint32_t* trow = tstart + (size_t)row * (nb + 1);
+        XYZZ* prow = partials + (size_t)row * max_tasks;
+        for (uint32_t i = 0; i < nh; i++) {
+            const uint32_t b = hrow[1 + i];
+            const uint32_t s0 = trow[b], s1 = trow[b + 1];
+            XYZZ acc = XYZZ::identity();
+            for (uint32_t s = s0 + lane; s < s1; s += 32) {
+                XYZZ v = load_xyzz(prow + s);
+                xyzz_add_call(&acc, &v);
+            }
+            for (int stride = 16; stride >= 1; stride >>= 1) {
+                wsm[lane] = acc;
+                __syncwarp();
+                XYZZ o = (lane < stride) ? wsm[lane + stride] : XYZZ::identity();
+                __syncwarp();
+                xyzz_add_call(&acc, &o);
+            }
+            if (lane == 0) store_xyzz(prow + s0, acc);
+            __syncwarp();
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kRedThreads)
 k_reduce(const XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, int rows, int nb, int tpr,
@@ -317,10 +362,9 @@ k_reduce(const XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart,
         uint32_t hi_slot = trow[lo + m];
         for (int b = lo + m - 1; b >= lo; b--) {
             const uint32_t lo_slot = trow[b];
-            for (uint32_t s = lo_slot; s < hi_slot; s++) {
-                XYZZ part = load_xyzz(prow + s);
-                xyzz_add_call(&run, &part);
-            }
+            // one partial per non-empty bucket (split buckets were folded by k_combine_heavy)
+            XYZZ part = (lo_slot < hi_slot) ? load_xyzz(prow + lo_slot) : XYZZ::identity();
+            xyzz_add_call(&run, &part);
             hi_slot = lo_slot;
             xyzz_add_call(&tot, &run);
         }

@@ -37,13 +37,13 @@ struct sbn_ctx {
     long chunk_rows = 512;
     long window_bits = 0;
     long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
-    long reduce_m = 16;     // buckets per reduction thread
+    long reduce_m = 32;     // buckets per reduction thread
     uint64_t launches = 0, h2d = 0, d2h = 0;
     // grow-only workspaces
     struct Slot {          // one in-flight chunk of rows: private workspace + stream
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf entries, tstart, tasks, partials;
+        DevBuf entries, tstart, tasks, partials, heavy;
     } slots[2];
     cudaEvent_t fork = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
@@ -142,7 +142,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
         release(*b);
     for (auto& sl : ctx->slots) {
         cudaStreamSynchronize(sl.stream);
-        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials}) release(*b);
+        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy}) release(*b);
         cudaStreamDestroy(sl.stream);
         cudaEventDestroy(sl.done);
     }
@@ -319,15 +319,16 @@ static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
 }
 
 template <int C>
-static void launch_sort(const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks, uint32_t* entries,
-                        uint32_t* tstart, Task* tasks, int rows, cudaStream_t s) {
-    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, 1, cap, E, max_tasks, entries, tstart, tasks);
+static void launch_sort(const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks, uint32_t max_heavy,
+                        uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows, cudaStream_t s) {
+    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy);
 }
 
 static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks,
-                         uint32_t* entries, uint32_t* tstart, Task* tasks, int rows, cudaStream_t s) {
+                         uint32_t max_heavy, uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows,
+                         cudaStream_t s) {
     switch (c) {
-#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, cap, E, max_tasks, entries, tstart, tasks, rows, s); return SBN_OK;
+#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows, s); return SBN_OK;
         SBN_CASE(4) SBN_CASE(5) SBN_CASE(6) SBN_CASE(7) SBN_CASE(8) SBN_CASE(9) SBN_CASE(10) SBN_CASE(11)
         SBN_CASE(12) SBN_CASE(13)
 #undef SBN_CASE
@@ -341,6 +342,8 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, con
     const uint32_t E = (uint32_t)b->W * (uint32_t)b->n1;
     const int cap = task_cap_for(ctx, b);
     const uint32_t max_tasks = (uint32_t)msm_max_tasks(E, b->nb, cap);
+    const uint32_t max_heavy = (uint32_t)msm_max_heavy(E, cap);
+    uint32_t* heavy = (uint32_t*)sl.heavy.p;
     uint32_t* entries = (uint32_t*)sl.entries.p;
     uint32_t* tstart = (uint32_t*)sl.tstart.p;
     Task* tasks = (Task*)sl.tasks.p;
@@ -352,19 +355,25 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, con
         ev_stage.push_back(stage);
     };
     mark(-1);
-    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, cap, E, max_tasks, entries, tstart, tasks, rows, stream));
+    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows,
+                          stream));
     mark(0);
     const size_t threads = (size_t)rows * max_tasks;
     const unsigned acc_blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     k_accumulate<<<acc_blocks, kAccThreads, 0, stream>>>(b->table, entries, tstart, tasks, partials, rows, b->nb, E, max_tasks);
     mark(1);
+    {   // fold the partials of split buckets; persistent grid, one warp per row at a time
+        const int warps_needed = rows;
+        const int blocks = std::max(1, std::min(148 * 4, (warps_needed * 32 + kHeavyThreads - 1) / kHeavyThreads));
+        k_combine_heavy<<<blocks, kHeavyThreads, 0, stream>>>(partials, tstart, heavy, rows, b->nb, max_tasks, max_heavy);
+    }
     int m = std::min((int)ctx->reduce_m, b->nb);
     int tpr = std::min(kRedThreads, b->nb / m);
     int rows_per_block = kRedThreads / tpr;
     k_reduce<<<(rows + rows_per_block - 1) / rows_per_block, kRedThreads, kRedThreads * sizeof(XYZZ), stream>>>(
         partials, tstart, rows, b->nb, tpr, max_tasks, totals_chunk);
     mark(2);
-    ctx->launches += 3;
+    ctx->launches += 4;
     SBN_CUDA(ctx, cudaGetLastError());
     return SBN_OK;
 }
@@ -380,6 +389,7 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
         SBN_TRY(ensure(ctx, sl.tstart, chunk * (b->nb + 1) * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.tasks, chunk * max_tasks * sizeof(Task)));
         SBN_TRY(ensure(ctx, sl.partials, chunk * max_tasks * sizeof(XYZZ)));
+        SBN_TRY(ensure(ctx, sl.heavy, chunk * (msm_max_heavy(E, task_cap_for(ctx, b)) + 1) * sizeof(uint32_t)));
     }
     SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
     return SBN_OK;

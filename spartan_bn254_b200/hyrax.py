@@ -246,5 +246,148 @@ class DensePolynomial:
         return ctx.bound(self.Z, L, 1 << left, 1 << right)
 
 
+# ------------------------------------------------------------------------------------------------
+# Fr helpers on the host (Python ints): Montgomery limbs <-> canonical values
+# ------------------------------------------------------------------------------------------------
+_RINV_R = pow(1 << 256, -1, R_MOD)
+
+
+def fr_to_int(limbs):
+    return _int(limbs) * _RINV_R % R_MOD
+
+
+def fr_from_int(v):
+    return np.array(_limbs((int(v) << 256) % R_MOD), dtype=np.uint64)
+
+
+def fr_vec_to_ints(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    return [fr_to_int(a) for a in arr]
+
+
+def fr_vec_from_ints(vals):
+    out = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = fr_from_int(v)
+    return out
+
+
+class EqPolynomial:
+    """hyrax.rs:340-383 on canonical ints."""
+
+    def __init__(self, r):
+        self.r = list(r)
+
+    def evals(self):
+        ell = len(self.r)
+        ev = [1] * (1 << ell)
+        size = 1
+        for j in range(ell):
+            size *= 2
+            for i in range(size - 1, -1, -2):
+                s = ev[i // 2]
+                ev[i] = s * self.r[j] % R_MOD
+                ev[i - 1] = (s - ev[i]) % R_MOD
+        return ev
+
+    def compute_factored_evals(self):
+        left, _ = compute_factored_lens(len(self.r))
+        return EqPolynomial(self.r[:left]).evals(), EqPolynomial(self.r[left:]).evals()
+
+
+class DotProductProofLog:
+    """nizk/mod.rs:418-522 (prover).  Every group operation runs on the GPU through the C ABI: the (n+1)-point
+    commitment Cx, the bullet reduction with device-resident generators, and the 2-point commitments."""
+
+    def __init__(self, L_vec, R_vec, delta, beta, z1, z2):
+        self.L_vec, self.R_vec, self.delta, self.beta, self.z1, self.z2 = L_vec, R_vec, delta, beta, z1, z2
+
+    @staticmethod
+    def _commit2(ctx, g, s, h, blind):
+        """Scalar::commit (commitments.rs:122-130): s * g + blind * h as a 2-point MSM."""
+        out, inf = ctx.msm(np.stack([g, h]), None, np.stack([fr_from_int(s), fr_from_int(blind)]))
+        return GroupElement(out, inf)
+
+    @staticmethod
+    def prove(gens, transcript, random_tape, x_vec, blind_x, a_vec, y, blind_y):
+        ctx = gens.gens_n.ctx
+        transcript.append_protocol_name(b"dot product proof (log)")
+        n = len(x_vec)
+        assert len(a_vec) == n and gens.n == n                              # mod.rs:451-452
+        lg_n = log_2(n)
+        d = random_tape.random_scalar(b"d")
+        r_delta = random_tape.random_scalar(b"r_delta")
+        r_beta = random_tape.random_scalar(b"r_delta")                      # sic (mod.rs:459)
+        v1 = random_tape.random_vector(b"blinds_vec_1", lg_n)
+        v2 = random_tape.random_vector(b"blinds_vec_2", lg_n)
+        x_m = fr_vec_from_ints(x_vec)
+        Cx = gens.gens_n.commit(x_m, fr_from_int(blind_x))                  # (n+1)-point MSM, mod.rs:470
+        transcript.append_point(b"Cx", Cx.compress())
+        h = gens.gens_n.h
+        G1 = gens.gens_1.G[0]
+        Cy = DotProductProofLog._commit2(ctx, G1, y, h, blind_y)            # mod.rs:473
+        transcript.append_point(b"Cy", Cy.compress())
+        transcript.append_scalars(b"a", a_vec)
+        r = transcript.challenge_scalar(b"r")
+        gens_1_scaled = gens.gens_1.scale(fr_from_int(r))                   # mod.rs:481
+        Q = gens_1_scaled.G[0]
+        blind_Gamma = (blind_x + r * blind_y) % R_MOD
+        # BulletReductionProof::prove (bullet.rs:24-126): G, a, b stay on the device; L, R and u cross the boundary
+        st = ctx.bullet_begin(gens.gens_n.device_bases(), Q, x_m, fr_vec_from_ints(a_vec), fr_from_int(blind_Gamma))
+        L_vec, R_vec = [], []
+        rhat = blind_Gamma
+        for i in range(lg_n):
+            (L, Li), (R, Ri) = st.round(fr_from_int(v1[i]), fr_from_int(v2[i]))
+            L, R = GroupElement(L, Li), GroupElement(R, Ri)
+            transcript.append_point(b"L", L.compress())
+            transcript.append_point(b"R", R.compress())
+            u = transcript.challenge_scalar(b"u")
+            u_inv = pow(u, -1, R_MOD)
+            st.fold(fr_from_int(u), fr_from_int(u_inv))
+            rhat = (u * u * v1[i] + rhat + u_inv * u_inv * v2[i]) % R_MOD
+            L_vec.append(L)
+            R_vec.append(R)
+        a_hat_m, b_hat_m, g_hat, g_inf = st.end()
+        st.close()
+        x_hat, a_hat = fr_to_int(a_hat_m), fr_to_int(b_hat_m)
+        y_hat = x_hat * a_hat % R_MOD
+        assert not g_inf
+        delta = DotProductProofLog._commit2(ctx, g_hat, d, h, r_delta)      # mod.rs:497-500
+        transcript.append_point(b"delta", delta.compress())
+        beta = DotProductProofLog._commit2(ctx, Q, d, h, r_beta)            # mod.rs:503
+        transcript.append_point(b"beta", beta.compress())
+        c = transcript.challenge_scalar(b"c")
+        z1 = (d + c * y_hat) % R_MOD
+        z2 = (a_hat * (c * rhat + r_beta) + r_delta) % R_MOD
+        return DotProductProofLog(L_vec, R_vec, delta, beta, z1, z2), Cx, Cy
+
+
+class PolyEvalProof:
+    """hyrax.rs:55-116 (prover)."""
+
+    def __init__(self, proof):
+        self.proof = proof
+
+    @staticmethod
+    def prove(poly, blinds, r, Zr, blind_Zr, gens, transcript, random_tape):
+        """poly: DensePolynomial; blinds: uint64[L,4] or None; r: list of canonical ints; Zr / blind_Zr: ints."""
+        ctx = gens.gens.gens_n.ctx
+        transcript.append_protocol_name(b"polynomial evaluation proof")
+        assert poly.get_num_vars() == len(r)                                 # hyrax.rs:77
+        left, right = compute_factored_lens(len(r))
+        L_size, R_size = 1 << left, 1 << right
+        Lv, Rv = EqPolynomial(r).compute_factored_evals()
+        LZ = poly.bound(fr_vec_from_ints(Lv), ctx)                           # GPU, hyrax.rs:100
+        LZ_blind = 0
+        if blinds is not None:
+            bl = fr_vec_to_ints(blinds)
+            assert len(bl) == L_size                                         # hyrax.rs:88
+            LZ_blind = sum(b * l for b, l in zip(bl, Lv)) % R_MOD
+        proof, _C_LR, C_Zr_prime = DotProductProofLog.prove(gens.gens, transcript, random_tape, fr_vec_to_ints(LZ),
+                                                            LZ_blind, Rv, Zr, blind_Zr or 0)
+        return PolyEvalProof(proof), C_Zr_prime
+
+
 __all__ = ["GroupElement", "MultiCommitGens", "DotProductProofGens", "PolyCommitmentGens", "PolyCommitment",
-           "DensePolynomial", "compute_factored_lens", "log_2", "SbnError"]
+           "DensePolynomial", "compute_factored_lens", "log_2", "SbnError", "EqPolynomial", "DotProductProofLog",
+           "PolyEvalProof", "fr_to_int", "fr_from_int", "fr_vec_to_ints", "fr_vec_from_ints"]

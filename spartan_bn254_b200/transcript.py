@@ -1,0 +1,151 @@
+"""Merlin transcript (STROBE-128 over Keccak-f[1600]) for the host-side mirror of the reference's
+Fiat-Shamir layer (reference transcript.rs, random.rs; third-party merlin 3.0).  The transcript is host
+logic in the reference too -- the GPU backend only needs the challenges it produces -- so this is a plain
+Python restatement used by the Python host mirror and its tests.  Check value: merlin's published test
+vector (tests/test_transcript.py)."""
+
+_MASK = (1 << 64) - 1
+_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+       0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+       0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+       0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+       0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+_RHO = [0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14]
+R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def _rol(x, n):
+    return ((x << n) | (x >> (64 - n))) & _MASK if n else x
+
+
+def keccak_f(a):
+    """In place on a list of 25 lanes (x + 5 y)."""
+    for rc in _RC:
+        c = [a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20] for x in range(5)]
+        d = [c[(x + 4) % 5] ^ _rol(c[(x + 1) % 5], 1) for x in range(5)]
+        a = [a[i] ^ d[i % 5] for i in range(25)]
+        b = [0] * 25
+        for x in range(5):
+            for y in range(5):
+                b[y + 5 * ((2 * x + 3 * y) % 5)] = _rol(a[x + 5 * y], _RHO[x + 5 * y])
+        a = [b[i] ^ (~b[(i % 5 + 1) % 5 + 5 * (i // 5)] & _MASK & b[(i % 5 + 2) % 5 + 5 * (i // 5)]) for i in range(25)]
+        a[0] ^= rc
+    return a
+
+
+_R = 166
+_FLAG_I, _FLAG_A, _FLAG_C, _FLAG_T, _FLAG_M, _FLAG_K = 1, 2, 4, 8, 16, 32
+
+
+class Transcript:
+    def __init__(self, label):
+        self.st = bytearray(200)
+        self.st[0:6] = bytes([1, _R + 2, 1, 0, 1, 96])
+        self.st[6:18] = b"STROBEv1.0.2"
+        self._permute()
+        self.pos = 0
+        self.pos_begin = 0
+        self.cur_flags = 0
+        self._meta_ad(b"Merlin v1.0", False)
+        self.append_message(b"dom-sep", label)
+
+    # ---- STROBE
+    def _permute(self):
+        lanes = [int.from_bytes(self.st[8 * i: 8 * i + 8], "little") for i in range(25)]
+        lanes = keccak_f(lanes)
+        for i, l in enumerate(lanes):
+            self.st[8 * i: 8 * i + 8] = l.to_bytes(8, "little")
+
+    def _run_f(self):
+        self.st[self.pos] ^= self.pos_begin
+        self.st[self.pos + 1] ^= 0x04
+        self.st[_R + 1] ^= 0x80
+        self._permute()
+        self.pos = 0
+        self.pos_begin = 0
+
+    def _absorb(self, data):
+        for b in data:
+            self.st[self.pos] ^= b
+            self.pos += 1
+            if self.pos == _R:
+                self._run_f()
+
+    def _squeeze(self, n):
+        out = bytearray()
+        for _ in range(n):
+            out.append(self.st[self.pos])
+            self.st[self.pos] = 0
+            self.pos += 1
+            if self.pos == _R:
+                self._run_f()
+        return bytes(out)
+
+    def _begin_op(self, flags, more):
+        if more:
+            assert self.cur_flags == flags
+            return
+        old_begin = self.pos_begin
+        self.pos_begin = self.pos + 1
+        self.cur_flags = flags
+        self._absorb(bytes([old_begin, flags]))
+        if flags & (_FLAG_C | _FLAG_K) and self.pos != 0:
+            self._run_f()
+
+    def _meta_ad(self, data, more):
+        self._begin_op(_FLAG_M | _FLAG_A, more)
+        self._absorb(data)
+
+    def _ad(self, data, more):
+        self._begin_op(_FLAG_A, more)
+        self._absorb(data)
+
+    def _prf(self, n, more):
+        self._begin_op(_FLAG_I | _FLAG_A | _FLAG_C, more)
+        return self._squeeze(n)
+
+    # ---- Merlin
+    def append_message(self, label, message):
+        self._meta_ad(label, False)
+        self._meta_ad(len(message).to_bytes(4, "little"), True)
+        self._ad(message, False)
+
+    def challenge_bytes(self, label, n):
+        self._meta_ad(label, False)
+        self._meta_ad(n.to_bytes(4, "little"), True)
+        return self._prf(n, False)
+
+    # ---- ProofTranscript (reference transcript.rs:37-80); scalars are canonical Python ints here
+    def append_protocol_name(self, name):
+        self.append_message(b"protocol-name", name)
+
+    def append_scalar(self, label, s):
+        self.append_message(label, int(s).to_bytes(32, "little"))          # scalar.rs:75-84
+
+    def append_scalars(self, label, scalars):
+        for s in scalars:
+            self.append_scalar(label, s)
+
+    def append_point(self, label, compressed32):
+        self.append_message(label, compressed32)
+
+    def challenge_scalar(self, label):
+        return int.from_bytes(self.challenge_bytes(label, 64), "little") % R_MOD   # transcript.rs:56-67
+
+    def challenge_scalars(self, label, n):
+        return [self.challenge_scalar(label) for _ in range(n)]
+
+
+class RandomTape:
+    """random.rs:10-31.  The reference seeds the tape from OsRng; here the seed scalar is injected so a proof
+    can be reproduced (and compared byte for byte with the CPU prover in the tests)."""
+
+    def __init__(self, name, seed_scalar):
+        self.tape = Transcript(name)
+        self.tape.append_scalar(b"init_randomness", seed_scalar)
+
+    def random_scalar(self, label):
+        return self.tape.challenge_scalar(label)
+
+    def random_vector(self, label, n):
+        return self.tape.challenge_scalars(label, n)

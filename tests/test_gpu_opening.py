@@ -183,3 +183,60 @@ def test_cpp_host_mirror(orc, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host mirror: ok" in out.stdout
+
+
+@pytest.mark.parametrize("ell,label,use_blinds", [(4, b"gens_r1cs_sat", True), (8, b"gens_r1cs_eval", False),
+                                                   (12, b"gens_r1cs_sat", True)])
+def test_poly_eval_proof_roundtrip_and_byte_parity(ctx, orc, ell, label, use_blinds):
+    """PolyEvalProof::prove (hyrax.rs:65-116) driven through the GPU -- bound, the (n+1)-point commitment Cx, the
+    device-resident bullet reduction, the 2-point commitments -- with Merlin challenges on the host:
+      * the proof verifies under the independent CPU verifier (hyrax.rs:118-137 restated in the oracle), like the
+        reference's own prove->verify tests (nizk/mod.rs:575-712);
+      * with the same injected random-tape seed it is byte-identical to the CPU prover's proof."""
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import (DensePolynomial, PolyCommitmentGens, PolyEvalProof, fr_vec_to_ints, fr_to_int,
+                                          compute_factored_lens)
+    from spartan_bn254_b200.transcript import Transcript, RandomTape
+    l, r_ = compute_factored_lens(ell)
+    L_size, n = 1 << l, 1 << r_
+    gens = PolyCommitmentGens(ell, label, ctx)
+    Z = synth.uniform_scalars(61, 1 << ell)
+    blinds = synth.uniform_scalars(62, L_size) if use_blinds else None
+    rpt = synth.uniform_scalars(63, ell)
+    poly = DensePolynomial(Z)
+    comm, _ = poly.commit(gens, blinds)
+    Zr_m = orc.evaluate(Z, rpt)
+    blind_Zr = 424242 if use_blinds else 0
+    seed = 987654321
+    tr = Transcript(b"example")
+    tape = RandomTape(b"proof", seed)
+    proof, C_Zr = PolyEvalProof.prove(poly, blinds, fr_vec_to_ints(rpt), fr_to_int(Zr_m), blind_Zr, gens, tr, tape)
+
+    gn, g1 = gens.gens.gens_n, gens.gens.gens_1
+    # CPU prover with the same tape
+    otr = orc.Transcript(b"example")
+    otape = orc.Transcript(b"proof")
+    otape.append_message(b"init_randomness", seed.to_bytes(32, "little"))
+    oproof, oC, oCi = orc.poly_eval_prove(Z, ell, blinds, rpt, Zr_m, orc.to_mont([blind_Zr])[0] if use_blinds else None,
+                                          gn.G, gn.h, g1.G[0], otr, otape)
+    od = oproof.to_dict()
+    p = proof.proof
+    assert len(p.L_vec) == len(od["L"]) == r_
+    for k in range(r_):
+        assert p.L_vec[k].inf == od["L"][k][1] and np.array_equal(p.L_vec[k].xy, od["L"][k][0]), k
+        assert p.R_vec[k].inf == od["R"][k][1] and np.array_equal(p.R_vec[k].xy, od["R"][k][0]), k
+    assert np.array_equal(p.delta.xy, od["delta"][0]) and np.array_equal(p.beta.xy, od["beta"][0])
+    assert orc.from_mont(od["z1"]) == [p.z1] and orc.from_mont(od["z2"]) == [p.z2]
+    assert np.array_equal(C_Zr.xy, oC) and C_Zr.inf == oCi
+    # both transcripts end in the same state
+    assert tr.challenge_bytes(b"final", 32) == otr.challenge_bytes(b"final", 32)
+
+    # independent verification of the GPU-made proof against the GPU-made commitment
+    gd = dict(L=[(e.xy, e.inf) for e in p.L_vec], R=[(e.xy, e.inf) for e in p.R_vec], delta=(p.delta.xy, p.delta.inf),
+              beta=(p.beta.xy, p.beta.inf), z1=orc.to_mont([p.z1])[0], z2=orc.to_mont([p.z2])[0])
+    assert orc.poly_eval_verify(orc.EvalProof.from_dict(gd), ell, rpt, C_Zr.xy, C_Zr.inf, comm.C, comm.inf, gn.G, gn.h,
+                                g1.G[0], orc.Transcript(b"example"))
+    gd["z2"] = gd["z2"].copy()
+    gd["z2"][0] ^= np.uint64(1)
+    assert not orc.poly_eval_verify(orc.EvalProof.from_dict(gd), ell, rpt, C_Zr.xy, C_Zr.inf, comm.C, comm.inf, gn.G, gn.h,
+                                    g1.G[0], orc.Transcript(b"example"))
