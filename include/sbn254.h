@@ -73,6 +73,11 @@ int sbn_host_free(void* p);
  * tables 2^(k*c) * G_j used by every later commit.  inf may be NULL (no identity among the bases). */
 int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* h,
                      sbn_bases** out);
+/* Same with one extra generator g1 kept resident beside G and h: DotProductProofGens (nizk/mod.rs:404-415) splits
+ * MultiCommitGens::new(n + 1) into gens_n = (G[0..n), h) and gens_1 = (G[n], h); passing g1 = G[n] lets the opening
+ * (sbn_bullet_begin with q_scalar) run every group operation of the bullet reduction on the window tables. */
+int sbn_bases_create_ext(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* g1,
+                         const sbn_g1a* h, sbn_bases** out);
 int sbn_bases_destroy(sbn_bases* bases);
 size_t sbn_bases_len(const sbn_bases* bases);                 /* n (without h) */
 int sbn_bases_window_bits(const sbn_bases* bases);
@@ -108,16 +113,28 @@ int sbn_g1_scale_points(sbn_ctx* ctx, const sbn_g1a* P, const uint8_t* inf, size
 /* ---- a11: DensePolynomial::bound (hyrax.rs:311-324): LZ[i] = sum_j L[j] * Z[j*R_size + i] */
 int sbn_bound(sbn_ctx* ctx, const sbn_fr* Z, const sbn_fr* L, size_t L_size, size_t R_size, sbn_fr* LZ_out);
 
-/* ---- a14: BulletReductionProof::prove (nizk/bullet.rs:24-126) with G, a, b resident on device.
+/* ---- resident polynomial: the evaluation vector of a DensePolynomial (hyrax.rs:155-160) uploaded once and used by
+ *      both its commitment (prove/encode time) and its opening (`bound`), so the scalars cross PCIe once. */
+typedef struct sbn_poly sbn_poly;
+int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_poly** out);
+int sbn_poly_destroy(sbn_poly* poly);
+int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_poly* poly, size_t L_size, size_t R_size,
+                    const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);                    /* = sbn_hyrax_commit */
+int sbn_poly_bound(sbn_ctx* ctx, const sbn_poly* poly, const sbn_fr* L, size_t L_size, size_t R_size, sbn_fr* LZ_out);
+
+/* ---- a14: BulletReductionProof::prove (nizk/bullet.rs:24-126) with a, b (and the generators) resident on device.
  * The Fiat-Shamir transcript stays on the host: each round returns (L, R), the caller appends them,
- * draws u and hands it back.
- *   begin : uploads a, b (n scalars each), uses bases' G[0..n) and h as H; computes
- *           Gamma = MSM(a,G) + <a,b> Q + blind H                              (bullet.rs:57-59)
- *   round : L = MSM(a_L,G_R) + c_L Q + blind_L H, R = MSM(a_R,G_L) + c_R Q + blind_R H (bullet.rs:70-76)
- *   fold  : G <- u^-1 G_L + u G_R, a <- u a_L + u^-1 a_R, b <- u^-1 b_L + u b_R       (bullet.rs:85-102)
- *   end   : a_hat, b_hat, g_hat                                                 (bullet.rs:110-112) */
-int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* a, const sbn_fr* b,
-                     size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf, sbn_bullet** out);
+ * draws u and hands it back.  `bases` supplies G[0..n) and H = h.  Q is given either
+ *   - as q_scalar (Q = q_scalar * g1, bases made by sbn_bases_create_ext) -- the form the reference's only caller
+ *     uses (nizk/mod.rs:480-485: Q = gens_1.scale(r).G[0]); every MSM of the reduction then runs on the window
+ *     tables and the generators are never folded (their fold coefficients are carried as scalars), or
+ *   - as an arbitrary point Q (q_scalar NULL): generators are folded explicitly as in bullet.rs:85-89.
+ *   begin : Gamma = MSM(a,G) + <a,b> Q + blind H                                         (bullet.rs:57-59)
+ *   round : L = MSM(a_L,G_R) + c_L Q + blind_L H, R = MSM(a_R,G_L) + c_R Q + blind_R H    (bullet.rs:70-76)
+ *   fold  : G <- u^-1 G_L + u G_R, a <- u a_L + u^-1 a_R, b <- u^-1 b_L + u b_R           (bullet.rs:85-102)
+ *   end   : a_hat, b_hat, g_hat                                                         (bullet.rs:110-112) */
+int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* q_scalar, const sbn_fr* a,
+                     const sbn_fr* b, size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf, sbn_bullet** out);
 int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn_fr* blind_R,
                      sbn_g1a* L_out, uint8_t* L_inf, sbn_g1a* R_out, uint8_t* R_inf);
 int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_inv);

@@ -32,7 +32,9 @@ extern "C" {
                       out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_bound(ctx: *mut sbn_ctx, z: *const SbnFr, l: *const SbnFr, l_size: usize, r_size: usize,
                      lz_out: *mut SbnFr) -> c_int;
-    pub fn sbn_bullet_begin(ctx: *mut sbn_ctx, b: *const sbn_bases, q: *const SbnG1a, a: *const SbnFr, bv: *const SbnFr,
+    pub fn sbn_bases_create_ext(ctx: *mut sbn_ctx, g: *const SbnG1a, g_inf: *const u8, n: usize, g1: *const SbnG1a,
+                                h: *const SbnG1a, out: *mut *mut sbn_bases) -> c_int;
+    pub fn sbn_bullet_begin(ctx: *mut sbn_ctx, b: *const sbn_bases, q: *const SbnG1a, q_scalar: *const SbnFr, a: *const SbnFr, bv: *const SbnFr,
                             n: usize, blind: *const SbnFr, gamma: *mut SbnG1a, gamma_inf: *mut u8,
                             out: *mut *mut sbn_bullet) -> c_int;
     pub fn sbn_bullet_round(st: *mut sbn_bullet, blind_l: *const SbnFr, blind_r: *const SbnFr, l_out: *mut SbnG1a,

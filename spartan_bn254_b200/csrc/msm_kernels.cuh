@@ -132,7 +132,7 @@ __host__ __device__ inline size_t msm_max_heavy(size_t E, int cap) { return E / 
 // heavy  [row * (max_heavy + 1)] : number of split buckets of the row, followed by their ids
 template <int C>
 __global__ void __launch_bounds__(kSortThreads)
-k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int scalars_are_mont, int cap,
+k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n1, int h_col, int scalars_are_mont, int cap,
            uint32_t E, uint32_t max_tasks, uint32_t max_heavy, uint32_t* __restrict__ entries,
            uint32_t* __restrict__ tstart, Task* __restrict__ tasks, uint32_t* __restrict__ heavy) {
     constexpr int NB = 1 << (C - 1);
@@ -145,8 +145,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
 
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n1 = R + 1;
-    const Fr* zrow = Z + (size_t)row * R;
+    const Fr* zrow = Z + (size_t)row * R;   // R scalars of the row go to table columns 0..R-1, the blind to column h_col
 
     for (int b = tid; b < NB; b += kSortThreads) counts[b] = 0;
     if (tid < kRankBins) rank_hist[tid] = 0;
@@ -163,7 +162,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
     };
 
     // pass 1: histogram
-    for (int j = tid; j < n1; j += kSortThreads) {
+    for (int j = tid; j <= R; j += kSortThreads) {
         Fr s;
         if (!load_scalar(j, s)) continue;
         for_each_digit<C>(s, [&](int, uint32_t bucket, bool) { atomicAdd(&counts[bucket], 1u); });
@@ -244,12 +243,13 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int s
 
     // pass 2: scatter
     uint32_t* erow = entries + (size_t)row * E;
-    for (int j = tid; j < n1; j += kSortThreads) {
+    for (int j = tid; j <= R; j += kSortThreads) {
         Fr s;
         if (!load_scalar(j, s)) continue;
+        const int col = j < R ? j : h_col;
         for_each_digit<C>(s, [&](int k, uint32_t bucket, bool negative) {
             uint32_t pos = atomicAdd(&cursor[bucket], 1u);
-            erow[pos] = (uint32_t)(k * n1 + j) | (negative ? 0x80000000u : 0u);
+            erow[pos] = (uint32_t)(k * n1 + col) | (negative ? 0x80000000u : 0u);
         });
     }
 }

@@ -199,6 +199,53 @@ k_fold_points(Affine* __restrict__ G, uint8_t* __restrict__ Ginf, int n2, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Table-based bullet rounds.  Folding the generators (bullet.rs:85-89, two full scalar multiplications per
+// element and round) is avoided: after i rounds  G_i[j] = sum_t coef[t] * G[j + t*m]  (m = n / 2^i) with
+// coef[t] = prod_r (bit_{i-1-r}(t) ? u_r : u_r^-1), so
+//     MSM(a_L, G_R) = sum_{k : k mod m >= m/2} a[k mod m - m/2] * coef[k div m] * G[k]
+//     MSM(a_R, G_L) = sum_{k : k mod m <  m/2} a[k mod m + m/2] * coef[k div m] * G[k]
+// are two rows over the ORIGINAL, table-resident generators; c * Q = (c * q) * g1 and blind * H are two more
+// columns of the same rows.  Only scalars are folded.
+// ---------------------------------------------------------------------------------------------
+// rows: 2 x (n + 1) Montgomery scalars; dots = (c_L, c_R)
+__global__ void k_bullet_expand(const Fr* __restrict__ a, const Fr* __restrict__ coef, int n, int m,
+                                const Fr* __restrict__ dots, const Fr* __restrict__ qs, Fr* __restrict__ rows) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n) return;
+    Fr l = Fr::zero(), r = Fr::zero();
+    if (k == n) {
+        const Fr q = load_fr(qs);
+        l = fr_mul_call(load_fr(dots), q);
+        r = fr_mul_call(load_fr(dots + 1), q);
+    } else {
+        const int h = m >> 1, jm = k % m;
+        const Fr c = load_fr(coef + k / m);
+        if (jm >= h) l = fr_mul_call(load_fr(a + jm - h), c);
+        else r = fr_mul_call(load_fr(a + jm + h), c);
+    }
+    store_fr(rows + k, l);
+    store_fr(rows + (size_t)(n + 1) + k, r);
+}
+// row[k < n] = vec[k]; row[n] = dot ? dot * qs : 0
+__global__ void k_bullet_row_single(const Fr* __restrict__ vec, int n, const Fr* __restrict__ dot, const Fr* __restrict__ qs,
+                                    Fr* __restrict__ row) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n) return;
+    Fr v = Fr::zero();
+    if (k < n) v = load_fr(vec + k);
+    else if (dot) v = fr_mul_call(load_fr(dot), load_fr(qs));
+    store_fr(row + k, v);
+}
+// out[2t] = in[t] * u^-1, out[2t + 1] = in[t] * u
+__global__ void k_coef_update(const Fr* __restrict__ in, int len, const Fr* __restrict__ uu, Fr* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= len) return;
+    const Fr c = load_fr(in + t);
+    store_fr(out + 2 * t, fr_mul_call(c, load_fr(uu + 1)));
+    store_fr(out + 2 * t + 1, fr_mul_call(c, load_fr(uu)));
+}
+
+// ---------------------------------------------------------------------------------------------
 // bound (hyrax.rs:311-324): LZ[i] = sum_j L[j] Z[j * R + i].  grid = (R / 128, slices): each block sums a
 // slice of the rows for 128 adjacent columns (coalesced 32 B loads); k_fr_colsum adds the slices.
 // ---------------------------------------------------------------------------------------------

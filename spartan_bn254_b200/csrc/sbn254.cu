@@ -56,7 +56,8 @@ struct sbn_ctx {
 struct sbn_bases {
     sbn_ctx* ctx = nullptr;
     size_t n = 0;      // generators without h
-    int n1 = 0;        // n + 1
+    int has_g1 = 0;    // extra generator g1 (DotProductProofGens::gens_1.G[0]) in column n
+    int n1 = 0;        // table columns: n + has_g1 + 1, h is the last one
     int c = 0, W = 0, nb = 0;
     Affine* table = nullptr;   // W * n1 affine points
 };
@@ -231,8 +232,8 @@ static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b);
 // ------------------------------------------------------------------------------------------------
 // bases
 // ------------------------------------------------------------------------------------------------
-extern "C" int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* h,
-                                sbn_bases** out) {
+static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* g1, const sbn_g1a* h,
+                        sbn_bases** out) {
     if (!ctx || !G || !h || !out) return SBN_ERR_ARG;
     *out = nullptr;
     if (n == 0 || n > (1u << 24)) return SBN_ERR_SHAPE;
@@ -242,7 +243,8 @@ extern "C" int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G
     if (!b) return SBN_ERR_OOM;
     b->ctx = ctx;
     b->n = n;
-    b->n1 = (int)n + 1;
+    b->has_g1 = g1 ? 1 : 0;
+    b->n1 = (int)n + 1 + b->has_g1;
     b->c = ctx->window_bits ? (int)ctx->window_bits : choose_window(n + 1);
     b->W = msm_num_windows(b->c);
     b->nb = 1 << (b->c - 1);
@@ -267,7 +269,8 @@ extern "C" int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G
     std::vector<uint8_t> inf_host(b->n1, 0);
     if (G_inf) memcpy(inf_host.data(), G_inf, n);
     if ((e = cudaMemcpyAsync(dbases, G, sizeof(Affine) * n, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dbases + n, h, sizeof(Affine), cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
+        (g1 && (e = cudaMemcpyAsync(dbases + n, g1, sizeof(Affine), cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess) ||
+        (e = cudaMemcpyAsync(dbases + (b->n1 - 1), h, sizeof(Affine), cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
         (e = cudaMemcpyAsync(dinf, inf_host.data(), b->n1, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess) {
         ctx->last_error = std::string("sbn_bases_create upload: ") + cudaGetErrorString(e);
         return fail(SBN_ERR_CUDA);
@@ -283,6 +286,16 @@ extern "C" int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G
     cudaFree(dinf);
     *out = b;
     return SBN_OK;
+}
+
+extern "C" int sbn_bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* h,
+                                sbn_bases** out) {
+    return bases_create(ctx, G, G_inf, n, nullptr, h, out);
+}
+extern "C" int sbn_bases_create_ext(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, size_t n, const sbn_g1a* g1,
+                                    const sbn_g1a* h, sbn_bases** out) {
+    if (!g1) return SBN_ERR_ARG;
+    return bases_create(ctx, G, G_inf, n, g1, h, out);
 }
 
 extern "C" int sbn_bases_destroy(sbn_bases* b) {
@@ -319,16 +332,17 @@ static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
 }
 
 template <int C>
-static void launch_sort(const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks, uint32_t max_heavy,
+static void launch_sort(const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks, uint32_t max_heavy,
                         uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows, cudaStream_t s) {
-    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy);
+    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks,
+                                                 heavy);
 }
 
-static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int cap, uint32_t E, uint32_t max_tasks,
+static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks,
                          uint32_t max_heavy, uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows,
                          cudaStream_t s) {
     switch (c) {
-#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows, s); return SBN_OK;
+#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, n1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows, s); return SBN_OK;
         SBN_CASE(4) SBN_CASE(5) SBN_CASE(6) SBN_CASE(7) SBN_CASE(8) SBN_CASE(9) SBN_CASE(10) SBN_CASE(11)
         SBN_CASE(12) SBN_CASE(13)
 #undef SBN_CASE
@@ -355,8 +369,8 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, con
         ev_stage.push_back(stage);
     };
     mark(-1);
-    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows,
-                          stream));
+    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy,
+                          rows, stream));
     mark(0);
     const size_t threads = (size_t)rows * max_tasks;
     const unsigned acc_blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
@@ -368,6 +382,7 @@ static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, con
         k_combine_heavy<<<blocks, kHeavyThreads, 0, stream>>>(partials, tstart, heavy, rows, b->nb, max_tasks, max_heavy);
     }
     int m = std::min((int)ctx->reduce_m, b->nb);
+    if (rows <= 64) m = std::min(m, 8);           // few rows: latency matters more than total work
     int tpr = std::min(kRedThreads, b->nb / m);
     int rows_per_block = kRedThreads / tpr;
     k_reduce<<<(rows + rows_per_block - 1) / rows_per_block, kRedThreads, kRedThreads * sizeof(XYZZ), stream>>>(
@@ -713,78 +728,196 @@ extern "C" int sbn_bound(sbn_ctx* ctx, const sbn_fr* Z, const sbn_fr* Lv, size_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// resident polynomial
+// ------------------------------------------------------------------------------------------------
+struct sbn_poly {
+    sbn_ctx* ctx = nullptr;
+    Fr* Z = nullptr;
+    size_t len = 0;
+};
+
+extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_poly** out) {
+    if (!ctx || !Z || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (len == 0 || len > (size_t(1) << 32)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    sbn_poly* p = new (std::nothrow) sbn_poly();
+    if (!p) return SBN_ERR_OOM;
+    p->ctx = ctx;
+    p->len = len;
+    if (cudaMalloc(&p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_poly_upload: cudaMalloc failed"; return SBN_ERR_OOM; }
+    if (cudaMemcpyAsync(p->Z, Z, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+        cudaFree(p->Z);
+        delete p;
+        ctx->last_error = "sbn_poly_upload: copy failed";
+        return SBN_ERR_CUDA;
+    }
+    ctx->h2d += len * sizeof(Fr);
+    *out = p;
+    return SBN_OK;
+}
+
+extern "C" int sbn_poly_destroy(sbn_poly* p) {
+    if (!p) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(p->ctx->mu);
+        cudaSetDevice(p->ctx->device);
+        cudaDeviceSynchronize();
+        cudaFree(p->Z);
+    }
+    delete p;
+    return SBN_OK;
+}
+
+extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly* poly, size_t L, size_t R, const sbn_fr* blinds,
+                               sbn_g1a* C_out, uint8_t* inf_out) {
+    if (!ctx || !b || !poly || !C_out || !inf_out || b->ctx != ctx || poly->ctx != ctx) return SBN_ERR_ARG;
+    SBN_TRY(check_commit_shape(b, L, R));
+    if (L * R != poly->len) return SBN_ERR_SHAPE;               // hyrax.rs:258
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
+    SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
+    SBN_TRY(ensure(ctx, ctx->dinf, L));
+    Fr* dbl = nullptr;
+    if (blinds) {
+        SBN_TRY(upload(ctx, ctx->dblinds, blinds, L * sizeof(Fr)));
+        dbl = (Fr*)ctx->dblinds.p;
+    }
+    std::vector<int> ev_stage;
+    SBN_TRY(run_commit(ctx, b, poly->Z, nullptr, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, ctx->compute, ev_stage));
+    SBN_TRY(download(ctx, C_out, ctx->dC.p, L * sizeof(Affine)));
+    SBN_TRY(download(ctx, inf_out, ctx->dinf.p, L));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    collect_profile(ctx, ev_stage);
+    return SBN_OK;
+}
+
+extern "C" int sbn_poly_bound(sbn_ctx* ctx, const sbn_poly* poly, const sbn_fr* Lv, size_t L, size_t R, sbn_fr* LZ_out) {
+    if (!ctx || !poly || !Lv || !LZ_out || poly->ctx != ctx) return SBN_ERR_ARG;
+    if (L == 0 || R == 0 || L * R != poly->len) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_TRY(upload(ctx, ctx->scratch0, Lv, L * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, R * sizeof(Fr)));
+    SBN_TRY(bound_device(ctx, poly->Z, (const Fr*)ctx->scratch0.p, L, R, (Fr*)ctx->scratch1.p, ctx->compute));
+    SBN_TRY(download(ctx, LZ_out, ctx->scratch1.p, R * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // a14: bullet reduction with device-resident G, a, b
 // ------------------------------------------------------------------------------------------------
 struct sbn_bullet {
     sbn_ctx* ctx = nullptr;
-    size_t n = 0;
-    Affine* G = nullptr;
+    const sbn_bases* bases = nullptr;
+    size_t n0 = 0;              // original length
+    size_t n = 0;               // current length of a, b (and of G on the folding path)
+    bool fast = false;          // table-based rounds (Q = q * g1); otherwise G is folded explicitly
+    Affine* G = nullptr;        // folding path only
     uint8_t* Ginf = nullptr;
     Fr *a = nullptr, *b = nullptr;
-    Affine* QH = nullptr;       // [Q, H, Q, H]
-    Fr* scal = nullptr;         // [c_L, blind_L, c_R, blind_R] + [u, u_inv]
-    XYZZ* partial = nullptr;    // 2 x blocks
-    XYZZ* terms = nullptr;      // 2 groups x 3
+    Affine* QH = nullptr;       // folding path: [Q, H, Q, H]
+    Fr* scal = nullptr;         // [c_L, c_R, blind_L, blind_R, u, u_inv, q, tmp]
+    XYZZ* partial = nullptr;    // folding path: 2 x blocks
+    XYZZ* terms = nullptr;      // folding path: 2 groups x 3
     Fr* frpart = nullptr;       // 2 x blocks
     Affine* outp = nullptr;     // 2
     uint8_t* outinf = nullptr;  // 2
+    Fr* coef[2] = {nullptr, nullptr};   // fast path: ping-pong coefficient vectors, length n0 / n
+    int coef_cur = 0;
+    Fr* rows = nullptr;         // fast path: 2 x (n0 + 1) expanded scalars
     unsigned max_blocks = 0;
 };
 
 static void bullet_free(sbn_bullet* st) {
     for (void* p : {(void*)st->G, (void*)st->Ginf, (void*)st->a, (void*)st->b, (void*)st->QH, (void*)st->scal,
-                    (void*)st->partial, (void*)st->terms, (void*)st->frpart, (void*)st->outp, (void*)st->outinf})
+                    (void*)st->partial, (void*)st->terms, (void*)st->frpart, (void*)st->outp, (void*)st->outinf,
+                    (void*)st->coef[0], (void*)st->coef[1], (void*)st->rows})
         if (p) cudaFree(p);
     delete st;
 }
 
-extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* a, const sbn_fr* b,
-                                size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf, sbn_bullet** out) {
-    if (!ctx || !bases || !Q || !a || !b || !blind || !Gamma_out || !Gamma_inf || !out || bases->ctx != ctx) return SBN_ERR_ARG;
+static const unsigned kBulletDotBlocks = 64;
+
+extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_g1a* Q, const sbn_fr* q_scalar, const sbn_fr* a,
+                                const sbn_fr* b, size_t n, const sbn_fr* blind, sbn_g1a* Gamma_out, uint8_t* Gamma_inf,
+                                sbn_bullet** out) {
+    if (!ctx || !bases || !a || !b || !blind || !Gamma_out || !Gamma_inf || !out || bases->ctx != ctx) return SBN_ERR_ARG;
+    if ((Q == nullptr) == (q_scalar == nullptr)) return SBN_ERR_ARG;        // exactly one description of Q
     *out = nullptr;
-    if (n == 0 || (n & (n - 1)) || n != bases->n) return SBN_ERR_SHAPE;   // bullet.rs:42-47
+    if (n == 0 || (n & (n - 1)) || n != bases->n) return SBN_ERR_SHAPE;     // bullet.rs:42-47
+    const bool fast = q_scalar != nullptr;
+    if (fast && !bases->has_g1) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->compute;
     sbn_bullet* st = new (std::nothrow) sbn_bullet();
     if (!st) return SBN_ERR_OOM;
     st->ctx = ctx;
-    st->n = n;
+    st->bases = bases;
+    st->n0 = st->n = n;
+    st->fast = fast;
     st->max_blocks = (unsigned)((n / 2 + kSmallThreads - 1) / kSmallThreads) + 1;
-    const unsigned dot_blocks = 64;
-    bool ok = cudaMalloc(&st->G, n * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->Ginf, n) == cudaSuccess &&
-              cudaMalloc(&st->a, n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->b, n * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->QH, 4 * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->scal, 6 * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
-              cudaMalloc(&st->terms, 6 * sizeof(XYZZ)) == cudaSuccess &&
-              cudaMalloc(&st->frpart, 2 * (dot_blocks + 1) * sizeof(Fr)) == cudaSuccess &&
+    bool ok = cudaMalloc(&st->a, n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->b, n * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->scal, 8 * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->frpart, 2 * (kBulletDotBlocks + 1) * sizeof(Fr)) == cudaSuccess &&
               cudaMalloc(&st->outp, 2 * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->outinf, 2) == cudaSuccess;
+    if (ok && fast)
+        ok = cudaMalloc(&st->coef[0], n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->coef[1], n * sizeof(Fr)) == cudaSuccess &&
+             cudaMalloc(&st->rows, 2 * (n + 1) * sizeof(Fr)) == cudaSuccess;
+    if (ok && !fast)
+        ok = cudaMalloc(&st->G, n * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->Ginf, n) == cudaSuccess &&
+             cudaMalloc(&st->QH, 4 * sizeof(Affine)) == cudaSuccess &&
+             cudaMalloc(&st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
+             cudaMalloc(&st->terms, 6 * sizeof(XYZZ)) == cudaSuccess;
     if (!ok) { bullet_free(st); ctx->last_error = "sbn_bullet_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
     auto fail = [&](int code) { bullet_free(st); return code; };
 #define BCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(SBN_ERR_CUDA); } } while (0)
-    // G <- the resident generators (window 0 of the tables), H = h
-    BCUDA(cudaMemcpyAsync(st->G, bases->table, n * sizeof(Affine), cudaMemcpyDeviceToDevice, s));
-    BCUDA(cudaMemsetAsync(st->Ginf, 0, n, s));
     BCUDA(cudaMemcpyAsync(st->a, a, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
     BCUDA(cudaMemcpyAsync(st->b, b, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
-    for (int k = 0; k < 2; k++) {
-        BCUDA(cudaMemcpyAsync(st->QH + 2 * k, Q, sizeof(Affine), cudaMemcpyHostToDevice, s));
-        BCUDA(cudaMemcpyAsync(st->QH + 2 * k + 1, bases->table + n, sizeof(Affine), cudaMemcpyDeviceToDevice, s));
-    }
-    BCUDA(cudaMemcpyAsync(st->scal + 1, blind, sizeof(Fr), cudaMemcpyHostToDevice, s));
-    ctx->h2d += 2 * n * sizeof(Fr) + sizeof(Affine) + sizeof(Fr);
-    // Gamma = MSM(a, G) + blind * H  (one row through the table pipeline) + <a, b> * Q   (bullet.rs:57-59)
-    int rc = ensure_commit_workspace(ctx, bases, 1, 1);
-    if (rc != SBN_OK) return fail(rc);
+    BCUDA(cudaMemcpyAsync(st->scal + 2, blind, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ctx->h2d += 2 * n * sizeof(Fr) + sizeof(Fr);
+    // <a, b>
+    k_fr_dot<<<dim3(kBulletDotBlocks, 1), kDotThreads, 0, s>>>(st->a, 0, st->b, 0, (int)n, st->frpart);
+    k_fr_sum<<<1, kDotThreads, 0, s>>>(st->frpart, (int)kBulletDotBlocks, st->scal, 1);
+    ctx->launches += 2;
     std::vector<int> ev_stage;
-    rc = run_commit(ctx, bases, st->a, nullptr, 1, n, st->scal + 1, nullptr, nullptr, s, ev_stage, false);
-    if (rc != SBN_OK) return fail(rc);
-    k_fr_dot<<<dim3(dot_blocks, 1), kDotThreads, 0, s>>>(st->a, 0, st->b, 0, (int)n, st->frpart);
-    k_fr_sum<<<1, kDotThreads, 0, s>>>(st->frpart, (int)dot_blocks, st->scal, 1);
-    k_scalar_mul_terms<<<1, 32, 0, s>>>(st->QH, st->scal, 1, st->terms + 1, 1, 0);
-    BCUDA(cudaMemcpyAsync(st->terms, ctx->totals.p, sizeof(XYZZ), cudaMemcpyDeviceToDevice, s));
-    k_combine<<<1, 1, 0, s>>>(st->terms, 1, 2, st->outp, st->outinf);
-    ctx->launches += 4;
+    int rc;
+    if (fast) {
+        // Gamma = one row [a, <a,b> * q] over (G, g1) with blind on h               (bullet.rs:57-59)
+        const sbn_fr one_mont = {{0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL}};
+        BCUDA(cudaMemcpyAsync(st->scal + 6, q_scalar, sizeof(Fr), cudaMemcpyHostToDevice, s));
+        BCUDA(cudaMemcpyAsync(st->coef[0], &one_mont, sizeof(Fr), cudaMemcpyHostToDevice, s));
+        k_bullet_row_single<<<(unsigned)((n + 128) / 128), 128, 0, s>>>(st->a, (int)n, st->scal, st->scal + 6, st->rows);
+        ctx->launches++;
+        rc = ensure_commit_workspace(ctx, bases, 2, 2);
+        if (rc != SBN_OK) return fail(rc);
+        rc = run_commit(ctx, bases, st->rows, nullptr, 1, n + 1, st->scal + 2, st->outp, st->outinf, s, ev_stage);
+        if (rc != SBN_OK) return fail(rc);
+    } else {
+        // G <- the resident generators (window 0 of the tables), H = h
+        BCUDA(cudaMemcpyAsync(st->G, bases->table, n * sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+        BCUDA(cudaMemsetAsync(st->Ginf, 0, n, s));
+        for (int k = 0; k < 2; k++) {
+            BCUDA(cudaMemcpyAsync(st->QH + 2 * k, Q, sizeof(Affine), cudaMemcpyHostToDevice, s));
+            BCUDA(cudaMemcpyAsync(st->QH + 2 * k + 1, bases->table + (bases->n1 - 1), sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+        }
+        ctx->h2d += sizeof(Affine);
+        // Gamma = MSM(a, G) + blind * H (one row through the table pipeline) + <a, b> * Q
+        rc = ensure_commit_workspace(ctx, bases, 1, 1);
+        if (rc != SBN_OK) return fail(rc);
+        rc = run_commit(ctx, bases, st->a, nullptr, 1, n, st->scal + 2, nullptr, nullptr, s, ev_stage, false);
+        if (rc != SBN_OK) return fail(rc);
+        k_scalar_mul_terms<<<1, 32, 0, s>>>(st->QH, st->scal, 1, st->terms + 1, 1, 0);
+        BCUDA(cudaMemcpyAsync(st->terms, ctx->totals.p, sizeof(XYZZ), cudaMemcpyDeviceToDevice, s));
+        k_combine<<<1, 1, 0, s>>>(st->terms, 1, 2, st->outp, st->outinf);
+        ctx->launches += 2;
+    }
     BCUDA(cudaGetLastError());
     BCUDA(cudaMemcpyAsync(Gamma_out, st->outp, sizeof(Affine), cudaMemcpyDeviceToHost, s));
     BCUDA(cudaMemcpyAsync(Gamma_inf, st->outinf, 1, cudaMemcpyDeviceToHost, s));
@@ -803,20 +936,35 @@ extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->compute;
     const long n2 = (long)(st->n / 2);
-    const unsigned blocks = (unsigned)((n2 + kSmallThreads - 1) / kSmallThreads);
-    const unsigned dot_blocks = (unsigned)std::min<long>(64, (n2 + kDotThreads - 1) / kDotThreads);
-    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 1, blind_L, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    const unsigned dot_blocks = (unsigned)std::min<long>(kBulletDotBlocks, (n2 + kDotThreads - 1) / kDotThreads);
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 2, blind_L, sizeof(Fr), cudaMemcpyHostToDevice, s));
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 3, blind_R, sizeof(Fr), cudaMemcpyHostToDevice, s));
-    // set 0: L = <a_L, G_R>, set 1: R = <a_R, G_L>                                        (bullet.rs:75-76)
-    k_msm_naive<<<dim3(blocks, 2), kSmallThreads, 0, s>>>(st->G + n2, st->Ginf + n2, -n2, st->a, n2, (int)n2, 1, st->partial);
-    k_points_sum<<<2, kSmallThreads, 0, s>>>(st->partial, (int)blocks, st->terms, 3);
     // set 0: c_L = <a_L, b_R>, set 1: c_R = <a_R, b_L>                                     (bullet.rs:70-71)
     k_fr_dot<<<dim3(dot_blocks, 2), kDotThreads, 0, s>>>(st->a, n2, st->b + n2, -n2, (int)n2, st->frpart);
-    k_fr_sum<<<2, kDotThreads, 0, s>>>(st->frpart, (int)dot_blocks, st->scal, 2);
-    // terms: [L_msm, c_L Q, blind_L H, R_msm, c_R Q, blind_R H]
-    k_scalar_mul_terms<<<4, 32, 0, s>>>(st->QH, st->scal, 4, st->terms + 1, 3, 2);
-    k_combine<<<1, 2, 0, s>>>(st->terms, 2, 3, st->outp, st->outinf);
-    ctx->launches += 6;
+    k_fr_sum<<<2, kDotThreads, 0, s>>>(st->frpart, (int)dot_blocks, st->scal, 1);
+    ctx->launches += 2;
+    if (st->fast) {
+        // rows 0 / 1 = L / R over the original generators, see opening_kernels.cuh        (bullet.rs:75-76)
+        const size_t n0 = st->n0;
+        k_bullet_expand<<<(unsigned)((n0 + 128) / 128), 128, 0, s>>>(st->a, st->coef[st->coef_cur], (int)n0, (int)st->n, st->scal,
+                                                                     st->scal + 6, st->rows);
+        ctx->launches++;
+        std::vector<int> ev_stage;
+        SBN_TRY(ensure_commit_workspace(ctx, st->bases, 2, 2));
+        SBN_TRY(run_commit(ctx, st->bases, st->rows, nullptr, 2, n0 + 1, st->scal + 2, st->outp, st->outinf, s, ev_stage));
+    } else {
+        const unsigned blocks = (unsigned)((n2 + kSmallThreads - 1) / kSmallThreads);
+        // set 0: L = <a_L, G_R>, set 1: R = <a_R, G_L>
+        k_msm_naive<<<dim3(blocks, 2), kSmallThreads, 0, s>>>(st->G + n2, st->Ginf + n2, -n2, st->a, n2, (int)n2, 1, st->partial);
+        k_points_sum<<<2, kSmallThreads, 0, s>>>(st->partial, (int)blocks, st->terms, 3);
+        // terms: [L_msm, c_L Q, blind_L H, R_msm, c_R Q, blind_R H];  scalars [c_L, blind_L, c_R, blind_R]
+        SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 7, st->scal + 1, sizeof(Fr), cudaMemcpyDeviceToDevice, s));   // c_R
+        SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 1, st->scal + 2, sizeof(Fr), cudaMemcpyDeviceToDevice, s));   // blind_L
+        SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 2, st->scal + 7, sizeof(Fr), cudaMemcpyDeviceToDevice, s));   // c_R
+        k_scalar_mul_terms<<<4, 32, 0, s>>>(st->QH, st->scal, 4, st->terms + 1, 3, 2);
+        k_combine<<<1, 2, 0, s>>>(st->terms, 2, 3, st->outp, st->outinf);
+        ctx->launches += 4;
+    }
     SBN_CUDA(ctx, cudaGetLastError());
     sbn_g1a pts[2];
     uint8_t infs[2];
@@ -840,12 +988,18 @@ extern "C" int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_
     const int n2 = (int)(st->n / 2);
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 4, u, sizeof(Fr), cudaMemcpyHostToDevice, s));
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 5, u_inv, sizeof(Fr), cudaMemcpyHostToDevice, s));
-    k_fold_points<<<(n2 + kSmallThreads - 1) / kSmallThreads, kSmallThreads, 0, s>>>(st->G, st->Ginf, n2, st->scal + 4);
+    if (st->fast) {
+        const int len = (int)(st->n0 / st->n);
+        k_coef_update<<<(len + 127) / 128, 128, 0, s>>>(st->coef[st->coef_cur], len, st->scal + 4, st->coef[st->coef_cur ^ 1]);
+        st->coef_cur ^= 1;
+    } else {
+        k_fold_points<<<(n2 + kSmallThreads - 1) / kSmallThreads, kSmallThreads, 0, s>>>(st->G, st->Ginf, n2, st->scal + 4);
+    }
     k_fold_scalars<<<(n2 + 127) / 128, 128, 0, s>>>(st->a, st->b, n2, st->scal + 4);
     ctx->launches += 2;
     ctx->h2d += 2 * sizeof(Fr);
     SBN_CUDA(ctx, cudaGetLastError());
-    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    if (!st->fast) SBN_CUDA(ctx, cudaStreamSynchronize(s));
     st->n = n2;
     return SBN_OK;
 }
@@ -857,10 +1011,22 @@ extern "C" int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->compute;
+    const Affine* gsrc = st->G;
+    const uint8_t* gisrc = st->Ginf;
+    if (st->fast) {   // g_hat = MSM(coef, G): one more row over the tables
+        const size_t n0 = st->n0;
+        k_bullet_row_single<<<(unsigned)((n0 + 128) / 128), 128, 0, s>>>(st->coef[st->coef_cur], (int)n0, nullptr, nullptr, st->rows);
+        ctx->launches++;
+        std::vector<int> ev_stage;
+        SBN_TRY(ensure_commit_workspace(ctx, st->bases, 2, 2));
+        SBN_TRY(run_commit(ctx, st->bases, st->rows, nullptr, 1, n0 + 1, nullptr, st->outp, st->outinf, s, ev_stage));
+        gsrc = st->outp;
+        gisrc = st->outinf;
+    }
     SBN_CUDA(ctx, cudaMemcpyAsync(a_hat, st->a, sizeof(Fr), cudaMemcpyDeviceToHost, s));
     SBN_CUDA(ctx, cudaMemcpyAsync(b_hat, st->b, sizeof(Fr), cudaMemcpyDeviceToHost, s));
-    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat, st->G, sizeof(Affine), cudaMemcpyDeviceToHost, s));
-    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat_inf, st->Ginf, 1, cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat, gsrc, sizeof(Affine), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(g_hat_inf, gisrc, 1, cudaMemcpyDeviceToHost, s));
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
     ctx->d2h += 2 * sizeof(Fr) + sizeof(Affine) + 1;
     if (*g_hat_inf) memset(g_hat, 0, sizeof(*g_hat));

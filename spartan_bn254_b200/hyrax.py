@@ -171,6 +171,14 @@ class DotProductProofGens:
     def __init__(self, n, label, ctx=None):
         self.n = n
         self.gens_n, self.gens_1 = MultiCommitGens.new(n + 1, label, ctx).split_at(n)
+        self._bases_ext = None
+
+    def device_bases_ext(self):
+        """gens_n (G, h) plus gens_1.G[0] resident with window tables: what the opening's bullet reduction uses."""
+        if self._bases_ext is None:
+            self._bases_ext = self.gens_n.ctx.bases(self.gens_n.G, self.gens_n.h, g1=self.gens_1.G[0])
+            self.gens_n._bases = self._bases_ext        # commits reuse the same resident tables
+        return self._bases_ext
 
 
 class PolyCommitmentGens:
@@ -210,6 +218,12 @@ class DensePolynomial:
     def get_num_vars(self):
         return self.num_vars
 
+    def resident(self, ctx=None):
+        """Uploads Z once; later commit_inner / bound calls reuse the device copy."""
+        if getattr(self, "_poly", None) is None:
+            self._poly = (ctx or default_context()).poly_upload(self.Z)
+        return self._poly
+
     def commit_inner(self, blinds, gens):
         """hyrax.rs:253-281: one batched GPU call instead of the rayon row loop."""
         blinds = np.ascontiguousarray(blinds, dtype=np.uint64).reshape(-1, 4)
@@ -220,7 +234,10 @@ class DensePolynomial:
         if gens.n != R_size:
             raise AssertionError("assert_eq!(gens_n.n, self.len())")             # commitments.rs:146
         zero_blinds = not blinds.any()
-        C, inf = gens.ctx.hyrax_commit(gens.device_bases(), self.Z, L_size, R_size, None if zero_blinds else blinds)
+        if getattr(self, "_poly", None) is not None:
+            C, inf = self._poly.commit(gens.device_bases(), L_size, R_size, None if zero_blinds else blinds)
+        else:
+            C, inf = gens.ctx.hyrax_commit(gens.device_bases(), self.Z, L_size, R_size, None if zero_blinds else blinds)
         return PolyCommitment(C, inf)
 
     def commit(self, gens, blinds=None):
@@ -242,6 +259,8 @@ class DensePolynomial:
     def bound(self, L, ctx=None):
         """hyrax.rs:311-324."""
         left, right = compute_factored_lens(self.get_num_vars())
+        if getattr(self, "_poly", None) is not None:
+            return self._poly.bound(L, 1 << left, 1 << right)
         ctx = ctx or default_context()
         return ctx.bound(self.Z, L, 1 << left, 1 << right)
 
@@ -333,7 +352,9 @@ class DotProductProofLog:
         Q = gens_1_scaled.G[0]
         blind_Gamma = (blind_x + r * blind_y) % R_MOD
         # BulletReductionProof::prove (bullet.rs:24-126): G, a, b stay on the device; L, R and u cross the boundary
-        st = ctx.bullet_begin(gens.gens_n.device_bases(), Q, x_m, fr_vec_from_ints(a_vec), fr_from_int(blind_Gamma))
+        # Q = r * gens_1.G[0]: handed over as the scalar r so every MSM of the reduction runs on the window tables
+        st = ctx.bullet_begin(gens.device_bases_ext(), None, x_m, fr_vec_from_ints(a_vec), fr_from_int(blind_Gamma),
+                              q_scalar=fr_from_int(r))
         L_vec, R_vec = [], []
         rhat = blind_Gamma
         for i in range(lg_n):

@@ -12,9 +12,10 @@ EXPORTS = [
     "sbn_strerror", "sbn_last_cuda_error", "sbn_version",
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
     "sbn_ctx_last_commit_profile", "sbn_host_alloc", "sbn_host_free",
-    "sbn_bases_create", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits",
+    "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits",
     "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
+    "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
@@ -110,8 +111,8 @@ class Context:
         return {names[i]: dict(ms=float(ms[i]), launches=int(n[i])) for i in range(4)}
 
     # ---- generators
-    def bases(self, G, h, G_inf=None):
-        return Bases(self, G, h, G_inf)
+    def bases(self, G, h, G_inf=None, g1=None):
+        return Bases(self, G, h, G_inf, g1)
 
     # ---- a7: DensePolynomial::commit_inner
     def hyrax_commit(self, bases, Z, L_size, R_size, blinds=None):
@@ -196,9 +197,15 @@ class Context:
         self._check(st, "sbn_bound")
         return out
 
+    # ---- resident polynomial
+    def poly_upload(self, Z):
+        return Poly(self, Z)
+
     # ---- a14: bullet reduction (state on device, transcript on host)
-    def bullet_begin(self, bases, Q, a, b, blind):
-        return BulletState(self, bases, Q, a, b, blind)
+    def bullet_begin(self, bases, Q, a, b, blind, q_scalar=None):
+        """Q: arbitrary point (generators are folded explicitly) -- or Q=None with q_scalar: Q = q_scalar * g1 of
+        bases created with g1 (table-based rounds)."""
+        return BulletState(self, bases, Q, a, b, blind, q_scalar)
 
     # ---- a16: sumcheck rounds
     def sumcheck_begin(self, tau, Az, Bz, Cz):
@@ -228,13 +235,17 @@ class Context:
 class Bases:
     """sbn_bases: a MultiCommitGens (G[0..n) + h) resident in HBM with its window tables."""
 
-    def __init__(self, ctx, G, h, G_inf=None):
+    def __init__(self, ctx, G, h, G_inf=None, g1=None):
         self.ctx = ctx
         G = _u64(G, 8)
         h = _u64(h, 8)
         infa = None if G_inf is None else np.ascontiguousarray(G_inf, dtype=np.uint8)
         hd = C.c_void_p()
-        st = ctx.lib.sbn_bases_create(ctx.h, _ptr(G), _ptr(infa), C.c_size_t(G.shape[0]), _ptr(h), C.byref(hd))
+        if g1 is None:
+            st = ctx.lib.sbn_bases_create(ctx.h, _ptr(G), _ptr(infa), C.c_size_t(G.shape[0]), _ptr(h), C.byref(hd))
+        else:
+            st = ctx.lib.sbn_bases_create_ext(ctx.h, _ptr(G), _ptr(infa), C.c_size_t(G.shape[0]), _ptr(_u64(g1, 8)), _ptr(h),
+                                              C.byref(hd))
         ctx._check(st, "sbn_bases_create")
         self.h = hd
         self.n = G.shape[0]
@@ -258,7 +269,7 @@ class Bases:
 class BulletState:
     """sbn_bullet: G, a, b of BulletReductionProof::prove (nizk/bullet.rs:24-126) resident on the GPU."""
 
-    def __init__(self, ctx, bases, Q, a, b, blind):
+    def __init__(self, ctx, bases, Q, a, b, blind, q_scalar=None):
         self.ctx = ctx
         a = _u64(a, 4)
         b = _u64(b, 4)
@@ -268,7 +279,9 @@ class BulletState:
         self.Gamma = np.zeros(8, dtype=np.uint64)
         ginf = np.zeros(1, dtype=np.uint8)
         h = C.c_void_p()
-        st = ctx.lib.sbn_bullet_begin(ctx.h, bases.h, _ptr(_u64(Q, 8)), _ptr(a), _ptr(b), C.c_size_t(self.n),
+        qp = None if Q is None else _u64(Q, 8)
+        qs = None if q_scalar is None else _u64(q_scalar, 4)
+        st = ctx.lib.sbn_bullet_begin(ctx.h, bases.h, _ptr(qp), _ptr(qs), _ptr(a), _ptr(b), C.c_size_t(self.n),
                                       _ptr(_u64(blind, 4)), _ptr(self.Gamma), _ptr(ginf), C.byref(h))
         ctx._check(st, "sbn_bullet_begin")
         self.Gamma_inf = int(ginf[0])
@@ -337,6 +350,47 @@ class SumcheckState:
     def close(self):
         if self.h and self.ctx.h:
             self.ctx.lib.sbn_sumcheck_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Poly:
+    """sbn_poly: the evaluation vector of a DensePolynomial resident in HBM (commit and bound reuse it)."""
+
+    def __init__(self, ctx, Z):
+        self.ctx = ctx
+        Z = _u64(Z, 4)
+        self.len = Z.shape[0]
+        h = C.c_void_p()
+        ctx._check(ctx.lib.sbn_poly_upload(ctx.h, _ptr(Z), C.c_size_t(self.len), C.byref(h)), "sbn_poly_upload")
+        self.h = h
+
+    def commit(self, bases, L_size, R_size, blinds=None):
+        bl = None if blinds is None else _u64(blinds, 4)
+        out = np.zeros((L_size, 8), dtype=np.uint64)
+        inf = np.zeros(L_size, dtype=np.uint8)
+        st = self.ctx.lib.sbn_poly_commit(self.ctx.h, bases.h, self.h, C.c_size_t(L_size), C.c_size_t(R_size), _ptr(bl),
+                                          _ptr(out), _ptr(inf))
+        self.ctx._check(st, "sbn_poly_commit")
+        return out, inf
+
+    def bound(self, Lvec, L_size, R_size):
+        Lvec = _u64(Lvec, 4)
+        if Lvec.shape[0] != L_size:
+            raise SbnError(-2, "sbn_poly_bound", "len(L) != L_size")
+        out = np.zeros((R_size, 4), dtype=np.uint64)
+        st = self.ctx.lib.sbn_poly_bound(self.ctx.h, self.h, _ptr(Lvec), C.c_size_t(L_size), C.c_size_t(R_size), _ptr(out))
+        self.ctx._check(st, "sbn_poly_bound")
+        return out
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_poly_destroy(self.h)
         self.h = None
 
     def __del__(self):

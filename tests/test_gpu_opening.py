@@ -81,8 +81,11 @@ def test_bound_golden(ctx, orc):
     assert orc.from_mont(ctx.bound(Z, L, 4, 8)) == [h2i(x) for x in g["LZ"]]
 
 
-def run_bullet(ctx, gens_n, Q, a, b, blind, bl, br, u, orc):
-    st = ctx.bullet_begin(gens_n.device_bases(), Q, a, b, blind)
+def run_bullet(ctx, gens_n, Q, a, b, blind, bl, br, u, orc, bases=None, q_scalar=None):
+    if q_scalar is not None:
+        st = ctx.bullet_begin(bases, None, a, b, blind, q_scalar=q_scalar)     # table-based rounds, Q = q * g1
+    else:
+        st = ctx.bullet_begin(gens_n.device_bases(), Q, a, b, blind)           # arbitrary Q, generators folded
     Ls, Rs = [], []
     lg = len(u)
     for i in range(lg):
@@ -114,8 +117,9 @@ def test_bullet_golden_n8(ctx, orc):
     assert orc.points_to_ints(res["g_hat"][0].reshape(1, 8), [res["g_hat"][1]]) == [pt(g["g_hat"])]
 
 
-@pytest.mark.parametrize("n,label", [(16, b"gens_r1cs_eval"), (256, b"gens_r1cs_eval"), (1024, b"gens_r1cs_sat")])
-def test_bullet_matches_oracle(ctx, orc, n, label):
+@pytest.mark.parametrize("path", ["fold", "tables"])
+@pytest.mark.parametrize("n,label", [(2, b"test"), (16, b"gens_r1cs_eval"), (256, b"gens_r1cs_eval"), (1024, b"gens_r1cs_sat")])
+def test_bullet_matches_oracle(ctx, orc, n, label, path):
     """Opening sizes of cfg3 (n = 1024) and the reference's n = 16 log-proof test (nizk/mod.rs:575-712)."""
     from spartan_bn254_b200 import synth
     from spartan_bn254_b200.hyrax import DotProductProofGens
@@ -128,7 +132,13 @@ def test_bullet_matches_oracle(ctx, orc, n, label):
     br = synth.uniform_scalars(35, lg)
     blind = synth.uniform_scalars(36, 1)[0]
     Q = gens.gens_1.G[0]
-    res = run_bullet(ctx, gens.gens_n, Q, a, b, blind, bl, br, u, orc)
+    if path == "fold":
+        res = run_bullet(ctx, gens.gens_n, Q, a, b, blind, bl, br, u, orc)
+    else:                                     # Q = q * g1 with q a full-width scalar (the reference's r * gens_1.G[0])
+        q = synth.uniform_scalars(37, 1)[0]
+        Q, qinf = orc.scalar_mul(gens.gens_1.G[0], 0, q)
+        assert not qinf
+        res = run_bullet(ctx, gens.gens_n, None, a, b, blind, bl, br, u, orc, bases=gens.device_bases_ext(), q_scalar=q)
     exp = orc.bullet_prove(Q, gens.gens_n.G, gens.gens_n.h, a, b, blind, bl, br, u)
     for k in range(lg):
         assert res["L"][k][1] == exp["L_inf"][k] and np.array_equal(res["L"][k][0], exp["L"][k]), k
@@ -240,3 +250,25 @@ def test_poly_eval_proof_roundtrip_and_byte_parity(ctx, orc, ell, label, use_bli
     gd["z2"][0] ^= np.uint64(1)
     assert not orc.poly_eval_verify(orc.EvalProof.from_dict(gd), ell, rpt, C_Zr.xy, C_Zr.inf, comm.C, comm.inf, gn.G, gn.h,
                                     g1.G[0], orc.Transcript(b"example"))
+
+
+def test_resident_polynomial_commit_and_bound(ctx, orc):
+    """sbn_poly_*: Z uploaded once, then committed and bound from HBM -- same results as the host-pointer calls."""
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import DensePolynomial, PolyCommitmentGens, compute_factored_lens
+    ell = 11
+    l, r_ = compute_factored_lens(ell)
+    gens = PolyCommitmentGens(ell, b"gens_r1cs_eval", ctx)
+    Z = synth.derefs_scalars(ell)
+    blinds = synth.uniform_scalars(4, 1 << l)
+    poly = DensePolynomial(Z)
+    poly.resident(ctx)
+    comm, _ = poly.commit(gens, blinds)
+    gn = gens.gens.gens_n
+    C, inf = orc.hyrax_commit(gn.G, gn.h, Z, 1 << l, 1 << r_, blinds)
+    assert np.array_equal(comm.C, C) and np.array_equal(comm.inf, inf)
+    Lv = synth.uniform_scalars(5, 1 << l)
+    assert np.array_equal(poly.bound(Lv, ctx), orc.bound(Z, Lv, 1 << l, 1 << r_))
+    from spartan_bn254_b200 import SbnError
+    with pytest.raises(SbnError):
+        poly.resident(ctx).bound(Lv, 1 << l, 1 << (r_ + 1))          # L * R != len
