@@ -145,9 +145,12 @@ int sbn_bullet_destroy(sbn_bullet* st);
  * Four tables (tau, Az, Bz, Cz) of `len` scalars stay on device across rounds. */
 int sbn_sumcheck_begin(sbn_ctx* ctx, const sbn_fr* tau, const sbn_fr* Az, const sbn_fr* Bz, const sbn_fr* Cz,
                        size_t len, sbn_sumcheck** out);
+/* phase 2 of the R1CS-sat proof (sumcheck.rs:657-811, loop :690-699): two tables (z, ABC), comb = z * ABC,
+ * evaluations at 0 and 2 only (round_eval leaves e3 untouched; it may be NULL). */
+int sbn_sumcheck_begin_quad(sbn_ctx* ctx, const sbn_fr* z, const sbn_fr* ABC, size_t len, sbn_sumcheck** out);
 int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2, sbn_fr* e3);
 int sbn_sumcheck_bind(sbn_sumcheck* st, const sbn_fr* r);
-int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]);   /* the four length-1 tables */
+int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]);   /* the length-1 tables (unused slots zero) */
 int sbn_sumcheck_destroy(sbn_sumcheck* st);
 
 /* ---- utilities used by tests / harnesses */

@@ -663,6 +663,20 @@ void orc_sumcheck_cubic_eval(const ofp* A, const ofp* B, const ofp* C, const ofp
     *e0 = s0; *e2 = s2; *e3 = s3;
 }
 
+void orc_sumcheck_quad_eval(const ofp* Zt, const ofp* ABC, size_t len2, ofp* e0, ofp* e2) {
+    /* sumcheck.rs:690-699 with comb = z * ABC (r1csproof.rs phase 2) */
+    size_t len = len2 / 2;
+    ofp s0, s2, t, a, b;
+    memset(&s0, 0, sizeof s0); memset(&s2, 0, sizeof s2);
+    for (size_t i = 0; i < len; i++) {
+        fp_mul(FR, &Zt[i], &ABC[i], &t); fp_add(FR, &s0, &t, &s0);
+        fp_add(FR, &Zt[len + i], &Zt[len + i], &a); fp_sub(FR, &a, &Zt[i], &a);
+        fp_add(FR, &ABC[len + i], &ABC[len + i], &b); fp_sub(FR, &b, &ABC[i], &b);
+        fp_mul(FR, &a, &b, &t); fp_add(FR, &s2, &t, &s2);
+    }
+    *e0 = s0; *e2 = s2;
+}
+
 /* ------------------------------------------------------------------ bullet reduction */
 static void fr_dot(const ofp* a, const ofp* b, size_t n, ofp* out) {
     ofp acc, t;

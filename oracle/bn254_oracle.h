@@ -62,6 +62,7 @@ void orc_bullet_prove(const og1a* Q, const og1a* G, size_t n, const og1a* H, con
 /* sumcheck.rs:501-530 cubic round evaluation + hyrax.rs:195-203 bind (a16) */
 void orc_sumcheck_cubic_eval(const ofp* A, const ofp* B, const ofp* C, const ofp* D, size_t len,
                              ofp* e0, ofp* e2, ofp* e3);
+void orc_sumcheck_quad_eval(const ofp* Z, const ofp* ABC, size_t len, ofp* e0, ofp* e2);   /* sumcheck.rs:690-699 */
 void orc_bind_top(ofp* Z, size_t len, const ofp* r);   /* in place: first len/2 entries valid */
 
 /* hashes (third-party sha3 0.10 in the reference: FIPS-202) */

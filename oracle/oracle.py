@@ -187,6 +187,13 @@ def sumcheck_cubic_eval(A, B, Cc, D):
     return e
 
 
+def sumcheck_quad_eval(Zt, ABC):
+    Zt, ABC = _u64(Zt).reshape(-1, 4), _u64(ABC).reshape(-1, 4)
+    e = [np.zeros(4, dtype=np.uint64) for _ in range(2)]
+    lib().orc_sumcheck_quad_eval(_p(Zt), _p(ABC), C.c_size_t(Zt.shape[0]), _p(e[0]), _p(e[1]))
+    return e
+
+
 def bullet_prove(Q, G, H, a, b, blind, blinds_L, blinds_R, u):
     G = _u64(G).reshape(-1, 8)
     n = G.shape[0]

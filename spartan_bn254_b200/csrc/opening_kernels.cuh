@@ -301,6 +301,23 @@ k_sumcheck_eval(const Fr* __restrict__ T0, const Fr* __restrict__ T1, const Fr* 
     if (threadIdx.x == 0) store_fr(partial + 2 * gridDim.x + blockIdx.x, e3);
 }
 
+// quadratic variant (sumcheck.rs:690-699): e_t = sum_i z_t * ABC_t at t = 0, 2; partial[e * gridDim.x + block]
+__global__ void __launch_bounds__(kDotThreads)
+k_sumcheck_eval_quad(const Fr* __restrict__ T0, const Fr* __restrict__ T1, int half, Fr* __restrict__ partial) {
+    __shared__ Fr sm[kDotThreads];
+    Fr e0 = Fr::zero(), e2 = Fr::zero();
+    for (int i = blockIdx.x * kDotThreads + threadIdx.x; i < half; i += gridDim.x * kDotThreads) {
+        const Fr z0 = load_fr(T0 + i), z1 = load_fr(T0 + half + i), a0 = load_fr(T1 + i), a1 = load_fr(T1 + half + i);
+        e0 = fp_add(e0, fr_mul_call(z0, a0));
+        e2 = fp_add(e2, fr_mul_call(fp_sub(fp_add(z1, z1), z0), fp_sub(fp_add(a1, a1), a0)));
+    }
+    e0 = block_sum_fr(e0, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(partial + blockIdx.x, e0);
+    __syncthreads();
+    e2 = block_sum_fr(e2, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(partial + gridDim.x + blockIdx.x, e2);
+}
+
 // bound_poly_var_top on four tables at once: T[i] <- T[i] + r (T[half + i] - T[i])
 __global__ void k_bind_top(Fr* __restrict__ T0, Fr* __restrict__ T1, Fr* __restrict__ T2, Fr* __restrict__ T3, int half,
                            const Fr* __restrict__ r) {
@@ -310,6 +327,7 @@ __global__ void k_bind_top(Fr* __restrict__ T0, Fr* __restrict__ T1, Fr* __restr
     Fr* T[4] = {T0, T1, T2, T3};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
+        if (!T[k]) continue;                  // the quadratic variant binds two tables
         const Fr lo = load_fr(T[k] + i), hi = load_fr(T[k] + half + i);
         store_fr(T[k] + i, fp_add(lo, fr_mul_call(rr, fp_sub(hi, lo))));
     }

@@ -1051,6 +1051,7 @@ struct sbn_sumcheck {
     sbn_ctx* ctx = nullptr;
     size_t len = 0;
     Fr* T[4] = {nullptr, nullptr, nullptr, nullptr};
+    int ntables = 4;         // 4: cubic with additive term (tau, Az, Bz, Cz); 2: quadratic (z, ABC)
     Fr* partial = nullptr;   // 3 x blocks
     Fr* out = nullptr;       // 3 evals + r
     unsigned blocks = 0;
@@ -1063,9 +1064,21 @@ static void sumcheck_free(sbn_sumcheck* st) {
     delete st;
 }
 
+static int sumcheck_begin(sbn_ctx* ctx, const sbn_fr* const* src, int ntables, size_t len, sbn_sumcheck** out);
+
 extern "C" int sbn_sumcheck_begin(sbn_ctx* ctx, const sbn_fr* tau, const sbn_fr* Az, const sbn_fr* Bz, const sbn_fr* Cz,
                                   size_t len, sbn_sumcheck** out) {
     if (!ctx || !tau || !Az || !Bz || !Cz || !out) return SBN_ERR_ARG;
+    const sbn_fr* src[4] = {tau, Az, Bz, Cz};
+    return sumcheck_begin(ctx, src, 4, len, out);
+}
+extern "C" int sbn_sumcheck_begin_quad(sbn_ctx* ctx, const sbn_fr* z, const sbn_fr* ABC, size_t len, sbn_sumcheck** out) {
+    if (!ctx || !z || !ABC || !out) return SBN_ERR_ARG;
+    const sbn_fr* src[4] = {z, ABC, nullptr, nullptr};
+    return sumcheck_begin(ctx, src, 2, len, out);
+}
+
+static int sumcheck_begin(sbn_ctx* ctx, const sbn_fr* const* src, int ntables, size_t len, sbn_sumcheck** out) {
     *out = nullptr;
     if (len < 1 || (len & (len - 1)) || len > (1u << 28)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -1075,25 +1088,25 @@ extern "C" int sbn_sumcheck_begin(sbn_ctx* ctx, const sbn_fr* tau, const sbn_fr*
     st->ctx = ctx;
     st->len = len;
     st->blocks = 592;
-    const sbn_fr* src[4] = {tau, Az, Bz, Cz};
+    st->ntables = ntables;
     bool ok = cudaMalloc(&st->partial, 3 * st->blocks * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->out, 4 * sizeof(Fr)) == cudaSuccess;
-    for (int k = 0; k < 4 && ok; k++) ok = cudaMalloc(&st->T[k], len * sizeof(Fr)) == cudaSuccess;
+    for (int k = 0; k < ntables && ok; k++) ok = cudaMalloc(&st->T[k], len * sizeof(Fr)) == cudaSuccess;
     if (!ok) { sumcheck_free(st); ctx->last_error = "sbn_sumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < ntables; k++) {
         if (cudaMemcpyAsync(st->T[k], src[k], len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess) {
             sumcheck_free(st);
             ctx->last_error = "sbn_sumcheck_begin: upload failed";
             return SBN_ERR_CUDA;
         }
     }
-    ctx->h2d += 4 * len * sizeof(Fr);
+    ctx->h2d += ntables * len * sizeof(Fr);
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     *out = st;
     return SBN_OK;
 }
 
 extern "C" int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2, sbn_fr* e3) {
-    if (!st || !e0 || !e2 || !e3) return SBN_ERR_ARG;
+    if (!st || !e0 || !e2 || (st->ntables == 4 && !e3)) return SBN_ERR_ARG;
     if (st->len < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -1101,15 +1114,18 @@ extern "C" int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2,
     cudaStream_t s = ctx->compute;
     const int half = (int)(st->len / 2);
     const unsigned blocks = (unsigned)std::min<size_t>(st->blocks, (half + kDotThreads - 1) / kDotThreads);
-    k_sumcheck_eval<<<blocks, kDotThreads, 0, s>>>(st->T[0], st->T[1], st->T[2], st->T[3], half, st->partial);
-    k_fr_sum<<<3, kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
+    const int nevals = st->ntables == 4 ? 3 : 2;
+    if (st->ntables == 4) k_sumcheck_eval<<<blocks, kDotThreads, 0, s>>>(st->T[0], st->T[1], st->T[2], st->T[3], half, st->partial);
+    else k_sumcheck_eval_quad<<<blocks, kDotThreads, 0, s>>>(st->T[0], st->T[1], half, st->partial);
+    k_fr_sum<<<nevals, kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
     ctx->launches += 2;
     SBN_CUDA(ctx, cudaGetLastError());
     sbn_fr host[3];
-    SBN_CUDA(ctx, cudaMemcpyAsync(host, st->out, 3 * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(host, st->out, nevals * sizeof(Fr), cudaMemcpyDeviceToHost, s));
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
-    ctx->d2h += 3 * sizeof(Fr);
-    *e0 = host[0]; *e2 = host[1]; *e3 = host[2];
+    ctx->d2h += nevals * sizeof(Fr);
+    *e0 = host[0]; *e2 = host[1];
+    if (nevals == 3) *e3 = host[2];
     return SBN_OK;
 }
 
@@ -1137,10 +1153,12 @@ extern "C" int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]) {
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int k = 0; k < 4; k++)
-        SBN_CUDA(ctx, cudaMemcpyAsync(&finals[k], st->T[k], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
+    for (int k = 0; k < 4; k++) {
+        if (k < st->ntables) SBN_CUDA(ctx, cudaMemcpyAsync(&finals[k], st->T[k], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
+        else memset(&finals[k], 0, sizeof(sbn_fr));
+    }
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    ctx->d2h += 4 * sizeof(Fr);
+    ctx->d2h += st->ntables * sizeof(Fr);
     return SBN_OK;
 }
 

@@ -17,7 +17,7 @@ EXPORTS = [
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
     "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
-    "sbn_sumcheck_begin", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
+    "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
 ]
 
@@ -211,6 +211,9 @@ class Context:
     def sumcheck_begin(self, tau, Az, Bz, Cz):
         return SumcheckState(self, tau, Az, Bz, Cz)
 
+    def sumcheck_begin_quad(self, z, ABC):
+        return SumcheckState(self, z, ABC)
+
     # ---- utilities
     def fr_from_canonical(self, canon):
         canon = _u64(canon, 4)
@@ -320,23 +323,28 @@ class BulletState:
 class SumcheckState:
     """sbn_sumcheck: the four tables of the R1CS-sat cubic sumcheck (sumcheck.rs:465-649) on the GPU."""
 
-    def __init__(self, ctx, tau, Az, Bz, Cz):
+    def __init__(self, ctx, *tables):
         self.ctx = ctx
-        t = [_u64(x, 4) for x in (tau, Az, Bz, Cz)]
+        t = [_u64(x, 4) for x in tables]
+        self.ntables = len(t)
         self.len = t[0].shape[0]
         if any(x.shape[0] != self.len for x in t):
             raise SbnError(-2, "sbn_sumcheck_begin", "table lengths differ")
         h = C.c_void_p()
-        st = ctx.lib.sbn_sumcheck_begin(ctx.h, _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), _ptr(t[3]), C.c_size_t(self.len),
-                                        C.byref(h))
+        if self.ntables == 4:
+            st = ctx.lib.sbn_sumcheck_begin(ctx.h, _ptr(t[0]), _ptr(t[1]), _ptr(t[2]), _ptr(t[3]), C.c_size_t(self.len),
+                                            C.byref(h))
+        else:
+            st = ctx.lib.sbn_sumcheck_begin_quad(ctx.h, _ptr(t[0]), _ptr(t[1]), C.c_size_t(self.len), C.byref(h))
         ctx._check(st, "sbn_sumcheck_begin")
         self.h = h
 
     def round_eval(self):
+        n = 3 if self.ntables == 4 else 2
         e = [np.zeros(4, dtype=np.uint64) for _ in range(3)]
         self.ctx._check(self.ctx.lib.sbn_sumcheck_round_eval(self.h, _ptr(e[0]), _ptr(e[1]), _ptr(e[2])),
                         "sbn_sumcheck_round_eval")
-        return e
+        return e[:n]
 
     def bind(self, r):
         self.ctx._check(self.ctx.lib.sbn_sumcheck_bind(self.h, _ptr(_u64(r, 4))), "sbn_sumcheck_bind")

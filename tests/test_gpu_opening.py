@@ -272,3 +272,22 @@ def test_resident_polynomial_commit_and_bound(ctx, orc):
     from spartan_bn254_b200 import SbnError
     with pytest.raises(SbnError):
         poly.resident(ctx).bound(Lv, 1 << l, 1 << (r_ + 1))          # L * R != len
+
+
+def test_sumcheck_quadratic_rounds_match_oracle(ctx, orc):
+    """Phase 2 of the R1CS-sat proof (sumcheck.rs:690-699): two tables, evaluations at 0 and 2, then bind."""
+    from spartan_bn254_b200 import synth
+    lg = 10
+    T = [synth.uniform_scalars(70 + k, 1 << lg) for k in range(2)]
+    rs = synth.uniform_scalars(72, lg)
+    st = ctx.sumcheck_begin_quad(*T)
+    cur = [t.copy() for t in T]
+    for j in range(lg):
+        e = st.round_eval()
+        exp = orc.sumcheck_quad_eval(*cur)
+        assert len(e) == 2 and np.array_equal(e[0], exp[0]) and np.array_equal(e[1], exp[1]), j
+        st.bind(rs[j])
+        cur = [orc.bind_top(t, rs[j]) for t in cur]
+    fin = st.end()
+    assert np.array_equal(fin[0], cur[0][0]) and np.array_equal(fin[1], cur[1][0]) and not fin[2:].any()
+    st.close()
