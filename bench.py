@@ -224,9 +224,7 @@ def main():
     # ---- integer roofline denominator, measured live (MEASURED_PEAKS.json has no integer-pipe figure)
     peak_imad = ctx.microbench(0)
 
-    # ---- device-resident timing (one chunk per commit: stages run back to back, so the per-stage CUDA
-    #      events of the profile pass below describe the same launches that are timed here)
-    ctx.set("chunk_rows", L)
+    # ---- device-resident timing (library defaults: chunks of 1024 rows, two pipeline slots)
     for i in range(args.warmup):
         step_device(i)
     barrier()
@@ -253,13 +251,15 @@ def main():
     points_per_step = L * R * world
     value = points_per_step * args.steps / (ms_max * 1e-3)
 
-    # ---- stage profile of one commit on the library's own stream (CUDA events inside the library)
+    # ---- stage profile of one commit on the library's own stream (CUDA events inside the library); a single chunk so
+    #      the stages run back to back and each event pair brackets exactly one launch of that kernel
+    ctx.set("chunk_rows", L)
     ctx.hyrax_commit_device(bases, dev_bufs[0].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=0)
     prof = ctx.last_commit_profile()
 
-    # ---- end to end: pinned host buffers through the host-pointer C ABI (chunks pipelined: the H2D copy
-    #      of chunk i+1 overlaps the kernels of chunk i)
-    ctx.set("chunk_rows", max(1, L // 2))
+    # ---- end to end: pinned host buffers through the host-pointer C ABI (library defaults: a short first chunk, then
+    #      chunks of 1024 rows; the H2D copy of chunk i+1 overlaps the kernels of chunk i)
+    ctx.set("chunk_rows", 1024)
     for i in range(args.warmup):
         step_e2e(i)
     barrier()

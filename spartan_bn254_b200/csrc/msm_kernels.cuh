@@ -400,7 +400,8 @@ __global__ void k_normalize(const XYZZ* __restrict__ in, int n, Affine* __restri
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     XYZZ p = load_xyzz(in + i);
-    Affine a = xyzz_to_affine<MulCall>(p);
+    // one warp per scheduler at most: pure dependency-chain latency, so the products are inlined here
+    Affine a = xyzz_to_affine<MulInline>(p);
     store_affine(out + i, a);
     if (inf) inf[i] = p.is_identity() ? 1 : 0;
 }

@@ -34,7 +34,7 @@ struct sbn_ctx {
     cudaStream_t compute = nullptr, copy = nullptr;
     std::mutex mu;
     std::string last_error;
-    long chunk_rows = 512;
+    long chunk_rows = 1024;
     long window_bits = 0;
     long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
     long reduce_m = 32;     // buckets per reduction thread
@@ -397,7 +397,7 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
     const size_t E = (size_t)b->W * b->n1;
     const size_t max_tasks = msm_max_tasks(E, b->nb, task_cap_for(ctx, b));
     if (max_tasks >= (1u << 24)) return SBN_ERR_SHAPE;
-    const size_t nslots = L > chunk ? 2 : 1;
+    const size_t nslots = (L > chunk || L > chunk / 4) ? 2 : 1;    // the host path may add a short first chunk
     for (size_t i = 0; i < nslots; i++) {
         auto& sl = ctx->slots[i];
         SBN_TRY(ensure(ctx, sl.entries, chunk * E * sizeof(uint32_t)));
@@ -438,7 +438,15 @@ static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
                       const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                       bool normalize = true) {
     const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
-    const size_t nchunks = (L + chunk - 1) / chunk;
+    // chunk schedule: equal chunks; when the scalars come from the host the first chunk is a quarter chunk so the
+    // kernels start after a short copy and the remaining copies hide behind them
+    std::vector<size_t> sched;
+    {
+        size_t done = 0;
+        if (host_Z && L > chunk / 4 && chunk >= 8) { sched.push_back(chunk / 4); done = chunk / 4; }
+        while (done < L) { size_t c = std::min(chunk, L - done); sched.push_back(c); done += c; }
+    }
+    const size_t nchunks = sched.size();
     XYZZ* totals = (XYZZ*)ctx->totals.p;
     size_t ev_idx = 0;
     const size_t handoff_base = 4 * nchunks + 8;    // copy->compute events live after the profiling events
@@ -446,9 +454,9 @@ static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
     const size_t nslots = nchunks > 1 ? 2 : 1;
     for (size_t i = 0; i < nslots; i++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->fork, 0));
     if (host_Z) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
-    for (size_t ci = 0, row0 = 0; row0 < L; row0 += chunk, ci++) {
+    for (size_t ci = 0, row0 = 0; ci < nchunks; row0 += sched[ci], ci++) {
         auto& sl = ctx->slots[ci % nslots];
-        int rows = (int)std::min(chunk, L - row0);
+        int rows = (int)sched[ci];
         if (host_Z) {
             SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0 * R), host_Z + row0 * R, (size_t)rows * R * sizeof(Fr),
                                           cudaMemcpyHostToDevice, ctx->copy));
