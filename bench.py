@@ -259,7 +259,7 @@ def main():
 
     # ---- end to end: pinned host buffers through the host-pointer C ABI (library defaults: a short first chunk, then
     #      chunks of 1024 rows; the H2D copy of chunk i+1 overlaps the kernels of chunk i)
-    ctx.set("chunk_rows", 1024)
+    ctx.set("chunk_rows", 0)      # back to the library default (auto)
     for i in range(args.warmup):
         step_e2e(i)
     barrier()

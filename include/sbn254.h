@@ -53,9 +53,9 @@ int sbn_version(void);                                  /* 100 * major + minor *
 int sbn_ctx_create(int device, sbn_ctx** out);
 int sbn_ctx_destroy(sbn_ctx* ctx);
 int sbn_ctx_synchronize(sbn_ctx* ctx);
-/* Tunables: "chunk_rows" (rows per pipeline stage), "window_bits" (0 = auto, applies to bases created
- * afterwards), "task_cap" (max entries one accumulation thread sums; fuller buckets are split; 0 = auto), "reduce_m"
- * (buckets per reduction thread). */
+/* Tunables: "chunk_rows" (rows per pipeline chunk; 0 = auto), "window_bits" (0 = auto, applies to bases created
+ * afterwards), "task_cap" (max entries one accumulation thread sums; fuller buckets are split; 0 = auto), "leaf_m"
+ * (buckets per leaf thread of the two-level bucket reduction; 0 = auto). */
 int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
 /* Counters since creation / last reset: kernels launched by this library, bytes copied H2D / D2H. */
 int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);

@@ -20,7 +20,7 @@ for c in cs:
     for chunk in chunks:
         for m in ms:
             for cap in caps:
-                ctx.set("chunk_rows", chunk); ctx.set("reduce_m", m); ctx.set("task_cap", cap)
+                ctx.set("chunk_rows", chunk); ctx.set("leaf_m", m); ctx.set("task_cap", cap)
                 best = 1e9
                 for it in range(4):
                     t0 = time.perf_counter()

@@ -1,4 +1,4 @@
-"""Device-resident sweep: wall time (CUDA events) of hyrax_commit_device vs chunk_rows / reduce_m / window."""
+"""Device-resident sweep: wall time (CUDA events) of hyrax_commit_device vs chunk_rows / leaf_m / window."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -21,7 +21,7 @@ for c in cs:
     bases = ctx.bases(G, h)
     for chunk in chunks:
         for m in ms_:
-            ctx.set("chunk_rows", max(1, chunk)); ctx.set("reduce_m", m)
+            ctx.set("chunk_rows", max(1, chunk)); ctx.set("leaf_m", m)
             for i in range(3):
                 ctx.hyrax_commit_device(bases, zs[i % 4].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=stream.cuda_stream)
             torch.cuda.synchronize()

@@ -111,7 +111,6 @@ __device__ __forceinline__ void for_each_digit(const Fr& canon, Fn&& f) {
     }
 }
 
-static constexpr int kSortThreads = 256;
 static constexpr int kRankBins = 256;
 static constexpr int kMaxTaskCap = 255;
 
@@ -130,7 +129,7 @@ __host__ __device__ inline size_t msm_max_heavy(size_t E, int cap) { return E / 
 // tstart [row * (NB + 1) + b]   : first task slot of bucket b (tstart[NB] = number of tasks of the row)
 // tasks  [row * max_tasks + rank]: tasks by decreasing length
 // heavy  [row * (max_heavy + 1)] : number of split buckets of the row, followed by their ids
-template <int C>
+template <int C, int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n1, int h_col, int scalars_are_mont, int cap,
            uint32_t E, uint32_t max_tasks, uint32_t max_heavy, uint32_t* __restrict__ entries,
@@ -287,25 +286,19 @@ k_accumulate(const Affine* __restrict__ table, const uint32_t* __restrict__ entr
 
 // ---------------------------------------------------------------------------------------------
 // K4a: per-row bucket reduction  T = sum_b (b + 1) * S_b,  S_b = the bucket's (folded) partial sum.
-//
-// T equals the sum of all suffix sums  Suf_j = sum_{b >= j} S_b.  TPR threads per row each own m
-// consecutive buckets: a sequential pass gives the thread's local suffix sums (their total `tot`) and
-// its bucket total A_t.  An inclusive suffix scan of A_t across the threads (shared memory,
-// Kogge-Stone) gives I_t = sum_{u >= t} A_u; every bucket of thread t is short of I_{t+1}, so
-//     T = sum_t tot_t + m * sum_{t >= 1} I_t .
-// Control flow is uniform (no per-thread scalar multiplication) and the XYZZ addition is a single
-// out-of-line function, so the kernel stays small.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kRedThreads = 128;
 
 // One out-of-line copy of the full addition with its 14 products inlined (instruction-level
 // parallelism between independent products matters at the 3-4 warps per scheduler this kernel runs at).
 __device__ __noinline__ void xyzz_add_call(XYZZ* acc, const XYZZ* q) { xyzz_add<MulInline, MulCall>(*acc, *q); }
 
-// Split buckets: one warp per (row, heavy bucket) folds the bucket's task partials into its first slot
-// (lanes take partials strided by 32, then a shared-memory tree), so the reduction below reads exactly
-// one partial per bucket.  Persistent grid: warps stride over the rows.
+// Split buckets: one warp per row folds the task partials of every split bucket into the bucket's first slot, so the
+// reduction below reads exactly one partial per bucket.  Lanes take one split bucket each and add its few partials
+// sequentially (uniform scalars at c = 13 split ~100 buckets of a row into 2 tasks each); a bucket with more than
+// kLaneFold partials (the 1-bit top window at c = 11, derefs-style repeated scalars) is folded by the whole warp:
+// lanes take partials strided by 32, then a shared-memory tree.  Persistent grid: warps stride over the rows.
 static constexpr int kHeavyThreads = 128;
+static constexpr uint32_t kLaneFold = 4;
 
 __global__ void __launch_bounds__(kHeavyThreads)
 k_combine_heavy(XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, const uint32_t* __restrict__ heavy,
@@ -320,77 +313,171 @@ k_combine_heavy(XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart
         const uint32_t nh = hrow[0];
         const uint32_t* trow = tstart + (size_t)row * (nb + 1);
         XYZZ* prow = partials + (size_t)row * max_tasks;
-        for (uint32_t i = 0; i < nh; i++) {
-            const uint32_t b = hrow[1 + i];
-            const uint32_t s0 = trow[b], s1 = trow[b + 1];
-            XYZZ acc = XYZZ::identity();
-            for (uint32_t s = s0 + lane; s < s1; s += 32) {
-                XYZZ v = load_xyzz(prow + s);
-                xyzz_add_call(&acc, &v);
+        for (uint32_t base = 0; base < nh; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t s0 = 0, s1 = 0;
+            if (i < nh) {
+                const uint32_t b = hrow[1 + i];
+                s0 = trow[b];
+                s1 = trow[b + 1];
             }
-            for (int stride = 16; stride >= 1; stride >>= 1) {
-                wsm[lane] = acc;
-                __syncwarp();
-                XYZZ o = (lane < stride) ? wsm[lane + stride] : XYZZ::identity();
-                __syncwarp();
-                xyzz_add_call(&acc, &o);
+            const bool big = s1 - s0 > kLaneFold;
+            if (i < nh && !big) {
+                XYZZ acc = load_xyzz(prow + s0);
+                for (uint32_t s = s0 + 1; s < s1; s++) {
+                    XYZZ v = load_xyzz(prow + s);
+                    xyzz_add_call(&acc, &v);
+                }
+                store_xyzz(prow + s0, acc);
             }
-            if (lane == 0) store_xyzz(prow + s0, acc);
-            __syncwarp();
+            uint32_t todo = __ballot_sync(0xffffffffu, big);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t t0 = __shfl_sync(0xffffffffu, s0, src), t1 = __shfl_sync(0xffffffffu, s1, src);
+                XYZZ acc = XYZZ::identity();
+                for (uint32_t s = t0 + lane; s < t1; s += 32) {
+                    XYZZ v = load_xyzz(prow + s);
+                    xyzz_add_call(&acc, &v);
+                }
+                for (int stride = 16; stride >= 1; stride >>= 1) {
+                    wsm[lane] = acc;
+                    __syncwarp();
+                    XYZZ o = (lane < stride) ? wsm[lane + stride] : XYZZ::identity();
+                    __syncwarp();
+                    xyzz_add_call(&acc, &o);
+                }
+                if (lane == 0) store_xyzz(prow + t0, acc);
+                __syncwarp();
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kRedThreads)
-k_reduce(const XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, int rows, int nb, int tpr,
-         uint32_t max_tasks, XYZZ* __restrict__ row_totals) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    XYZZ* sm = reinterpret_cast<XYZZ*>(smem_raw);
-    const int rows_per_block = kRedThreads / tpr;
-    const int local_row = threadIdx.x / tpr;
-    const int t = threadIdx.x % tpr;
-    const int row = blockIdx.x * rows_per_block + local_row;
-    const int m = nb / tpr;
-    const bool active = row < rows;
+// ---------------------------------------------------------------------------------------------
+// K4a (two-level form).  Level 1 (k_reduce_leaf): one thread per (row, t) owns m consecutive buckets and computes
+//     tot_t = sum_i (i + 1) * S_{tm+i}   and   A_t = sum_i S_{tm+i}
+// with the running-sum recurrence  run += S ; tot += run.  The loop is written over half-steps so that the inlined
+// 14-product addition appears ONCE in the instruction stream (acc/q register roles are swapped around it and `tot`
+// rests in shared memory while `run` is being advanced): the kernel is then a single straight-line loop like
+// k_accumulate -- no barriers, no calls, and as many independent threads as rows * nb / m.
+// Level 2 (k_reduce_top): one warp per row folds the tpr (tot_t, A_t) pairs:
+//     T = sum_t tot_t + m * sum_t t * A_t .
+// ---------------------------------------------------------------------------------------------
+static constexpr int kLeafThreads = 128;
 
-    XYZZ tot = XYZZ::identity();   // sum of the local suffix sums
-    XYZZ run = XYZZ::identity();   // A_t, then I_t
-    if (active) {
-        const XYZZ* prow = partials + (size_t)row * max_tasks;
-        const uint32_t* trow = tstart + (size_t)row * (nb + 1);
-        const int lo = t * m;
-        uint32_t hi_slot = trow[lo + m];
-        for (int b = lo + m - 1; b >= lo; b--) {
-            const uint32_t lo_slot = trow[b];
+struct LeafPair { XYZZ tot, A; };
+
+__global__ void __launch_bounds__(kLeafThreads)
+k_reduce_leaf(const XYZZ* __restrict__ partials, const uint32_t* __restrict__ tstart, int rows, int nb, int m,
+              uint32_t max_tasks, LeafPair* __restrict__ pairs) {
+    __shared__ uint4 tot_sm[8][kLeafThreads];     // [128-bit slice][thread]: conflict-free LDS.128 / STS.128
+    auto tot_store = [&](const XYZZ& v) {
+        const Fq* f[4] = {&v.X, &v.Y, &v.ZZ, &v.ZZZ};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            tot_sm[2 * c][threadIdx.x] = make_uint4(f[c]->l[0], f[c]->l[1], f[c]->l[2], f[c]->l[3]);
+            tot_sm[2 * c + 1][threadIdx.x] = make_uint4(f[c]->l[4], f[c]->l[5], f[c]->l[6], f[c]->l[7]);
+        }
+    };
+    auto tot_load = [&]() {
+        XYZZ v;
+        Fq* f[4] = {&v.X, &v.Y, &v.ZZ, &v.ZZZ};
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 a = tot_sm[2 * c][threadIdx.x], b = tot_sm[2 * c + 1][threadIdx.x];
+            f[c]->l[0] = a.x; f[c]->l[1] = a.y; f[c]->l[2] = a.z; f[c]->l[3] = a.w;
+            f[c]->l[4] = b.x; f[c]->l[5] = b.y; f[c]->l[6] = b.z; f[c]->l[7] = b.w;
+        }
+        return v;
+    };
+    const int tpr = nb / m;
+    const size_t gid = (size_t)blockIdx.x * kLeafThreads + threadIdx.x;
+    if (gid >= (size_t)rows * tpr) return;
+    // thread -> (t, row) with the row fastest, so a warp reads the same bucket range of 32 rows (uniform trip count)
+    const int row = (int)(gid % rows);
+    const int t = (int)(gid / rows);
+    const XYZZ* prow = partials + (size_t)row * max_tasks;
+    const uint32_t* trow = tstart + (size_t)row * (nb + 1);
+    const int lo = t * m;
+    uint32_t hi_slot = trow[lo + m];
+    XYZZ X = XYZZ::identity(), Y;    // X: accumulator role, Y: addend role
+    tot_store(XYZZ::identity());
+#pragma unroll 1
+    for (int h = 0; h < 2 * m; h++) {
+        const bool advance = !(h & 1);
+        if (advance) {            // run (X) += S_b
+            const uint32_t lo_slot = trow[lo + m - 1 - (h >> 1)];
             // one partial per non-empty bucket (split buckets were folded by k_combine_heavy)
-            XYZZ part = (lo_slot < hi_slot) ? load_xyzz(prow + lo_slot) : XYZZ::identity();
-            xyzz_add_call(&run, &part);
+            Y = (lo_slot < hi_slot) ? load_xyzz(prow + lo_slot) : XYZZ::identity();
             hi_slot = lo_slot;
-            xyzz_add_call(&tot, &run);
+        } else {                  // tot += run: the accumulator role goes to tot, run becomes the addend
+            Y = X;
+            X = tot_load();
+        }
+        xyzz_add<MulInline, MulCall>(X, Y);
+        if (!advance) {
+            tot_store(X);
+            X = Y;
         }
     }
-    // inclusive suffix scan of A_t over the tpr threads of the row
-    for (int off = 1; off < tpr; off <<= 1) {
-        sm[threadIdx.x] = run;
-        __syncthreads();
-        XYZZ v = (t + off < tpr) ? sm[threadIdx.x + off] : XYZZ::identity();
-        __syncthreads();
-        xyzz_add_call(&run, &v);
+    LeafPair* out = pairs + (size_t)row * tpr + t;
+    store_xyzz(&out->A, X);
+    store_xyzz(&out->tot, tot_load());
+}
+
+__device__ __forceinline__ XYZZ shfl_xyzz(const XYZZ& v, int src) {
+    XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.l[i] = __shfl_sync(0xffffffffu, v.X.l[i], src);
+        r.Y.l[i] = __shfl_sync(0xffffffffu, v.Y.l[i], src);
+        r.ZZ.l[i] = __shfl_sync(0xffffffffu, v.ZZ.l[i], src);
+        r.ZZZ.l[i] = __shfl_sync(0xffffffffu, v.ZZZ.l[i], src);
     }
-    // V_t = tot_t + (t >= 1 ? m * I_t : 0)
-    if (t >= 1) {
-        for (int k = 1; k < m; k <<= 1) run = xyzz_dbl<MulCall>(run);
-        xyzz_add_call(&tot, &run);
+    return r;
+}
+
+static constexpr int kTopThreads = 64;
+
+// Warp per row.  Lane l owns e = max(1, tpr / 32) consecutive pairs u = l*e + j:
+//   locT = sum_j tot_u,  locA = sum_j A_u,  locZ = sum_j j * A_u   (running suffix sums again)
+//   T = sum_l [ locT_l + m * (locZ_l + e * (l >= 1 ? I_l : 0)) ],   I_l = sum_{v >= l} locA_v  (suffix scan by shuffles)
+__global__ void __launch_bounds__(kTopThreads)
+k_reduce_top(const LeafPair* __restrict__ pairs, int rows, int tpr, int log_m, XYZZ* __restrict__ row_totals) {
+    const int lane = threadIdx.x & 31;
+    const int row = (blockIdx.x * kTopThreads + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int e = tpr >= 32 ? tpr / 32 : 1;
+    const LeafPair* prow = pairs + (size_t)row * tpr;
+    XYZZ locT = XYZZ::identity(), run = XYZZ::identity(), locZ = XYZZ::identity();
+    const int u0 = lane * e;
+    for (int j = e - 1; j >= 0; j--) {
+        if (u0 + j >= tpr) continue;
+        if (j < e - 1) xyzz_add_call(&locZ, &run);
+        XYZZ a = load_xyzz(&prow[u0 + j].A), tt = load_xyzz(&prow[u0 + j].tot);
+        xyzz_add_call(&run, &a);
+        xyzz_add_call(&locT, &tt);
     }
-    // tree sum of V_t
-    for (int stride = tpr >> 1; stride >= 1; stride >>= 1) {
-        sm[threadIdx.x] = tot;
-        __syncthreads();
-        XYZZ o = (t < stride) ? sm[threadIdx.x + stride] : XYZZ::identity();
-        __syncthreads();
-        xyzz_add_call(&tot, &o);
+    // inclusive suffix scan of locA (= run) over the lanes
+    XYZZ I = run;
+    for (int off = 1; off < 32; off <<= 1) {
+        XYZZ v = shfl_xyzz(I, (lane + off) & 31);
+        if (lane + off >= 32) v = XYZZ::identity();
+        xyzz_add_call(&I, &v);
     }
-    if (active && t == 0) store_xyzz(row_totals + row, tot);
+    if (lane >= 1) {
+        for (int k = 1; k < e; k <<= 1) I = xyzz_dbl<MulCall>(I);
+        xyzz_add_call(&locZ, &I);
+    }
+    for (int k = 0; k < log_m; k++) locZ = xyzz_dbl<MulCall>(locZ);
+    xyzz_add_call(&locT, &locZ);
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        XYZZ o = shfl_xyzz(locT, (lane + stride) & 31);
+        if (lane >= stride) o = XYZZ::identity();
+        xyzz_add_call(&locT, &o);
+    }
+    if (lane == 0) store_xyzz(row_totals + row, locT);
 }
 
 // ---------------------------------------------------------------------------------------------

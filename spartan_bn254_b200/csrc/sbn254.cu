@@ -34,18 +34,20 @@ struct sbn_ctx {
     cudaStream_t compute = nullptr, copy = nullptr;
     std::mutex mu;
     std::string last_error;
-    long chunk_rows = 1024;
+    long chunk_rows = 0;    // 0 = auto (see commit_chunk_rows)
     long window_bits = 0;
     long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
-    long reduce_m = 32;     // buckets per reduction thread
+    long leaf_m = 0;        // buckets per leaf thread of the two-level reduction; 0 = auto
     uint64_t launches = 0, h2d = 0, d2h = 0;
     // grow-only workspaces
-    struct Slot {          // one in-flight chunk of rows: private workspace + stream
-        cudaStream_t stream = nullptr;
-        cudaEvent_t done = nullptr;
-        DevBuf entries, tstart, tasks, partials, heavy;
+    struct Slot {          // one in-flight chunk of rows: private workspace
+        DevBuf entries, tstart, tasks, partials, heavy, pairs;
     } slots[2];
-    cudaEvent_t fork = nullptr;
+    // Pipeline streams.  The latency-bound stages (sort, split-bucket fold, bucket reduction) run on a HIGH priority
+    // stream and the IMAD-bound accumulation on LOW priority ones, so that while chunk i accumulates, the blocks of
+    // sort(i+1) and reduce(i-1) are placed first as accumulation blocks retire and fill its idle issue slots.
+    cudaStream_t hi = nullptr, lo[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
     // last-commit profile
     std::vector<cudaEvent_t> ev_pool;
@@ -122,9 +124,12 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
               cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming) == cudaSuccess;
-    for (auto& sl : ctx->slots)
-        ok = ok && cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) == cudaSuccess;
+    int prio_least = 0, prio_greatest = 0;
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&ctx->lo[0], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&ctx->lo[1], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->join_hi, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return SBN_ERR_CUDA;
@@ -141,13 +146,12 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
                       &ctx->scratch2})
         release(*b);
-    for (auto& sl : ctx->slots) {
-        cudaStreamSynchronize(sl.stream);
-        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy}) release(*b);
-        cudaStreamDestroy(sl.stream);
-        cudaEventDestroy(sl.done);
-    }
+    for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]})
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (auto& sl : ctx->slots)
+        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs}) release(*b);
     cudaEventDestroy(ctx->fork);
+    if (ctx->join_hi) cudaEventDestroy(ctx->join_hi);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
@@ -168,14 +172,14 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!strcmp(key, "chunk_rows")) {
-        if (value < 1) return SBN_ERR_ARG;
+        if (value < 0) return SBN_ERR_ARG;
         ctx->chunk_rows = value;
     } else if (!strcmp(key, "task_cap")) {
         if (value < 0 || value > kMaxTaskCap) return SBN_ERR_ARG;
         ctx->task_cap = value;
-    } else if (!strcmp(key, "reduce_m")) {
-        if (value < 1 || (value & (value - 1))) return SBN_ERR_ARG;
-        ctx->reduce_m = value;
+    } else if (!strcmp(key, "leaf_m")) {
+        if (value < 0 || (value & (value - 1))) return SBN_ERR_ARG;
+        ctx->leaf_m = value;
     } else if (!strcmp(key, "window_bits")) {
         if (value != 0 && (value < kMinWindowBits || value > kMaxWindowBits)) return SBN_ERR_ARG;
         ctx->window_bits = value;
@@ -334,8 +338,15 @@ static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
 template <int C>
 static void launch_sort(const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks, uint32_t max_heavy,
                         uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows, cudaStream_t s) {
-    k_sort_row<C><<<rows, kSortThreads, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks,
-                                                 heavy);
+    // Rows of >= 1024 scalars get one 1024-thread CTA: the same number of resident threads per SM as four 256-thread
+    // CTAs, but a quarter of the rows in flight, so the rows being scattered (E * 4 bytes each) stay inside L2 and their
+    // 32-byte sectors fill up before they are evicted (2.4x faster at 8192 generators).
+    if (n1 >= 1024)
+        k_sort_row<C, 1024><<<rows, 1024, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart,
+                                                  tasks, heavy);
+    else
+        k_sort_row<C, 256><<<rows, 256, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks,
+                                                heavy);
 }
 
 static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks,
@@ -350,47 +361,102 @@ static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, in
     }
 }
 
-// Runs the first three stages for `rows` rows in pipeline slot `sl`; dZ_chunk points at the chunk's first row.
-static int commit_chunk(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const Fr* dZ_chunk, const Fr* dblinds_chunk,
-                        int rows, int R, XYZZ* totals_chunk, size_t& ev_idx, std::vector<int>& ev_stage) {
-    const uint32_t E = (uint32_t)b->W * (uint32_t)b->n1;
-    const int cap = task_cap_for(ctx, b);
-    const uint32_t max_tasks = (uint32_t)msm_max_tasks(E, b->nb, cap);
-    const uint32_t max_heavy = (uint32_t)msm_max_heavy(E, cap);
-    uint32_t* heavy = (uint32_t*)sl.heavy.p;
-    uint32_t* entries = (uint32_t*)sl.entries.p;
-    uint32_t* tstart = (uint32_t*)sl.tstart.p;
-    Task* tasks = (Task*)sl.tasks.p;
-    XYZZ* partials = (XYZZ*)sl.partials.p;
-    cudaStream_t stream = sl.stream;
-    auto mark = [&](int stage) {
+// Per-commit launch plan shared by the stages of one chunk.
+struct ChunkPlan {
+    uint32_t E, max_tasks, max_heavy;
+    int cap;
+};
+static ChunkPlan chunk_plan(const sbn_ctx* ctx, const sbn_bases* b) {
+    ChunkPlan p;
+    p.E = (uint32_t)b->W * (uint32_t)b->n1;
+    p.cap = task_cap_for(ctx, b);
+    p.max_tasks = (uint32_t)msm_max_tasks(p.E, b->nb, p.cap);
+    p.max_heavy = (uint32_t)msm_max_heavy(p.E, p.cap);
+    return p;
+}
+
+// Stage timing: two timing events bracket the launches of one stage on the stream they run on.
+struct StageMarks {
+    sbn_ctx* ctx;
+    size_t& ev_idx;
+    std::vector<int>& ev_stage;
+    void mark(int stage, cudaStream_t st) {
         cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, stream);
+        if (e) cudaEventRecord(e, st);
         ev_stage.push_back(stage);
-    };
-    mark(-1);
-    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy,
-                          rows, stream));
-    mark(0);
-    const size_t threads = (size_t)rows * max_tasks;
+    }
+};
+
+static int stage_sort(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const Fr* dZ_chunk, const Fr* dblinds_chunk, int rows,
+                      int R, cudaStream_t st, StageMarks& m) {
+    const ChunkPlan p = chunk_plan(ctx, b);
+    m.mark(-1, st);
+    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, p.cap, p.E, p.max_tasks, p.max_heavy, (uint32_t*)sl.entries.p,
+                          (uint32_t*)sl.tstart.p, (Task*)sl.tasks.p, (uint32_t*)sl.heavy.p, rows, st));
+    m.mark(0, st);
+    ctx->launches += 1;
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
+static int stage_accumulate(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, cudaStream_t st, StageMarks& m) {
+    const ChunkPlan p = chunk_plan(ctx, b);
+    const size_t threads = (size_t)rows * p.max_tasks;
     const unsigned acc_blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
-    k_accumulate<<<acc_blocks, kAccThreads, 0, stream>>>(b->table, entries, tstart, tasks, partials, rows, b->nb, E, max_tasks);
-    mark(1);
+    m.mark(-1, st);
+    k_accumulate<<<acc_blocks, kAccThreads, 0, st>>>(b->table, (const uint32_t*)sl.entries.p, (const uint32_t*)sl.tstart.p,
+                                                     (const Task*)sl.tasks.p, (XYZZ*)sl.partials.p, rows, b->nb, p.E, p.max_tasks);
+    m.mark(1, st);
+    ctx->launches += 1;
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
+// Buckets per leaf thread of the two-level reduction: as few as keeps the leaf grid at a few waves of the machine
+// (the top level costs ~3 additions per leaf thread), at most 256 leaf threads per row.
+static int reduce_leaf_m(const sbn_ctx* ctx, int nb, int rows) {
+    if (ctx->leaf_m) return (int)std::min<long>(nb, std::max<long>(ctx->leaf_m, std::max(4, nb / 256)));
+    int m = std::max(4, nb / 256);
+    while (m < 32 && m * 2 <= nb && (size_t)rows * (nb / (m * 2)) >= 60000) m *= 2;
+    return std::min(m, nb);
+}
+
+static int stage_reduce(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, XYZZ* totals_chunk, cudaStream_t st,
+                        StageMarks& mk) {
+    const ChunkPlan p = chunk_plan(ctx, b);
+    XYZZ* partials = (XYZZ*)sl.partials.p;
+    const uint32_t* tstart = (const uint32_t*)sl.tstart.p;
+    mk.mark(-1, st);
     {   // fold the partials of split buckets; persistent grid, one warp per row at a time
         const int warps_needed = rows;
         const int blocks = std::max(1, std::min(148 * 4, (warps_needed * 32 + kHeavyThreads - 1) / kHeavyThreads));
-        k_combine_heavy<<<blocks, kHeavyThreads, 0, stream>>>(partials, tstart, heavy, rows, b->nb, max_tasks, max_heavy);
+        k_combine_heavy<<<blocks, kHeavyThreads, 0, st>>>(partials, tstart, (const uint32_t*)sl.heavy.p, rows, b->nb, p.max_tasks,
+                                                          p.max_heavy);
     }
-    int m = std::min((int)ctx->reduce_m, b->nb);
-    if (rows <= 64) m = std::min(m, 8);           // few rows: latency matters more than total work
-    int tpr = std::min(kRedThreads, b->nb / m);
-    int rows_per_block = kRedThreads / tpr;
-    k_reduce<<<(rows + rows_per_block - 1) / rows_per_block, kRedThreads, kRedThreads * sizeof(XYZZ), stream>>>(
-        partials, tstart, rows, b->nb, tpr, max_tasks, totals_chunk);
-    mark(2);
-    ctx->launches += 4;
+    {   // two-level reduction
+        const int m = reduce_leaf_m(ctx, b->nb, rows);
+        const int tpr = b->nb / m;
+        int log_m = 0;
+        while ((1 << log_m) < m) log_m++;
+        const size_t threads = (size_t)rows * tpr;
+        k_reduce_leaf<<<(unsigned)((threads + kLeafThreads - 1) / kLeafThreads), kLeafThreads, 0, st>>>(
+            partials, tstart, rows, b->nb, m, p.max_tasks, (LeafPair*)sl.pairs.p);
+        k_reduce_top<<<(rows * 32 + kTopThreads - 1) / kTopThreads, kTopThreads, 0, st>>>((const LeafPair*)sl.pairs.p, rows, tpr,
+                                                                                         log_m, totals_chunk);
+    }
+    mk.mark(2, st);
+    ctx->launches += 3;
     SBN_CUDA(ctx, cudaGetLastError());
     return SBN_OK;
+}
+
+// Rows per pipeline chunk.  Measured on B200 (scripts/sweep_dev.py, sweep_e2e.py): chunks of 1024 rows are as fast as
+// any; below ~512 rows the per-chunk launches and the tail of each accumulation grid start to cost.  Chunks bound the
+// workspace (entries + partial sums: ~0.5 MB per row at 1024 generators, ~5 MB per row at 8192) and let the host path
+// overlap the H2D copy of chunk i+1 with the kernels of chunk i.
+static size_t commit_chunk_rows(const sbn_ctx* ctx, size_t L) {
+    if (ctx->chunk_rows > 0) return std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    return std::min<size_t>(L, 1024);
 }
 
 static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chunk, size_t L) {
@@ -405,6 +471,7 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
         SBN_TRY(ensure(ctx, sl.tasks, chunk * max_tasks * sizeof(Task)));
         SBN_TRY(ensure(ctx, sl.partials, chunk * max_tasks * sizeof(XYZZ)));
         SBN_TRY(ensure(ctx, sl.heavy, chunk * (msm_max_heavy(E, task_cap_for(ctx, b)) + 1) * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.pairs, chunk * (size_t)(b->nb / std::max(4, b->nb / 256) + 1) * sizeof(LeafPair)));
     }
     SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
     return SBN_OK;
@@ -430,16 +497,18 @@ static int check_commit_shape(const sbn_bases* b, size_t L, size_t R) {
     return SBN_OK;
 }
 
-// The pipeline shared by both entry points.  Chunks of rows alternate between two slots (streams with
-// private workspaces) so one chunk's latency-bound reduction overlaps the next chunk's accumulation; when
-// `host_Z` is given each chunk's H2D copy is issued on the copy stream and handed over by an event.
-// `main` is the stream the caller's inputs are ordered on and on which the normalisation runs.
+// The pipeline shared by all entry points.  Rows are cut into chunks that alternate between two workspaces.  Issue order
+//   hi : sort(0) sort(1) | wait acc(0) | reduce(0) sort(2) | wait acc(1) | reduce(1) sort(3) | ...
+//   lo : wait sort(i) | acc(i)                       (two low-priority streams alternate so tails overlap heads)
+// so reduce(i-1) and sort(i+1) run underneath acc(i).  When `host_Z` is given each chunk's H2D copy is issued on the
+// copy stream and handed to the sort by an event.  `main` is the stream the caller's inputs are ordered on and on which
+// the normalisation runs.
 static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                       const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                       bool normalize = true) {
-    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
-    // chunk schedule: equal chunks; when the scalars come from the host the first chunk is a quarter chunk so the
-    // kernels start after a short copy and the remaining copies hide behind them
+    const size_t chunk = commit_chunk_rows(ctx, L);
+    // chunk schedule: equal chunks; when the scalars come from the host the first chunk is a short one so the kernels
+    // start after a short copy and the remaining copies hide behind them
     std::vector<size_t> sched;
     {
         size_t done = 0;
@@ -447,45 +516,52 @@ static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
         while (done < L) { size_t c = std::min(chunk, L - done); sched.push_back(c); done += c; }
     }
     const size_t nchunks = sched.size();
+    std::vector<size_t> row0(nchunks, 0);
+    for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
     XYZZ* totals = (XYZZ*)ctx->totals.p;
     size_t ev_idx = 0;
-    const size_t handoff_base = 4 * nchunks + 8;    // copy->compute events live after the profiling events
+    StageMarks marks{ctx, ev_idx, ev_stage};
+    const size_t sync_base = 6 * nchunks + 8;       // hand-off events live after the profiling events: 3 per chunk
+    auto sync_event = [&](size_t ci, int kind) { return get_event(ctx, sync_base + 3 * ci + kind); };   // 0 copied, 1 sorted, 2 accumulated
+    if (!sync_event(nchunks, 0)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
     SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
-    const size_t nslots = nchunks > 1 ? 2 : 1;
-    for (size_t i = 0; i < nslots; i++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[i].stream, ctx->fork, 0));
+    for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]}) SBN_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork, 0));
     if (host_Z) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
-    for (size_t ci = 0, row0 = 0; ci < nchunks; row0 += sched[ci], ci++) {
-        auto& sl = ctx->slots[ci % nslots];
-        int rows = (int)sched[ci];
+
+    auto issue_sort = [&](size_t ci) -> int {
+        auto& sl = ctx->slots[ci & 1];
+        const int rows = (int)sched[ci];
         if (host_Z) {
-            SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0 * R), host_Z + row0 * R, (size_t)rows * R * sizeof(Fr),
+            SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0[ci] * R), host_Z + row0[ci] * R, (size_t)rows * R * sizeof(Fr),
                                           cudaMemcpyHostToDevice, ctx->copy));
             ctx->h2d += (size_t)rows * R * sizeof(Fr);
-            cudaEvent_t copied = get_event(ctx, handoff_base + ci);
-            if (!copied) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
-            SBN_CUDA(ctx, cudaEventRecord(copied, ctx->copy));
-            SBN_CUDA(ctx, cudaStreamWaitEvent(sl.stream, copied, 0));
+            SBN_CUDA(ctx, cudaEventRecord(sync_event(ci, 0), ctx->copy));
+            SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->hi, sync_event(ci, 0), 0));
         }
-        SBN_TRY(commit_chunk(ctx, b, sl, dZ + row0 * R, dblinds ? dblinds + row0 : nullptr, rows, (int)R, totals + row0,
-                             ev_idx, ev_stage));
+        SBN_TRY(stage_sort(ctx, b, sl, dZ + row0[ci] * R, dblinds ? dblinds + row0[ci] : nullptr, rows, (int)R, ctx->hi, marks));
+        SBN_CUDA(ctx, cudaEventRecord(sync_event(ci, 1), ctx->hi));
+        return SBN_OK;
+    };
+    SBN_TRY(issue_sort(0));
+    if (nchunks > 1) SBN_TRY(issue_sort(1));
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        auto& sl = ctx->slots[ci & 1];
+        const int rows = (int)sched[ci];
+        cudaStream_t lo = ctx->lo[ci & 1];
+        SBN_CUDA(ctx, cudaStreamWaitEvent(lo, sync_event(ci, 1), 0));
+        SBN_TRY(stage_accumulate(ctx, b, sl, rows, lo, marks));
+        SBN_CUDA(ctx, cudaEventRecord(sync_event(ci, 2), lo));
+        SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->hi, sync_event(ci, 2), 0));
+        SBN_TRY(stage_reduce(ctx, b, sl, rows, totals + row0[ci], ctx->hi, marks));
+        if (ci + 2 < nchunks) SBN_TRY(issue_sort(ci + 2));
     }
-    for (size_t i = 0; i < nslots; i++) {
-        SBN_CUDA(ctx, cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream));
-        SBN_CUDA(ctx, cudaStreamWaitEvent(main, ctx->slots[i].done, 0));
-    }
+    SBN_CUDA(ctx, cudaEventRecord(ctx->join_hi, ctx->hi));     // hi has waited on every accumulation
+    SBN_CUDA(ctx, cudaStreamWaitEvent(main, ctx->join_hi, 0));
     if (!normalize) return SBN_OK;     // caller consumes the XYZZ row totals in ctx->totals
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, main);
-        ev_stage.push_back(-1);
-    }
+    marks.mark(-1, main);
     k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, main>>>(totals, (int)L, dC, dinf);
     ctx->launches++;
-    {
-        cudaEvent_t e = get_event(ctx, ev_idx++);
-        if (e) cudaEventRecord(e, main);
-        ev_stage.push_back(3);
-    }
+    marks.mark(3, main);
     SBN_CUDA(ctx, cudaGetLastError());
     return SBN_OK;
 }
@@ -497,7 +573,7 @@ extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const v
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->compute;
-    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     std::vector<int> ev_stage;
     SBN_TRY(run_commit(ctx, b, (const Fr*)dZ, nullptr, L, R, (const Fr*)dblinds, (Affine*)dC_out, (uint8_t*)dinf_out,
@@ -517,7 +593,7 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     SBN_TRY(ensure(ctx, ctx->dZ, L * R * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
@@ -786,7 +862,7 @@ extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly*
     if (L * R != poly->len) return SBN_ERR_SHAPE;               // hyrax.rs:258
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t chunk = std::min<size_t>(L, (size_t)ctx->chunk_rows);
+    const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
     SBN_TRY(ensure(ctx, ctx->dinf, L));
