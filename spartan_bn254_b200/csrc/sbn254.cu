@@ -412,13 +412,22 @@ static int stage_accumulate(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl,
     return SBN_OK;
 }
 
-// Buckets per leaf thread of the two-level reduction: as few as keeps the leaf grid at a few waves of the machine
-// (the top level costs ~3 additions per leaf thread), at most 256 leaf threads per row.
+// Buckets per leaf thread (m) of the two-level reduction, by a small cost model fitted on B200: the leaf kernel is the
+// slower of its dependency chain (2m additions, ~7 us each when a warp runs alone) and its share of the multiplier
+// (28 Montgomery products per bucket at ~6.9e10 /s, ~75 % efficient); the top kernel is a pure dependency chain of
+// 3e + 12 additions (e = pairs per lane, ~8.4 us each).
 static int reduce_leaf_m(const sbn_ctx* ctx, int nb, int rows) {
-    if (ctx->leaf_m) return (int)std::min<long>(nb, std::max<long>(ctx->leaf_m, std::max(4, nb / 256)));
-    int m = std::max(4, nb / 256);
-    while (m < 32 && m * 2 <= nb && (size_t)rows * (nb / (m * 2)) >= 60000) m *= 2;
-    return std::min(m, nb);
+    const int m_min = std::max(4, nb / 256);
+    if (ctx->leaf_m) return (int)std::min<long>(nb, std::max<long>(ctx->leaf_m, m_min));
+    int best = m_min;
+    double best_t = 1e300;
+    for (int m = m_min; m <= std::min(nb, 32); m *= 2) {
+        const double leaf = std::max(2.0 * m * 7e-6, double(rows) * nb * 28.0 / 6.9e10 / 0.75);
+        const int tpr = nb / m, e = tpr >= 32 ? tpr / 32 : 1;
+        const double top = (3.0 * e + 12.0) * 8.4e-6;
+        if (leaf + top < best_t) { best_t = leaf + top; best = m; }
+    }
+    return best;
 }
 
 static int stage_reduce(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, XYZZ* totals_chunk, cudaStream_t st,
