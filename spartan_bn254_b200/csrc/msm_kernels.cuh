@@ -125,14 +125,16 @@ struct Task {
 __host__ __device__ inline size_t msm_max_tasks(size_t E, int nb, int cap) { return E / cap + nb + 1; }
 __host__ __device__ inline size_t msm_max_heavy(size_t E, int cap) { return E / cap + 1; }   // buckets with > cap entries
 
-// entries[row * E + ...]        : bucket-sorted list of (k * n1 + j) | (negative << 31)
+// entries[row * E + ...]        : bucket-sorted list of (k * n1 + j) | (negative << 31); with align_log > 0 every bucket
+//                                 starts at a multiple of 2^align_log (the caller pre-fills the array with NULL entries)
+//                                 and tasks / task slots count POINTS AFTER the batched-affine rounds (ba_kernels.cuh)
 // tstart [row * (NB + 1) + b]   : first task slot of bucket b (tstart[NB] = number of tasks of the row)
 // tasks  [row * max_tasks + rank]: tasks by decreasing length
 // heavy  [row * (max_heavy + 1)] : number of split buckets of the row, followed by their ids
 template <int C, int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n1, int h_col, int scalars_are_mont, int cap,
-           uint32_t E, uint32_t max_tasks, uint32_t max_heavy, uint32_t* __restrict__ entries,
+           int align_log, uint32_t E, uint32_t max_tasks, uint32_t max_heavy, uint32_t* __restrict__ entries,
            uint32_t* __restrict__ tstart, Task* __restrict__ tasks, uint32_t* __restrict__ heavy) {
     constexpr int NB = 1 << (C - 1);
     constexpr int PER = (NB + kSortThreads - 1) / kSortThreads;   // buckets per thread in the scans
@@ -169,15 +171,17 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n
     __syncthreads();
 
     // exclusive scans over buckets: entry offsets (-> cursor) and task slots (-> tstart)
+    const uint32_t amask = (1u << align_log) - 1;
     uint32_t loc_e[PER], loc_t[PER];
     uint32_t sum_e = 0, sum_t = 0;
 #pragma unroll
     for (int i = 0; i < PER; i++) {
         int b = tid * PER + i;
         uint32_t v = (b < NB) ? counts[b] : 0;
+        v = (v + amask) >> align_log;          // points of the bucket after the batched-affine rounds (v itself without)
         loc_e[i] = sum_e;
         loc_t[i] = sum_t;
-        sum_e += v;
+        sum_e += v << align_log;               // bucket starts are aligned to 2^align_log entries
         sum_t += (v + cap - 1) / cap;
     }
     uint32_t inc_e = sum_e, inc_t = sum_t;
@@ -199,7 +203,7 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n
             cursor[b] = base_e + loc_e[i];
             trow[b] = base_t + loc_t[i];
             // task-length histogram: (nt - 1) full tasks + one remainder
-            uint32_t n = counts[b];
+            uint32_t n = (counts[b] + amask) >> align_log;
             if (n) {
                 uint32_t nt = (n + cap - 1) / cap;
                 if (nt > 1) atomicAdd(&rank_hist[cap], nt - 1);
@@ -223,8 +227,8 @@ k_sort_row(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n
     for (int i = 0; i < PER; i++) {
         int b = tid * PER + i;
         if (b >= NB) continue;
-        uint32_t n = counts[b];
-        uint32_t start = cursor[b];          // not yet advanced: pass 2 starts after the next barrier
+        uint32_t n = (counts[b] + amask) >> align_log;
+        uint32_t start = cursor[b] >> align_log;   // (cursor not yet advanced: pass 2 starts after the next barrier)
         uint32_t slot = base_t + loc_t[i];
         if (n > (uint32_t)cap) heavy[(size_t)row * (max_heavy + 1) + 1 + atomicAdd(&heavy_n, 1u)] = (uint32_t)b;
         while (n) {

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -14,6 +15,7 @@
 
 #include "msm_kernels.cuh"
 #include "opening_kernels.cuh"
+#include "ba_kernels.cuh"
 
 using namespace sbn;
 
@@ -37,11 +39,14 @@ struct sbn_ctx {
     long chunk_rows = 0;    // 0 = auto (see commit_chunk_rows)
     long window_bits = 0;
     long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
+    long ba_rounds = -1;    // batched-affine pre-reduction rounds before the XYZZ accumulation (0..3); -1 = auto
+    long ba_batch = 0;      // pairs per thread in a round; 0 = auto
     long leaf_m = 0;        // buckets per leaf thread of the two-level reduction; 0 = auto
     uint64_t launches = 0, h2d = 0, d2h = 0;
     // grow-only workspaces
     struct Slot {          // one in-flight chunk of rows: private workspace
         DevBuf entries, tstart, tasks, partials, heavy, pairs;
+        DevBuf pts[3], prefix, other, wtot, winv;      // batched-affine rounds (ba_kernels.cuh)
     } slots[2];
     // Pipeline streams.  The latency-bound stages (sort, split-bucket fold, bucket reduction) run on a HIGH priority
     // stream and the IMAD-bound accumulation on LOW priority ones, so that while chunk i accumulates, the blocks of
@@ -134,6 +139,10 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
         delete ctx;
         return SBN_ERR_CUDA;
     }
+    if (const char* e = getenv("SBN_BA_ROUNDS")) {     // test hook: default number of batched-affine rounds
+        long v = atol(e);
+        if (v >= -1 && v <= 3) ctx->ba_rounds = v;
+    }
     *out = ctx;
     return SBN_OK;
 }
@@ -149,7 +158,9 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto& sl : ctx->slots)
-        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs}) release(*b);
+        for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs, &sl.pts[0], &sl.pts[1], &sl.pts[2],
+                          &sl.prefix, &sl.other, &sl.wtot, &sl.winv})
+            release(*b);
     cudaEventDestroy(ctx->fork);
     if (ctx->join_hi) cudaEventDestroy(ctx->join_hi);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -177,6 +188,12 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     } else if (!strcmp(key, "task_cap")) {
         if (value < 0 || value > kMaxTaskCap) return SBN_ERR_ARG;
         ctx->task_cap = value;
+    } else if (!strcmp(key, "ba_rounds")) {
+        if (value < -1 || value > 3) return SBN_ERR_ARG;
+        ctx->ba_rounds = value;
+    } else if (!strcmp(key, "ba_batch")) {
+        if (value != 0 && (value < 4 || value > 256)) return SBN_ERR_ARG;
+        ctx->ba_batch = value;
     } else if (!strcmp(key, "leaf_m")) {
         if (value < 0 || (value & (value - 1))) return SBN_ERR_ARG;
         ctx->leaf_m = value;
@@ -231,7 +248,7 @@ static int choose_window(size_t n1) {
 
 // Natural buckets (Poisson around the mean occupancy) stay whole; only genuinely heavy ones -- the top
 // window of a 254-bit scalar has few distinct digits, derefs-style inputs repeat scalars -- are split.
-static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b);
+static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b, int ba);
 
 // ------------------------------------------------------------------------------------------------
 // bases
@@ -319,9 +336,23 @@ extern "C" int sbn_bases_window_bits(const sbn_bases* b) { return b ? b->c : 0; 
 // ------------------------------------------------------------------------------------------------
 // commit pipeline
 // ------------------------------------------------------------------------------------------------
-static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b) {
+// Batched-affine rounds for a chunk of `rows` rows.  Measured on B200: one round takes ~8 % off the accumulation at 1024
+// generators, two rounds ~14 % at 8192, and every round adds ~0.2 ms of dependency-chain latency (the shared
+// inversion) -- so the rounds only pay once a chunk holds more than ~16 M list entries.
+static int ba_rounds_for(const sbn_ctx* ctx, const sbn_bases* b, size_t rows) {
+    if (ctx->ba_rounds >= 0) return (int)ctx->ba_rounds;
+    const double entries = double(rows) * b->W * b->n1;
+    if (entries < 16e6) return 0;
+    return b->n1 >= 4096 ? 2 : 1;
+}
+
+static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b, int ba) {
     if (ctx->task_cap) return (int)ctx->task_cap;
     double mean = double(b->W) * b->n1 / b->nb;
+    if (ba) {    // tasks count points after the batched-affine rounds
+        mean = mean / double(1 << ba) + 0.5;
+        return std::max(8, std::min(kMaxTaskCap, (int)(2.5 * mean + 0.5)));
+    }
     int cap = (int)(2.5 * mean + 0.5);
     return std::max(32, std::min(kMaxTaskCap, cap));
 }
@@ -336,24 +367,25 @@ static cudaEvent_t get_event(sbn_ctx* ctx, size_t idx) {
 }
 
 template <int C>
-static void launch_sort(const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks, uint32_t max_heavy,
-                        uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows, cudaStream_t s) {
+static void launch_sort(const Fr* Z, const Fr* blinds, int R, int n1, int cap, int align_log, uint32_t E, uint32_t max_tasks,
+                        uint32_t max_heavy, uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows,
+                        cudaStream_t s) {
     // Rows of >= 1024 scalars get one 1024-thread CTA: the same number of resident threads per SM as four 256-thread
     // CTAs, but a quarter of the rows in flight, so the rows being scattered (E * 4 bytes each) stay inside L2 and their
     // 32-byte sectors fill up before they are evicted (2.4x faster at 8192 generators).
     if (n1 >= 1024)
-        k_sort_row<C, 1024><<<rows, 1024, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart,
-                                                  tasks, heavy);
+        k_sort_row<C, 1024><<<rows, 1024, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, align_log, E, max_tasks, max_heavy, entries,
+                                                  tstart, tasks, heavy);
     else
-        k_sort_row<C, 256><<<rows, 256, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, E, max_tasks, max_heavy, entries, tstart, tasks,
-                                                heavy);
+        k_sort_row<C, 256><<<rows, 256, 0, s>>>(Z, blinds, R, n1, n1 - 1, 1, cap, align_log, E, max_tasks, max_heavy, entries,
+                                                tstart, tasks, heavy);
 }
 
-static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, int cap, uint32_t E, uint32_t max_tasks,
-                         uint32_t max_heavy, uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy, int rows,
-                         cudaStream_t s) {
+static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, int cap, int align_log, uint32_t E,
+                         uint32_t max_tasks, uint32_t max_heavy, uint32_t* entries, uint32_t* tstart, Task* tasks, uint32_t* heavy,
+                         int rows, cudaStream_t s) {
     switch (c) {
-#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, n1, cap, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows, s); return SBN_OK;
+#define SBN_CASE(CC) case CC: launch_sort<CC>(Z, blinds, R, n1, cap, align_log, E, max_tasks, max_heavy, entries, tstart, tasks, heavy, rows, s); return SBN_OK;
         SBN_CASE(4) SBN_CASE(5) SBN_CASE(6) SBN_CASE(7) SBN_CASE(8) SBN_CASE(9) SBN_CASE(10) SBN_CASE(11)
         SBN_CASE(12) SBN_CASE(13)
 #undef SBN_CASE
@@ -363,15 +395,21 @@ static int dispatch_sort(int c, const Fr* Z, const Fr* blinds, int R, int n1, in
 
 // Per-commit launch plan shared by the stages of one chunk.
 struct ChunkPlan {
-    uint32_t E, max_tasks, max_heavy;
-    int cap;
+    uint32_t E;          // row stride of the entry array (padded for aligned bucket starts when ba > 0)
+    uint32_t Epts;       // list elements per row that the XYZZ accumulation sees: E >> ba
+    uint32_t max_tasks, max_heavy;
+    int cap, ba;
 };
-static ChunkPlan chunk_plan(const sbn_ctx* ctx, const sbn_bases* b) {
+static ChunkPlan chunk_plan(const sbn_ctx* ctx, const sbn_bases* b, size_t rows) {
     ChunkPlan p;
-    p.E = (uint32_t)b->W * (uint32_t)b->n1;
-    p.cap = task_cap_for(ctx, b);
-    p.max_tasks = (uint32_t)msm_max_tasks(p.E, b->nb, p.cap);
-    p.max_heavy = (uint32_t)msm_max_heavy(p.E, p.cap);
+    p.ba = ba_rounds_for(ctx, b, rows);
+    const uint64_t E0 = (uint64_t)b->W * (uint64_t)b->n1;
+    const uint64_t A = 1ull << p.ba;
+    p.E = (uint32_t)((E0 + (uint64_t)b->nb * (A - 1) + A - 1) / A * A);
+    p.Epts = p.E >> p.ba;
+    p.cap = task_cap_for(ctx, b, p.ba);
+    p.max_tasks = (uint32_t)msm_max_tasks(p.Epts, b->nb, p.cap);
+    p.max_heavy = (uint32_t)msm_max_heavy(p.Epts, p.cap);
     return p;
 }
 
@@ -389,25 +427,63 @@ struct StageMarks {
 
 static int stage_sort(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const Fr* dZ_chunk, const Fr* dblinds_chunk, int rows,
                       int R, cudaStream_t st, StageMarks& m) {
-    const ChunkPlan p = chunk_plan(ctx, b);
+    const ChunkPlan p = chunk_plan(ctx, b, (size_t)rows);
     m.mark(-1, st);
-    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, p.cap, p.E, p.max_tasks, p.max_heavy, (uint32_t*)sl.entries.p,
-                          (uint32_t*)sl.tstart.p, (Task*)sl.tasks.p, (uint32_t*)sl.heavy.p, rows, st));
+    if (p.ba) SBN_CUDA(ctx, cudaMemsetAsync(sl.entries.p, 0xff, (size_t)rows * p.E * sizeof(uint32_t), st));   // NULL padding
+    SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, p.cap, p.ba, p.E, p.max_tasks, p.max_heavy,
+                          (uint32_t*)sl.entries.p, (uint32_t*)sl.tstart.p, (Task*)sl.tasks.p, (uint32_t*)sl.heavy.p, rows, st));
     m.mark(0, st);
     ctx->launches += 1;
     SBN_CUDA(ctx, cudaGetLastError());
     return SBN_OK;
 }
 
+static int ba_pairs_per_thread(const sbn_ctx* ctx, size_t npairs) {
+    if (ctx->ba_batch) return (int)ctx->ba_batch;
+    return (int)std::max<size_t>(4, std::min<size_t>(32, npairs / 150000));   // keep >= ~150k threads in a round
+}
+
 static int stage_accumulate(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, cudaStream_t st, StageMarks& m) {
-    const ChunkPlan p = chunk_plan(ctx, b);
+    const ChunkPlan p = chunk_plan(ctx, b, (size_t)rows);
     const size_t threads = (size_t)rows * p.max_tasks;
     const unsigned acc_blocks = (unsigned)((threads + kAccThreads - 1) / kAccThreads);
     m.mark(-1, st);
-    k_accumulate<<<acc_blocks, kAccThreads, 0, st>>>(b->table, (const uint32_t*)sl.entries.p, (const uint32_t*)sl.tstart.p,
-                                                     (const Task*)sl.tasks.p, (XYZZ*)sl.partials.p, rows, b->nb, p.E, p.max_tasks);
+    if (p.ba == 0) {
+        k_accumulate<<<acc_blocks, kAccThreads, 0, st>>>(b->table, (const uint32_t*)sl.entries.p, (const uint32_t*)sl.tstart.p,
+                                                         (const Task*)sl.tasks.p, (XYZZ*)sl.partials.p, rows, b->nb, p.E,
+                                                         p.max_tasks);
+        ctx->launches += 1;
+    } else {
+        // batched-affine rounds over the flat pair arrays of the chunk (rows concatenate: p.E is a multiple of 2^ba)
+        const Affine* in = nullptr;
+        for (int k = 0; k < p.ba; k++) {
+            const size_t npairs = ((size_t)rows * p.E) >> (k + 1);
+            const int B = ba_pairs_per_thread(ctx, npairs);
+            const unsigned blocks = (unsigned)((npairs + (size_t)kBaThreads * B - 1) / ((size_t)kBaThreads * B));
+            const size_t nwarps = (size_t)blocks * kBaThreads / 32;
+            Affine* out = (Affine*)sl.pts[k].p;
+            if (k == 0) {
+                k_ba_prefix<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->table, nullptr, npairs, B,
+                                                                 (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->table, nullptr, npairs, B,
+                                                                 (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
+                                                                 (const Fq*)sl.winv.p, out);
+            } else {
+                k_ba_prefix<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
+                                                                  (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p,
+                                                                  (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
+            }
+            in = out;
+            ctx->launches += 3;
+        }
+        k_accumulate_pts<<<acc_blocks, kAccThreads, 0, st>>>(in, p.Epts, (const uint32_t*)sl.tstart.p, (const Task*)sl.tasks.p,
+                                                             (XYZZ*)sl.partials.p, rows, b->nb, p.max_tasks);
+        ctx->launches += 1;
+    }
     m.mark(1, st);
-    ctx->launches += 1;
     SBN_CUDA(ctx, cudaGetLastError());
     return SBN_OK;
 }
@@ -432,7 +508,7 @@ static int reduce_leaf_m(const sbn_ctx* ctx, int nb, int rows) {
 
 static int stage_reduce(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, XYZZ* totals_chunk, cudaStream_t st,
                         StageMarks& mk) {
-    const ChunkPlan p = chunk_plan(ctx, b);
+    const ChunkPlan p = chunk_plan(ctx, b, (size_t)rows);
     XYZZ* partials = (XYZZ*)sl.partials.p;
     const uint32_t* tstart = (const uint32_t*)sl.tstart.p;
     mk.mark(-1, st);
@@ -469,8 +545,11 @@ static size_t commit_chunk_rows(const sbn_ctx* ctx, size_t L) {
 }
 
 static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chunk, size_t L) {
-    const size_t E = (size_t)b->W * b->n1;
-    const size_t max_tasks = msm_max_tasks(E, b->nb, task_cap_for(ctx, b));
+    // a short chunk may run without the batched-affine rounds: size for both plans
+    const ChunkPlan plan = chunk_plan(ctx, b, chunk), plain = chunk_plan(ctx, b, 1);
+    const size_t E = std::max(plan.E, plain.E);
+    const size_t max_tasks = std::max(plan.max_tasks, plain.max_tasks);
+    const size_t max_heavy = std::max(plan.max_heavy, plain.max_heavy);
     if (max_tasks >= (1u << 24)) return SBN_ERR_SHAPE;
     const size_t nslots = (L > chunk || L > chunk / 4) ? 2 : 1;    // the host path may add a short first chunk
     for (size_t i = 0; i < nslots; i++) {
@@ -479,8 +558,18 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
         SBN_TRY(ensure(ctx, sl.tstart, chunk * (b->nb + 1) * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.tasks, chunk * max_tasks * sizeof(Task)));
         SBN_TRY(ensure(ctx, sl.partials, chunk * max_tasks * sizeof(XYZZ)));
-        SBN_TRY(ensure(ctx, sl.heavy, chunk * (msm_max_heavy(E, task_cap_for(ctx, b)) + 1) * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.heavy, chunk * (max_heavy + 1) * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.pairs, chunk * (size_t)(b->nb / std::max(4, b->nb / 256) + 1) * sizeof(LeafPair)));
+        const int ba = std::max(plan.ba, plain.ba);
+        if (ba) {
+            const size_t np1 = chunk * E / 2;                       // pairs of the first round
+            for (int k = 0; k < ba; k++) SBN_TRY(ensure(ctx, sl.pts[k], (np1 >> k) * sizeof(Affine)));
+            SBN_TRY(ensure(ctx, sl.prefix, np1 * sizeof(Fq)));
+            const size_t nthreads = np1 / 4 + 2 * kBaThreads;       // >= 4 pairs per thread
+            SBN_TRY(ensure(ctx, sl.other, nthreads * sizeof(Fq)));
+            SBN_TRY(ensure(ctx, sl.wtot, (nthreads / 32 + 1) * sizeof(Fq)));
+            SBN_TRY(ensure(ctx, sl.winv, (nthreads / 32 + 1) * sizeof(Fq)));
+        }
     }
     SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
     return SBN_OK;

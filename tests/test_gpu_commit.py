@@ -137,6 +137,53 @@ def test_commit_chunking_and_window_override(ctx, orc):
         c2.close()
 
 
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+@pytest.mark.parametrize("gens_kind,kind,ell", [("ref", "uniform", 12), ("ref", "derefs", 15), ("distinct", "uniform", 13),
+                                               ("ref", "small", 14)])
+def test_batched_affine_rounds_match_oracle(orc, rounds, gens_kind, kind, ell):
+    """The batched-affine pre-reduction (ba_kernels.cuh) is normally chosen only for chunks of > 16 M list entries; forced
+    here on small shapes.  The reference generators repeat the same point (group.rs:110-132), so the P + P, P + (-P) and
+    identity cases of the affine rounds are all exercised; results must stay bit-exact."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.hyrax import MultiCommitGens, compute_factored_lens
+    c2 = Context(0)
+    c2.set("ba_rounds", rounds)
+    l, r = compute_factored_lens(ell)
+    L, R = 1 << l, 1 << r
+    if gens_kind == "ref":
+        g = MultiCommitGens.new(R, b"gens_r1cs_eval", c2)
+        G, h = g.G, g.h
+    else:
+        G, h = synth.distinct_generators(c2, R)
+    if kind == "uniform":
+        Z = synth.uniform_scalars(5, L * R)
+    elif kind == "derefs":
+        Z = synth.derefs_scalars(ell)
+    else:
+        Z = c2.fr_from_canonical(synth.small_scalars_canonical(8, L * R))
+    blinds = synth.uniform_scalars(6, L)
+    bases = c2.bases(G, h)
+    C, inf = c2.hyrax_commit(bases, Z, L, R, blinds)
+    Co, info = orc.hyrax_commit(G, h, Z, L, R, blinds)
+    assert np.array_equal(inf, info) and np.array_equal(C, Co)
+    # an adversarial row set on the same context: cancellations and repeated bases
+    if gens_kind == "ref":
+        rmod = h2i(GOLD["constants"]["r"])
+        sc, kinds = orc.gen_scalars(b"gens_r1cs_eval", R)
+        ones = [i for i in range(R) if kinds[i] == 2]
+        Zr = [[0] * R for _ in range(4)]
+        Zr[0][ones[0]] = 5; Zr[0][ones[1]] = rmod - 5
+        Zr[1] = [7] * R
+        Zr[2][ones[0]] = 9; Zr[2][ones[1]] = 9; Zr[2][ones[2]] = 9; Zr[2][ones[3]] = rmod - 9
+        Zm = orc.to_mont([v for row in Zr for v in row])
+        C, inf = c2.hyrax_commit(bases, Zm, 4, R, None)
+        Co, info = orc.hyrax_commit(G, h, Zm, 4, R, None)
+        assert np.array_equal(inf, info) and np.array_equal(C, Co)
+        assert inf[0] == 1 and inf[3] == 1
+    bases.close()
+    c2.close()
+
+
 def test_shape_errors(ctx):
     """Reference preconditions (commitments.rs:146, hyrax.rs:258) surface as SBN_ERR_SHAPE / AssertionError."""
     from spartan_bn254_b200 import SbnError, synth
