@@ -35,6 +35,8 @@ typedef struct sbn_ctx sbn_ctx;        /* one CUDA device + streams + workspace 
 typedef struct sbn_bases sbn_bases;    /* generator set resident in HBM with window tables */
 typedef struct sbn_bullet sbn_bullet;  /* device-resident state of one bullet reduction    */
 typedef struct sbn_sumcheck sbn_sumcheck;
+typedef struct sbn_prodcircuit sbn_prodcircuit;
+typedef struct sbn_bsumcheck sbn_bsumcheck;
 
 typedef enum {
     SBN_OK = 0,
@@ -152,6 +154,29 @@ int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2, sbn_fr* e3
 int sbn_sumcheck_bind(sbn_sumcheck* st, const sbn_fr* r);
 int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]);   /* the length-1 tables (unused slots zero) */
 int sbn_sumcheck_destroy(sbn_sumcheck* st);
+
+/* ---- f1: the product layer of the Spark argument, pure Fr.
+ * Product circuit = ProductCircuit::new (product_tree.rs:39-57): every layer of pairwise products of a 2^k-entry
+ * polynomial, resident on device; evaluate = ProductCircuit::evaluate (:59-64). */
+int sbn_prodcircuit_create(sbn_ctx* ctx, const sbn_fr* poly, size_t len, sbn_prodcircuit** out);
+int sbn_prodcircuit_evaluate(sbn_prodcircuit* pc, sbn_fr* out);
+size_t sbn_prodcircuit_num_layers(const sbn_prodcircuit* pc);
+int sbn_prodcircuit_destroy(sbn_prodcircuit* pc);
+/* Batched cubic sumcheck = the table work of SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:165-330) as
+ * ProductCircuitEvalProofBatched::prove drives it (product_tree.rs:251-392): P "parallel" instances (left_vec[layer],
+ * right_vec[layer] of each circuit) share poly_C = EqPolynomial(rand).evals() (built on device, hyrax.rs:355-369);
+ * S "sequential" instances (dot-product circuits, :292-305) bring their own three tables of 2^n_rand scalars.
+ * The transcript stays on the host: round_eval returns (e0, e2, e3) per instance in instance order (parallel first),
+ * the caller combines them with its coefficients, draws r_j and calls bind; end returns the length-1 tables:
+ * A_final / B_final per instance, C_final[0] = poly_C_par[0] followed by one entry per sequential instance.
+ * The circuits' layer tables are bound IN PLACE, as the reference consumes them. */
+int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
+                        size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB, const sbn_fr* const* seqC,
+                        size_t S, sbn_bsumcheck** out);
+int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals /* (P + S) x 3 */);
+int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r);
+int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final);
+int sbn_bsumcheck_destroy(sbn_bsumcheck* st);
 
 /* ---- utilities used by tests / harnesses */
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);

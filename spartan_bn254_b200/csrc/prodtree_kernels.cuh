@@ -1,0 +1,74 @@
+// Kernels of the product-layer argument (sm_100a): product circuits and the batched cubic sumcheck.
+//
+//   reference product_tree.rs:21-57     ProductCircuit::compute_layer / new   -> k_product_layer
+//   reference hyrax.rs:355-369          EqPolynomial::evals                   -> k_eq_expand
+//   reference sumcheck.rs:201-271       round evaluations of A * B * C at 0, 2, 3, one triple per instance
+//                                                                             -> k_cubic_eval_batched
+//   reference sumcheck.rs:293-306       bound_poly_var_top on every table     -> k_bind_top_batched
+//
+// Pure Fr arithmetic over tables that halve every round: the kernels stream 32-byte scalars from HBM (192 B and six
+// products per index and instance in the evaluation; 64 B in, 32 B out and one product per index in the bind), so they
+// are bound by HBM for the first rounds and by launch latency for the last ones.
+#pragma once
+#include "opening_kernels.cuh"
+
+namespace sbn {
+
+// next[i] = cur[i] * cur[half + i]: a layer's (left | right) halves multiplied element-wise give the next layer, which
+// is again stored as (left | right) (product_tree.rs:26-33 splits the products at len / 4).
+__global__ void k_product_layer(const Fr* __restrict__ cur, size_t half, Fr* __restrict__ next) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    store_fr(next + i, fp_mul(load_fr(cur + i), load_fr(cur + half + i)));
+}
+
+// One doubling step of EqPolynomial::evals: out[2i + 1] = in[i] * r_j, out[2i] = in[i] - out[2i + 1].
+__global__ void k_eq_expand(const Fr* __restrict__ in, size_t size, const Fr* __restrict__ rj, Fr* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const Fr s = load_fr(in + i);
+    const Fr hi = fp_mul(s, load_fr(rj));
+    store_fr(out + 2 * i + 1, hi);
+    store_fr(out + 2 * i, fp_sub(s, hi));
+}
+
+struct CubicTriple { const Fr *A, *B, *C; };
+
+// partial[(inst * 3 + e) * gridDim.x + block] = this block's share of sum_i A_t[i] B_t[i] C_t[i] at t = 0, 2, 3 with
+// X_t = lo + t (hi - lo); blockIdx.y = instance.
+__global__ void __launch_bounds__(kDotThreads)
+k_cubic_eval_batched(const CubicTriple* __restrict__ triples, size_t half, Fr* __restrict__ partial) {
+    __shared__ Fr sm[kDotThreads];
+    const CubicTriple t = triples[blockIdx.y];
+    Fr e0 = Fr::zero(), e2 = Fr::zero(), e3 = Fr::zero();
+    for (size_t i = (size_t)blockIdx.x * kDotThreads + threadIdx.x; i < half; i += (size_t)gridDim.x * kDotThreads) {
+        const Fr a0 = load_fr(t.A + i), a1 = load_fr(t.A + half + i);
+        const Fr b0 = load_fr(t.B + i), b1 = load_fr(t.B + half + i);
+        const Fr c0 = load_fr(t.C + i), c1 = load_fr(t.C + half + i);
+        const Fr a2 = fp_sub(fp_add(a1, a1), a0), b2 = fp_sub(fp_add(b1, b1), b0), c2 = fp_sub(fp_add(c1, c1), c0);
+        const Fr a3 = fp_sub(fp_add(a2, a1), a0), b3 = fp_sub(fp_add(b2, b1), b0), c3 = fp_sub(fp_add(c2, c1), c0);
+        e0 = fp_add(e0, fr_mul_call(fr_mul_call(a0, b0), c0));
+        e2 = fp_add(e2, fr_mul_call(fr_mul_call(a2, b2), c2));
+        e3 = fp_add(e3, fr_mul_call(fr_mul_call(a3, b3), c3));
+    }
+    Fr* out = partial + (size_t)blockIdx.y * 3 * gridDim.x;
+    e0 = block_sum_fr(e0, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + blockIdx.x, e0);
+    __syncthreads();
+    e2 = block_sum_fr(e2, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + gridDim.x + blockIdx.x, e2);
+    __syncthreads();
+    e3 = block_sum_fr(e3, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + 2 * gridDim.x + blockIdx.x, e3);
+}
+
+// T[i] <- T[i] + r (T[half + i] - T[i]) for every table of the list; blockIdx.y = table.
+__global__ void k_bind_top_batched(Fr* const* __restrict__ tables, size_t half, const Fr* __restrict__ r) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    Fr* T = tables[blockIdx.y];
+    const Fr lo = load_fr(T + i), hi = load_fr(T + half + i);
+    store_fr(T + i, fp_add(lo, fp_mul(load_fr(r), fp_sub(hi, lo))));
+}
+
+}  // namespace sbn

@@ -16,6 +16,7 @@
 #include "msm_kernels.cuh"
 #include "opening_kernels.cuh"
 #include "ba_kernels.cuh"
+#include "prodtree_kernels.cuh"
 
 using namespace sbn;
 
@@ -1352,5 +1353,252 @@ extern "C" int sbn_sumcheck_destroy(sbn_sumcheck* st) {
         cudaStreamSynchronize(st->ctx->compute);
     }
     sumcheck_free(st);
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f1: product circuits and the batched cubic sumcheck of the product layer
+// ------------------------------------------------------------------------------------------------
+struct sbn_prodcircuit {
+    sbn_ctx* ctx = nullptr;
+    size_t len = 0;
+    int num_layers = 0;
+    Fr* buf = nullptr;               // layer l = (left | right) of len >> l scalars at buf + off[l]
+    std::vector<size_t> off;
+};
+
+extern "C" int sbn_prodcircuit_create(sbn_ctx* ctx, const sbn_fr* poly, size_t len, sbn_prodcircuit** out) {
+    if (!ctx || !poly || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (len < 2 || (len & (len - 1)) || len > (size_t(1) << 30)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    sbn_prodcircuit* pc = new (std::nothrow) sbn_prodcircuit();
+    if (!pc) return SBN_ERR_OOM;
+    pc->ctx = ctx;
+    pc->len = len;
+    size_t total = 0;
+    for (size_t n = len; n >= 2; n >>= 1) { pc->off.push_back(total); total += n; pc->num_layers++; }
+    if (cudaMalloc(&pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; ctx->last_error = "sbn_prodcircuit_create: cudaMalloc failed"; return SBN_ERR_OOM; }
+    cudaStream_t s = ctx->compute;
+    cudaError_t e = cudaMemcpyAsync(pc->buf, poly, len * sizeof(Fr), cudaMemcpyHostToDevice, s);
+    ctx->h2d += len * sizeof(Fr);
+    for (int l = 0; l + 1 < pc->num_layers && e == cudaSuccess; l++) {
+        const size_t half = (len >> l) / 2;
+        k_product_layer<<<(unsigned)((half + 127) / 128), 128, 0, s>>>(pc->buf + pc->off[l], half, pc->buf + pc->off[l + 1]);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        ctx->last_error = std::string("sbn_prodcircuit_create: ") + cudaGetErrorString(e);
+        cudaFree(pc->buf);
+        delete pc;
+        return SBN_ERR_CUDA;
+    }
+    *out = pc;
+    return SBN_OK;
+}
+
+extern "C" int sbn_prodcircuit_evaluate(sbn_prodcircuit* pc, sbn_fr* out) {
+    if (!pc || !out) return SBN_ERR_ARG;
+    sbn_ctx* ctx = pc->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr top[2];
+    SBN_CUDA(ctx, cudaMemcpyAsync(top, pc->buf + pc->off[pc->num_layers - 1], 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->d2h += 2 * sizeof(Fr);
+    const Fr v = fp_mul(top[0], top[1]);                 // product_tree.rs:59-64
+    memcpy(out, &v, sizeof(Fr));
+    return SBN_OK;
+}
+
+extern "C" size_t sbn_prodcircuit_num_layers(const sbn_prodcircuit* pc) { return pc ? (size_t)pc->num_layers : 0; }
+
+extern "C" int sbn_prodcircuit_destroy(sbn_prodcircuit* pc) {
+    if (!pc) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(pc->ctx->mu);
+        cudaSetDevice(pc->ctx->device);
+        cudaStreamSynchronize(pc->ctx->compute);
+        cudaFree(pc->buf);
+    }
+    delete pc;
+    return SBN_OK;
+}
+
+struct sbn_bsumcheck {
+    sbn_ctx* ctx = nullptr;
+    size_t P = 0, S = 0, len = 0;
+    std::vector<Fr*> A, B, C;        // per instance (C of a parallel instance = the shared eq table)
+    Fr* eq[2] = {nullptr, nullptr};  // ping-pong buffers of EqPolynomial::evals; eq[cur] is poly_C_par
+    int eq_cur = 0;
+    Fr* seq = nullptr;               // 3 * S tables of the sequential instances
+    CubicTriple* d_triples = nullptr;
+    Fr** d_tables = nullptr;
+    int ntables = 0;
+    Fr* partial = nullptr;
+    Fr* out = nullptr;               // 3 * (P + S) evaluations, then r
+    unsigned max_blocks = 0;
+};
+
+static void bsumcheck_free(sbn_bsumcheck* st) {
+    for (void* p : {(void*)st->eq[0], (void*)st->eq[1], (void*)st->seq, (void*)st->d_triples, (void*)st->d_tables,
+                    (void*)st->partial, (void*)st->out})
+        if (p) cudaFree(p);
+    delete st;
+}
+
+extern "C" int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
+                                   size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB,
+                                   const sbn_fr* const* seqC, size_t S, sbn_bsumcheck** out) {
+    if (!ctx || !out || !circuits || P == 0 || (n_rand && !rand) || (S && (!seqA || !seqB || !seqC))) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (n_rand > 30 || P + S > 4096) return SBN_ERR_SHAPE;
+    const size_t T = size_t(1) << n_rand;                      // table length: poly_C_par = eq(rand) has 2^|rand| entries
+    for (size_t i = 0; i < P; i++) {
+        if (!circuits[i] || circuits[i]->ctx != ctx) return SBN_ERR_ARG;
+        if (layer_id >= (size_t)circuits[i]->num_layers) return SBN_ERR_SHAPE;
+        if ((circuits[i]->len >> layer_id) != 2 * T) return SBN_ERR_SHAPE;      // product_tree.rs:272 assert_eq!(poly_C_par.len(), len / 2)
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    sbn_bsumcheck* st = new (std::nothrow) sbn_bsumcheck();
+    if (!st) return SBN_ERR_OOM;
+    st->ctx = ctx;
+    st->P = P;
+    st->S = S;
+    st->len = T;
+    const size_t n = P + S;
+    st->max_blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((T / 2 + kDotThreads - 1) / kDotThreads, std::max<size_t>(16, 1184 / n)));
+    bool ok = cudaMalloc(&st->eq[0], T * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->eq[1], T * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->d_triples, n * sizeof(CubicTriple)) == cudaSuccess &&
+              cudaMalloc(&st->d_tables, (2 * P + 1 + 3 * S) * sizeof(Fr*)) == cudaSuccess &&
+              cudaMalloc(&st->partial, 3 * n * st->max_blocks * sizeof(Fr)) == cudaSuccess &&
+              cudaMalloc(&st->out, (3 * n + n_rand + 2) * sizeof(Fr)) == cudaSuccess &&
+              (S == 0 || cudaMalloc(&st->seq, 3 * S * T * sizeof(Fr)) == cudaSuccess);
+    if (!ok) { bsumcheck_free(st); ctx->last_error = "sbn_bsumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
+    auto fail = [&](const char* what, cudaError_t e) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        bsumcheck_free(st);
+        return SBN_ERR_CUDA;
+    };
+    cudaError_t e;
+    // poly_C_par = EqPolynomial::new(rand).evals()                                  (hyrax.rs:355-369)
+    Fr* rdev = st->out + 3 * n + 2;
+    const Fr one = Fr::one();
+    if ((e = cudaMemcpyAsync(st->eq[0], &one, sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("eq seed", e);
+    if (n_rand && (e = cudaMemcpyAsync(rdev, rand, n_rand * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("rand upload", e);
+    ctx->h2d += (n_rand + 1) * sizeof(Fr);
+    for (size_t j = 0; j < n_rand; j++) {
+        const size_t size = size_t(1) << j;
+        k_eq_expand<<<(unsigned)((size + 127) / 128), 128, 0, s>>>(st->eq[st->eq_cur], size, rdev + j, st->eq[st->eq_cur ^ 1]);
+        st->eq_cur ^= 1;
+        ctx->launches++;
+    }
+    for (size_t k = 0; k < S; k++) {
+        const sbn_fr* src[3] = {seqA[k], seqB[k], seqC[k]};
+        for (int w = 0; w < 3; w++) {
+            if (!src[w]) { bsumcheck_free(st); return SBN_ERR_ARG; }
+            if ((e = cudaMemcpyAsync(st->seq + (3 * k + w) * T, src[w], T * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+                return fail("sequential instance upload", e);
+        }
+        ctx->h2d += 3 * T * sizeof(Fr);
+    }
+    std::vector<CubicTriple> triples(n);
+    std::vector<Fr*> tables;
+    for (size_t i = 0; i < P; i++) {
+        Fr* layer = circuits[i]->buf + circuits[i]->off[layer_id];
+        st->A.push_back(layer);                 // left_vec[layer_id]
+        st->B.push_back(layer + T);             // right_vec[layer_id]
+        st->C.push_back(st->eq[st->eq_cur]);
+        tables.push_back(layer);
+        tables.push_back(layer + T);
+    }
+    tables.push_back(st->eq[st->eq_cur]);
+    for (size_t k = 0; k < S; k++) {
+        for (int w = 0; w < 3; w++) tables.push_back(st->seq + (3 * k + w) * T);
+        st->A.push_back(st->seq + (3 * k) * T);
+        st->B.push_back(st->seq + (3 * k + 1) * T);
+        st->C.push_back(st->seq + (3 * k + 2) * T);
+    }
+    for (size_t i = 0; i < n; i++) triples[i] = CubicTriple{st->A[i], st->B[i], st->C[i]};
+    st->ntables = (int)tables.size();
+    if ((e = cudaMemcpyAsync(st->d_triples, triples.data(), n * sizeof(CubicTriple), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(st->d_tables, tables.data(), tables.size() * sizeof(Fr*), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess)
+        return fail("sbn_bsumcheck_begin", e);
+    *out = st;
+    return SBN_OK;
+}
+
+extern "C" int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals) {
+    if (!st || !evals) return SBN_ERR_ARG;
+    if (st->len < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t half = st->len / 2, n = st->P + st->S;
+    const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
+    k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
+    k_fr_sum<<<(unsigned)(3 * n), kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_CUDA(ctx, cudaMemcpyAsync(evals, st->out, 3 * n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += 3 * n * sizeof(Fr);
+    return SBN_OK;
+}
+
+extern "C" int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r) {
+    if (!st || !r) return SBN_ERR_ARG;
+    if (st->len < 2) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t half = st->len / 2, n = st->P + st->S;
+    Fr* rdev = st->out + 3 * n;
+    SBN_CUDA(ctx, cudaMemcpyAsync(rdev, r, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    k_bind_top_batched<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, rdev);
+    ctx->launches += 1;
+    ctx->h2d += sizeof(Fr);
+    SBN_CUDA(ctx, cudaGetLastError());
+    st->len = half;
+    return SBN_OK;
+}
+
+extern "C" int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final) {
+    if (!st || !A_final || !B_final || !C_final) return SBN_ERR_ARG;
+    if (st->len != 1) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t n = st->P + st->S;
+    for (size_t i = 0; i < n; i++) {
+        SBN_CUDA(ctx, cudaMemcpyAsync(A_final + i, st->A[i], sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        SBN_CUDA(ctx, cudaMemcpyAsync(B_final + i, st->B[i], sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    }
+    // C_final[0] = poly_C_par[0], then one per sequential instance            (sumcheck.rs:309-327)
+    SBN_CUDA(ctx, cudaMemcpyAsync(C_final, st->eq[st->eq_cur], sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    for (size_t k = 0; k < st->S; k++)
+        SBN_CUDA(ctx, cudaMemcpyAsync(C_final + 1 + k, st->C[st->P + k], sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += (2 * n + 1 + st->S) * sizeof(Fr);
+    return SBN_OK;
+}
+
+extern "C" int sbn_bsumcheck_destroy(sbn_bsumcheck* st) {
+    if (!st) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(st->ctx->mu);
+        cudaSetDevice(st->ctx->device);
+        cudaStreamSynchronize(st->ctx->compute);
+    }
+    bsumcheck_free(st);
     return SBN_OK;
 }

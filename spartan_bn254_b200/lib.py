@@ -19,6 +19,8 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+    "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
+    "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
 
 
@@ -46,6 +48,8 @@ def load_library():
     lib.sbn_bases_len.restype = C.c_size_t
     lib.sbn_bases_len.argtypes = [C.c_void_p]
     lib.sbn_bases_window_bits.argtypes = [C.c_void_p]
+    lib.sbn_prodcircuit_num_layers.restype = C.c_size_t
+    lib.sbn_prodcircuit_num_layers.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -399,6 +403,84 @@ class Poly:
     def close(self):
         if self.h and self.ctx.h:
             self.ctx.lib.sbn_poly_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ProdCircuit:
+    """sbn_prodcircuit: every layer of a ProductCircuit (product_tree.rs:39-57) resident in HBM."""
+
+    def __init__(self, ctx, poly):
+        self.ctx = ctx
+        Z = _u64(poly, 4)
+        self.len = Z.shape[0]
+        h = C.c_void_p()
+        ctx._check(ctx.lib.sbn_prodcircuit_create(ctx.h, _ptr(Z), C.c_size_t(self.len), C.byref(h)), "sbn_prodcircuit_create")
+        self.h = h
+        self.num_layers = int(ctx.lib.sbn_prodcircuit_num_layers(h))
+
+    def evaluate(self):
+        out = np.zeros(4, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_prodcircuit_evaluate(self.h, _ptr(out)), "sbn_prodcircuit_evaluate")
+        return out
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_prodcircuit_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchedSumcheckState:
+    """sbn_bsumcheck: the tables of one layer's batched cubic sumcheck (sumcheck.rs:165-330) on the GPU."""
+
+    def __init__(self, ctx, circuits, layer_id, rand, seq=()):
+        self.ctx = ctx
+        self.P, self.S = len(circuits), len(seq)
+        rand = np.zeros((0, 4), dtype=np.uint64) if rand is None or len(rand) == 0 else _u64(rand, 4)
+        self.len = 1 << rand.shape[0]
+        handles = (C.c_void_p * self.P)(*[c.h for c in circuits])
+        keep = [[_u64(t, 4) for t in inst] for inst in seq]
+        for inst in keep:
+            if len(inst) != 3 or any(t.shape[0] != self.len for t in inst):
+                raise SbnError(-2, "sbn_bsumcheck_begin", "a sequential instance needs three tables of 2^|rand| scalars")
+        arrs = [(C.c_void_p * max(1, self.S))(*[inst[w].ctypes.data for inst in keep]) for w in range(3)]
+        h = C.c_void_p()
+        st = ctx.lib.sbn_bsumcheck_begin(ctx.h, handles, C.c_size_t(self.P), C.c_size_t(layer_id), _ptr(rand) if rand.shape[0] else None,
+                                         C.c_size_t(rand.shape[0]), arrs[0] if self.S else None, arrs[1] if self.S else None,
+                                         arrs[2] if self.S else None, C.c_size_t(self.S), C.byref(h))
+        ctx._check(st, "sbn_bsumcheck_begin")
+        self.h = h
+
+    def round_eval(self):
+        e = np.zeros((self.P + self.S, 3, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_bsumcheck_round_eval(self.h, _ptr(e)), "sbn_bsumcheck_round_eval")
+        return e
+
+    def bind(self, r):
+        self.ctx._check(self.ctx.lib.sbn_bsumcheck_bind(self.h, _ptr(_u64(r, 4))), "sbn_bsumcheck_bind")
+        self.len //= 2
+
+    def end(self):
+        n = self.P + self.S
+        a = np.zeros((n, 4), dtype=np.uint64); b = np.zeros((n, 4), dtype=np.uint64)
+        c = np.zeros((1 + self.S, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_bsumcheck_end(self.h, _ptr(a), _ptr(b), _ptr(c)), "sbn_bsumcheck_end")
+        return a, b, c
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_bsumcheck_destroy(self.h)
         self.h = None
 
     def __del__(self):

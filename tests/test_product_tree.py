@@ -1,0 +1,112 @@
+"""Product-layer argument: product circuits + batched cubic sumcheck.
+
+CPU part: the oracle's prover (oracle/product_model.py over the C Merlin restatement) must be accepted by the package's
+verifier (pure-Python Merlin) -- two independent transcripts and two independent restatements of product_tree.rs.
+GPU part: the GPU-backed prover must reproduce the oracle's proof integer for integer (bit-exact field elements) and be
+accepted by the verifier; at full size (2^20 entries) acceptance is the size-independent property."""
+import random
+
+import numpy as np
+import pytest
+
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def _instance(seed, n, P, S):
+    rnd = random.Random(seed)
+    prod = [[rnd.randrange(R) for _ in range(n)] for _ in range(P)]
+    dotp = [tuple([rnd.randrange(R) for _ in range(n // 2)] for _ in range(3)) for _ in range(S)]
+    return prod, dotp
+
+
+def _verify(proof_layers, claims_dotp, claims_prod, dotp_claims, n, label=b"prodtest"):
+    from spartan_bn254_b200.product_tree import (ProductCircuitEvalProofBatched, LayerProofBatched, SumcheckInstanceProof,
+                                                 CompressedUniPoly)
+    from spartan_bn254_b200.transcript import Transcript
+    layers = [LayerProofBatched(SumcheckInstanceProof([CompressedUniPoly(c) for c in polys]), left, right)
+              for polys, left, right in proof_layers]
+    proof = ProductCircuitEvalProofBatched(layers, claims_dotp)
+    return proof.verify(claims_prod, dotp_claims, n, Transcript(label))
+
+
+@pytest.mark.parametrize("n,P,S", [(2, 1, 0), (16, 2, 0), (64, 3, 2), (256, 1, 4)])
+def test_oracle_prover_accepted_by_host_verifier(n, P, S):
+    import oracle as orc
+    import product_model as pm
+    prod, dotp = _instance(7 + n, n, P, S)
+    out = pm.prove_batched(prod, dotp, orc.Transcript(b"prodtest"))
+    assert len(out["layers"]) == n.bit_length() - 1
+    dotp_claims = [pm.dotp_evaluate(*d) for d in dotp]
+    claims, claims_dotp, rand = _verify(out["layers"], out["claims_dotp"], out["claims_prod"], dotp_claims, n)
+    assert rand == out["rand"]
+    # the final claims are the circuits' input polynomials evaluated at rand (product_tree.rs doc of verify)
+    eq = pm.eq_evals(rand)
+    for p, c in zip(prod, claims):
+        assert sum(a * b for a, b in zip(p, eq)) % R == c
+    # a tampered claim is rejected
+    bad = list(out["claims_prod"])
+    bad[0] = (bad[0] + 1) % R
+    with pytest.raises(ValueError):
+        _verify(out["layers"], out["claims_dotp"], bad, dotp_claims, n)
+
+
+def test_unipoly_matches_reference_kats():
+    """unipoly.rs:130-184 tests: interpolation of 2x^2+3x+1 and x^3+2x^2+3x+1 from evaluations."""
+    from spartan_bn254_b200.product_tree import UniPoly
+    q = UniPoly.from_evals([1, 6, 15])
+    assert q.coeffs == [1, 3, 2]
+    c = UniPoly.from_evals([1, 7, 23, 55])
+    assert c.coeffs == [1, 3, 2, 1]
+    assert c.compress().decompress((c.eval_at_zero() + c.eval_at_one()) % R).coeffs == c.coeffs
+    assert c.evaluate(4) == 109
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,P,S", [(2, 1, 0), (8, 2, 1), (64, 3, 2), (1024, 2, 0), (4096, 1, 2)])
+def test_gpu_prover_matches_oracle(ctx, orc, n, P, S):
+    import product_model as pm
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints
+    from spartan_bn254_b200.product_tree import ProductCircuit, DotProductCircuit, ProductCircuitEvalProofBatched
+    from spartan_bn254_b200.transcript import Transcript
+    prod, dotp = _instance(100 + n, n, P, S)
+    want = pm.prove_batched(prod, dotp, orc.Transcript(b"prodtest"))
+    circuits = [ProductCircuit(ctx, fr_vec_from_ints(p)) for p in prod]
+    assert [c.evaluate() for c in circuits] == want["claims_prod"]
+    dcs = [DotProductCircuit(*[fr_vec_from_ints(t) for t in d]) for d in dotp]
+    proof, rand = ProductCircuitEvalProofBatched.prove(ctx, circuits, dcs, Transcript(b"prodtest"))
+    assert rand == want["rand"]
+    assert len(proof.proof) == len(want["layers"])
+    for got, (polys, left, right) in zip(proof.proof, want["layers"]):
+        assert [cp.coeffs_except_linear_term for cp in got.proof.compressed_polys] == polys
+        assert got.claims_prod_left == left and got.claims_prod_right == right
+    assert tuple(proof.claims_dotp) == tuple(want["claims_dotp"])
+    dotp_claims = [pm.dotp_evaluate(*d) for d in dotp]
+    proof.verify(want["claims_prod"], dotp_claims, n, Transcript(b"prodtest"))
+    for c in circuits:
+        c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_prover_full_size_is_accepted(ctx):
+    """2^20-entry circuits (the hash-layer size of a 2^18-constraint instance): acceptance by the verifier, whose work is
+    logarithmic, plus the final claims against a GPU-independent evaluation of one input polynomial at rand."""
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import fr_vec_to_ints, EqPolynomial
+    from spartan_bn254_b200.product_tree import ProductCircuit, ProductCircuitEvalProofBatched
+    from spartan_bn254_b200.transcript import Transcript
+    n, P = 1 << 20, 3
+    polys = [synth.uniform_scalars(40 + i, n) for i in range(P)]
+    circuits = [ProductCircuit(ctx, p) for p in polys]
+    claims = [c.evaluate() for c in circuits]
+    proof, rand = ProductCircuitEvalProofBatched.prove(ctx, circuits, [], Transcript(b"full"))
+    final, _, rand_v = proof.verify(claims, [], n, Transcript(b"full"))
+    assert rand_v == rand
+    # final claim of circuit 0 = its input polynomial at rand: check through the GPU `bound` of the Hyrax path
+    # (a different kernel) with the factored eq tables, then the short dot product on the host
+    from spartan_bn254_b200.hyrax import DensePolynomial, fr_vec_from_ints
+    Lv, Rv = EqPolynomial(rand).compute_factored_evals()
+    LZ = DensePolynomial(polys[0]).bound(fr_vec_from_ints(Lv), ctx)
+    val = sum(a * b for a, b in zip(fr_vec_to_ints(LZ), Rv)) % R
+    assert val == final[0]
+    for c in circuits:
+        c.close()
