@@ -37,6 +37,7 @@ typedef struct sbn_bullet sbn_bullet;  /* device-resident state of one bullet re
 typedef struct sbn_sumcheck sbn_sumcheck;
 typedef struct sbn_prodcircuit sbn_prodcircuit;
 typedef struct sbn_bsumcheck sbn_bsumcheck;
+typedef struct sbn_addrs sbn_addrs;
 
 typedef enum {
     SBN_OK = 0,
@@ -178,7 +179,25 @@ int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r);
 int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final);
 int sbn_bsumcheck_destroy(sbn_bsumcheck* st);
 
+/* ---- f2: the derefs polynomial built on the device.
+ * The address vectors of the Spark commitment are fixed at encode time (sparse_mlpoly_full.rs:204-243); they are
+ * uploaded once (batch x N row addresses, batch x N column addresses).  At prove time only rx / ry cross the bus:
+ * sbn_derefs_commit builds mem_rx = eq(rx), mem_ry = eq(ry) in HBM (:1713-1718), gathers
+ * comb = merge(mem_rx[row_s] ..., mem_ry[col_s] ...) (:245-257, :292-297; zero-padded to a power of two, hyrax.rs:237-247)
+ * and commits it with zero blinds (:301-304 -> hyrax.rs:283-308) over `bases` (R_size = 2^(ell - ell/2) generators).
+ * C_out / inf_out hold 2^(ell/2) points.  poly_out (may be NULL) receives the resident polynomial for its opening. */
+int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const uint32_t* col_addrs, size_t batch, size_t N,
+                     sbn_addrs** out);
+int sbn_addrs_destroy(sbn_addrs* addrs);
+int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                      const sbn_fr* ry, size_t ny, sbn_g1a* C_out, uint8_t* inf_out, sbn_poly** poly_out);
+size_t sbn_poly_len(const sbn_poly* poly);
+int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
+
 /* ---- utilities used by tests / harnesses */
+/* Keccak-f[1600] on a 25-lane little-endian state, in place (host only): the permutation under the Merlin transcript of
+ * the host mirrors (transcript.rs; merlin 3.0 = STROBE-128). */
+void sbn_keccak_f1600(uint64_t* state);
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
 int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
 /* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for

@@ -6,9 +6,10 @@
 //                                                                             -> k_cubic_eval_batched
 //   reference sumcheck.rs:293-306       bound_poly_var_top on every table     -> k_bind_top_batched
 //
-// Pure Fr arithmetic over tables that halve every round: the kernels stream 32-byte scalars from HBM (192 B and six
-// products per index and instance in the evaluation; 64 B in, 32 B out and one product per index in the bind), so they
-// are bound by HBM for the first rounds and by launch latency for the last ones.
+// Pure Fr arithmetic over tables that halve every round.  The evaluation does six Montgomery products per 192 B it
+// streams (32 B per product; the multiplier sustains 6.9e10 products/s = 2.2 TB/s of operands, a third of HBM), so its
+// first rounds are bound by the IMAD pipe, not by HBM (1.41 ms for 12 x 2^21 triples = 78 % of that bound, 1.5 TB/s);
+// the bind (one product per 96 B) is HBM-bound; the last rounds of every layer are launch-latency-bound.
 #pragma once
 #include "opening_kernels.cuh"
 
@@ -47,9 +48,10 @@ k_cubic_eval_batched(const CubicTriple* __restrict__ triples, size_t half, Fr* _
         const Fr c0 = load_fr(t.C + i), c1 = load_fr(t.C + half + i);
         const Fr a2 = fp_sub(fp_add(a1, a1), a0), b2 = fp_sub(fp_add(b1, b1), b0), c2 = fp_sub(fp_add(c1, c1), c0);
         const Fr a3 = fp_sub(fp_add(a2, a1), a0), b3 = fp_sub(fp_add(b2, b1), b0), c3 = fp_sub(fp_add(c2, c1), c0);
-        e0 = fp_add(e0, fr_mul_call(fr_mul_call(a0, b0), c0));
-        e2 = fp_add(e2, fr_mul_call(fr_mul_call(a2, b2), c2));
-        e3 = fp_add(e3, fr_mul_call(fr_mul_call(a3, b3), c3));
+        // six products, inlined: three independent chains of two give the scheduler something to overlap
+        e0 = fp_add(e0, fp_mul(fp_mul(a0, b0), c0));
+        e2 = fp_add(e2, fp_mul(fp_mul(a2, b2), c2));
+        e3 = fp_add(e3, fp_mul(fp_mul(a3, b3), c3));
     }
     Fr* out = partial + (size_t)blockIdx.y * 3 * gridDim.x;
     e0 = block_sum_fr(e0, sm, kDotThreads);
@@ -69,6 +71,19 @@ __global__ void k_bind_top_batched(Fr* const* __restrict__ tables, size_t half, 
     Fr* T = tables[blockIdx.y];
     const Fr lo = load_fr(T + i), hi = load_fr(T + half + i);
     store_fr(T + i, fp_add(lo, fp_mul(load_fr(r), fp_sub(hi, lo))));
+}
+
+// Derefs (sparse_mlpoly_full.rs:245-257 deref_mem, :292-297 Derefs::new, hyrax.rs:237-247 merge): segment s < batch gathers
+// mem_rx[row_addr[s][i]], segment batch + s gathers mem_ry[col_addr[s][i]]; the tail up to the next power of two is zero.
+__global__ void k_derefs_gather(const Fr* __restrict__ mem_rx, const Fr* __restrict__ mem_ry, const uint32_t* __restrict__ row_addr,
+                                const uint32_t* __restrict__ col_addr, size_t batch, size_t N, size_t total, Fr* __restrict__ Z) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t seg = i / N, k = i - seg * N;
+    Fr v = Fr::zero();
+    if (seg < batch) v = load_fr(mem_rx + row_addr[seg * N + k]);
+    else if (seg < 2 * batch) v = load_fr(mem_ry + col_addr[(seg - batch) * N + k]);
+    store_fr(Z + i, v);
 }
 
 }  // namespace sbn

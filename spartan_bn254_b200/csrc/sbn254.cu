@@ -17,6 +17,7 @@
 #include "opening_kernels.cuh"
 #include "ba_kernels.cuh"
 #include "prodtree_kernels.cuh"
+#include "host/keccak.hpp"
 
 using namespace sbn;
 
@@ -117,6 +118,8 @@ extern "C" const char* sbn_strerror(int s) {
 }
 extern "C" const char* sbn_last_cuda_error(const sbn_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
 extern "C" int sbn_version(void) { return 1; }
+// host utility: Keccak-f[1600] for the host mirrors' Merlin transcript (200-byte little-endian state, in place)
+extern "C" void sbn_keccak_f1600(uint64_t* state) { sbn::keccak::permute(state); }
 
 extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
     if (!out) return SBN_ERR_ARG;
@@ -1600,5 +1603,140 @@ extern "C" int sbn_bsumcheck_destroy(sbn_bsumcheck* st) {
         cudaStreamSynchronize(st->ctx->compute);
     }
     bsumcheck_free(st);
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f2: derefs built on the device (address vectors resident, eq tables generated in HBM)
+// ------------------------------------------------------------------------------------------------
+struct sbn_addrs {
+    sbn_ctx* ctx = nullptr;
+    size_t batch = 0, N = 0;
+    uint32_t *row = nullptr, *col = nullptr;
+    uint32_t max_row = 0, max_col = 0;
+};
+
+extern "C" int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const uint32_t* col_addrs, size_t batch, size_t N,
+                                sbn_addrs** out) {
+    if (!ctx || !row_addrs || !col_addrs || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (batch == 0 || N == 0 || batch * N > (size_t(1) << 31)) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    sbn_addrs* a = new (std::nothrow) sbn_addrs();
+    if (!a) return SBN_ERR_OOM;
+    a->ctx = ctx;
+    a->batch = batch;
+    a->N = N;
+    for (size_t i = 0; i < batch * N; i++) {           // the bound checked against the eq-table sizes at every gather
+        a->max_row = std::max(a->max_row, row_addrs[i]);
+        a->max_col = std::max(a->max_col, col_addrs[i]);
+    }
+    const size_t bytes = batch * N * sizeof(uint32_t);
+    if (cudaMalloc(&a->row, bytes) != cudaSuccess || cudaMalloc(&a->col, bytes) != cudaSuccess ||
+        cudaMemcpyAsync(a->row, row_addrs, bytes, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
+        cudaMemcpyAsync(a->col, col_addrs, bytes, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+        if (a->row) cudaFree(a->row);
+        if (a->col) cudaFree(a->col);
+        delete a;
+        ctx->last_error = "sbn_addrs_upload failed";
+        return SBN_ERR_CUDA;
+    }
+    ctx->h2d += 2 * bytes;
+    *out = a;
+    return SBN_OK;
+}
+
+extern "C" int sbn_addrs_destroy(sbn_addrs* a) {
+    if (!a) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(a->ctx->mu);
+        cudaSetDevice(a->ctx->device);
+        cudaStreamSynchronize(a->ctx->compute);
+        cudaFree(a->row);
+        cudaFree(a->col);
+    }
+    delete a;
+    return SBN_OK;
+}
+
+// eq(r) evaluations into `dst` (2^n scalars), using `tmp` (same size) as the other ping-pong buffer; r already on device
+static Fr* eq_evals_device(sbn_ctx* ctx, const Fr* r_dev, size_t n, Fr* dst, Fr* tmp, cudaStream_t s) {
+    Fr* buf[2] = {(n & 1) ? tmp : dst, (n & 1) ? dst : tmp};       // an even/odd number of steps ends in dst
+    const Fr one = Fr::one();
+    cudaMemcpyAsync(buf[0], &one, sizeof(Fr), cudaMemcpyHostToDevice, s);
+    int cur = 0;
+    for (size_t j = 0; j < n; j++) {
+        const size_t size = size_t(1) << j;
+        k_eq_expand<<<(unsigned)((size + 127) / 128), 128, 0, s>>>(buf[cur], size, r_dev + j, buf[cur ^ 1]);
+        cur ^= 1;
+        ctx->launches++;
+    }
+    return buf[cur];
+}
+
+extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                                 const sbn_fr* ry, size_t ny, sbn_g1a* C_out, uint8_t* inf_out, sbn_poly** poly_out) {
+    if (!ctx || !b || !addrs || !rx || !ry || !C_out || !inf_out || b->ctx != ctx || addrs->ctx != ctx) return SBN_ERR_ARG;
+    if (nx == 0 || ny == 0 || nx > 30 || ny > 30) return SBN_ERR_SHAPE;
+    if (addrs->max_row >= (size_t(1) << nx) || addrs->max_col >= (size_t(1) << ny)) return SBN_ERR_SHAPE;   // would index past mem_rx / mem_ry
+    // comb = merge(row_ops_val ++ col_ops_val) zero-padded to a power of two (hyrax.rs:237-247); Hyrax shape hyrax.rs:292
+    const size_t used = 2 * addrs->batch * addrs->N;
+    size_t len = 1;
+    int ell = 0;
+    while (len < used) { len <<= 1; ell++; }
+    const size_t L = size_t(1) << (ell / 2), R = len / L;
+    SBN_TRY(check_commit_shape(b, L, R));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    sbn_poly* p = new (std::nothrow) sbn_poly();
+    if (!p) return SBN_ERR_OOM;
+    p->ctx = ctx;
+    p->len = len;
+    if (cudaMalloc(&p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_derefs_commit: cudaMalloc failed"; return SBN_ERR_OOM; }
+    auto fail = [&](int code) { cudaFree(p->Z); delete p; return code; };
+    const size_t tx = size_t(1) << nx, ty = size_t(1) << ny;
+    int rc;
+    if ((rc = ensure(ctx, ctx->scratch0, 2 * tx * sizeof(Fr))) != SBN_OK || (rc = ensure(ctx, ctx->scratch1, 2 * ty * sizeof(Fr))) != SBN_OK ||
+        (rc = ensure(ctx, ctx->scratch2, (nx + ny) * sizeof(Fr))) != SBN_OK)
+        return fail(rc);
+    Fr* rdev = (Fr*)ctx->scratch2.p;
+    if (cudaMemcpyAsync(rdev, rx, nx * sizeof(Fr), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(rdev + nx, ry, ny * sizeof(Fr), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+        ctx->last_error = "sbn_derefs_commit: upload failed";
+        return fail(SBN_ERR_CUDA);
+    }
+    ctx->h2d += (nx + ny) * sizeof(Fr);
+    const Fr* mem_rx = eq_evals_device(ctx, rdev, nx, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + tx, s);
+    const Fr* mem_ry = eq_evals_device(ctx, rdev + nx, ny, (Fr*)ctx->scratch1.p, (Fr*)ctx->scratch1.p + ty, s);
+    k_derefs_gather<<<(unsigned)((len + 255) / 256), 256, 0, s>>>(mem_rx, mem_ry, addrs->row, addrs->col, addrs->batch, addrs->N, len, p->Z);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) { ctx->last_error = "k_derefs_gather launch failed"; return fail(SBN_ERR_CUDA); }
+    const size_t chunk = commit_chunk_rows(ctx, L);
+    if ((rc = ensure_commit_workspace(ctx, b, chunk, L)) != SBN_OK || (rc = ensure(ctx, ctx->dC, L * sizeof(Affine))) != SBN_OK ||
+        (rc = ensure(ctx, ctx->dinf, L)) != SBN_OK)
+        return fail(rc);
+    std::vector<int> ev_stage;
+    if ((rc = run_commit(ctx, b, p->Z, nullptr, L, R, nullptr, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, s, ev_stage)) != SBN_OK)
+        return fail(rc);
+    if ((rc = download(ctx, C_out, ctx->dC.p, L * sizeof(Affine))) != SBN_OK || (rc = download(ctx, inf_out, ctx->dinf.p, L)) != SBN_OK)
+        return fail(rc);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->last_error = "sbn_derefs_commit: synchronize failed"; return fail(SBN_ERR_CUDA); }
+    collect_profile(ctx, ev_stage);
+    if (poly_out) *poly_out = p;        // the derefs polynomial stays resident for its opening (DerefsEvalProof)
+    else { cudaFree(p->Z); delete p; }
+    return SBN_OK;
+}
+
+extern "C" size_t sbn_poly_len(const sbn_poly* p) { return p ? p->len : 0; }
+
+extern "C" int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* p, sbn_fr* out) {
+    if (!ctx || !p || !out || p->ctx != ctx) return SBN_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_TRY(download(ctx, out, p->Z, p->len * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
 }

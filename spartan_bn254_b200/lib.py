@@ -19,6 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+    "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
@@ -48,6 +49,8 @@ def load_library():
     lib.sbn_bases_len.restype = C.c_size_t
     lib.sbn_bases_len.argtypes = [C.c_void_p]
     lib.sbn_bases_window_bits.argtypes = [C.c_void_p]
+    lib.sbn_poly_len.restype = C.c_size_t
+    lib.sbn_poly_len.argtypes = [C.c_void_p]
     lib.sbn_prodcircuit_num_layers.restype = C.c_size_t
     lib.sbn_prodcircuit_num_layers.argtypes = [C.c_void_p]
     _lib = lib
@@ -391,6 +394,11 @@ class Poly:
         self.ctx._check(st, "sbn_poly_commit")
         return out, inf
 
+    def download(self):
+        out = np.zeros((self.len, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_poly_download(self.ctx.h, self.h, _ptr(out)), "sbn_poly_download")
+        return out
+
     def bound(self, Lvec, L_size, R_size):
         Lvec = _u64(Lvec, 4)
         if Lvec.shape[0] != L_size:
@@ -481,6 +489,51 @@ class BatchedSumcheckState:
     def close(self):
         if self.h and self.ctx.h:
             self.ctx.lib.sbn_bsumcheck_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Addrs:
+    """sbn_addrs: the row / column address vectors of a Spark commitment, resident in HBM (uint32[batch, N] each)."""
+
+    def __init__(self, ctx, row_addrs, col_addrs):
+        self.ctx = ctx
+        row = np.ascontiguousarray(row_addrs, dtype=np.uint32)
+        col = np.ascontiguousarray(col_addrs, dtype=np.uint32)
+        if row.ndim != 2 or row.shape != col.shape:
+            raise SbnError(-2, "sbn_addrs_upload", "row / col address arrays must both be [batch, N]")
+        self.batch, self.N = row.shape
+        h = C.c_void_p()
+        ctx._check(ctx.lib.sbn_addrs_upload(ctx.h, _ptr(row), _ptr(col), C.c_size_t(self.batch), C.c_size_t(self.N), C.byref(h)),
+                   "sbn_addrs_upload")
+        self.h = h
+
+    def derefs_commit(self, bases, rx, ry, keep=True):
+        """Returns (C, inf, Poly or None): the Hyrax commitment of the derefs polynomial built on the device."""
+        rx, ry = _u64(rx, 4), _u64(ry, 4)
+        used = 2 * self.batch * self.N
+        ell = max(0, (used - 1).bit_length())
+        L = 1 << (ell // 2)
+        out = np.zeros((L, 8), dtype=np.uint64)
+        inf = np.zeros(L, dtype=np.uint8)
+        ph = C.c_void_p()
+        st = self.ctx.lib.sbn_derefs_commit(self.ctx.h, bases.h, self.h, _ptr(rx), C.c_size_t(rx.shape[0]), _ptr(ry),
+                                            C.c_size_t(ry.shape[0]), _ptr(out), _ptr(inf), C.byref(ph) if keep else None)
+        self.ctx._check(st, "sbn_derefs_commit")
+        poly = None
+        if keep:
+            poly = Poly.__new__(Poly)
+            poly.ctx, poly.h, poly.len = self.ctx, ph, int(self.ctx.lib.sbn_poly_len(ph))
+        return out, inf, poly
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_addrs_destroy(self.h)
         self.h = None
 
     def __del__(self):

@@ -4,6 +4,8 @@ logic in the reference too -- the GPU backend only needs the challenges it produ
 Python restatement used by the Python host mirror and its tests.  Check value: merlin's published test
 vector (tests/test_transcript.py)."""
 
+import ctypes as _ctypes
+
 _MASK = (1 << 64) - 1
 _RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
        0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
@@ -33,6 +35,24 @@ def keccak_f(a):
     return a
 
 
+_native = False
+
+
+def _native_keccak():
+    """sbn_keccak_f1600 from libsbn254.so when the library has been built; the Python permutation above otherwise (the
+    transcript is host logic and needs no GPU)."""
+    global _native
+    if _native is False:
+        try:
+            from .lib import load_library
+            fn = load_library().sbn_keccak_f1600
+            fn.restype = None
+            _native = fn
+        except Exception:
+            _native = None
+    return _native
+
+
 _R = 166
 _FLAG_I, _FLAG_A, _FLAG_C, _FLAG_T, _FLAG_M, _FLAG_K = 1, 2, 4, 8, 16, 32
 
@@ -51,6 +71,11 @@ class Transcript:
 
     # ---- STROBE
     def _permute(self):
+        f = _native_keccak()
+        if f is not None:           # libsbn254's host-side Keccak-f (a product-layer proof draws thousands of challenges)
+            buf = (_ctypes.c_uint64 * 25).from_buffer(self.st)
+            f(buf)
+            return
         lanes = [int.from_bytes(self.st[8 * i: 8 * i + 8], "little") for i in range(25)]
         lanes = keccak_f(lanes)
         for i, l in enumerate(lanes):
