@@ -33,6 +33,7 @@ WORKLOADS = {
     "cfg1_1024x1024": (1024, 1024),
     "cfg2_4096x4096": (4096, 4096),
     "cfg2_4096x8192": (4096, 8192),
+    "enc_8192x8192": (8192, 8192),      # comb_ops of the keyless encode (sparse_mlpoly_full.rs:183); use with --scalars small
 }
 A_ADDS_PER_POINT = {1024: 26.0, 2048: 24.0, 4096: 22.0, 8192: 21.0}
 IMAD_PER_FQMUL = 264       # 8x8 (lo+hi) products + Montgomery reduction, 32-bit limbs
@@ -48,7 +49,8 @@ def parse():
     ap.add_argument("--workload", default="cfg1_1024x1024", choices=sorted(WORKLOADS))
     ap.add_argument("--gens", default="distinct", choices=["distinct", "ref"],
                     help="distinct: k_j*G random (throughput headline); ref: the reference's degenerate MultiCommitGens")
-    ap.add_argument("--scalars", default="uniform", choices=["uniform", "derefs"])
+    ap.add_argument("--scalars", default="uniform", choices=["uniform", "derefs", "small"],
+                    help="uniform mod r | derefs-style gathers with zero rows | small: 21-bit values (comb_ops-like)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -190,11 +192,15 @@ def main():
     bases = ctx.bases(G, h)
     nbuf = max(2, -(-(160 << 20) // (L * R * 32)) + 1)      # rotate inputs: total > 126 MiB L2
     nbuf = min(nbuf, 8)
+    if L * R * 32 > (1 << 30):
+        nbuf = 1                                            # one 2 GiB input already exceeds L2 many times over
     host_bufs, dev_bufs = [], []
     for i in range(nbuf):
         seed = 1 + 131 * rank + i
         if args.scalars == "uniform":
             z = synth.uniform_scalars(seed, L * R)
+        elif args.scalars == "small":
+            z = ctx.fr_from_canonical(synth.small_scalars_canonical(seed, L * R))
         else:
             z = synth.derefs_scalars((L * R).bit_length() - 1, seed_table=2 + seed, seed_addr=3 + seed)
         t = torch.from_numpy(z.view(np.int64)).pin_memory()
@@ -251,10 +257,12 @@ def main():
     points_per_step = L * R * world
     value = points_per_step * args.steps / (ms_max * 1e-3)
 
-    # ---- stage profile of one commit on the library's own stream (CUDA events inside the library); a single chunk so
-    #      the stages run back to back and each event pair brackets exactly one launch of that kernel
-    ctx.set("chunk_rows", L)
-    ctx.hyrax_commit_device(bases, dev_bufs[0].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=0)
+    # ---- stage profile on the library's own stream (CUDA events inside the library): the first `prof_rows` rows as ONE
+    #      chunk, so the stages run back to back and each event pair brackets exactly one launch set of that stage
+    #      (a single chunk of every row would need > 100 GB of workspace at 8192 x 8192)
+    prof_rows = L if L * R <= (1 << 24) else max(1024, (1 << 24) // R)
+    ctx.set("chunk_rows", prof_rows)
+    ctx.hyrax_commit_device(bases, dev_bufs[0].data_ptr(), prof_rows, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=0)
     prof = ctx.last_commit_profile()
 
     # ---- end to end: pinned host buffers through the host-pointer C ABI (library defaults: a short first chunk, then
@@ -278,13 +286,13 @@ def main():
         W = (254 + bases.window_bits) // bases.window_bits
         # algorithmic integer work of the dominant kernel (bucket accumulation): one XYZZ mixed addition per
         # (scalar, window) pair = W * 10 * 264 32-bit multiply-adds per point, all launches of a commit
-        alg_imad_acc = float(L) * R * W * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
+        alg_imad_acc = float(prof_rows) * R * W * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         achieved = alg_imad_acc / (acc["ms"] * 1e-3) if acc["ms"] > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get("k_accumulate_dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get(args.workload, {}).get("accumulate_stage_dram_bytes_per_commit")
             except Exception:
                 traffic = None
         step_alg = A_ADDS_PER_POINT.get(R, 26.0) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
@@ -302,18 +310,23 @@ def main():
             "clocks": clocks,
             "roofline": {
                 "bound": "int32 multiply-add (IMAD pipe); not hbm, not tensor: modular integer arithmetic",
-                "kernel": "k_accumulate", "achieved": achieved / 1e12, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
+                "kernel": "bucket accumulation stage (k_accumulate; with batched-affine rounds: k_ba_prefix / k_ba_invert / "
+                          "k_ba_finish + k_accumulate_pts)",
+                "achieved": achieved / 1e12, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
                 "frac": achieved / peak_imad if peak_imad else None, "traffic": traffic,
+                "frac_note": "algorithmic work is counted as SURVEY 8(d) defines it (W x 10 x 264 IMAD per point, i.e. XYZZ "
+                             "mixed additions); the batched-affine rounds replace part of those 10-product additions by "
+                             "6-product affine ones, so the algorithmic rate may exceed the pipe's peak",
                 "peak_source": "measured live on this GPU: independent mad.lo.u32 streams (sbn_microbench kind 0); "
                                "MEASURED_PEAKS.json has no integer-pipe figure",
                 "algorithmic_imad_per_launch_set": alg_imad_acc,
-                "kernel_ms_per_commit": acc["ms"], "kernel_launches_per_commit": acc["launches"],
+                "kernel_ms_per_launch_set": acc["ms"], "rows_per_launch_set": prof_rows,
                 "whole_step_frac": (value / world) * step_alg / peak_imad if peak_imad else None,
                 "whole_step_imad_alg_per_point": step_alg,
                 "hbm": {"algorithmic_bytes_per_step": L * R * 32 + L * 64,
                         "achieved_GBps": (L * R * 32 + L * 64) / (ms_max / args.steps * 1e-3) / 1e9},
             },
-            "stage_ms": {k: v["ms"] for k, v in prof.items()},
+            "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_rows": prof_rows,
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(R, L)
