@@ -16,10 +16,10 @@
 //                d_j (x2 - x1; 2*y1 for a doubling; 1 for a pair with nothing to add) and their running products,
 //                which it stores; a shuffle scan gives every thread the product O_t of the OTHER lanes' totals and the
 //                warp the product T of all of them.
-//   k_ba_invert  one thread per warp of the previous launch: T^-1 (Fermat).
+//   k_ba_invert  one thread per warp of the previous launch: T^-1 (safegcd division steps, fp.cuh).
 //   k_ba_finish  running = T^-1 * O_t = (own total)^-1; walking the pairs backwards yields each 1/d_j with two
 //                products, then lambda, x3, y3 with three more: 6 products per addition in total, plus
-//                (11 + 1) / B for the scans and 380 / (32 B) for the inversion.
+//                (11 + 1) / B for the scans and ~70 / (32 B) for the inversion.
 //
 // P + P, P + (-P), identity operands and NULL padding are explicit cases (the reference's generators repeat the same
 // point -- group.rs:110-132 -- so doublings are common, not exceptional).
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(64)
 k_ba_invert(const Fq* __restrict__ warp_tot, size_t n, Fq* __restrict__ inv) {
     const size_t i = (size_t)blockIdx.x * 64 + threadIdx.x;
     if (i >= n) return;
-    store_fq(inv + i, fq_inv<MulInline>(load_fq(warp_tot + i)));
+    store_fq(inv + i, fp_inv_fast(load_fq(warp_tot + i)));
 }
 
 template <bool FIRST>

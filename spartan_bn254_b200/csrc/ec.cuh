@@ -158,7 +158,7 @@ SBN_HD Fq fq_inv(const Fq& a) {
 template <class MP = MulInline>
 SBN_HD Affine xyzz_to_affine(const XYZZ& p) {
     if (p.is_identity()) return Affine::identity();
-    Fq I = fq_inv<MP>(MP::mul(p.ZZ, p.ZZZ));
+    Fq I = fp_inv_fast(MP::mul(p.ZZ, p.ZZZ));      // safegcd division steps: ~5x fewer instructions than x^(p-2)
     Affine r;
     r.x = MP::mul(p.X, MP::mul(p.ZZZ, I));
     r.y = MP::mul(p.Y, MP::mul(p.ZZ, I));

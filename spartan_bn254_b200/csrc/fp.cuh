@@ -75,6 +75,15 @@ struct FqParams {   // base field of BN254 (coordinates of G1)
         return v[i];
     }
     static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32
+    static SBN_HD constexpr int32_t P30(int i) {  // p in nine 30-bit limbs (fp_inv_plain)
+        constexpr int32_t v[9] = {0x187cfd47, 0x3082305b, 0x71ca8d3, 0x205aa45a, 0x1585d97, 0x116da06, 0x1a029b85, 0x139cb84c, 0x3064};
+        return v[i];
+    }
+    static constexpr uint32_t INV30 = 0x1b799c77u;  // p^-1 mod 2^30
+    static SBN_HD constexpr uint32_t R3(int i) {  // 2^768 mod p
+        constexpr uint32_t v[8] = {0xda1530dfu, 0xb1cd6dafu, 0xa7283db6u, 0x62f210e6u, 0x0ada0afbu, 0xef7f0b0cu, 0x2d592544u, 0x20fd6e90u};
+        return v[i];
+    }
 };
 struct FrParams {   // scalar field of BN254
     static SBN_HD constexpr uint32_t P(int i) {
@@ -90,6 +99,15 @@ struct FrParams {   // scalar field of BN254
         return v[i];
     }
     static constexpr uint32_t INV = 0xefffffffu;
+    static SBN_HD constexpr int32_t P30(int i) {
+        constexpr int32_t v[9] = {0x30000001, 0xf87d64f, 0x1b970914, 0xcfa121e, 0x1585d28, 0x116da06, 0x1a029b85, 0x139cb84c, 0x3064};
+        return v[i];
+    }
+    static constexpr uint32_t INV30 = 0x10000001u;
+    static SBN_HD constexpr uint32_t R3(int i) {
+        constexpr uint32_t v[8] = {0xb4bf0040u, 0x5e94d8e1u, 0x1cfbb6b8u, 0x2a489cbeu, 0xa19fcfedu, 0x893cc664u, 0x7fcc657cu, 0x0cf8594bu};
+        return v[i];
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +288,119 @@ SBN_HD Fp<F> fp_inv(const Fp<F>& a) {
         }
     }
     return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inversion by the Bernstein-Yang "safegcd" division steps (2019/266), in the 30-bit signed-limb form libsecp256k1
+// popularised: 20 batches of 30 branch-free division steps on the low words of (f, g) = (p, x), each batch summarised by a
+// 2x2 integer matrix that is then applied to the full-width (f, g) and, modulo p, to (d, e).  After 600 steps g = 0,
+// f = +-1 and d = +-x^-1.  About 20 k instructions against ~108 k for Fermat's x^(p-2) (380 Montgomery products), and no
+// data-dependent branch -- the 32 lanes of a warp invert 32 different values in lockstep.  Works on plain integers mod p.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+SBN_HD void fp_inv_plain(const uint32_t x[8], uint32_t out[8]) {
+    const int32_t M30 = (int32_t)((1u << 30) - 1);
+    int32_t d[9], e[9], f[9], g[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { d[i] = 0; e[i] = 0; f[i] = F::P30(i); }
+    e[0] = 1;
+    // 8 x 32 bits -> 9 x 30 bits
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int bit = 30 * i, w = bit >> 5, off = bit & 31;
+        uint32_t v = w < 8 ? x[w] >> off : 0u;
+        if (off > 2 && w + 1 < 8) v |= x[w + 1] << (32 - off);
+        g[i] = (int32_t)(v & (uint32_t)M30);
+    }
+    int32_t zeta = -1;   // -(delta + 1/2), delta = 1/2 initially
+#pragma unroll 1
+    for (int batch = 0; batch < 20; batch++) {
+        // 30 division steps on the low limbs
+        uint32_t u = 1, v = 0, q = 0, r = 1;
+        uint32_t fl = (uint32_t)f[0], gl = (uint32_t)g[0];
+#pragma unroll 6
+        for (int i = 0; i < 30; i++) {
+            uint32_t c1 = (uint32_t)(zeta >> 31);
+            const uint32_t c2 = 0u - (gl & 1u);
+            const uint32_t xx = (fl ^ c1) - c1, yy = (u ^ c1) - c1, zz = (v ^ c1) - c1;
+            gl += xx & c2; q += yy & c2; r += zz & c2;
+            c1 &= c2;
+            zeta = (int32_t)(((uint32_t)zeta ^ c1) - 1u);
+            fl += gl & c1; u += q & c1; v += r & c1;
+            gl >>= 1; u <<= 1; v <<= 1;
+        }
+        const int64_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)r;
+        // (d, e) <- t * (d, e) / 2^30 mod p
+        {
+            const int32_t sd = d[8] >> 31, se = e[8] >> 31;
+            int32_t md = ((int32_t)tu & sd) + ((int32_t)tv & se), me = ((int32_t)tq & sd) + ((int32_t)tr & se);
+            int64_t cd = tu * d[0] + tv * e[0], ce = tq * d[0] + tr * e[0];
+            md -= (int32_t)((F::INV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+            me -= (int32_t)((F::INV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+            cd += (int64_t)F::P30(0) * md;
+            ce += (int64_t)F::P30(0) * me;
+            cd >>= 30; ce >>= 30;
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                cd += tu * d[i] + tv * e[i] + (int64_t)F::P30(i) * md;
+                ce += tq * d[i] + tr * e[i] + (int64_t)F::P30(i) * me;
+                d[i - 1] = (int32_t)cd & M30; cd >>= 30;
+                e[i - 1] = (int32_t)ce & M30; ce >>= 30;
+            }
+            d[8] = (int32_t)cd;
+            e[8] = (int32_t)ce;
+        }
+        // (f, g) <- t * (f, g) / 2^30
+        {
+            int64_t cf = tu * f[0] + tv * g[0], cg = tq * f[0] + tr * g[0];
+            cf >>= 30; cg >>= 30;
+#pragma unroll
+            for (int i = 1; i < 9; i++) {
+                cf += tu * f[i] + tv * g[i];
+                cg += tq * f[i] + tr * g[i];
+                f[i - 1] = (int32_t)cf & M30; cf >>= 30;
+                g[i - 1] = (int32_t)cg & M30; cg >>= 30;
+            }
+            f[8] = (int32_t)cf;
+            g[8] = (int32_t)cg;
+        }
+    }
+    // d in (-2p, p), times the sign of f; bring it to [0, p)
+    {
+        int32_t cond_add = d[8] >> 31;
+#pragma unroll
+        for (int i = 0; i < 9; i++) d[i] += F::P30(i) & cond_add;
+        const int32_t cond_neg = f[8] >> 31;
+#pragma unroll
+        for (int i = 0; i < 9; i++) d[i] = (d[i] ^ cond_neg) - cond_neg;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+        cond_add = d[8] >> 31;
+#pragma unroll
+        for (int i = 0; i < 9; i++) d[i] += F::P30(i) & cond_add;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+    }
+    // 9 x 30 bits -> 8 x 32 bits
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int bit = 32 * w, i = bit / 30, off = bit % 30;
+        uint32_t v = (uint32_t)d[i] >> off;
+        v |= (uint32_t)d[i + 1] << (30 - off);
+        if (30 - off + 30 < 32 && i + 2 < 9) v |= (uint32_t)d[i + 2] << (60 - off);
+        out[w] = v;
+    }
+}
+
+// Montgomery-form inverse: a = xR  ->  x^-1 R = (xR)^-1 * R^2 = montmul((xR)^-1, R^3).  a == 0 returns 0.
+template <class F>
+SBN_HD Fp<F> fp_inv_fast(const Fp<F>& a) {
+    Fp<F> t;
+    fp_inv_plain<F>(a.l, t.l);
+    Fp<F> r3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r3.l[i] = F::R3(i);
+    return fp_mul(t, r3);
 }
 
 typedef Fp<FqParams> Fq;

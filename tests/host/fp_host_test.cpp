@@ -74,6 +74,18 @@ static int run(int mod, const char* name) {
         Fp<F> inv = fp_inv(a), prod = fp_mul(a, inv), one = Fp<F>::one();
         if (!(prod == one)) { printf("%s inverse mismatch\n", name); fails++; }
     }
+    // safegcd inverse (fp_inv_fast) against the oracle's inverse and the Fermat chain, including 0, 1, p - 1
+    for (int it = 0; it < 5000; it++) {
+        Fp<F> a;
+        rand_elem<F>(mod, a, it < 5 ? it : 0);
+        ofp oa, oi;
+        memcpy(oa.l, a.l, 32);
+        const int nonzero = orc_fp_inv(mod, &oa, &oi);
+        Fp<F> fast = fp_inv_fast(a);
+        if (!nonzero) { if (!fast.is_zero()) { printf("%s fast inverse of 0 != 0\n", name); fails++; } continue; }
+        if (memcmp(fast.l, oi.l, 32)) { if (fails < 5) printf("%s fast inverse mismatch at it=%d\n", name, it); fails++; }
+        if (it < 50 && !(fast == fp_inv(a))) { printf("%s fast inverse != Fermat\n", name); fails++; }
+    }
     // mont round trip
     {
         Fp<F> a;
