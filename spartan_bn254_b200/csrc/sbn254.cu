@@ -340,14 +340,14 @@ extern "C" int sbn_bases_window_bits(const sbn_bases* b) { return b ? b->c : 0; 
 // ------------------------------------------------------------------------------------------------
 // commit pipeline
 // ------------------------------------------------------------------------------------------------
-// Batched-affine rounds for a chunk of `rows` rows.  Measured on B200: one round takes ~8 % off the accumulation at 1024
-// generators, two rounds ~14 % at 8192, and every round adds ~0.2 ms of dependency-chain latency (the shared
-// inversion) -- so the rounds only pay once a chunk holds more than ~16 M list entries.
+// Batched-affine rounds for a chunk of `rows` rows.  Measured on B200 (scripts/sweep_sort.py ... ba_rounds): one round
+// takes 8-13 % off the accumulation once a chunk holds more than ~8 M list entries (below that the three extra launches
+// per round cost what they save); a second round adds ~4 % at >= 4096 generators; a third loses to the padding.
 static int ba_rounds_for(const sbn_ctx* ctx, const sbn_bases* b, size_t rows) {
     if (ctx->ba_rounds >= 0) return (int)ctx->ba_rounds;
     const double entries = double(rows) * b->W * b->n1;
-    if (entries < 16e6) return 0;
-    return b->n1 >= 4096 ? 2 : 1;
+    if (entries < 8e6) return 0;
+    return (b->n1 >= 4096 && entries >= 32e6) ? 2 : 1;
 }
 
 static int task_cap_for(const sbn_ctx* ctx, const sbn_bases* b, int ba) {

@@ -141,7 +141,7 @@ def test_commit_chunking_and_window_override(ctx, orc):
 @pytest.mark.parametrize("gens_kind,kind,ell", [("ref", "uniform", 12), ("ref", "derefs", 15), ("distinct", "uniform", 13),
                                                ("ref", "small", 14)])
 def test_batched_affine_rounds_match_oracle(orc, rounds, gens_kind, kind, ell):
-    """The batched-affine pre-reduction (ba_kernels.cuh) is normally chosen only for chunks of > 16 M list entries; forced
+    """The batched-affine pre-reduction (ba_kernels.cuh) is normally chosen only for chunks of > 8 M list entries; forced
     here on small shapes.  The reference generators repeat the same point (group.rs:110-132), so the P + P, P + (-P) and
     identity cases of the affine rounds are all exercised; results must stay bit-exact."""
     from spartan_bn254_b200 import Context, synth
