@@ -51,6 +51,9 @@ def parse():
                     help="distinct: k_j*G random (throughput headline); ref: the reference's degenerate MultiCommitGens")
     ap.add_argument("--scalars", default="uniform", choices=["uniform", "derefs", "small"],
                     help="uniform mod r | derefs-style gathers with zero rows | small: 21-bit values (comb_ops-like)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU commits the workload's rows (default); strong: the workload's rows are divided "
+                         "across the GPUs (BASELINE configs[2]: the keyless derefs commitment sharded by rows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -182,6 +185,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ctx = Context(local_rank)
     L, R = WORKLOADS[args.workload]
+    if args.scaling == "strong":
+        if L % world:
+            raise SystemExit("--scaling strong needs the row count to divide by the number of GPUs")
+        L //= world             # contiguous row block of this rank (hyrax.rs:259-265: rows are independent)
 
     # ---- generators (resident for the whole run) and synthetic scalars
     if args.gens == "distinct":
@@ -284,6 +291,8 @@ def main():
     if rank == 0:
         acc = prof["accumulate"]
         W = (254 + bases.window_bits) // bases.window_bits
+        if args.scalars == "small":     # 21-bit values: only the windows that can hold a non-zero digit count as work
+            W = min(W, -(-22 // bases.window_bits))
         # algorithmic integer work of the dominant kernel (bucket accumulation): one XYZZ mixed addition per
         # (scalar, window) pair = W * 10 * 264 32-bit multiply-adds per point, all launches of a commit
         alg_imad_acc = float(prof_rows) * R * W * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
@@ -296,9 +305,11 @@ def main():
             except Exception:
                 traffic = None
         step_alg = A_ADDS_PER_POINT.get(R, 26.0) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
+        if args.scalars == "small":
+            step_alg = (W + 2.0 * (1 << (bases.window_bits - 1)) / R) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32x8 Montgomery (integer, IMAD.WIDE carry chains)", "data": "synthetic",
             "config": {"workload": args.workload, "rows_per_gpu": L, "generators": R, "window_bits": bases.window_bits,
                        "gens": args.gens, "scalars": args.scalars, "blinds": "zero (derefs-style, hyrax.rs:301-305)",
