@@ -191,6 +191,17 @@ int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const uint32_t* co
 int sbn_addrs_destroy(sbn_addrs* addrs);
 int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
                       const sbn_fr* ry, size_t ny, sbn_g1a* C_out, uint8_t* inf_out, sbn_poly** poly_out);
+/* Memory-checking timestamps of the same commitment (AddrTimestamps::new, sparse_mlpoly_full.rs:212-243): read_ts per
+ * operation (batch x N) and audit_ts per memory cell (num_cells, a power of two) for the row and the column side. */
+int sbn_addrs_set_timestamps(sbn_addrs* addrs, const uint32_t* row_read_ts, const uint32_t* row_audit_ts,
+                             const uint32_t* col_read_ts, const uint32_t* col_audit_ts, size_t num_cells);
+/* Layers::new for one side (0 = row over eq(rx), 1 = column over eq(ry); sparse_mlpoly_full.rs:745-841): hashes
+ * h(addr, val, ts) = ts r_hash^2 + val r_hash + addr - r_multiset_check of the init / read / write / audit sets and
+ * builds their product circuits, all on the device.  circuits_out receives 2 + 2 * batch handles in the order of
+ * ProductLayer: init, read_vec[0..batch), write_vec[0..batch), audit. */
+int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* addrs, int side, const sbn_fr* r, size_t nr, const sbn_fr* r_hash,
+                        const sbn_fr* r_multiset_check, sbn_prodcircuit** circuits_out);
+int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer, sbn_fr* out /* len >> layer scalars */);
 size_t sbn_poly_len(const sbn_poly* poly);
 int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
 

@@ -13,6 +13,9 @@ reference line by line on plain lists of canonical integers mod r and drives the
   reference sumcheck.rs:165-330       SumcheckInstanceProof::prove_cubic_batched       -> prove_cubic_batched()
   reference product_tree.rs:251-392   ProductCircuitEvalProofBatched::prove            -> prove_batched()
 
+  reference sparse_mlpoly_full.rs:212-243 AddrTimestamps::new                          -> addr_timestamps()
+  reference sparse_mlpoly_full.rs:745-798 Layers::build_hash_layer                     -> build_hash_layer()
+
 PARITY STATUS: unpinned by reference fixtures (the reference has no known-answer tests for this argument and cannot be
 built here); pinned by exact field arithmetic (every quantity is a field element, so any correct implementation produces
 the same integers) and by the verifier restated in the package accepting the proofs.
@@ -174,3 +177,33 @@ def prove_batched(prod_polys, dotp, t):
         layers.append((polys, left, right))
     return {"layers": layers, "claims_dotp": claims_dotp_final, "rand": rand,
             "claims_prod": [c.evaluate() for c in circuits]}
+
+
+def addr_timestamps(num_cells, ops_addr):
+    """ops_addr: list of address lists (one per instance).  Returns (read_ts per instance, audit_ts)."""
+    audit_ts = [0] * num_cells
+    read_ts_vec = []
+    for inst in ops_addr:
+        read_ts = [0] * len(inst)
+        for i, addr in enumerate(inst):
+            assert addr < num_cells
+            r_ts = audit_ts[addr]
+            read_ts[i] = r_ts
+            audit_ts[addr] = r_ts + 1
+        read_ts_vec.append(read_ts)
+    return read_ts_vec, audit_ts
+
+
+def build_hash_layer(eval_table, addrs_vec, derefs_vec, read_ts_vec, audit_ts, r_hash, r_multiset_check):
+    r_hash_sqr = r_hash * r_hash % R
+
+    def h(addr, val, ts):
+        return (ts * r_hash_sqr + val * r_hash + addr) % R
+
+    init = [(h(i, eval_table[i], 0) - r_multiset_check) % R for i in range(len(eval_table))]
+    audit = [(h(i, eval_table[i], audit_ts[i]) - r_multiset_check) % R for i in range(len(eval_table))]
+    reads, writes = [], []
+    for addrs, derefs, read_ts in zip(addrs_vec, derefs_vec, read_ts_vec):
+        reads.append([(h(a, d, t) - r_multiset_check) % R for a, d, t in zip(addrs, derefs, read_ts)])
+        writes.append([(h(a, d, t + 1) - r_multiset_check) % R for a, d, t in zip(addrs, derefs, read_ts)])
+    return init, reads, writes, audit

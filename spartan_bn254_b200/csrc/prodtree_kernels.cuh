@@ -86,4 +86,45 @@ __global__ void k_derefs_gather(const Fr* __restrict__ mem_rx, const Fr* __restr
     store_fr(Z + i, v);
 }
 
+// Hash layer of the memory-checking argument (sparse_mlpoly_full.rs:745-798 build_hash_layer):
+//     h(addr, val, ts) = ts * r_hash^2 + val * r_hash + addr - r_multiset_check .
+// Addresses and timestamps are small integers kept as uint32; they enter Montgomery form through one product each:
+// montmul(c, R^2) = c R for an address, montmul(c, r_hash^2 R^2) = c r_hash^2 R for a timestamp (`rh2_R2`).
+struct HashParams { Fr rh, rh2, rh2_R2, r_ms; };
+
+__device__ __forceinline__ Fr fr_R2() {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = FrParams::R2(i);
+    return r;
+}
+__device__ __forceinline__ Fr fr_from_u32(uint32_t c) {
+    Fr v = Fr::zero();
+    v.l[0] = c;
+    return v;
+}
+
+// init[i] = h(i, mem[i], 0), audit[i] = h(i, mem[i], audit_ts[i])                       (:758-770)
+__global__ void k_hash_mem(const Fr* __restrict__ mem, const uint32_t* __restrict__ audit_ts, size_t M, HashParams hp,
+                           Fr* __restrict__ init_out, Fr* __restrict__ audit_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const Fr base = fp_sub(fp_add(fp_mul(load_fr(mem + i), hp.rh), fp_mul(fr_from_u32((uint32_t)i), fr_R2())), hp.r_ms);
+    store_fr(init_out + i, base);
+    store_fr(audit_out + i, fp_add(base, fp_mul(fr_from_u32(audit_ts[i]), hp.rh2_R2)));
+}
+
+// read[j] = h(addr[j], mem[addr[j]], read_ts[j]), write[j] = h(addr[j], mem[addr[j]], read_ts[j] + 1)   (:775-793);
+// mem[addr[j]] is the derefs value of the operation (deref_mem, :245-251).
+__global__ void k_hash_ops(const Fr* __restrict__ mem, const uint32_t* __restrict__ addr, const uint32_t* __restrict__ read_ts,
+                           size_t N, HashParams hp, Fr* __restrict__ read_out, Fr* __restrict__ write_out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint32_t a = addr[j];
+    Fr v = fp_add(fp_mul(load_fr(mem + a), hp.rh), fp_mul(fr_from_u32(a), fr_R2()));
+    v = fp_sub(fp_add(v, fp_mul(fr_from_u32(read_ts[j]), hp.rh2_R2)), hp.r_ms);
+    store_fr(read_out + j, v);
+    store_fr(write_out + j, fp_add(v, hp.rh2));
+}
+
 }  // namespace sbn

@@ -1614,6 +1614,9 @@ struct sbn_addrs {
     size_t batch = 0, N = 0;
     uint32_t *row = nullptr, *col = nullptr;
     uint32_t max_row = 0, max_col = 0;
+    // memory-checking timestamps (AddrTimestamps::new, sparse_mlpoly_full.rs:212-243): read_ts per operation, audit_ts per cell
+    size_t num_cells = 0;
+    uint32_t *read_ts[2] = {nullptr, nullptr}, *audit_ts[2] = {nullptr, nullptr};
 };
 
 extern "C" int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const uint32_t* col_addrs, size_t batch, size_t N,
@@ -1656,8 +1659,35 @@ extern "C" int sbn_addrs_destroy(sbn_addrs* a) {
         cudaStreamSynchronize(a->ctx->compute);
         cudaFree(a->row);
         cudaFree(a->col);
+        for (int k = 0; k < 2; k++) {
+            if (a->read_ts[k]) cudaFree(a->read_ts[k]);
+            if (a->audit_ts[k]) cudaFree(a->audit_ts[k]);
+        }
     }
     delete a;
+    return SBN_OK;
+}
+
+extern "C" int sbn_addrs_set_timestamps(sbn_addrs* a, const uint32_t* row_read_ts, const uint32_t* row_audit_ts,
+                                        const uint32_t* col_read_ts, const uint32_t* col_audit_ts, size_t num_cells) {
+    if (!a || !row_read_ts || !row_audit_ts || !col_read_ts || !col_audit_ts) return SBN_ERR_ARG;
+    if (num_cells == 0 || (num_cells & (num_cells - 1)) || a->max_row >= num_cells || a->max_col >= num_cells) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = a->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t* src_r[2] = {row_read_ts, col_read_ts};
+    const uint32_t* src_a[2] = {row_audit_ts, col_audit_ts};
+    const size_t ops_bytes = a->batch * a->N * sizeof(uint32_t), mem_bytes = num_cells * sizeof(uint32_t);
+    for (int k = 0; k < 2; k++) {
+        if (!a->read_ts[k]) SBN_CUDA(ctx, cudaMalloc(&a->read_ts[k], ops_bytes));
+        if (a->audit_ts[k] && a->num_cells != num_cells) { cudaFree(a->audit_ts[k]); a->audit_ts[k] = nullptr; }
+        if (!a->audit_ts[k]) SBN_CUDA(ctx, cudaMalloc(&a->audit_ts[k], mem_bytes));
+        SBN_CUDA(ctx, cudaMemcpyAsync(a->read_ts[k], src_r[k], ops_bytes, cudaMemcpyHostToDevice, ctx->compute));
+        SBN_CUDA(ctx, cudaMemcpyAsync(a->audit_ts[k], src_a[k], mem_bytes, cudaMemcpyHostToDevice, ctx->compute));
+    }
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    ctx->h2d += 2 * (ops_bytes + mem_bytes);
+    a->num_cells = num_cells;
     return SBN_OK;
 }
 
@@ -1737,6 +1767,87 @@ extern "C" int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* p, sbn_fr* out) {
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     SBN_TRY(download(ctx, out, p->Z, p->len * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f1 (cont.): hash layer + product circuits of one side of the memory-checking network, built on the device
+// ------------------------------------------------------------------------------------------------
+static sbn_prodcircuit* prodcircuit_alloc(sbn_ctx* ctx, size_t len) {
+    sbn_prodcircuit* pc = new (std::nothrow) sbn_prodcircuit();
+    if (!pc) return nullptr;
+    pc->ctx = ctx;
+    pc->len = len;
+    size_t total = 0;
+    for (size_t n = len; n >= 2; n >>= 1) { pc->off.push_back(total); total += n; pc->num_layers++; }
+    if (cudaMalloc(&pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; return nullptr; }
+    return pc;
+}
+
+static void prodcircuit_build_upper(sbn_ctx* ctx, sbn_prodcircuit* pc, cudaStream_t s) {
+    for (int l = 0; l + 1 < pc->num_layers; l++) {
+        const size_t half = (pc->len >> l) / 2;
+        k_product_layer<<<(unsigned)((half + 127) / 128), 128, 0, s>>>(pc->buf + pc->off[l], half, pc->buf + pc->off[l + 1]);
+        ctx->launches++;
+    }
+}
+
+extern "C" int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* a, int side, const sbn_fr* r, size_t nr, const sbn_fr* r_hash,
+                                   const sbn_fr* r_multiset_check, sbn_prodcircuit** circuits_out) {
+    if (!ctx || !a || !r || !r_hash || !r_multiset_check || !circuits_out || a->ctx != ctx || (side != 0 && side != 1)) return SBN_ERR_ARG;
+    if (!a->read_ts[side] || !a->audit_ts[side]) return SBN_ERR_ARG;                 // sbn_addrs_set_timestamps first
+    if (nr == 0 || nr > 30 || (size_t(1) << nr) != a->num_cells || a->N < 2 || (a->N & (a->N - 1)) || a->num_cells < 2) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t M = a->num_cells, N = a->N, B = a->batch, ncirc = 2 + 2 * B;
+    for (size_t i = 0; i < ncirc; i++) circuits_out[i] = nullptr;
+    auto fail = [&](int code) {
+        for (size_t i = 0; i < ncirc; i++)
+            if (circuits_out[i]) { cudaFree(circuits_out[i]->buf); delete circuits_out[i]; circuits_out[i] = nullptr; }
+        return code;
+    };
+    for (size_t i = 0; i < ncirc; i++) {
+        const bool mem_sized = i == 0 || i == ncirc - 1;
+        circuits_out[i] = prodcircuit_alloc(ctx, mem_sized ? M : N);
+        if (!circuits_out[i]) { ctx->last_error = "sbn_hashlayer_build: cudaMalloc failed"; return fail(SBN_ERR_OOM); }
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->scratch0, 2 * M * sizeof(Fr))) != SBN_OK || (rc = ensure(ctx, ctx->scratch2, nr * sizeof(Fr))) != SBN_OK)
+        return fail(rc);
+    Fr* rdev = (Fr*)ctx->scratch2.p;
+    if (cudaMemcpyAsync(rdev, r, nr * sizeof(Fr), cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(SBN_ERR_CUDA);
+    ctx->h2d += nr * sizeof(Fr);
+    const Fr* mem = eq_evals_device(ctx, rdev, nr, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + M, s);      // eval_table
+    HashParams hp;
+    memcpy(&hp.rh, r_hash, sizeof(Fr));
+    memcpy(&hp.r_ms, r_multiset_check, sizeof(Fr));
+    hp.rh2 = fp_mul(hp.rh, hp.rh);
+    Fr R2;
+    for (int i = 0; i < 8; i++) R2.l[i] = FrParams::R2(i);
+    hp.rh2_R2 = fp_mul(hp.rh2, R2);
+    k_hash_mem<<<(unsigned)((M + 127) / 128), 128, 0, s>>>(mem, a->audit_ts[side], M, hp, circuits_out[0]->buf, circuits_out[ncirc - 1]->buf);
+    const uint32_t* addr = side == 0 ? a->row : a->col;
+    for (size_t k = 0; k < B; k++)
+        k_hash_ops<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(mem, addr + k * N, a->read_ts[side] + k * N, N, hp,
+                                                               circuits_out[1 + k]->buf, circuits_out[1 + B + k]->buf);
+    ctx->launches += 1 + B;
+    for (size_t i = 0; i < ncirc; i++) prodcircuit_build_upper(ctx, circuits_out[i], s);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        ctx->last_error = "sbn_hashlayer_build: kernel failure";
+        return fail(SBN_ERR_CUDA);
+    }
+    return SBN_OK;
+}
+
+extern "C" int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer, sbn_fr* out) {
+    if (!pc || !out) return SBN_ERR_ARG;
+    if (layer >= (size_t)pc->num_layers) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = pc->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_TRY(download(ctx, out, pc->buf + pc->off[layer], (pc->len >> layer) * sizeof(Fr)));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
 }

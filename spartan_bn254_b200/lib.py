@@ -19,6 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+    "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
@@ -432,9 +433,22 @@ class ProdCircuit:
         self.h = h
         self.num_layers = int(ctx.lib.sbn_prodcircuit_num_layers(h))
 
+    @classmethod
+    def _from_handle(cls, ctx, h, length):
+        self = cls.__new__(cls)
+        self.ctx, self.h, self.len = ctx, h, length
+        self.num_layers = int(ctx.lib.sbn_prodcircuit_num_layers(h))
+        return self
+
     def evaluate(self):
         out = np.zeros(4, dtype=np.uint64)
         self.ctx._check(self.ctx.lib.sbn_prodcircuit_evaluate(self.h, _ptr(out)), "sbn_prodcircuit_evaluate")
+        return out
+
+    def layer(self, l):
+        out = np.zeros((self.len >> l, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.sbn_prodcircuit_download_layer(self.h, C.c_size_t(l), _ptr(out)),
+                        "sbn_prodcircuit_download_layer")
         return out
 
     def close(self):
@@ -512,6 +526,26 @@ class Addrs:
         ctx._check(ctx.lib.sbn_addrs_upload(ctx.h, _ptr(row), _ptr(col), C.c_size_t(self.batch), C.c_size_t(self.N), C.byref(h)),
                    "sbn_addrs_upload")
         self.h = h
+
+    def set_timestamps(self, row_read_ts, row_audit_ts, col_read_ts, col_audit_ts):
+        arrs = [np.ascontiguousarray(x, dtype=np.uint32) for x in (row_read_ts, row_audit_ts, col_read_ts, col_audit_ts)]
+        if arrs[0].shape != (self.batch, self.N) or arrs[2].shape != (self.batch, self.N) or arrs[1].shape != arrs[3].shape:
+            raise SbnError(-2, "sbn_addrs_set_timestamps", "read_ts must be [batch, N], audit_ts [num_cells]")
+        self.num_cells = arrs[1].shape[0]
+        st = self.ctx.lib.sbn_addrs_set_timestamps(self.h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]),
+                                                   C.c_size_t(self.num_cells))
+        self.ctx._check(st, "sbn_addrs_set_timestamps")
+
+    def hashlayer(self, side, r, r_hash, r_multiset_check):
+        """Layers::new for one side: returns [init, read..., write..., audit] as ProdCircuit handles."""
+        r = _u64(r, 4)
+        n = 2 + 2 * self.batch
+        handles = (C.c_void_p * n)()
+        st = self.ctx.lib.sbn_hashlayer_build(self.ctx.h, self.h, C.c_int(side), _ptr(r), C.c_size_t(r.shape[0]),
+                                              _ptr(_u64(r_hash, 4)), _ptr(_u64(r_multiset_check, 4)), handles)
+        self.ctx._check(st, "sbn_hashlayer_build")
+        lens = [self.num_cells] + [self.N] * (2 * self.batch) + [self.num_cells]
+        return [ProdCircuit._from_handle(self.ctx, C.c_void_p(handles[i]), lens[i]) for i in range(n)]
 
     def derefs_commit(self, bases, rx, ry, keep=True):
         """Returns (C, inf, Poly or None): the Hyrax commitment of the derefs polynomial built on the device."""
