@@ -14,8 +14,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from spartan_bn254_b200 import Context, synth
 from spartan_bn254_b200.hyrax import DotProductProofGens, MultiCommitGens, fr_vec_from_ints
-from spartan_bn254_b200.lib import Addrs
-from spartan_bn254_b200.product_tree import ProductCircuit, DotProductCircuit, ProductCircuitEvalProofBatched
+from spartan_bn254_b200.product_tree import ProductCircuit, ProductCircuitEvalProofBatched
 from spartan_bn254_b200.transcript import Transcript
 
 R_MOD = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
@@ -100,44 +99,38 @@ wpoly.close()
 del T, T2
 
 # ---- R1CSEvalProof: derefs on device (sparse_mlpoly_full.rs:1713-1724)
+from spartan_bn254_b200.sparse_mlpoly import SparkAddresses, PolyEvalNetwork
 N = 1 << nnz
+M = 1 << (k + 1)
 rng = np.random.default_rng(3)
-row = rng.integers(0, 1 << (k + 1), size=(3, N), dtype=np.uint32); col = rng.integers(0, 1 << (k + 1), size=(3, N), dtype=np.uint32)
+row = rng.integers(0, M, size=(3, N), dtype=np.uint32); col = rng.integers(0, M, size=(3, N), dtype=np.uint32)
 row[:, 3 * N // 4:] = 0; col[:, 3 * N // 4:] = 0
 ell_d = nnz + 3
 gens_derefs = MultiCommitGens.new(1 << (ell_d - ell_d // 2), b"gens_r1cs_eval", ctx)
-addrs = timed("encode.addrs_upload(one-off)", lambda: Addrs(ctx, row, col))
+spark = timed("encode.addresses+timestamps_upload(one-off)", lambda: SparkAddresses(ctx, M, row, col))
 rx = synth.uniform_scalars(21, k + 1); ry = synth.uniform_scalars(22, k + 1)
-_, _, p0 = addrs.derefs_commit(gens_derefs.device_bases(), rx, ry); p0.close()
-C, inf, dpoly = timed("eval.eq_tables+derefs_gather+derefs_commit(2^%d)" % ell_d, lambda: addrs.derefs_commit(gens_derefs.device_bases(), rx, ry))
+_, _, p0 = spark.derefs_commit(gens_derefs, rx, ry); p0.close()
+C, inf, dpoly = timed("eval.eq_tables+derefs_gather+derefs_commit(2^%d)" % ell_d, lambda: spark.derefs_commit(gens_derefs, rx, ry))
 out["derefs_identity_rows"] = int(inf.sum())
 
-# ---- product layer (sparse_mlpoly_full.rs:1306-1428 -> product_tree.rs:251-392): ops group and mem group
-base = synth.uniform_scalars(60, N)
-ops = [ProductCircuit(ctx, np.roll(base, 17 * i, axis=0)) for i in range(12)]
-half = N // 2
-dot = [DotProductCircuit(np.roll(base, 5 * i, axis=0)[:half], np.roll(base, 7 * i, axis=0)[:half], np.roll(base, 11 * i, axis=0)[:half])
-       for i in range(6)]
-_warm = [ProductCircuit(ctx, base[:64]) for _ in range(2)]         # warm-up on a tiny instance
+# ---- network construction (sparse_mlpoly_full.rs:853-866) and product layers (:1306-1428 -> product_tree.rs:251-392)
+gam = synth.uniform_scalars(23, 2)
+warm = PolyEvalNetwork(spark, rx, ry, (gam[0], gam[1]))
+for lay in (warm.row_layers, warm.col_layers):
+    for c in lay.prod_layer.all():
+        c.close()
+net = timed("eval.network_construction(hash layers + 16 product circuits)", lambda: PolyEvalNetwork(spark, rx, ry, (gam[0], gam[1])))
+_warm = [ProductCircuit(ctx, synth.uniform_scalars(60, 64)) for _ in range(2)]         # warm-up on a tiny instance
 ProductCircuitEvalProofBatched.prove(ctx, _warm, [], Transcript(b"warm"))
 for c in _warm:
     c.close()
-
-
-def prod_ops():
-    return ProductCircuitEvalProofBatched.prove(ctx, ops, dot, Transcript(b"phase"))
-
-
-if k <= 16:
-    timed("eval.product_layer_ops(12 circuits 2^%d + 6 dot-product 2^%d, Merlin)" % (nnz, nnz - 1), prod_ops)
-else:   # the host mirror evaluates the dot-product circuits' claims with Python integers: too slow at 2^21, leave them out
-    dot = []
-    timed("eval.product_layer_ops(12 circuits 2^%d, Merlin)" % nnz, prod_ops)
-for c in ops:
-    c.close()
-mem = [ProductCircuit(ctx, np.roll(base, 3 * i, axis=0)[: 1 << (k + 1)]) for i in range(4)]
+rl, cl = net.row_layers.prod_layer, net.col_layers.prod_layer
+ops = rl.read_vec + rl.write_vec + cl.read_vec + cl.write_vec
+mem = [rl.init, rl.audit, cl.init, cl.audit]
+timed("eval.product_layer_ops(12 circuits 2^%d, Merlin; the 6 dot-product circuits of the reference are left out)" % nnz,
+      lambda: ProductCircuitEvalProofBatched.prove(ctx, ops, [], Transcript(b"phase")))
 timed("eval.product_layer_mem(4 circuits 2^%d, Merlin)" % (k + 1), lambda: ProductCircuitEvalProofBatched.prove(ctx, mem, [], Transcript(b"phase2")))
-for c in mem:
+for c in ops + mem:
     c.close()
 
 # ---- hash layer openings (sparse_mlpoly_full.rs:945, 1000, 1026)
