@@ -202,6 +202,8 @@ int sbn_addrs_set_timestamps(sbn_addrs* addrs, const uint32_t* row_read_ts, cons
 int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* addrs, int side, const sbn_fr* r, size_t nr, const sbn_fr* r_hash,
                         const sbn_fr* r_multiset_check, sbn_prodcircuit** circuits_out);
 int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer, sbn_fr* out /* len >> layer scalars */);
+/* DensePolynomial::evaluate (hyrax.rs:217-222) of the 2^nr evaluations poly[offset .. offset + 2^nr) at the point r. */
+int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offset, const sbn_fr* r, size_t nr, sbn_fr* out);
 size_t sbn_poly_len(const sbn_poly* poly);
 int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
 

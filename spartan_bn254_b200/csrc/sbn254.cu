@@ -1851,3 +1851,31 @@ extern "C" int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer,
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
 }
+
+// DensePolynomial::evaluate (hyrax.rs:217-222) of a resident polynomial, or of a 2^nr-entry segment of it (the hash layer
+// evaluates the individual polynomials merged into derefs / comb_ops / comb_mem, sparse_mlpoly_full.rs:907-976):
+// <Z[offset ..], eq(r)> with the eq table built in HBM.
+extern "C" int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offset, const sbn_fr* r, size_t nr, sbn_fr* out) {
+    if (!ctx || !poly || !r || !out || poly->ctx != ctx) return SBN_ERR_ARG;
+    if (nr == 0 || nr > 30) return SBN_ERR_SHAPE;
+    const size_t n = size_t(1) << nr;
+    if (offset > poly->len || n > poly->len - offset) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const unsigned blocks = (unsigned)std::min<size_t>(592, (n + kDotThreads - 1) / kDotThreads);
+    SBN_TRY(ensure(ctx, ctx->scratch0, 2 * n * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, (blocks + 1) * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, nr * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaMemcpyAsync(ctx->scratch2.p, r, nr * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ctx->h2d += nr * sizeof(Fr);
+    const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, nr, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + n, s);
+    Fr* partial = (Fr*)ctx->scratch1.p;
+    k_fr_dot<<<dim3(blocks, 1), kDotThreads, 0, s>>>(poly->Z + offset, 0, eq, 0, (int)n, partial);
+    k_fr_sum<<<1, kDotThreads, 0, s>>>(partial, (int)blocks, partial + blocks, 1);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, partial + blocks, sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}

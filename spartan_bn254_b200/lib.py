@@ -19,7 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
-    "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
+    "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
@@ -394,6 +394,14 @@ class Poly:
                                           _ptr(out), _ptr(inf))
         self.ctx._check(st, "sbn_poly_commit")
         return out, inf
+
+    def evaluate(self, r, offset=0):
+        """DensePolynomial::evaluate of the 2^len(r) evaluations starting at `offset`."""
+        r = _u64(r, 4)
+        out = np.zeros(4, dtype=np.uint64)
+        st = self.ctx.lib.sbn_poly_evaluate(self.ctx.h, self.h, C.c_size_t(offset), _ptr(r), C.c_size_t(r.shape[0]), _ptr(out))
+        self.ctx._check(st, "sbn_poly_evaluate")
+        return out
 
     def download(self):
         out = np.zeros((self.len, 4), dtype=np.uint64)

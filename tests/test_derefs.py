@@ -50,3 +50,21 @@ def test_derefs_address_out_of_range_is_a_shape_error(ctx):
         addrs.derefs_commit(gens.device_bases(), synth.uniform_scalars(1, 5), synth.uniform_scalars(2, 5))
     assert e.value.status == -2
     addrs.close()
+
+
+@pytest.mark.parametrize("ell,seg", [(10, None), (12, 9), (16, 13), (1, None)])
+def test_resident_polynomial_evaluate(ctx, orc, ell, seg):
+    """DensePolynomial::evaluate (hyrax.rs:217-222), whole polynomial and an inner segment (the hash layer evaluates the
+    polynomials merged into derefs / comb_ops one by one, sparse_mlpoly_full.rs:907-976)."""
+    from spartan_bn254_b200 import SbnError, synth
+    Z = synth.uniform_scalars(70 + ell, 1 << ell)
+    poly = ctx.poly_upload(Z)
+    r = synth.uniform_scalars(71, ell)
+    assert np.array_equal(poly.evaluate(r), orc.evaluate(Z, r))
+    if seg is not None:
+        off = 3 << seg
+        rs = synth.uniform_scalars(72, seg)
+        assert np.array_equal(poly.evaluate(rs, offset=off), orc.evaluate(Z[off: off + (1 << seg)], rs))
+        with pytest.raises(SbnError):
+            poly.evaluate(rs, offset=(1 << ell) - 5)
+    poly.close()
