@@ -174,6 +174,11 @@ int sbn_prodcircuit_destroy(sbn_prodcircuit* pc);
 int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
                         size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB, const sbn_fr* const* seqC,
                         size_t S, sbn_bsumcheck** out);
+/* Same, with the 3 * S tables of the sequential instances given as segments of resident polynomials
+ * (seq_polys[3k + w], seq_offsets[3k + w]; w = 0 left, 1 right, 2 weight): they are copied device to device. */
+int sbn_bsumcheck_begin_resident(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
+                                 size_t n_rand, const sbn_poly* const* seq_polys, const size_t* seq_offsets, size_t S,
+                                 sbn_bsumcheck** out);
 int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals /* (P + S) x 3 */);
 int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r);
 int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final);
@@ -204,6 +209,14 @@ int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* addrs, int side, const sb
 int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer, sbn_fr* out /* len >> layer scalars */);
 /* DensePolynomial::evaluate (hyrax.rs:217-222) of the 2^nr evaluations poly[offset .. offset + 2^nr) at the point r. */
 int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offset, const sbn_fr* r, size_t nr, sbn_fr* out);
+/* comb_ops = merge(row.ops_addr, row.read_ts, col.ops_addr, col.read_ts, val) (zero-padded to a power of two) and
+ * comb_mem = row.audit_ts ++ col.audit_ts (sparse_mlpoly_full.rs:155-170) as resident polynomials, built from the
+ * resident addresses / timestamps and the host `val` (batch x N Montgomery scalars). */
+int sbn_spark_comb_polys(sbn_ctx* ctx, const sbn_addrs* addrs, const sbn_fr* val, sbn_poly** comb_ops, sbn_poly** comb_mem);
+/* sum_{i < n} A[offA + i] * B[offB + i] * C[offC + i] over resident polynomials (DotProductCircuit::evaluate,
+ * product_tree.rs:81-86). */
+int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA, const sbn_poly* B, size_t offB, const sbn_poly* C,
+                        size_t offC, size_t n, sbn_fr* out);
 size_t sbn_poly_len(const sbn_poly* poly);
 int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
 

@@ -127,4 +127,22 @@ __global__ void k_hash_ops(const Fr* __restrict__ mem, const uint32_t* __restric
     store_fr(write_out + j, fp_add(v, hp.rh2));
 }
 
+// dst[i] = Montgomery form of the integer src[i] (DensePolynomial::from_usize, hyrax.rs:249-251)
+__global__ void k_u32_to_fr(const uint32_t* __restrict__ src, size_t n, Fr* __restrict__ dst) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store_fr(dst + i, fp_mul(fr_from_u32(src[i]), fr_R2()));
+}
+
+// partial[block] = sum_i a[i] b[i] c[i]   (DotProductCircuit::evaluate, product_tree.rs:81-86)
+__global__ void __launch_bounds__(kDotThreads)
+k_fr_triple_dot(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, size_t n, Fr* __restrict__ partial) {
+    __shared__ Fr sm[kDotThreads];
+    Fr acc = Fr::zero();
+    for (size_t i = (size_t)blockIdx.x * kDotThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kDotThreads)
+        acc = fp_add(acc, fp_mul(fp_mul(load_fr(a + i), load_fr(b + i)), load_fr(c + i)));
+    acc = block_sum_fr(acc, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(partial + blockIdx.x, acc);
+}
+
 }  // namespace sbn

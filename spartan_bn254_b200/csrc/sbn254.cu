@@ -1453,10 +1453,11 @@ static void bsumcheck_free(sbn_bsumcheck* st) {
     delete st;
 }
 
-extern "C" int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
-                                   size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB,
-                                   const sbn_fr* const* seqC, size_t S, sbn_bsumcheck** out) {
-    if (!ctx || !out || !circuits || P == 0 || (n_rand && !rand) || (S && (!seqA || !seqB || !seqC))) return SBN_ERR_ARG;
+// seq_dev != nullptr: the 3 * S tables of the sequential instances are device pointers (copied device-to-device)
+static int bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
+                           size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB, const sbn_fr* const* seqC,
+                           const Fr* const* seq_dev, size_t S, sbn_bsumcheck** out) {
+    if (!ctx || !out || !circuits || P == 0 || (n_rand && !rand) || (S && !seq_dev && (!seqA || !seqB || !seqC))) return SBN_ERR_ARG;
     *out = nullptr;
     if (n_rand > 30 || P + S > 4096) return SBN_ERR_SHAPE;
     const size_t T = size_t(1) << n_rand;                      // table length: poly_C_par = eq(rand) has 2^|rand| entries
@@ -1502,13 +1503,14 @@ extern "C" int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuit
         ctx->launches++;
     }
     for (size_t k = 0; k < S; k++) {
-        const sbn_fr* src[3] = {seqA[k], seqB[k], seqC[k]};
         for (int w = 0; w < 3; w++) {
-            if (!src[w]) { bsumcheck_free(st); return SBN_ERR_ARG; }
-            if ((e = cudaMemcpyAsync(st->seq + (3 * k + w) * T, src[w], T * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            const void* src = seq_dev ? (const void*)seq_dev[3 * k + w] : (const void*)(w == 0 ? seqA[k] : w == 1 ? seqB[k] : seqC[k]);
+            if (!src) { bsumcheck_free(st); return SBN_ERR_ARG; }
+            if ((e = cudaMemcpyAsync(st->seq + (3 * k + w) * T, src, T * sizeof(Fr),
+                                     seq_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s)) != cudaSuccess)
                 return fail("sequential instance upload", e);
         }
-        ctx->h2d += 3 * T * sizeof(Fr);
+        if (!seq_dev) ctx->h2d += 3 * T * sizeof(Fr);
     }
     std::vector<CubicTriple> triples(n);
     std::vector<Fr*> tables;
@@ -1535,6 +1537,27 @@ extern "C" int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuit
         return fail("sbn_bsumcheck_begin", e);
     *out = st;
     return SBN_OK;
+}
+
+extern "C" int sbn_bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id, const sbn_fr* rand,
+                                   size_t n_rand, const sbn_fr* const* seqA, const sbn_fr* const* seqB,
+                                   const sbn_fr* const* seqC, size_t S, sbn_bsumcheck** out) {
+    return bsumcheck_begin(ctx, circuits, P, layer_id, rand, n_rand, seqA, seqB, seqC, nullptr, S, out);
+}
+
+extern "C" int sbn_bsumcheck_begin_resident(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_t P, size_t layer_id,
+                                            const sbn_fr* rand, size_t n_rand, const sbn_poly* const* seq_polys,
+                                            const size_t* seq_offsets, size_t S, sbn_bsumcheck** out) {
+    if (S && (!seq_polys || !seq_offsets)) return SBN_ERR_ARG;
+    if (n_rand > 30) return SBN_ERR_SHAPE;
+    const size_t T = size_t(1) << n_rand;
+    std::vector<const Fr*> dev(3 * S);
+    for (size_t i = 0; i < 3 * S; i++) {
+        if (!seq_polys[i] || seq_polys[i]->ctx != ctx) return SBN_ERR_ARG;
+        if (seq_offsets[i] > seq_polys[i]->len || T > seq_polys[i]->len - seq_offsets[i]) return SBN_ERR_SHAPE;
+        dev[i] = seq_polys[i]->Z + seq_offsets[i];
+    }
+    return bsumcheck_begin(ctx, circuits, P, layer_id, rand, n_rand, nullptr, nullptr, nullptr, S ? dev.data() : nullptr, S, out);
 }
 
 extern "C" int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals) {
@@ -1872,6 +1895,76 @@ extern "C" int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offs
     const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, nr, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + n, s);
     Fr* partial = (Fr*)ctx->scratch1.p;
     k_fr_dot<<<dim3(blocks, 1), kDotThreads, 0, s>>>(poly->Z + offset, 0, eq, 0, (int)n, partial);
+    k_fr_sum<<<1, kDotThreads, 0, s>>>(partial, (int)blocks, partial + blocks, 1);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, partial + blocks, sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// f4 building blocks: the dense representation of a multi-sparse-matrix commitment, resident
+// ------------------------------------------------------------------------------------------------
+// comb_ops = merge(row.ops_addr, row.read_ts, col.ops_addr, col.read_ts, val) and comb_mem = row.audit_ts ++ col.audit_ts
+// (sparse_mlpoly_full.rs:155-170), built in HBM from the resident addresses / timestamps and the host `val` (batch x N).
+extern "C" int sbn_spark_comb_polys(sbn_ctx* ctx, const sbn_addrs* a, const sbn_fr* val, sbn_poly** comb_ops, sbn_poly** comb_mem) {
+    if (!ctx || !a || !val || !comb_ops || !comb_mem || a->ctx != ctx) return SBN_ERR_ARG;
+    if (!a->read_ts[0] || !a->audit_ts[0]) return SBN_ERR_ARG;
+    *comb_ops = *comb_mem = nullptr;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t seg = a->batch * a->N, used = 5 * seg;
+    size_t len = 1;
+    while (len < used) len <<= 1;
+    sbn_poly* po = new (std::nothrow) sbn_poly();
+    sbn_poly* pm = new (std::nothrow) sbn_poly();
+    if (!po || !pm) { delete po; delete pm; return SBN_ERR_OOM; }
+    po->ctx = pm->ctx = ctx;
+    po->len = len;
+    pm->len = 2 * a->num_cells;
+    auto fail = [&](int code) {
+        if (po->Z) cudaFree(po->Z);
+        if (pm->Z) cudaFree(pm->Z);
+        delete po; delete pm;
+        return code;
+    };
+    if (cudaMalloc(&po->Z, po->len * sizeof(Fr)) != cudaSuccess || cudaMalloc(&pm->Z, pm->len * sizeof(Fr)) != cudaSuccess) {
+        ctx->last_error = "sbn_spark_comb_polys: cudaMalloc failed";
+        return fail(SBN_ERR_OOM);
+    }
+    const uint32_t* src[4] = {a->row, a->read_ts[0], a->col, a->read_ts[1]};
+    for (int k = 0; k < 4; k++) k_u32_to_fr<<<(unsigned)((seg + 255) / 256), 256, 0, s>>>(src[k], seg, po->Z + k * seg);
+    for (int k = 0; k < 2; k++)
+        k_u32_to_fr<<<(unsigned)((a->num_cells + 255) / 256), 256, 0, s>>>(a->audit_ts[k], a->num_cells, pm->Z + k * a->num_cells);
+    ctx->launches += 6;
+    if (cudaMemcpyAsync(po->Z + 4 * seg, val, seg * sizeof(Fr), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemsetAsync(po->Z + used, 0, (len - used) * sizeof(Fr), s) != cudaSuccess ||
+        cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        ctx->last_error = "sbn_spark_comb_polys failed";
+        return fail(SBN_ERR_CUDA);
+    }
+    ctx->h2d += seg * sizeof(Fr);
+    *comb_ops = po;
+    *comb_mem = pm;
+    return SBN_OK;
+}
+
+// sum_i A[offA + i] B[offB + i] C[offC + i], i < n, over resident polynomials (DotProductCircuit::evaluate,
+// product_tree.rs:81-86; SparseMatPolynomial::evaluate_with_tables, sparse_mlpoly_full.rs:103-108)
+extern "C" int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA, const sbn_poly* B, size_t offB, const sbn_poly* Cp,
+                                   size_t offC, size_t n, sbn_fr* out) {
+    if (!ctx || !A || !B || !Cp || !out || A->ctx != ctx || B->ctx != ctx || Cp->ctx != ctx) return SBN_ERR_ARG;
+    if (n == 0 || offA > A->len || n > A->len - offA || offB > B->len || n > B->len - offB || offC > Cp->len || n > Cp->len - offC)
+        return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const unsigned blocks = (unsigned)std::min<size_t>(592, (n + kDotThreads - 1) / kDotThreads);
+    SBN_TRY(ensure(ctx, ctx->scratch1, (blocks + 1) * sizeof(Fr)));
+    Fr* partial = (Fr*)ctx->scratch1.p;
+    k_fr_triple_dot<<<blocks, kDotThreads, 0, s>>>(A->Z + offA, B->Z + offB, Cp->Z + offC, n, partial);
     k_fr_sum<<<1, kDotThreads, 0, s>>>(partial, (int)blocks, partial + blocks, 1);
     ctx->launches += 2;
     SBN_CUDA(ctx, cudaGetLastError());

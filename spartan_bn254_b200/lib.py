@@ -19,6 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+    "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
@@ -403,6 +404,15 @@ class Poly:
         self.ctx._check(st, "sbn_poly_evaluate")
         return out
 
+    @staticmethod
+    def triple_dot(A, offA, B, offB, Cp, offC, n):
+        """sum_i A[offA + i] * B[offB + i] * C[offC + i] over resident polynomials."""
+        out = np.zeros(4, dtype=np.uint64)
+        st = A.ctx.lib.sbn_poly_triple_dot(A.ctx.h, A.h, C.c_size_t(offA), B.h, C.c_size_t(offB), Cp.h, C.c_size_t(offC),
+                                           C.c_size_t(n), _ptr(out))
+        A.ctx._check(st, "sbn_poly_triple_dot")
+        return out
+
     def download(self):
         out = np.zeros((self.len, 4), dtype=np.uint64)
         self.ctx._check(self.ctx.lib.sbn_poly_download(self.ctx.h, self.h, _ptr(out)), "sbn_poly_download")
@@ -474,12 +484,27 @@ class ProdCircuit:
 class BatchedSumcheckState:
     """sbn_bsumcheck: the tables of one layer's batched cubic sumcheck (sumcheck.rs:165-330) on the GPU."""
 
-    def __init__(self, ctx, circuits, layer_id, rand, seq=()):
+    def __init__(self, ctx, circuits, layer_id, rand, seq=(), seq_resident=()):
+        """seq: host tables (left, right, weight) per sequential instance; seq_resident: the same as segments of resident
+        polynomials, ((Poly, offset), (Poly, offset), (Poly, offset)) per instance (not both)."""
         self.ctx = ctx
-        self.P, self.S = len(circuits), len(seq)
+        self.P, self.S = len(circuits), len(seq) + len(seq_resident)
         rand = np.zeros((0, 4), dtype=np.uint64) if rand is None or len(rand) == 0 else _u64(rand, 4)
         self.len = 1 << rand.shape[0]
         handles = (C.c_void_p * self.P)(*[c.h for c in circuits])
+        if seq_resident:
+            if seq:
+                raise SbnError(-1, "sbn_bsumcheck_begin", "host and resident sequential instances cannot be mixed")
+            flat = [pair for inst in seq_resident for pair in inst]
+            polys = (C.c_void_p * len(flat))(*[p.h for p, _ in flat])
+            offs = (C.c_size_t * len(flat))(*[int(o) for _, o in flat])
+            h = C.c_void_p()
+            st = ctx.lib.sbn_bsumcheck_begin_resident(ctx.h, handles, C.c_size_t(self.P), C.c_size_t(layer_id),
+                                                      _ptr(rand) if rand.shape[0] else None, C.c_size_t(rand.shape[0]), polys, offs,
+                                                      C.c_size_t(self.S), C.byref(h))
+            ctx._check(st, "sbn_bsumcheck_begin_resident")
+            self.h = h
+            return
         keep = [[_u64(t, 4) for t in inst] for inst in seq]
         for inst in keep:
             if len(inst) != 3 or any(t.shape[0] != self.len for t in inst):
@@ -543,6 +568,21 @@ class Addrs:
         st = self.ctx.lib.sbn_addrs_set_timestamps(self.h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]),
                                                    C.c_size_t(self.num_cells))
         self.ctx._check(st, "sbn_addrs_set_timestamps")
+
+    def comb_polys(self, val):
+        """(comb_ops, comb_mem) as resident polynomials (sparse_mlpoly_full.rs:155-170); val: uint64[batch * N, 4]."""
+        val = _u64(val, 4)
+        if val.shape[0] != self.batch * self.N:
+            raise SbnError(-2, "sbn_spark_comb_polys", "val must hold batch * N scalars")
+        po, pm = C.c_void_p(), C.c_void_p()
+        self.ctx._check(self.ctx.lib.sbn_spark_comb_polys(self.ctx.h, self.h, _ptr(val), C.byref(po), C.byref(pm)),
+                        "sbn_spark_comb_polys")
+        out = []
+        for h in (po, pm):
+            p = Poly.__new__(Poly)
+            p.ctx, p.h, p.len = self.ctx, h, int(self.ctx.lib.sbn_poly_len(h))
+            out.append(p)
+        return out[0], out[1]
 
     def hashlayer(self, side, r, r_hash, r_multiset_check):
         """Layers::new for one side: returns [init, read..., write..., audit] as ProdCircuit handles."""

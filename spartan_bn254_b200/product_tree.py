@@ -180,14 +180,18 @@ class ProductCircuitEvalProofBatched:
         claims_to_verify = [c.evaluate() for c in prod_circuits]
         rand = []
         for layer_id in reversed(range(num_layers)):
-            seq = []
+            seq, seq_resident = [], []
             if layer_id == 0 and dotp_circuits:
                 for d in dotp_circuits:
                     claims_to_verify.append(d.evaluate())
-                    assert len(d.left) == 1 << len(rand)
-                seq = [(d.left, d.right, d.weight) for d in dotp_circuits]
+                    if isinstance(d.left, tuple):       # (Poly, offset) segments of resident polynomials
+                        assert d.n == 1 << len(rand)
+                        seq_resident.append((d.left, d.right, d.weight))
+                    else:
+                        assert len(d.left) == 1 << len(rand)
+                        seq.append((d.left, d.right, d.weight))
             state = BatchedSumcheckState(ctx, [c.gpu for c in prod_circuits], layer_id,
-                                         fr_vec_from_ints(rand) if rand else None, seq)
+                                         fr_vec_from_ints(rand) if rand else None, seq, seq_resident)
             num_rounds = len(rand)                                  # log2(len / 2), len / 2 = |eq(rand)|
             coeff_vec = transcript.challenge_scalars(b"rand_coeffs_next_layer", len(claims_to_verify))
             claim = sum(a * b for a, b in zip(claims_to_verify, coeff_vec)) % R_MOD
