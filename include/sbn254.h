@@ -213,6 +213,10 @@ int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offset, const s
  * comb_mem = row.audit_ts ++ col.audit_ts (sparse_mlpoly_full.rs:155-170) as resident polynomials, built from the
  * resident addresses / timestamps and the host `val` (batch x N Montgomery scalars). */
 int sbn_spark_comb_polys(sbn_ctx* ctx, const sbn_addrs* addrs, const sbn_fr* val, sbn_poly** comb_ops, sbn_poly** comb_mem);
+/* SparseMatPolynomial::multi_evaluate (sparse_mlpoly_full.rs:110-118) of the batch behind `addrs`, values read from the val
+ * segment of the resident comb_ops: out[s] = sum_i val_s[i] * eq(rx)[row_s[i]] * eq(ry)[col_s[i]], s < batch. */
+int sbn_spark_evaluate(sbn_ctx* ctx, const sbn_addrs* addrs, const sbn_poly* comb_ops, const sbn_fr* rx, size_t nx,
+                       const sbn_fr* ry, size_t ny, sbn_fr* out);
 /* sum_{i < n} A[offA + i] * B[offB + i] * C[offC + i] over resident polynomials (DotProductCircuit::evaluate,
  * product_tree.rs:81-86). */
 int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA, const sbn_poly* B, size_t offB, const sbn_poly* C,

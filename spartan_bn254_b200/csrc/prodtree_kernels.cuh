@@ -145,4 +145,20 @@ k_fr_triple_dot(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __
     if (threadIdx.x == 0) store_fr(partial + blockIdx.x, acc);
 }
 
+// SparseMatPolynomial::evaluate_with_tables (sparse_mlpoly_full.rs:103-108): partial[block] of
+// sum_i val[i] * mem_rx[row[i]] * mem_ry[col[i]]
+__global__ void __launch_bounds__(kDotThreads)
+k_sparse_eval(const Fr* __restrict__ val, const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+              const Fr* __restrict__ mem_rx, const Fr* __restrict__ mem_ry, size_t n, Fr* __restrict__ partial) {
+    __shared__ Fr sm[kDotThreads];
+    Fr acc = Fr::zero();
+    for (size_t i = (size_t)blockIdx.x * kDotThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kDotThreads) {
+        const Fr v = load_fr(val + i);
+        if (v.is_zero()) continue;                       // padding entries
+        acc = fp_add(acc, fp_mul(fp_mul(v, load_fr(mem_rx + row[i])), load_fr(mem_ry + col[i])));
+    }
+    acc = block_sum_fr(acc, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(partial + blockIdx.x, acc);
+}
+
 }  // namespace sbn

@@ -1972,3 +1972,36 @@ extern "C" int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA,
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
     return SBN_OK;
 }
+
+// SparseMatPolynomial::multi_evaluate (sparse_mlpoly_full.rs:110-118) for the batch behind `addrs`, with the values read from
+// the val segment of the resident comb_ops: out[s] = sum_i val_s[i] * eq(rx)[row_s[i]] * eq(ry)[col_s[i]].
+extern "C" int sbn_spark_evaluate(sbn_ctx* ctx, const sbn_addrs* a, const sbn_poly* comb_ops, const sbn_fr* rx, size_t nx,
+                                  const sbn_fr* ry, size_t ny, sbn_fr* out) {
+    if (!ctx || !a || !comb_ops || !rx || !ry || !out || a->ctx != ctx || comb_ops->ctx != ctx) return SBN_ERR_ARG;
+    if (nx == 0 || ny == 0 || nx > 30 || ny > 30) return SBN_ERR_SHAPE;
+    if (a->max_row >= (size_t(1) << nx) || a->max_col >= (size_t(1) << ny) || comb_ops->len < 5 * a->batch * a->N) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t tx = size_t(1) << nx, ty = size_t(1) << ny, N = a->N, B = a->batch;
+    const unsigned blocks = (unsigned)std::min<size_t>(592, (N + kDotThreads - 1) / kDotThreads);
+    SBN_TRY(ensure(ctx, ctx->scratch0, 2 * tx * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, 2 * ty * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, (nx + ny + (blocks + 1) * B) * sizeof(Fr)));
+    Fr* rdev = (Fr*)ctx->scratch2.p;
+    Fr* partial = rdev + nx + ny;
+    SBN_CUDA(ctx, cudaMemcpyAsync(rdev, rx, nx * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(rdev + nx, ry, ny * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ctx->h2d += (nx + ny) * sizeof(Fr);
+    const Fr* mem_rx = eq_evals_device(ctx, rdev, nx, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + tx, s);
+    const Fr* mem_ry = eq_evals_device(ctx, rdev + nx, ny, (Fr*)ctx->scratch1.p, (Fr*)ctx->scratch1.p + ty, s);
+    for (size_t k = 0; k < B; k++)
+        k_sparse_eval<<<blocks, kDotThreads, 0, s>>>(comb_ops->Z + (4 * B + k) * N, a->row + k * N, a->col + k * N, mem_rx, mem_ry, N,
+                                                     partial + k * blocks);
+    k_fr_sum<<<(unsigned)B, kDotThreads, 0, s>>>(partial, (int)blocks, partial + B * blocks, 1);
+    ctx->launches += B + 1;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, partial + B * blocks, B * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}

@@ -19,7 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
-    "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
+    "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
@@ -583,6 +583,15 @@ class Addrs:
             p.ctx, p.h, p.len = self.ctx, h, int(self.ctx.lib.sbn_poly_len(h))
             out.append(p)
         return out[0], out[1]
+
+    def evaluate(self, comb_ops, rx, ry):
+        """multi_evaluate (sparse_mlpoly_full.rs:110-118) on the device: uint64[batch, 4]."""
+        rx, ry = _u64(rx, 4), _u64(ry, 4)
+        out = np.zeros((self.batch, 4), dtype=np.uint64)
+        st = self.ctx.lib.sbn_spark_evaluate(self.ctx.h, self.h, comb_ops.h, _ptr(rx), C.c_size_t(rx.shape[0]), _ptr(ry),
+                                             C.c_size_t(ry.shape[0]), _ptr(out))
+        self.ctx._check(st, "sbn_spark_evaluate")
+        return out
 
     def hashlayer(self, side, r, r_hash, r_multiset_check):
         """Layers::new for one side: returns [init, read..., write..., audit] as ProdCircuit handles."""

@@ -105,6 +105,11 @@ class MultiSparseMatPolynomialAsDense:
         self.comb_ops, self.comb_mem = self.spark.gpu.comb_polys(val_mont)
         return self
 
+    def multi_evaluate(self, rx, ry):
+        """SparseMatPolynomial::multi_evaluate (:110-118) on the device (rx, ry canonical ints, already equalised)."""
+        from .hyrax import fr_vec_to_ints
+        return fr_vec_to_ints(self.spark.gpu.evaluate(self.comb_ops, fr_vec_from_ints(rx), fr_vec_from_ints(ry)))
+
     def close(self):
         self.comb_ops.close()
         self.comb_mem.close()

@@ -35,6 +35,8 @@ def _prove(ctx, polys, nvx, nvy, seed):
     rx = [rnd.randrange(R) for _ in range(nvx)]
     ry = [rnd.randrange(R) for _ in range(nvy)]
     evals = SparseMatPolynomial.multi_evaluate(polys, rx, ry)
+    from spartan_bn254_b200.spark import equalize
+    assert dense.multi_evaluate(*equalize(rx, ry)) == evals          # the device-side multi_evaluate agrees with the host one
     proof = SparseMatPolyEvalProof.prove(dense, rx, ry, evals, gens, Transcript(b"spark"), RandomTape(b"proof", 777))
     dense.close()
     return proof, comm, gens, rx, ry, evals
