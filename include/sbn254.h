@@ -38,6 +38,7 @@ typedef struct sbn_sumcheck sbn_sumcheck;
 typedef struct sbn_prodcircuit sbn_prodcircuit;
 typedef struct sbn_bsumcheck sbn_bsumcheck;
 typedef struct sbn_addrs sbn_addrs;
+typedef struct sbn_spmat sbn_spmat;
 
 typedef enum {
     SBN_OK = 0,
@@ -223,6 +224,18 @@ int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA, const sbn_
                         size_t offC, size_t n, sbn_fr* out);
 size_t sbn_poly_len(const sbn_poly* poly);
 int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
+
+/* ---- R1CS-sat helpers (r1csproof.rs:285, :380): a sparse matrix in compressed-row form resident on the device, and
+ * out[i] = sum_m coeffs[m] * (M_m * vec)[i] for up to three matrices of the same shape (coeffs NULL = plain sum).
+ * multiply_vec (sparse_mlpoly.rs:77-87) uses the row-sorted copy with vec = z; compute_eval_table_sparse (:145-160) the
+ * column-sorted copy with vec = eq(rx) and coeffs = (r_A, r_B, r_C). */
+int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr /* n + 1 */, const uint32_t* idx, const sbn_fr* val, size_t n,
+                     size_t nnz, size_t ncols, sbn_spmat** out);
+int sbn_spmat_destroy(sbn_spmat* m);
+int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* coeffs, size_t nm, const sbn_fr* vec,
+                     size_t veclen, sbn_fr* out);
+/* EqPolynomial::evals (hyrax.rs:355-369): the 2^n evaluations of eq(r, .), computed on the device. */
+int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out);
 
 /* ---- utilities used by tests / harnesses */
 /* Keccak-f[1600] on a 25-lane little-endian state, in place (host only): the permutation under the Merlin transcript of

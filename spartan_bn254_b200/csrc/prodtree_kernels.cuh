@@ -161,4 +161,26 @@ k_sparse_eval(const Fr* __restrict__ val, const uint32_t* __restrict__ row, cons
     if (threadIdx.x == 0) store_fr(partial + blockIdx.x, acc);
 }
 
+// Sparse matrix times vector, compressed-row form: out[i] = sum_m coeff_m * sum_{k in [ptr_m[i], ptr_m[i+1])} val_m[k] * vec[idx_m[k]]
+// (SparseMatPolynomial::multiply_vec, sparse_mlpoly.rs:77-87, on a row-sorted copy; compute_eval_table_sparse, :145-160, on a
+// column-sorted copy with vec = eq(rx)).  Up to three matrices are combined in one pass (r_A A + r_B B + r_C C).
+struct SpMat { const uint32_t* ptr; const uint32_t* idx; const Fr* val; };
+
+__global__ void k_spmv(SpMat m0, SpMat m1, SpMat m2, Fr c0, Fr c1, Fr c2, int nm, int use_coeff, const Fr* __restrict__ vec, size_t n,
+                       Fr* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SpMat mats[3] = {m0, m1, m2};
+    const Fr coeffs[3] = {c0, c1, c2};
+    Fr total = Fr::zero();
+    for (int m = 0; m < nm; m++) {
+        Fr acc = Fr::zero();
+        for (uint32_t k = mats[m].ptr[i]; k < mats[m].ptr[i + 1]; k++)
+            acc = fp_add(acc, fr_mul_call(load_fr(mats[m].val + k), load_fr(vec + mats[m].idx[k])));
+        if (use_coeff) acc = fr_mul_call(acc, coeffs[m]);
+        total = fp_add(total, acc);
+    }
+    store_fr(out + i, total);
+}
+
 }  // namespace sbn

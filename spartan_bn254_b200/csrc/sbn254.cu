@@ -2005,3 +2005,106 @@ extern "C" int sbn_spark_evaluate(sbn_ctx* ctx, const sbn_addrs* a, const sbn_po
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
     return SBN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// R1CS-sat helpers: resident sparse matrices (compressed rows) and eq tables
+// ------------------------------------------------------------------------------------------------
+struct sbn_spmat {
+    sbn_ctx* ctx = nullptr;
+    size_t n = 0, nnz = 0, ncols = 0;
+    uint32_t *ptr = nullptr, *idx = nullptr;
+    Fr* val = nullptr;
+};
+
+extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_t* idx, const sbn_fr* val, size_t n, size_t nnz,
+                                size_t ncols, sbn_spmat** out) {
+    if (!ctx || !ptr || !out || (nnz && (!idx || !val))) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (n == 0 || n > (size_t(1) << 30) || nnz > (size_t(1) << 31) || ptr[0] != 0 || ptr[n] != nnz) return SBN_ERR_SHAPE;
+    for (size_t i = 0; i < n; i++) if (ptr[i] > ptr[i + 1]) return SBN_ERR_SHAPE;
+    for (size_t k = 0; k < nnz; k++) if (idx[k] >= ncols) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    sbn_spmat* m = new (std::nothrow) sbn_spmat();
+    if (!m) return SBN_ERR_OOM;
+    m->ctx = ctx; m->n = n; m->nnz = nnz; m->ncols = ncols;
+    cudaStream_t s = ctx->compute;
+    bool ok = cudaMalloc(&m->ptr, (n + 1) * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&m->idx, std::max<size_t>(1, nnz) * sizeof(uint32_t)) == cudaSuccess &&
+              cudaMalloc(&m->val, std::max<size_t>(1, nnz) * sizeof(Fr)) == cudaSuccess &&
+              cudaMemcpyAsync(m->ptr, ptr, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+              (nnz == 0 || (cudaMemcpyAsync(m->idx, idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
+                            cudaMemcpyAsync(m->val, val, nnz * sizeof(Fr), cudaMemcpyHostToDevice, s) == cudaSuccess)) &&
+              cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) {
+        if (m->ptr) cudaFree(m->ptr);
+        if (m->idx) cudaFree(m->idx);
+        if (m->val) cudaFree(m->val);
+        delete m;
+        ctx->last_error = "sbn_spmat_upload failed";
+        return SBN_ERR_CUDA;
+    }
+    ctx->h2d += (n + 1 + nnz) * sizeof(uint32_t) + nnz * sizeof(Fr);
+    *out = m;
+    return SBN_OK;
+}
+
+extern "C" int sbn_spmat_destroy(sbn_spmat* m) {
+    if (!m) return SBN_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(m->ctx->mu);
+        cudaSetDevice(m->ctx->device);
+        cudaStreamSynchronize(m->ctx->compute);
+        cudaFree(m->ptr); cudaFree(m->idx); cudaFree(m->val);
+    }
+    delete m;
+    return SBN_OK;
+}
+
+// out[i] = sum_m coeffs[m] * (M_m vec)[i]   (coeffs == NULL: plain sum); 1 <= nm <= 3 matrices of equal shape
+extern "C" int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* coeffs, size_t nm, const sbn_fr* vec,
+                                size_t veclen, sbn_fr* out) {
+    if (!ctx || !mats || !vec || !out || nm < 1 || nm > 3) return SBN_ERR_ARG;
+    for (size_t m = 0; m < nm; m++) {
+        if (!mats[m] || mats[m]->ctx != ctx) return SBN_ERR_ARG;
+        if (mats[m]->n != mats[0]->n || mats[m]->ncols > veclen) return SBN_ERR_SHAPE;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t n = mats[0]->n;
+    SBN_TRY(upload(ctx, ctx->scratch0, vec, veclen * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, n * sizeof(Fr)));
+    SpMat sm[3];
+    Fr c[3];
+    for (size_t m = 0; m < 3; m++) {
+        const sbn_spmat* src = mats[m < nm ? m : 0];
+        sm[m] = SpMat{src->ptr, src->idx, src->val};
+        if (coeffs && m < nm) memcpy(&c[m], &coeffs[m], sizeof(Fr)); else c[m] = Fr::zero();
+    }
+    k_spmv<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sm[0], sm[1], sm[2], c[0], c[1], c[2], (int)nm, coeffs ? 1 : 0,
+                                                        (const Fr*)ctx->scratch0.p, n, (Fr*)ctx->scratch1.p);
+    ctx->launches++;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, ctx->scratch1.p, n * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}
+
+// EqPolynomial::evals (hyrax.rs:355-369) computed in HBM and copied back: out holds 2^n scalars
+extern "C" int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out) {
+    if (!ctx || !out || (n && !r)) return SBN_ERR_ARG;
+    if (n > 28) return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t len = size_t(1) << n;
+    SBN_TRY(ensure(ctx, ctx->scratch0, 2 * len * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, std::max<size_t>(1, n) * sizeof(Fr)));
+    if (n) SBN_CUDA(ctx, cudaMemcpyAsync(ctx->scratch2.p, r, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + len, s);
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, eq, len * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}

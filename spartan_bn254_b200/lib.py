@@ -19,6 +19,7 @@ EXPORTS = [
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
+    "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
@@ -632,3 +633,51 @@ class Addrs:
             self.close()
         except Exception:
             pass
+
+
+class SpMat:
+    """sbn_spmat: a sparse matrix in compressed-row form resident on the device (entries: (row, col, Montgomery value))."""
+
+    def __init__(self, ctx, n, ncols, rows, cols, vals):
+        self.ctx = ctx
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        order = np.argsort(rows, kind="stable")
+        ptr = np.zeros(n + 1, dtype=np.uint32)
+        ptr[1:] = np.cumsum(np.bincount(rows, minlength=n)).astype(np.uint32)
+        idx = np.ascontiguousarray(np.asarray(cols)[order], dtype=np.uint32)
+        val = np.ascontiguousarray(_u64(vals, 4)[order])
+        self.n, self.ncols = n, ncols
+        h = C.c_void_p()
+        ctx._check(ctx.lib.sbn_spmat_upload(ctx.h, _ptr(ptr), _ptr(idx), _ptr(val), C.c_size_t(n), C.c_size_t(len(rows)),
+                                            C.c_size_t(ncols), C.byref(h)), "sbn_spmat_upload")
+        self.h = h
+
+    @staticmethod
+    def mulvec(mats, vec, coeffs=None):
+        ctx = mats[0].ctx
+        vec = _u64(vec, 4)
+        out = np.zeros((mats[0].n, 4), dtype=np.uint64)
+        hs = (C.c_void_p * len(mats))(*[m.h for m in mats])
+        cf = None if coeffs is None else _u64(coeffs, 4)
+        ctx._check(ctx.lib.sbn_spmat_mulvec(ctx.h, hs, _ptr(cf), C.c_size_t(len(mats)), _ptr(vec), C.c_size_t(vec.shape[0]),
+                                            _ptr(out)), "sbn_spmat_mulvec")
+        return out
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.sbn_spmat_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eq_evals(ctx, r):
+    """EqPolynomial::evals on the device: uint64[2^len(r), 4]."""
+    r = np.zeros((0, 4), dtype=np.uint64) if len(r) == 0 else _u64(r, 4)
+    out = np.zeros((1 << r.shape[0], 4), dtype=np.uint64)
+    ctx._check(ctx.lib.sbn_eq_evals(ctx.h, _ptr(r) if r.shape[0] else None, C.c_size_t(r.shape[0]), _ptr(out)), "sbn_eq_evals")
+    return out

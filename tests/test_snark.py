@@ -1,0 +1,84 @@
+"""SNARK::prove end to end (snark.rs:428-484): R1CS-sat proof + instance evaluations + Spark evaluation proof through the GPU
+path, on a synthetic satisfiable R1CS, accepted by the oracle's independent restatement of SNARK::verify (the reference's own
+tests are prove -> verify round trips of this kind, snark.rs:535-616, r1csproof.rs:651-681)."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
+
+def synthetic_r1cs(seed, num_cons, num_vars, num_inputs):
+    """Row i: (sum of 3 terms) * (sum of 2 terms) = c_i * 1; columns in Spartan's z layout [vars, 1, inputs, padding]."""
+    rnd = random.Random(seed)
+    vars_ = [rnd.randrange(R) for _ in range(num_vars)]
+    inputs = [rnd.randrange(R) for _ in range(num_inputs)]
+    z = vars_ + [1] + inputs + [0] * (num_vars - 1 - num_inputs)
+    used = list(range(num_vars + 1 + num_inputs))
+    A, B, C = [], [], []
+    for i in range(num_cons):
+        ta = [(rnd.choice(used), rnd.randrange(1, R)) for _ in range(3)]
+        tb = [(rnd.choice(used), rnd.randrange(1, R)) for _ in range(2)]
+        az = sum(z[c] * v for c, v in ta) % R
+        bz = sum(z[c] * v for c, v in tb) % R
+        A += [(i, c, v) for c, v in ta]
+        B += [(i, c, v) for c, v in tb]
+        C.append((i, num_vars, az * bz % R))
+    return vars_, inputs, A, B, C
+
+
+def _arrays(entries):
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints
+    return (np.array([e[0] for e in entries], dtype=np.uint32), np.array([e[1] for e in entries], dtype=np.uint32),
+            fr_vec_from_ints([e[2] for e in entries]))
+
+
+def _prove_and_verify(ctx, orc, num_cons, num_vars, num_inputs, seed, tamper=None):
+    import snark_model as snm
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints
+    from spartan_bn254_b200.r1csproof import R1CSShape, SNARK, SNARKGens
+    from spartan_bn254_b200.transcript import Transcript
+    vars_, inputs, A, B, C = synthetic_r1cs(seed, num_cons, num_vars, num_inputs)
+    inst = R1CSShape(ctx, num_cons, num_vars, num_inputs, _arrays(A), _arrays(B), _arrays(C))
+    gens = SNARKGens(ctx, num_cons, num_vars, num_inputs, inst.max_nnz())
+    comm, decomm = SNARK.encode(inst, gens)
+    proof = SNARK.prove(inst, comm, decomm, fr_vec_from_ints(vars_), fr_vec_from_ints(inputs), gens, Transcript(b"snark"), 4242)
+    decomm.close()
+    g = lambda x: (x.gens.gens_n.G, x.gens.gens_n.h, x.gens.gens_1.G[0])
+    sat = gens.gens_r1cs_sat
+    gens_sat = dict(gens_1=snm.Gens(sat.gens_sc.gens_1.G, sat.gens_sc.gens_1.h), gens_3=snm.Gens(sat.gens_sc.gens_3.G, sat.gens_sc.gens_3.h),
+                    gens_4=snm.Gens(sat.gens_sc.gens_4.G, sat.gens_sc.gens_4.h), pc=g(sat.gens_pc),
+                    pc_1=snm.Gens(sat.gens_pc.gens.gens_1.G, sat.gens_pc.gens.gens_1.h))
+    ev = gens.gens_r1cs_eval
+    gens_eval = dict(ops=g(ev.gens_ops), mem=g(ev.gens_mem), derefs=g(ev.gens_derefs))
+    c = comm.comm
+    cd = dict(num_cons=comm.num_cons, num_vars=comm.num_vars, num_inputs=comm.num_inputs, batch_size=c.batch_size, num_ops=c.num_ops,
+              num_mem_cells=c.num_mem_cells, comb_ops=(c.comm_comb_ops.C, c.comm_comb_ops.inf),
+              comb_mem=(c.comm_comb_mem.C, c.comm_comb_mem.inf))
+    if tamper:
+        tamper(proof, inputs)
+    return snm.snark_verify(proof, cd, inputs, gens_sat, gens_eval, orc.Transcript(b"snark"))
+
+
+@pytest.mark.parametrize("num_cons,num_vars,num_inputs", [(4, 4, 1), (16, 16, 2), (64, 32, 3), (32, 64, 0)])
+def test_snark_prove_is_accepted(ctx, orc, num_cons, num_vars, num_inputs):
+    assert _prove_and_verify(ctx, orc, num_cons, num_vars, num_inputs, 100 + num_cons)
+
+
+def test_snark_rejections(ctx, orc):
+    import snark_model as snm
+
+    def bad_input(proof, inputs):
+        inputs[0] = (inputs[0] + 1) % R
+
+    def bad_eval(proof, inputs):
+        proof.inst_evals = ((proof.inst_evals[0] + 1) % R,) + tuple(proof.inst_evals[1:])
+
+    def bad_sigma(proof, inputs):
+        proof.r1cs_sat_proof.proof_eq_sc_phase1.z = (proof.r1cs_sat_proof.proof_eq_sc_phase1.z + 1) % R
+
+    for tamper in (bad_input, bad_eval, bad_sigma):
+        with pytest.raises(snm.VerifyError):
+            _prove_and_verify(ctx, orc, 16, 16, 2, 7, tamper)
