@@ -241,6 +241,12 @@ int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out);
 /* Keccak-f[1600] on a 25-lane little-endian state, in place (host only): the permutation under the Merlin transcript of
  * the host mirrors (transcript.rs; merlin 3.0 = STROBE-128). */
 void sbn_keccak_f1600(uint64_t* state);
+/* The Merlin transcript itself (merlin 3.0 = STROBE-128; transcript.rs:37-80 wraps it): `state` is 203 caller-owned bytes.
+ * append_many appends `count` messages of `mlen` bytes under the same label (append_scalars, transcript.rs:46-52). */
+void sbn_merlin_init(void* state, const uint8_t* label, size_t label_len);
+void sbn_merlin_append(void* state, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
+void sbn_merlin_append_many(void* state, const uint8_t* label, size_t label_len, const uint8_t* msgs, size_t msg_len, size_t count);
+void sbn_merlin_challenge(void* state, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
 int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
 /* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for

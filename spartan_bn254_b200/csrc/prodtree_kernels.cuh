@@ -165,6 +165,7 @@ k_sparse_eval(const Fr* __restrict__ val, const uint32_t* __restrict__ row, cons
 // (SparseMatPolynomial::multiply_vec, sparse_mlpoly.rs:77-87, on a row-sorted copy; compute_eval_table_sparse, :145-160, on a
 // column-sorted copy with vec = eq(rx)).  Up to three matrices are combined in one pass (r_A A + r_B B + r_C C).
 struct SpMat { const uint32_t* ptr; const uint32_t* idx; const Fr* val; };
+static constexpr uint32_t kSpmvHeavy = 2048;      // rows longer than this (the constant-1 column of an R1CS transpose) get a block
 
 __global__ void k_spmv(SpMat m0, SpMat m1, SpMat m2, Fr c0, Fr c1, Fr c2, int nm, int use_coeff, const Fr* __restrict__ vec, size_t n,
                        Fr* __restrict__ out) {
@@ -175,12 +176,29 @@ __global__ void k_spmv(SpMat m0, SpMat m1, SpMat m2, Fr c0, Fr c1, Fr c2, int nm
     Fr total = Fr::zero();
     for (int m = 0; m < nm; m++) {
         Fr acc = Fr::zero();
-        for (uint32_t k = mats[m].ptr[i]; k < mats[m].ptr[i + 1]; k++)
+        const uint32_t k0 = mats[m].ptr[i], k1 = mats[m].ptr[i + 1];
+        if (k1 - k0 > kSpmvHeavy) continue;                // a whole block sums this row in k_spmv_heavy
+        for (uint32_t k = k0; k < k1; k++)
             acc = fp_add(acc, fr_mul_call(load_fr(mats[m].val + k), load_fr(vec + mats[m].idx[k])));
         if (use_coeff) acc = fr_mul_call(acc, coeffs[m]);
         total = fp_add(total, acc);
     }
     store_fr(out + i, total);
+}
+
+// out[row] += coeff * sum_k val[k] * vec[idx[k]] for the heavy rows of one matrix: one block per heavy row.
+__global__ void __launch_bounds__(kDotThreads)
+k_spmv_heavy(SpMat m, const uint32_t* __restrict__ heavy_rows, Fr coeff, int use_coeff, const Fr* __restrict__ vec, Fr* __restrict__ out) {
+    __shared__ Fr sm[kDotThreads];
+    const uint32_t row = heavy_rows[blockIdx.x];
+    Fr acc = Fr::zero();
+    for (uint32_t k = m.ptr[row] + threadIdx.x; k < m.ptr[row + 1]; k += kDotThreads)
+        acc = fp_add(acc, fp_mul(load_fr(m.val + k), load_fr(vec + m.idx[k])));
+    acc = block_sum_fr(acc, sm, kDotThreads);
+    if (threadIdx.x == 0) {
+        if (use_coeff) acc = fp_mul(acc, coeff);
+        store_fr(out + row, fp_add(load_fr(out + row), acc));
+    }
 }
 
 }  // namespace sbn

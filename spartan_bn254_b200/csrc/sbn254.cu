@@ -18,6 +18,7 @@
 #include "ba_kernels.cuh"
 #include "prodtree_kernels.cuh"
 #include "host/keccak.hpp"
+#include "host/merlin.hpp"
 
 using namespace sbn;
 
@@ -56,6 +57,11 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
+    // allocates and releases ~5 GB of them, and cudaFree costs ~35 ms per 268 MB buffer (574 ms per keyless-scale proof).
+    // Everything that touches them is ordered on `compute`, so a released buffer can be handed out again without a sync.
+    std::vector<std::pair<size_t, void*>> mem_pool;
+    size_t mem_pool_bytes = 0;
     // last-commit profile
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[4] = {0, 0, 0, 0};
@@ -99,6 +105,43 @@ static int ensure(sbn_ctx* ctx, DevBuf& b, size_t bytes) {
     b.cap = want;
     return SBN_OK;
 }
+static constexpr size_t kPoolMinBytes = size_t(1) << 20, kPoolMaxBytes = size_t(48) << 30;
+
+static void pool_flush(sbn_ctx* ctx) {
+    for (auto& e : ctx->mem_pool) cudaFree(e.second);
+    ctx->mem_pool.clear();
+    ctx->mem_pool_bytes = 0;
+}
+static cudaError_t pool_alloc(sbn_ctx* ctx, void** out, size_t bytes) {
+    if (bytes >= kPoolMinBytes)
+        for (size_t i = 0; i < ctx->mem_pool.size(); i++)
+            if (ctx->mem_pool[i].first == bytes) {
+                *out = ctx->mem_pool[i].second;
+                ctx->mem_pool_bytes -= bytes;
+                ctx->mem_pool.erase(ctx->mem_pool.begin() + i);
+                return cudaSuccess;
+            }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->mem_pool.empty()) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->compute);
+        pool_flush(ctx);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+template <class T>
+static cudaError_t pool_alloc(sbn_ctx* ctx, T** out, size_t bytes) { return pool_alloc(ctx, (void**)out, bytes); }
+static void pool_free(sbn_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes >= kPoolMinBytes && ctx->mem_pool_bytes + bytes <= kPoolMaxBytes) {
+        ctx->mem_pool.emplace_back(bytes, p);
+        ctx->mem_pool_bytes += bytes;
+    } else {
+        cudaFree(p);
+    }
+}
+
 static void release(DevBuf& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
@@ -120,6 +163,17 @@ extern "C" const char* sbn_last_cuda_error(const sbn_ctx* ctx) { return ctx ? ct
 extern "C" int sbn_version(void) { return 1; }
 // host utility: Keccak-f[1600] for the host mirrors' Merlin transcript (200-byte little-endian state, in place)
 extern "C" void sbn_keccak_f1600(uint64_t* state) { sbn::keccak::permute(state); }
+// host utilities: the Merlin transcript of the host mirrors (state = 203 bytes owned by the caller)
+extern "C" void sbn_merlin_init(void* state, const uint8_t* label, size_t llen) { sbn::merlin::init(*(sbn::merlin::State*)state, label, llen); }
+extern "C" void sbn_merlin_append(void* state, const uint8_t* label, size_t llen, const uint8_t* msg, size_t mlen) {
+    sbn::merlin::append_message(*(sbn::merlin::State*)state, label, llen, msg, mlen);
+}
+extern "C" void sbn_merlin_append_many(void* state, const uint8_t* label, size_t llen, const uint8_t* msgs, size_t mlen, size_t count) {
+    for (size_t i = 0; i < count; i++) sbn::merlin::append_message(*(sbn::merlin::State*)state, label, llen, msgs + i * mlen, mlen);
+}
+extern "C" void sbn_merlin_challenge(void* state, const uint8_t* label, size_t llen, uint8_t* out, size_t n) {
+    sbn::merlin::challenge_bytes(*(sbn::merlin::State*)state, label, llen, out, n);
+}
 
 extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
     if (!out) return SBN_ERR_ARG;
@@ -165,6 +219,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
         for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs, &sl.pts[0], &sl.pts[1], &sl.pts[2],
                           &sl.prefix, &sl.other, &sl.wtot, &sl.winv})
             release(*b);
+    pool_flush(ctx);
     cudaEventDestroy(ctx->fork);
     if (ctx->join_hi) cudaEventDestroy(ctx->join_hi);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -932,7 +987,7 @@ extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_po
     if (!p) return SBN_ERR_OOM;
     p->ctx = ctx;
     p->len = len;
-    if (cudaMalloc(&p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_poly_upload: cudaMalloc failed"; return SBN_ERR_OOM; }
+    if (pool_alloc(ctx, &p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_poly_upload: cudaMalloc failed"; return SBN_ERR_OOM; }
     if (cudaMemcpyAsync(p->Z, Z, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
         cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
         cudaFree(p->Z);
@@ -950,8 +1005,7 @@ extern "C" int sbn_poly_destroy(sbn_poly* p) {
     {
         std::lock_guard<std::mutex> g(p->ctx->mu);
         cudaSetDevice(p->ctx->device);
-        cudaDeviceSynchronize();
-        cudaFree(p->Z);
+        pool_free(p->ctx, p->Z, p->len * sizeof(Fr));      // stream-ordered reuse, see sbn_ctx::mem_pool
     }
     delete p;
     return SBN_OK;
@@ -1382,7 +1436,7 @@ extern "C" int sbn_prodcircuit_create(sbn_ctx* ctx, const sbn_fr* poly, size_t l
     pc->len = len;
     size_t total = 0;
     for (size_t n = len; n >= 2; n >>= 1) { pc->off.push_back(total); total += n; pc->num_layers++; }
-    if (cudaMalloc(&pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; ctx->last_error = "sbn_prodcircuit_create: cudaMalloc failed"; return SBN_ERR_OOM; }
+    if (pool_alloc(ctx, &pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; ctx->last_error = "sbn_prodcircuit_create: cudaMalloc failed"; return SBN_ERR_OOM; }
     cudaStream_t s = ctx->compute;
     cudaError_t e = cudaMemcpyAsync(pc->buf, poly, len * sizeof(Fr), cudaMemcpyHostToDevice, s);
     ctx->h2d += len * sizeof(Fr);
@@ -1395,7 +1449,7 @@ extern "C" int sbn_prodcircuit_create(sbn_ctx* ctx, const sbn_fr* poly, size_t l
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) {
         ctx->last_error = std::string("sbn_prodcircuit_create: ") + cudaGetErrorString(e);
-        cudaFree(pc->buf);
+        pool_free(ctx, pc->buf, total * sizeof(Fr));
         delete pc;
         return SBN_ERR_CUDA;
     }
@@ -1424,8 +1478,7 @@ extern "C" int sbn_prodcircuit_destroy(sbn_prodcircuit* pc) {
     {
         std::lock_guard<std::mutex> g(pc->ctx->mu);
         cudaSetDevice(pc->ctx->device);
-        cudaStreamSynchronize(pc->ctx->compute);
-        cudaFree(pc->buf);
+        pool_free(pc->ctx, pc->buf, (2 * pc->len - 2) * sizeof(Fr));
     }
     delete pc;
     return SBN_OK;
@@ -1433,7 +1486,7 @@ extern "C" int sbn_prodcircuit_destroy(sbn_prodcircuit* pc) {
 
 struct sbn_bsumcheck {
     sbn_ctx* ctx = nullptr;
-    size_t P = 0, S = 0, len = 0;
+    size_t P = 0, S = 0, len = 0, T0 = 0;
     std::vector<Fr*> A, B, C;        // per instance (C of a parallel instance = the shared eq table)
     Fr* eq[2] = {nullptr, nullptr};  // ping-pong buffers of EqPolynomial::evals; eq[cur] is poly_C_par
     int eq_cur = 0;
@@ -1447,8 +1500,10 @@ struct sbn_bsumcheck {
 };
 
 static void bsumcheck_free(sbn_bsumcheck* st) {
-    for (void* p : {(void*)st->eq[0], (void*)st->eq[1], (void*)st->seq, (void*)st->d_triples, (void*)st->d_tables,
-                    (void*)st->partial, (void*)st->out})
+    pool_free(st->ctx, st->eq[0], st->T0 * sizeof(Fr));
+    pool_free(st->ctx, st->eq[1], st->T0 * sizeof(Fr));
+    pool_free(st->ctx, st->seq, 3 * st->S * st->T0 * sizeof(Fr));
+    for (void* p : {(void*)st->d_triples, (void*)st->d_tables, (void*)st->partial, (void*)st->out})
         if (p) cudaFree(p);
     delete st;
 }
@@ -1477,12 +1532,13 @@ static int bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_
     st->len = T;
     const size_t n = P + S;
     st->max_blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((T / 2 + kDotThreads - 1) / kDotThreads, std::max<size_t>(16, 1184 / n)));
-    bool ok = cudaMalloc(&st->eq[0], T * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->eq[1], T * sizeof(Fr)) == cudaSuccess &&
+    st->T0 = T;
+    bool ok = pool_alloc(ctx, &st->eq[0], T * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->eq[1], T * sizeof(Fr)) == cudaSuccess &&
               cudaMalloc(&st->d_triples, n * sizeof(CubicTriple)) == cudaSuccess &&
               cudaMalloc(&st->d_tables, (2 * P + 1 + 3 * S) * sizeof(Fr*)) == cudaSuccess &&
               cudaMalloc(&st->partial, 3 * n * st->max_blocks * sizeof(Fr)) == cudaSuccess &&
               cudaMalloc(&st->out, (3 * n + n_rand + 2) * sizeof(Fr)) == cudaSuccess &&
-              (S == 0 || cudaMalloc(&st->seq, 3 * S * T * sizeof(Fr)) == cudaSuccess);
+              (S == 0 || pool_alloc(ctx, &st->seq, 3 * S * T * sizeof(Fr)) == cudaSuccess);
     if (!ok) { bsumcheck_free(st); ctx->last_error = "sbn_bsumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
     auto fail = [&](const char* what, cudaError_t e) {
         ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -1748,8 +1804,8 @@ extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_add
     if (!p) return SBN_ERR_OOM;
     p->ctx = ctx;
     p->len = len;
-    if (cudaMalloc(&p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_derefs_commit: cudaMalloc failed"; return SBN_ERR_OOM; }
-    auto fail = [&](int code) { cudaFree(p->Z); delete p; return code; };
+    if (pool_alloc(ctx, &p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_derefs_commit: cudaMalloc failed"; return SBN_ERR_OOM; }
+    auto fail = [&](int code) { pool_free(ctx, p->Z, len * sizeof(Fr)); delete p; return code; };
     const size_t tx = size_t(1) << nx, ty = size_t(1) << ny;
     int rc;
     if ((rc = ensure(ctx, ctx->scratch0, 2 * tx * sizeof(Fr))) != SBN_OK || (rc = ensure(ctx, ctx->scratch1, 2 * ty * sizeof(Fr))) != SBN_OK ||
@@ -1779,7 +1835,7 @@ extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_add
     if (cudaStreamSynchronize(s) != cudaSuccess) { ctx->last_error = "sbn_derefs_commit: synchronize failed"; return fail(SBN_ERR_CUDA); }
     collect_profile(ctx, ev_stage);
     if (poly_out) *poly_out = p;        // the derefs polynomial stays resident for its opening (DerefsEvalProof)
-    else { cudaFree(p->Z); delete p; }
+    else { pool_free(ctx, p->Z, len * sizeof(Fr)); delete p; }
     return SBN_OK;
 }
 
@@ -1804,7 +1860,7 @@ static sbn_prodcircuit* prodcircuit_alloc(sbn_ctx* ctx, size_t len) {
     pc->len = len;
     size_t total = 0;
     for (size_t n = len; n >= 2; n >>= 1) { pc->off.push_back(total); total += n; pc->num_layers++; }
-    if (cudaMalloc(&pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; return nullptr; }
+    if (pool_alloc(ctx, &pc->buf, total * sizeof(Fr)) != cudaSuccess) { delete pc; return nullptr; }
     return pc;
 }
 
@@ -1828,7 +1884,11 @@ extern "C" int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* a, int side, c
     for (size_t i = 0; i < ncirc; i++) circuits_out[i] = nullptr;
     auto fail = [&](int code) {
         for (size_t i = 0; i < ncirc; i++)
-            if (circuits_out[i]) { cudaFree(circuits_out[i]->buf); delete circuits_out[i]; circuits_out[i] = nullptr; }
+            if (circuits_out[i]) {
+                pool_free(ctx, circuits_out[i]->buf, (2 * circuits_out[i]->len - 2) * sizeof(Fr));
+                delete circuits_out[i];
+                circuits_out[i] = nullptr;
+            }
         return code;
     };
     for (size_t i = 0; i < ncirc; i++) {
@@ -1925,12 +1985,12 @@ extern "C" int sbn_spark_comb_polys(sbn_ctx* ctx, const sbn_addrs* a, const sbn_
     po->len = len;
     pm->len = 2 * a->num_cells;
     auto fail = [&](int code) {
-        if (po->Z) cudaFree(po->Z);
-        if (pm->Z) cudaFree(pm->Z);
+        pool_free(ctx, po->Z, po->len * sizeof(Fr));
+        pool_free(ctx, pm->Z, pm->len * sizeof(Fr));
         delete po; delete pm;
         return code;
     };
-    if (cudaMalloc(&po->Z, po->len * sizeof(Fr)) != cudaSuccess || cudaMalloc(&pm->Z, pm->len * sizeof(Fr)) != cudaSuccess) {
+    if (pool_alloc(ctx, &po->Z, po->len * sizeof(Fr)) != cudaSuccess || pool_alloc(ctx, &pm->Z, pm->len * sizeof(Fr)) != cudaSuccess) {
         ctx->last_error = "sbn_spark_comb_polys: cudaMalloc failed";
         return fail(SBN_ERR_OOM);
     }
@@ -2014,6 +2074,8 @@ struct sbn_spmat {
     size_t n = 0, nnz = 0, ncols = 0;
     uint32_t *ptr = nullptr, *idx = nullptr;
     Fr* val = nullptr;
+    uint32_t* heavy = nullptr;      // rows with more than kSpmvHeavy entries
+    size_t nheavy = 0;
 };
 
 extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_t* idx, const sbn_fr* val, size_t n, size_t nnz,
@@ -2023,6 +2085,8 @@ extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_
     if (n == 0 || n > (size_t(1) << 30) || nnz > (size_t(1) << 31) || ptr[0] != 0 || ptr[n] != nnz) return SBN_ERR_SHAPE;
     for (size_t i = 0; i < n; i++) if (ptr[i] > ptr[i + 1]) return SBN_ERR_SHAPE;
     for (size_t k = 0; k < nnz; k++) if (idx[k] >= ncols) return SBN_ERR_SHAPE;
+    std::vector<uint32_t> heavy_rows;
+    for (size_t i = 0; i < n; i++) if (ptr[i + 1] - ptr[i] > kSpmvHeavy) heavy_rows.push_back((uint32_t)i);
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     sbn_spmat* m = new (std::nothrow) sbn_spmat();
@@ -2036,7 +2100,13 @@ extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_
               (nnz == 0 || (cudaMemcpyAsync(m->idx, idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
                             cudaMemcpyAsync(m->val, val, nnz * sizeof(Fr), cudaMemcpyHostToDevice, s) == cudaSuccess)) &&
               cudaStreamSynchronize(s) == cudaSuccess;
+    if (ok && !heavy_rows.empty()) {
+        m->nheavy = heavy_rows.size();
+        ok = cudaMalloc(&m->heavy, m->nheavy * sizeof(uint32_t)) == cudaSuccess &&
+             cudaMemcpy(m->heavy, heavy_rows.data(), m->nheavy * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (!ok) {
+        if (m->heavy) cudaFree(m->heavy);
         if (m->ptr) cudaFree(m->ptr);
         if (m->idx) cudaFree(m->idx);
         if (m->val) cudaFree(m->val);
@@ -2056,6 +2126,7 @@ extern "C" int sbn_spmat_destroy(sbn_spmat* m) {
         cudaSetDevice(m->ctx->device);
         cudaStreamSynchronize(m->ctx->compute);
         cudaFree(m->ptr); cudaFree(m->idx); cudaFree(m->val);
+        if (m->heavy) cudaFree(m->heavy);
     }
     delete m;
     return SBN_OK;
@@ -2085,6 +2156,12 @@ extern "C" int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, cons
     k_spmv<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sm[0], sm[1], sm[2], c[0], c[1], c[2], (int)nm, coeffs ? 1 : 0,
                                                         (const Fr*)ctx->scratch0.p, n, (Fr*)ctx->scratch1.p);
     ctx->launches++;
+    for (size_t m = 0; m < nm; m++)
+        if (mats[m]->nheavy) {
+            k_spmv_heavy<<<(unsigned)mats[m]->nheavy, kDotThreads, 0, s>>>(sm[m], mats[m]->heavy, c[m], coeffs ? 1 : 0,
+                                                                          (const Fr*)ctx->scratch0.p, (Fr*)ctx->scratch1.p);
+            ctx->launches++;
+        }
     SBN_CUDA(ctx, cudaGetLastError());
     SBN_TRY(download(ctx, out, ctx->scratch1.p, n * sizeof(Fr)));
     SBN_CUDA(ctx, cudaStreamSynchronize(s));

@@ -279,16 +279,32 @@ def fr_from_int(v):
     return np.array(_limbs((int(v) << 256) % R_MOD), dtype=np.uint64)
 
 
+_BULK = 128     # vectors at least this long change form on the GPU (one kernel) instead of element by element
+
+
+def _bulk_ctx():
+    from . import lib as _lib
+    return _lib._live_contexts[-1] if _lib._live_contexts else None
+
+
 def fr_vec_to_ints(arr):
     arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
-    return [fr_to_int(a) for a in arr]
+    ctx = _bulk_ctx() if arr.shape[0] >= _BULK else None
+    if ctx is None:
+        return [fr_to_int(a) for a in arr]
+    data = ctx.fr_to_canonical(arr).tobytes()
+    return [int.from_bytes(data[32 * i: 32 * i + 32], "little") for i in range(arr.shape[0])]
 
 
 def fr_vec_from_ints(vals):
-    out = np.zeros((len(vals), 4), dtype=np.uint64)
-    for i, v in enumerate(vals):
-        out[i] = fr_from_int(v)
-    return out
+    ctx = _bulk_ctx() if len(vals) >= _BULK else None
+    if ctx is None:
+        out = np.zeros((len(vals), 4), dtype=np.uint64)
+        for i, v in enumerate(vals):
+            out[i] = fr_from_int(v)
+        return out
+    data = b"".join((int(v) % R_MOD).to_bytes(32, "little") for v in vals)
+    return ctx.fr_from_canonical(np.frombuffer(data, dtype=np.uint64).reshape(-1, 4))
 
 
 class EqPolynomial:

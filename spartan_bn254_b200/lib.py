@@ -22,7 +22,7 @@ EXPORTS = [
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
-    "sbn_keccak_f1600", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
+    "sbn_keccak_f1600", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
@@ -71,6 +71,9 @@ def _u64(a, cols):
     return a.reshape(-1, cols)
 
 
+_live_contexts = []          # most recent last: the host mirrors' bulk Fr conversions borrow one (hyrax._bulk_ctx)
+
+
 class Context:
     """sbn_ctx: one CUDA device."""
 
@@ -83,6 +86,7 @@ class Context:
                            " -- a CUDA device is required, there is no CPU fallback")
         self.h = h
         self.device = device
+        _live_contexts.append(self)
 
     def _check(self, st, what):
         if st != 0:
@@ -91,6 +95,8 @@ class Context:
             raise SbnError(st, what, detail + (": " + cuda if cuda and st in (-3, -4) else ""))
 
     def close(self):
+        if self in _live_contexts:
+            _live_contexts.remove(self)
         if self.h:
             self.lib.sbn_ctx_destroy(self.h)
             self.h = None

@@ -23,10 +23,15 @@ from .spark import (MultiSparseMatPolynomialAsDense, SparseMatPolyCommitmentGens
                     append_poly_commitment, commit_dense, equalize)
 
 
-def commit_scalars(gens, scalars, blind):
-    """Commitments::commit (commitments.rs:118-154) for the short vectors of the Sigma-protocols: sum s_i G_i + blind h."""
+def commit_scalars(gens, scalars, blind, resident=True):
+    """Commitments::commit (commitments.rs:118-154) for the short vectors of the Sigma-protocols: sum s_i G_i + blind h.
+    The generator sets of the sumchecks are fixed, so the commitment runs over their resident window tables (one row of the
+    commit pipeline, ~0.2 ms) rather than as a variable-base MSM (a 254-step double-and-add chain, ~2.4 ms)."""
     n = len(scalars)
     assert gens.n == n, "assert_eq!(gens_n.n, self.len())"
+    if resident:
+        out, inf = gens.ctx.commit(gens.device_bases(), fr_vec_from_ints(list(scalars)), fr_from_int(blind))
+        return GroupElement(out, inf)
     pts = np.concatenate([gens.G[:n].reshape(n, 8), gens.h.reshape(1, 8)])
     out, inf = gens.ctx.msm(pts, None, fr_vec_from_ints(list(scalars) + [blind]))
     return GroupElement(out, inf)
@@ -94,7 +99,7 @@ class ProductProof:
         beta = commit_scalars(gens_n, [b3], b4)
         _append(transcript, b"beta", beta)
         gens_X = MultiCommitGens.from_generators(X.xy.reshape(1, 8), gens_n.h, gens_n.ctx)      # mod.rs:203-206
-        delta = commit_scalars(gens_X, [b3], b5)
+        delta = commit_scalars(gens_X, [b3], b5, resident=False)    # one-off generator X: variable-base MSM
         _append(transcript, b"delta", delta)
         c = transcript.challenge_scalar(b"c")
         zs = [(b1 + c * x) % R_MOD, (b2 + c * rX) % R_MOD, (b3 + c * y) % R_MOD, (b4 + c * rY) % R_MOD,

@@ -270,12 +270,20 @@ class PolyEvalNetworkProof:
         self.proof_prod_layer, self.proof_hash_layer = proof_prod_layer, proof_hash_layer
 
     @staticmethod
-    def prove(ctx, network, dense, derefs_poly, evals, gens, transcript, random_tape):
+    def prove(ctx, network, dense, derefs_poly, evals, gens, transcript, random_tape, timings=None):
         """sparse_mlpoly_full.rs:1546-1578."""
+        import time
         transcript.append_protocol_name(b"Sparse polynomial evaluation proof")
+        t0 = time.perf_counter()
         prod, rand_mem, rand_ops = ProductLayerProof.prove(ctx, network.row_layers.prod_layer, network.col_layers.prod_layer,
                                                            dense, derefs_poly, evals, transcript)
+        ctx.synchronize()
+        t1 = time.perf_counter()
         hashp = HashLayerProof.prove((rand_mem, rand_ops), dense, derefs_poly, gens, transcript, random_tape)
+        ctx.synchronize()
+        if timings is not None:
+            timings["network_proof.product_layers_ms"] = 1e3 * (t1 - t0)
+            timings["network_proof.hash_layer(evaluations + 3 openings)_ms"] = 1e3 * (time.perf_counter() - t1)
         return PolyEvalNetworkProof(prod, hashp)
 
 
@@ -322,10 +330,11 @@ class SparseMatPolyEvalProof:
         lap("transcript_commitment_ms")
         net = PolyEvalNetwork(dense.spark, rx_m, ry_m, (fr_from_int(r_mem_check[0]), fr_from_int(r_mem_check[1])))
         lap("network_construction_ms")
-        proof = PolyEvalNetworkProof.prove(ctx, net, dense, derefs_poly, evals, gens, transcript, random_tape)
+        proof = PolyEvalNetworkProof.prove(ctx, net, dense, derefs_poly, evals, gens, transcript, random_tape, timings)
         lap("network_proof_ms")
         for lay in (net.row_layers, net.col_layers):
             for c in lay.prod_layer.all():
                 c.close()
         derefs_poly.close()
+        lap("free_device_tables_ms")
         return SparseMatPolyEvalProof(comm_derefs, proof)

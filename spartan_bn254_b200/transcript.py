@@ -57,8 +57,67 @@ _R = 166
 _FLAG_I, _FLAG_A, _FLAG_C, _FLAG_T, _FLAG_M, _FLAG_K = 1, 2, 4, 8, 16, 32
 
 
+def _native_merlin():
+    """libsbn254's host-side Merlin (csrc/host/merlin.hpp) when the library has been built."""
+    try:
+        from .lib import load_library
+        lib = load_library()
+        for f in (lib.sbn_merlin_init, lib.sbn_merlin_append, lib.sbn_merlin_append_many, lib.sbn_merlin_challenge):
+            f.restype = None
+        return lib
+    except Exception:
+        return None
+
+
 class Transcript:
-    def __init__(self, label):
+    """Merlin transcript.  With libsbn254 built, the STROBE state lives in a 203-byte buffer driven by the library's host
+    code (a keyless-scale proof appends ~60 000 scalars); otherwise the pure-Python STROBE below runs (PyTranscript)."""
+
+    def __new__(cls, label, native=True):
+        if cls is Transcript and (not native or _native_merlin() is None):
+            return object.__new__(PyTranscript)
+        return object.__new__(cls)
+
+    def __init__(self, label, native=True):
+        self._lib = _native_merlin()
+        self._st = _ctypes.create_string_buffer(208)
+        self._lib.sbn_merlin_init(self._st, label, _ctypes.c_size_t(len(label)))
+
+    def append_message(self, label, message):
+        message = bytes(message)
+        self._lib.sbn_merlin_append(self._st, label, _ctypes.c_size_t(len(label)), message, _ctypes.c_size_t(len(message)))
+
+    def challenge_bytes(self, label, n):
+        out = _ctypes.create_string_buffer(n)
+        self._lib.sbn_merlin_challenge(self._st, label, _ctypes.c_size_t(len(label)), out, _ctypes.c_size_t(n))
+        return out.raw
+
+    # ---- ProofTranscript (reference transcript.rs:37-80); scalars are canonical Python ints here
+    def append_protocol_name(self, name):
+        self.append_message(b"protocol-name", name)
+
+    def append_scalar(self, label, s):
+        self.append_message(label, int(s).to_bytes(32, "little"))          # scalar.rs:75-84
+
+    def append_scalars(self, label, scalars):
+        data = b"".join(int(s).to_bytes(32, "little") for s in scalars)
+        self._lib.sbn_merlin_append_many(self._st, label, _ctypes.c_size_t(len(label)), data, _ctypes.c_size_t(32),
+                                         _ctypes.c_size_t(len(data) // 32))
+
+    def append_point(self, label, compressed32):
+        self.append_message(label, compressed32)
+
+    def challenge_scalar(self, label):
+        return int.from_bytes(self.challenge_bytes(label, 64), "little") % R_MOD   # transcript.rs:56-67
+
+    def challenge_scalars(self, label, n):
+        return [self.challenge_scalar(label) for _ in range(n)]
+
+
+class PyTranscript(Transcript):
+    """The same transcript in pure Python (no library needed)."""
+
+    def __init__(self, label, native=False):
         self.st = bytearray(200)
         self.st[0:6] = bytes([1, _R + 2, 1, 0, 1, 96])
         self.st[6:18] = b"STROBEv1.0.2"
@@ -150,6 +209,9 @@ class Transcript:
     def append_scalars(self, label, scalars):
         for s in scalars:
             self.append_scalar(label, s)
+
+    def append_scalar(self, label, s):
+        self.append_message(label, int(s).to_bytes(32, "little"))
 
     def append_point(self, label, compressed32):
         self.append_message(label, compressed32)

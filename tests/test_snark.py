@@ -82,3 +82,31 @@ def test_snark_rejections(ctx, orc):
     for tamper in (bad_input, bad_eval, bad_sigma):
         with pytest.raises(snm.VerifyError):
             _prove_and_verify(ctx, orc, 16, 16, 2, 7, tamper)
+
+
+def test_sparse_matvec_with_heavy_rows(ctx):
+    """sbn_spmat_mulvec against host integers, including a row of 5000 entries (handled by a whole block) and the combined
+    r_A A + r_B B form."""
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints, fr_vec_to_ints
+    from spartan_bn254_b200.lib import SpMat
+    rnd = random.Random(3)
+    n, ncols = 64, 97
+    mats = []
+    for m in range(2):
+        ent = [(rnd.randrange(n), rnd.randrange(ncols), rnd.randrange(R)) for _ in range(300)]
+        ent += [(5 + m, rnd.randrange(ncols), rnd.randrange(R)) for _ in range(5000)]
+        mats.append(ent)
+    vec = [rnd.randrange(R) for _ in range(ncols)]
+    coeffs = [rnd.randrange(R), rnd.randrange(R)]
+    want = [0] * n
+    single = [0] * n
+    for m, ent in enumerate(mats):
+        for r, c, v in ent:
+            want[r] = (want[r] + coeffs[m] * v % R * vec[c]) % R
+            if m == 0:
+                single[r] = (single[r] + v * vec[c]) % R
+    sp = [SpMat(ctx, n, ncols, [e[0] for e in ent], [e[1] for e in ent], fr_vec_from_ints([e[2] for e in ent])) for ent in mats]
+    assert fr_vec_to_ints(SpMat.mulvec(sp, fr_vec_from_ints(vec), fr_vec_from_ints(coeffs))) == want
+    assert fr_vec_to_ints(SpMat.mulvec(sp[:1], fr_vec_from_ints(vec))) == single
+    for s_ in sp:
+        s_.close()

@@ -23,3 +23,26 @@ def test_matches_c_oracle_transcript(orc):
     ot = orc.Transcript(b"proof")
     ot.append_message(b"init_randomness", (12345).to_bytes(32, "little"))
     assert orc.from_mont(ot.challenge_scalar(b"d")) == [tape.random_scalar(b"d")]
+
+
+def test_native_and_python_transcripts_agree():
+    """The library's host-side Merlin (csrc/host/merlin.hpp) and the pure-Python STROBE produce the same challenges on a
+    random sequence of operations."""
+    import random
+    from spartan_bn254_b200.transcript import Transcript, PyTranscript
+    a, b = Transcript(b"agree"), Transcript(b"agree", native=False)
+    assert isinstance(b, PyTranscript) and not isinstance(a, PyTranscript)
+    rnd = random.Random(1)
+    for _ in range(200):
+        k = rnd.randrange(4)
+        if k == 0:
+            m = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 400)))
+            a.append_message(b"lab", m); b.append_message(b"lab", m)
+        elif k == 1:
+            v = [rnd.randrange(1 << 250) for _ in range(rnd.randrange(1, 9))]
+            a.append_scalars(b"sc", v); b.append_scalars(b"sc", v)
+        elif k == 2:
+            assert a.challenge_scalar(b"c") == b.challenge_scalar(b"c")
+        else:
+            n = rnd.randrange(1, 200)
+            assert a.challenge_bytes(b"cb", n) == b.challenge_bytes(b"cb", n)
