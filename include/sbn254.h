@@ -222,6 +222,11 @@ int sbn_spark_evaluate(sbn_ctx* ctx, const sbn_addrs* addrs, const sbn_poly* com
  * product_tree.rs:81-86). */
 int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA, const sbn_poly* B, size_t offB, const sbn_poly* C,
                         size_t offC, size_t n, sbn_fr* out);
+/* Multi-GPU form of sbn_derefs_commit: builds the whole polynomial, commits rows [row0, row0 + nrows) of its Hyrax matrix
+ * (C_out / inf_out hold nrows points); ranks gather their blocks. */
+int sbn_derefs_commit_rows(sbn_ctx* ctx, const sbn_bases* bases, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                           const sbn_fr* ry, size_t ny, size_t row0, size_t nrows, sbn_g1a* C_out, uint8_t* inf_out,
+                           sbn_poly** poly_out);
 size_t sbn_poly_len(const sbn_poly* poly);
 int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* poly, sbn_fr* out);
 

@@ -2,6 +2,9 @@
 (2^k constraints, 2^k variables, one public input, three non-zeros per row in the densest matrix so that nnz pads to
 2^(k+2), as the Aptos-keyless circuit does) is encoded, proved through the GPU path with real Merlin transcripts, and the
 proof is checked by the oracle's independent CPU restatement of SNARK::verify.  The reference has no .r1cs/.wtns offline.
+Under torchrun (one process per GPU) every rank holds the instance and runs the prover; the derefs commitment -- the only
+table-sized step that shards without an exchange per round -- is split by rows across the ranks and its row blocks are
+all-gathered over NCCL; the reported time is the maximum over ranks.
 Usage: bench_snark.py [log2_constraints=20] [--no-verify]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,14 +22,25 @@ verify = "--no-verify" not in sys.argv
 n = 1 << k
 num_cons = num_vars = n
 num_inputs = 1
-ctx = Context(0)
-out = {"log2_constraints": k, "num_vars": num_vars, "num_inputs": num_inputs, "ms": {}}
+rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+shard = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    from spartan_bn254_b200.parallel import make_all_gather
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    shard = (rank, world, make_all_gather(torch.device("cuda", local_rank)))
+ctx = Context(local_rank)
+out = {"log2_constraints": k, "num_vars": num_vars, "num_inputs": num_inputs, "n_gpus": world, "ms": {}}
 
 
 def timed(name, fn):
     ctx.synchronize(); t0 = time.perf_counter(); r = fn(); ctx.synchronize()
     out["ms"][name] = round(1e3 * (time.perf_counter() - t0), 3)
-    print(name, out["ms"][name], "ms", flush=True)
+    if rank == 0:
+        print(name, out["ms"][name], "ms", flush=True)
     return r
 
 
@@ -52,16 +66,38 @@ gens = timed("setup.generators(one-off)", lambda: SNARKGens(ctx, num_cons, num_v
 comm, decomm = SNARK.encode(inst, gens)
 decomm.close()
 comm, decomm = timed("encode(dense representation + comb_ops/comb_mem commitments)", lambda: SNARK.encode(inst, gens))
+def barrier():
+    if world > 1:
+        dist.barrier()
+
+
 timings = {}
+barrier()
 t0 = time.perf_counter()
-proof = SNARK.prove(inst, comm, decomm, vars_m, input_m, gens, Transcript(b"snark"), 1, timings=timings)
+proof = SNARK.prove(inst, comm, decomm, vars_m, input_m, gens, Transcript(b"snark"), 1, timings=timings, shard=shard)
 ctx.synchronize()
 out["ms"]["prove.first_call(cold kernels and workspaces)"] = round(1e3 * (time.perf_counter() - t0), 3)
-timings = {}
-t0 = time.perf_counter()
-proof = SNARK.prove(inst, comm, decomm, vars_m, input_m, gens, Transcript(b"snark"), 1, timings=timings)
-ctx.synchronize()
-out["ms"]["prove.SNARK_total"] = round(1e3 * (time.perf_counter() - t0), 3)
+best = None
+for rep in range(3):
+    timings = {}
+    barrier()
+    t0 = time.perf_counter()
+    proof = SNARK.prove(inst, comm, decomm, vars_m, input_m, gens, Transcript(b"snark"), 1, timings=timings, shard=shard)
+    ctx.synchronize()
+    dt = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    if best is None or dt < best[0]:
+        best = (dt, timings)
+out["ms"]["prove.SNARK_total"] = round(best[0], 3)
+out["prove_total_note"] = "best of 3 warm proofs; with N > 1 the maximum over ranks of each proof"
+timings = best[1]
+if rank != 0:
+    barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 out["prove_phases_ms"] = {a: (round(b, 3) if not isinstance(b, dict) else {x: round(y, 3) for x, y in b.items()}) for a, b in timings.items()}
 print(json.dumps(out["prove_phases_ms"], indent=1), flush=True)
 if verify:
@@ -87,4 +123,7 @@ out["reference_published_M2Max_1thread_s"] = {"r1cs_sat_proof": 3.45, "instance_
                                              "total_prove": 208.8, "encode": 60.7, "verify": 0.39,
                                              "source": "BENCHMARK_RESULTS.md:22-42 (Aptos keyless: 1 040 083 constraints, nnz padded to 2^22)"}
 print(json.dumps(out, indent=1))
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "snark_%d.json" % k), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "snark_%d%s.json" % (k, "" if world == 1 else "_n%d" % world)), "w"), indent=1)
+if world > 1:
+    barrier()
+    dist.destroy_process_group()

@@ -1785,8 +1785,9 @@ static Fr* eq_evals_device(sbn_ctx* ctx, const Fr* r_dev, size_t n, Fr* dst, Fr*
     return buf[cur];
 }
 
-extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
-                                 const sbn_fr* ry, size_t ny, sbn_g1a* C_out, uint8_t* inf_out, sbn_poly** poly_out) {
+static int derefs_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                              const sbn_fr* ry, size_t ny, size_t row0, size_t nrows, bool all_rows, sbn_g1a* C_out,
+                              uint8_t* inf_out, sbn_poly** poly_out) {
     if (!ctx || !b || !addrs || !rx || !ry || !C_out || !inf_out || b->ctx != ctx || addrs->ctx != ctx) return SBN_ERR_ARG;
     if (nx == 0 || ny == 0 || nx > 30 || ny > 30) return SBN_ERR_SHAPE;
     if (addrs->max_row >= (size_t(1) << nx) || addrs->max_col >= (size_t(1) << ny)) return SBN_ERR_SHAPE;   // would index past mem_rx / mem_ry
@@ -1795,7 +1796,10 @@ extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_add
     size_t len = 1;
     int ell = 0;
     while (len < used) { len <<= 1; ell++; }
-    const size_t L = size_t(1) << (ell / 2), R = len / L;
+    const size_t Lfull = size_t(1) << (ell / 2), R = len / Lfull;
+    if (all_rows) { row0 = 0; nrows = Lfull; }
+    if (nrows == 0 || row0 > Lfull || nrows > Lfull - row0) return SBN_ERR_SHAPE;
+    const size_t L = nrows;                               // rows committed by this call (a rank's block of the Hyrax matrix)
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1828,7 +1832,7 @@ extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_add
         (rc = ensure(ctx, ctx->dinf, L)) != SBN_OK)
         return fail(rc);
     std::vector<int> ev_stage;
-    if ((rc = run_commit(ctx, b, p->Z, nullptr, L, R, nullptr, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, s, ev_stage)) != SBN_OK)
+    if ((rc = run_commit(ctx, b, p->Z + row0 * R, nullptr, L, R, nullptr, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, s, ev_stage)) != SBN_OK)
         return fail(rc);
     if ((rc = download(ctx, C_out, ctx->dC.p, L * sizeof(Affine))) != SBN_OK || (rc = download(ctx, inf_out, ctx->dinf.p, L)) != SBN_OK)
         return fail(rc);
@@ -1837,6 +1841,18 @@ extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_add
     if (poly_out) *poly_out = p;        // the derefs polynomial stays resident for its opening (DerefsEvalProof)
     else { pool_free(ctx, p->Z, len * sizeof(Fr)); delete p; }
     return SBN_OK;
+}
+
+extern "C" int sbn_derefs_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                                 const sbn_fr* ry, size_t ny, sbn_g1a* C_out, uint8_t* inf_out, sbn_poly** poly_out) {
+    return derefs_commit_rows(ctx, b, addrs, rx, nx, ry, ny, 0, 0, true, C_out, inf_out, poly_out);
+}
+// Multi-GPU form: the whole derefs polynomial is built (it is needed for the opening), rows [row0, row0 + nrows) of its
+// Hyrax matrix are committed; the caller gathers the row blocks of the ranks (hyrax.rs:259-265: rows are independent).
+extern "C" int sbn_derefs_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs* addrs, const sbn_fr* rx, size_t nx,
+                                      const sbn_fr* ry, size_t ny, size_t row0, size_t nrows, sbn_g1a* C_out, uint8_t* inf_out,
+                                      sbn_poly** poly_out) {
+    return derefs_commit_rows(ctx, b, addrs, rx, nx, ry, ny, row0, nrows, false, C_out, inf_out, poly_out);
 }
 
 extern "C" size_t sbn_poly_len(const sbn_poly* p) { return p ? p->len : 0; }

@@ -22,7 +22,7 @@ EXPORTS = [
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
-    "sbn_keccak_f1600", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
+    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
@@ -611,18 +611,23 @@ class Addrs:
         lens = [self.num_cells] + [self.N] * (2 * self.batch) + [self.num_cells]
         return [ProdCircuit._from_handle(self.ctx, C.c_void_p(handles[i]), lens[i]) for i in range(n)]
 
-    def derefs_commit(self, bases, rx, ry, keep=True):
-        """Returns (C, inf, Poly or None): the Hyrax commitment of the derefs polynomial built on the device."""
-        rx, ry = _u64(rx, 4), _u64(ry, 4)
+    def derefs_rows(self):
+        """Rows of the Hyrax matrix of the derefs polynomial (2^(ell/2))."""
         used = 2 * self.batch * self.N
-        ell = max(0, (used - 1).bit_length())
-        L = 1 << (ell // 2)
+        return 1 << (max(0, (used - 1).bit_length()) // 2)
+
+    def derefs_commit(self, bases, rx, ry, keep=True, rows=None):
+        """Returns (C, inf, Poly or None): the Hyrax commitment of the derefs polynomial built on the device; rows =
+        (row0, nrows) commits only that block of rows (multi-GPU sharding)."""
+        rx, ry = _u64(rx, 4), _u64(ry, 4)
+        row0, L = rows if rows is not None else (0, self.derefs_rows())
         out = np.zeros((L, 8), dtype=np.uint64)
         inf = np.zeros(L, dtype=np.uint8)
         ph = C.c_void_p()
-        st = self.ctx.lib.sbn_derefs_commit(self.ctx.h, bases.h, self.h, _ptr(rx), C.c_size_t(rx.shape[0]), _ptr(ry),
-                                            C.c_size_t(ry.shape[0]), _ptr(out), _ptr(inf), C.byref(ph) if keep else None)
-        self.ctx._check(st, "sbn_derefs_commit")
+        st = self.ctx.lib.sbn_derefs_commit_rows(self.ctx.h, bases.h, self.h, _ptr(rx), C.c_size_t(rx.shape[0]), _ptr(ry),
+                                                 C.c_size_t(ry.shape[0]), C.c_size_t(row0), C.c_size_t(L), _ptr(out), _ptr(inf),
+                                                 C.byref(ph) if keep else None)
+        self.ctx._check(st, "sbn_derefs_commit_rows")
         poly = None
         if keep:
             poly = Poly.__new__(Poly)

@@ -51,3 +51,21 @@ def commit_sharded(commit_fn, Z_local, n_local, L_size, R_size, blinds_local=Non
         Cs.append(a[:n, :8].view(np.uint64))
         infs.append(a[:n, 8].astype(np.uint8))
     return np.concatenate(Cs), np.concatenate(infs)
+
+
+def make_all_gather(device=None, group=None):
+    """-> all_gather(array) returning the list of every rank's (equal-shaped) numpy array: the only exchange of a sharded
+    prove (the commitment row blocks).  NCCL when `device` is a CUDA device, gloo on CPU."""
+    import torch
+    import torch.distributed as dist
+
+    def all_gather(arr):
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
+        if device is not None:
+            t = t.to(device)
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(out, t, group=group)
+        return [o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in out]
+
+    return all_gather

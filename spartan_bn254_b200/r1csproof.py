@@ -350,7 +350,7 @@ class SNARK:
         return R1CSCommitment(inst.num_cons, inst.num_vars, inst.num_inputs, comm), dense
 
     @staticmethod
-    def prove(inst, comm, decomm, vars_m, input_m, gens, transcript, tape_seed, timings=None):
+    def prove(inst, comm, decomm, vars_m, input_m, gens, transcript, tape_seed, timings=None, shard=None):
         """snark.rs:428-484.  The reference seeds its random tape from the OS; the seed is injected here."""
         import time
         from .transcript import RandomTape
@@ -365,7 +365,8 @@ class SNARK:
         inst_evals = decomm.multi_evaluate(rx_e, ry_e)                     # inst.evaluate(rx, ry), r1cs.rs:126-129
         inst.ctx.synchronize()
         t2 = time.perf_counter()
-        eval_proof = SparseMatPolyEvalProof.prove(decomm, rx, ry, inst_evals, gens.gens_r1cs_eval, transcript, tape, timings=eval_t)
+        eval_proof = SparseMatPolyEvalProof.prove(decomm, rx, ry, inst_evals, gens.gens_r1cs_eval, transcript, tape, timings=eval_t,
+                                                  shard=shard)
         inst.ctx.synchronize()
         t3 = time.perf_counter()
         if timings is not None:

@@ -302,7 +302,7 @@ class SparseMatPolyEvalProof:
         self.comm_derefs, self.poly_eval_network_proof = comm_derefs, poly_eval_network_proof
 
     @staticmethod
-    def prove(dense, rx, ry, evals, gens, transcript, random_tape, timings=None):
+    def prove(dense, rx, ry, evals, gens, transcript, random_tape, timings=None, shard=None):
         """sparse_mlpoly_full.rs:1694-1755 (Hyrax mode).  rx, ry, evals: canonical ints.  `timings` (dict) receives the wall
         time of the phases keyless_benchmark.rs times separately ([a]-[e], examples/keyless_benchmark.rs:190-235)."""
         import time
@@ -320,7 +320,7 @@ class SparseMatPolyEvalProof:
         rx_ext, ry_ext = equalize(rx, ry)
         rx_m, ry_m = fr_vec_from_ints(rx_ext), fr_vec_from_ints(ry_ext)
         # [a] eq tables, [b] derefs, [c] derefs commitment: one call, everything in HBM
-        C, inf, derefs_poly = dense.spark.derefs_commit(gens.gens_derefs.gens.gens_n, rx_m, ry_m)
+        C, inf, derefs_poly = dense.spark.derefs_commit(gens.gens_derefs.gens.gens_n, rx_m, ry_m, shard)
         comm_derefs = PolyCommitment(C, inf)
         lap("eq_tables+derefs+derefs_commitment_ms")
         transcript.append_message(b"derefs_commitment", b"begin_derefs_commitment")

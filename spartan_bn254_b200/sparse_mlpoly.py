@@ -44,9 +44,17 @@ class SparkAddresses:
         self.gpu.set_timestamps(self.row.read_ts, self.row.audit_ts, self.col.read_ts, self.col.audit_ts)
         self.batch = self.gpu.batch
 
-    def derefs_commit(self, gens_n, rx, ry):
-        """dense.deref(mem_rx, mem_ry) + derefs.commit(gens_derefs) (:1720-1724): returns (C, inf, resident polynomial)."""
-        return self.gpu.derefs_commit(gens_n.device_bases(), rx, ry)
+    def derefs_commit(self, gens_n, rx, ry, shard=None):
+        """dense.deref(mem_rx, mem_ry) + derefs.commit(gens_derefs) (:1720-1724): returns (C, inf, resident polynomial).
+        shard = (rank, world, all_gather): this rank commits its contiguous block of rows and `all_gather(array)` returns the
+        list of every rank's block (rows are independent, hyrax.rs:259-265; no other collective on the data path)."""
+        if shard is None or shard[1] == 1:
+            return self.gpu.derefs_commit(gens_n.device_bases(), rx, ry)
+        rank, world, all_gather = shard
+        L = self.gpu.derefs_rows()
+        assert L % world == 0
+        C, inf, poly = self.gpu.derefs_commit(gens_n.device_bases(), rx, ry, rows=(rank * (L // world), L // world))
+        return np.concatenate(all_gather(C)), np.concatenate(all_gather(inf)), poly
 
     def close(self):
         self.gpu.close()
