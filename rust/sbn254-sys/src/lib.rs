@@ -15,6 +15,12 @@ use std::os::raw::{c_char, c_int, c_long, c_void};
 #[repr(C)] pub struct sbn_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct sbn_bases { _p: [u8; 0] }
 #[repr(C)] pub struct sbn_bullet { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_sumcheck { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_poly { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_prodcircuit { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_bsumcheck { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_addrs { _p: [u8; 0] }
+#[repr(C)] pub struct sbn_spmat { _p: [u8; 0] }
 
 extern "C" {
     pub fn sbn_strerror(status: c_int) -> *const c_char;
@@ -43,6 +49,55 @@ extern "C" {
     pub fn sbn_bullet_end(st: *mut sbn_bullet, a_hat: *mut SbnFr, b_hat: *mut SbnFr, g_hat: *mut SbnG1a,
                           g_hat_inf: *mut u8) -> c_int;
     pub fn sbn_bullet_destroy(st: *mut sbn_bullet) -> c_int;
+    // resident polynomials (hyrax.rs:217-222, 283-324)
+    pub fn sbn_poly_upload(ctx: *mut sbn_ctx, z: *const SbnFr, len: usize, out: *mut *mut sbn_poly) -> c_int;
+    pub fn sbn_poly_destroy(p: *mut sbn_poly) -> c_int;
+    pub fn sbn_poly_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, p: *const sbn_poly, l_size: usize, r_size: usize,
+                           blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_poly_bound(ctx: *mut sbn_ctx, p: *const sbn_poly, l: *const SbnFr, l_size: usize, r_size: usize, lz_out: *mut SbnFr) -> c_int;
+    pub fn sbn_poly_evaluate(ctx: *mut sbn_ctx, p: *const sbn_poly, offset: usize, r: *const SbnFr, nr: usize, out: *mut SbnFr) -> c_int;
+    pub fn sbn_poly_triple_dot(ctx: *mut sbn_ctx, a: *const sbn_poly, off_a: usize, b: *const sbn_poly, off_b: usize,
+                               c: *const sbn_poly, off_c: usize, n: usize, out: *mut SbnFr) -> c_int;
+    // R1CS-sat sumcheck rounds (sumcheck.rs:501-530, 690-699) and their inputs (r1csproof.rs:285, 380)
+    pub fn sbn_sumcheck_begin(ctx: *mut sbn_ctx, tau: *const SbnFr, az: *const SbnFr, bz: *const SbnFr, cz: *const SbnFr,
+                              len: usize, out: *mut *mut sbn_sumcheck) -> c_int;
+    pub fn sbn_sumcheck_begin_quad(ctx: *mut sbn_ctx, z: *const SbnFr, abc: *const SbnFr, len: usize, out: *mut *mut sbn_sumcheck) -> c_int;
+    pub fn sbn_sumcheck_round_eval(st: *mut sbn_sumcheck, e0: *mut SbnFr, e2: *mut SbnFr, e3: *mut SbnFr) -> c_int;
+    pub fn sbn_sumcheck_bind(st: *mut sbn_sumcheck, r: *const SbnFr) -> c_int;
+    pub fn sbn_sumcheck_end(st: *mut sbn_sumcheck, finals: *mut SbnFr) -> c_int;
+    pub fn sbn_sumcheck_destroy(st: *mut sbn_sumcheck) -> c_int;
+    pub fn sbn_spmat_upload(ctx: *mut sbn_ctx, ptr: *const u32, idx: *const u32, val: *const SbnFr, n: usize, nnz: usize,
+                            ncols: usize, out: *mut *mut sbn_spmat) -> c_int;
+    pub fn sbn_spmat_destroy(m: *mut sbn_spmat) -> c_int;
+    pub fn sbn_spmat_mulvec(ctx: *mut sbn_ctx, mats: *const *const sbn_spmat, coeffs: *const SbnFr, nm: usize, vec: *const SbnFr,
+                            veclen: usize, out: *mut SbnFr) -> c_int;
+    pub fn sbn_eq_evals(ctx: *mut sbn_ctx, r: *const SbnFr, n: usize, out: *mut SbnFr) -> c_int;
+    // Spark: addresses / timestamps resident, derefs, hash layer, product layer (sparse_mlpoly_full.rs, product_tree.rs)
+    pub fn sbn_addrs_upload(ctx: *mut sbn_ctx, row: *const u32, col: *const u32, batch: usize, n: usize, out: *mut *mut sbn_addrs) -> c_int;
+    pub fn sbn_addrs_set_timestamps(a: *mut sbn_addrs, row_read: *const u32, row_audit: *const u32, col_read: *const u32,
+                                    col_audit: *const u32, num_cells: usize) -> c_int;
+    pub fn sbn_addrs_destroy(a: *mut sbn_addrs) -> c_int;
+    pub fn sbn_spark_comb_polys(ctx: *mut sbn_ctx, a: *const sbn_addrs, val: *const SbnFr, comb_ops: *mut *mut sbn_poly,
+                                comb_mem: *mut *mut sbn_poly) -> c_int;
+    pub fn sbn_spark_evaluate(ctx: *mut sbn_ctx, a: *const sbn_addrs, comb_ops: *const sbn_poly, rx: *const SbnFr, nx: usize,
+                              ry: *const SbnFr, ny: usize, out: *mut SbnFr) -> c_int;
+    pub fn sbn_derefs_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, a: *const sbn_addrs, rx: *const SbnFr, nx: usize, ry: *const SbnFr,
+                             ny: usize, c_out: *mut SbnG1a, inf_out: *mut u8, poly_out: *mut *mut sbn_poly) -> c_int;
+    pub fn sbn_derefs_commit_rows(ctx: *mut sbn_ctx, b: *const sbn_bases, a: *const sbn_addrs, rx: *const SbnFr, nx: usize,
+                                  ry: *const SbnFr, ny: usize, row0: usize, nrows: usize, c_out: *mut SbnG1a, inf_out: *mut u8,
+                                  poly_out: *mut *mut sbn_poly) -> c_int;
+    pub fn sbn_hashlayer_build(ctx: *mut sbn_ctx, a: *const sbn_addrs, side: c_int, r: *const SbnFr, nr: usize, r_hash: *const SbnFr,
+                               r_multiset_check: *const SbnFr, circuits_out: *mut *mut sbn_prodcircuit) -> c_int;
+    pub fn sbn_prodcircuit_create(ctx: *mut sbn_ctx, poly: *const SbnFr, len: usize, out: *mut *mut sbn_prodcircuit) -> c_int;
+    pub fn sbn_prodcircuit_evaluate(pc: *mut sbn_prodcircuit, out: *mut SbnFr) -> c_int;
+    pub fn sbn_prodcircuit_destroy(pc: *mut sbn_prodcircuit) -> c_int;
+    pub fn sbn_bsumcheck_begin_resident(ctx: *mut sbn_ctx, circuits: *const *mut sbn_prodcircuit, p: usize, layer_id: usize,
+                                        rand: *const SbnFr, n_rand: usize, seq_polys: *const *const sbn_poly,
+                                        seq_offsets: *const usize, s: usize, out: *mut *mut sbn_bsumcheck) -> c_int;
+    pub fn sbn_bsumcheck_round_eval(st: *mut sbn_bsumcheck, evals: *mut SbnFr) -> c_int;
+    pub fn sbn_bsumcheck_bind(st: *mut sbn_bsumcheck, r: *const SbnFr) -> c_int;
+    pub fn sbn_bsumcheck_end(st: *mut sbn_bsumcheck, a_final: *mut SbnFr, b_final: *mut SbnFr, c_final: *mut SbnFr) -> c_int;
+    pub fn sbn_bsumcheck_destroy(st: *mut sbn_bsumcheck) -> c_int;
 }
 
 fn check(status: c_int, what: &str) {
