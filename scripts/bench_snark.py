@@ -5,10 +5,10 @@ proof is checked by the oracle's independent CPU restatement of SNARK::verify.  
 Under torchrun (one process per GPU) every rank holds the instance and runs the prover; the derefs commitment -- the only
 table-sized step that shards without an exchange per round -- is split by rows across the ranks and its row blocks are
 all-gathered over NCCL; the reported time is the maximum over ranks.
-Usage: bench_snark.py [log2_constraints=20] [--no-verify]"""
+Usage: bench_snark.py [log2_constraints=20] [--verify]   (--verify: also run the oracle's CPU verifier on the proof)"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
 from spartan_bn254_b200 import Context, synth
 from spartan_bn254_b200.hyrax import fr_from_int, fr_vec_to_ints
@@ -18,9 +18,11 @@ from spartan_bn254_b200.transcript import Transcript
 
 
 
-def run(k=20, verify=True, quiet=False, ctx_in=None):
-    """Builds the instance, encodes, proves (3 warm proofs, best; max over ranks) and optionally verifies; returns the result
-    dict on rank 0 and None on the other ranks.  Under torchrun every rank must call it."""
+def run(k=20, verify=False, quiet=False, ctx_in=None, keep=None):
+    """Builds the instance, encodes and proves (3 warm proofs, best; max over ranks); returns the result dict on rank 0 and None
+    on the other ranks.  Under torchrun every rank must call it.  `keep` (dict) receives the proof and what a verifier needs
+    (tests/test_snark.py checks the keyless-scale proof with the oracle's verifier that way); verify=True does the same check
+    here -- the oracle is imported only then, as the checker."""
     own_group = False
     n = 1 << k
     num_cons = num_vars = n
@@ -110,7 +112,10 @@ def run(k=20, verify=True, quiet=False, ctx_in=None):
     out["prove_phases_ms"] = {a: (round(b, 3) if not isinstance(b, dict) else {x: round(y, 3) for x, y in b.items()}) for a, b in timings.items()}
     if not quiet:
         print(json.dumps(out["prove_phases_ms"], indent=1), flush=True)
+    if keep is not None:
+        keep.update(proof=proof, comm=comm, gens=gens, inputs=fr_vec_to_ints(input_m))
     if verify:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as orc
         import snark_model as snm
         orc.build()
@@ -148,4 +153,4 @@ def run(k=20, verify=True, quiet=False, ctx_in=None):
 
 if __name__ == "__main__":
     pos = [a for a in sys.argv[1:] if not a.startswith("-")]
-    run(int(pos[0]) if pos else 20, "--no-verify" not in sys.argv)
+    run(int(pos[0]) if pos else 20, "--verify" in sys.argv)

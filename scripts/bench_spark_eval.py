@@ -2,10 +2,10 @@
 three synthetic sparse matrices with 2^k constraints / variables and nnz padded to 2^(k+2) (keyless: 2^20, 2^22), encode
 (comb_ops / comb_mem commitments), prove through the GPU path with a real Merlin transcript, then verification by the
 oracle's independent CPU restatement of the reference verifier.  Phases as examples/keyless_benchmark.rs:190-235 times them.
-Usage: bench_spark_eval.py [log2_constraints=20] [--no-verify]"""
+Usage: bench_spark_eval.py [log2_constraints=20] [--verify]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
 from spartan_bn254_b200 import Context, synth
 from spartan_bn254_b200.hyrax import fr_vec_to_ints
@@ -14,7 +14,7 @@ from spartan_bn254_b200.spark import (MultiSparseMatPolynomialAsDense, SparseMat
 from spartan_bn254_b200.transcript import Transcript, RandomTape
 
 k = int([a for a in sys.argv[1:] if not a.startswith("-")][0]) if [a for a in sys.argv[1:] if not a.startswith("-")] else 20
-verify = "--no-verify" not in sys.argv
+verify = "--verify" in sys.argv      # the oracle (test infrastructure) is imported only then, as the checker
 nvx, nvy = k, k + 1                      # 2^k constraints, 2^(k+1) columns (vars + inputs), as R1CSShape pads them
 N = 1 << (k + 2)
 M = 1 << max(nvx, nvy)
@@ -62,6 +62,7 @@ out["ms"]["prove.R1CSEvalProof_total"] = round(1e3 * (time.perf_counter() - t0),
 out["prove_phases_ms"] = {n: round(v, 3) for n, v in phases.items()}
 print(json.dumps(out["prove_phases_ms"]), flush=True)
 if verify:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     import spark_model as sm
     orc.build()

@@ -110,3 +110,28 @@ def test_sparse_matvec_with_heavy_rows(ctx):
     assert fr_vec_to_ints(SpMat.mulvec(sp[:1], fr_vec_from_ints(vec))) == single
     for s_ in sp:
         s_.close()
+
+
+def test_keyless_scale_proof_is_accepted(ctx, orc):
+    """BASELINE configs[4] at full size: the proof scripts/bench_snark.py times (2^20 constraints, nnz padded to 2^22) is
+    accepted by the oracle's CPU restatement of SNARK::verify."""
+    import os
+    import sys
+    import snark_model as snm
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import bench_snark
+    keep = {}
+    out = bench_snark.run(20, verify=False, quiet=True, ctx_in=ctx, keep=keep)
+    assert out["ms"]["prove.SNARK_total"] > 0
+    gens, comm, proof = keep["gens"], keep["comm"], keep["proof"]
+    g = lambda x: (x.gens.gens_n.G, x.gens.gens_n.h, x.gens.gens_1.G[0])
+    sat = gens.gens_r1cs_sat
+    gens_sat = dict(gens_1=snm.Gens(sat.gens_sc.gens_1.G, sat.gens_sc.gens_1.h), gens_3=snm.Gens(sat.gens_sc.gens_3.G, sat.gens_sc.gens_3.h),
+                    gens_4=snm.Gens(sat.gens_sc.gens_4.G, sat.gens_sc.gens_4.h), pc=g(sat.gens_pc),
+                    pc_1=snm.Gens(sat.gens_pc.gens.gens_1.G, sat.gens_pc.gens.gens_1.h))
+    ev = gens.gens_r1cs_eval
+    c = comm.comm
+    cd = dict(num_cons=comm.num_cons, num_vars=comm.num_vars, num_inputs=comm.num_inputs, batch_size=c.batch_size, num_ops=c.num_ops,
+              num_mem_cells=c.num_mem_cells, comb_ops=(c.comm_comb_ops.C, c.comm_comb_ops.inf), comb_mem=(c.comm_comb_mem.C, c.comm_comb_mem.inf))
+    assert snm.snark_verify(proof, cd, keep["inputs"], gens_sat, dict(ops=g(ev.gens_ops), mem=g(ev.gens_mem), derefs=g(ev.gens_derefs)),
+                            orc.Transcript(b"snark"))
