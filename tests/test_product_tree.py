@@ -110,3 +110,46 @@ def test_gpu_prover_full_size_is_accepted(ctx):
     assert val == final[0]
     for c in circuits:
         c.close()
+
+
+@pytest.mark.gpu
+def test_prover_entry_points_reject_bad_shapes(ctx):
+    """The C ABI returns SBN_ERR_SHAPE / SBN_ERR_ARG instead of unwinding where the reference would assert
+    (product_tree.rs:272,298-300; sumcheck rounds past the last one; non-power-of-two tables)."""
+    from spartan_bn254_b200 import SbnError, synth
+    from spartan_bn254_b200.lib import ProdCircuit, BatchedSumcheckState, SpMat, Addrs
+    with pytest.raises(SbnError) as e:
+        ProdCircuit(ctx, synth.uniform_scalars(1, 24))                       # not a power of two
+    assert e.value.status == -2
+    with pytest.raises(SbnError):
+        ProdCircuit(ctx, synth.uniform_scalars(1, 1))                        # a product circuit needs two entries
+    pc = ProdCircuit(ctx, synth.uniform_scalars(1, 16))
+    with pytest.raises(SbnError) as e:                                       # layer 0 has 8 + 8 entries: |eq(rand)| must be 8
+        BatchedSumcheckState(ctx, [pc], 0, synth.uniform_scalars(2, 2))
+    assert e.value.status == -2
+    with pytest.raises(SbnError):
+        BatchedSumcheckState(ctx, [pc], 9, synth.uniform_scalars(2, 3))       # no such layer
+    with pytest.raises(SbnError):                                            # a sequential instance of the wrong length
+        BatchedSumcheckState(ctx, [pc], 0, synth.uniform_scalars(2, 3), [tuple(synth.uniform_scalars(3 + i, 4) for i in range(3))])
+    st = BatchedSumcheckState(ctx, [pc], 0, synth.uniform_scalars(2, 3))
+    with pytest.raises(SbnError):
+        st.end()                                                             # tables not yet of length 1
+    for j in range(3):
+        st.round_eval()
+        st.bind(synth.uniform_scalars(9 + j, 1)[0])
+    with pytest.raises(SbnError):
+        st.round_eval()                                                      # no round left
+    st.end()
+    st.close()
+    pc.close()
+    with pytest.raises(SbnError):                                            # column index outside the vector
+        SpMat(ctx, 4, 4, [0, 1], [0, 7], synth.uniform_scalars(5, 2))
+    m = SpMat(ctx, 4, 4, [0, 1], [0, 3], synth.uniform_scalars(5, 2))
+    with pytest.raises(SbnError):
+        SpMat.mulvec([m], synth.uniform_scalars(6, 2))                        # vector shorter than the matrix is wide
+    m.close()
+    a = Addrs(ctx, np.zeros((1, 8), dtype=np.uint32), np.zeros((1, 8), dtype=np.uint32))
+    with pytest.raises(SbnError):                                            # hash layer before the timestamps were uploaded
+        a.num_cells = 8
+        a.hashlayer(0, synth.uniform_scalars(7, 3), synth.uniform_scalars(8, 1)[0], synth.uniform_scalars(9, 1)[0])
+    a.close()
