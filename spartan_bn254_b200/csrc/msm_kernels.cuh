@@ -111,6 +111,55 @@ __device__ __forceinline__ void for_each_digit(const Fr& canon, Fn&& f) {
     }
 }
 
+// Duplicate generators.  About two thirds of the reference's Pedersen generators are the SAME point (group.rs:110-132 falls
+// through to Scalar::one()), so sum_j z_j G_j collapses to sum_g (sum_{j in g} z_j) P_g over the distinct points P_g: the
+// scalars of every group are added up (mod r, Montgomery form is linear) before the sort, and the tables, the bucket lists
+// and the accumulation only ever see the distinct points.  gptr / gcols: the columns of each group (CSR); column n_cols - 1
+// is h and takes the row's blind.  One block per row; groups larger than kAggBig are summed by the whole block.
+static constexpr int kAggThreads = 256;
+static constexpr uint32_t kAggBig = 64;
+
+__device__ __forceinline__ void store_fr_raw(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__global__ void __launch_bounds__(kAggThreads)
+k_aggregate_rows(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n_cols, const uint32_t* __restrict__ gptr,
+                 const uint32_t* __restrict__ gcols, int n_groups, const uint32_t* __restrict__ big, int n_big,
+                 Fr* __restrict__ Zagg) {
+    __shared__ Fr sm[kAggThreads];
+    const int row = blockIdx.x;
+    const Fr* zrow = Z + (size_t)row * R;
+    Fr* out = Zagg + (size_t)row * n_groups;
+    auto scalar_of = [&](uint32_t col) -> Fr {
+        if ((int)col < R) return load_fr(zrow + col);
+        if ((int)col == n_cols - 1 && blinds) return load_fr(blinds + row);
+        return Fr::zero();
+    };
+    for (int g = threadIdx.x; g < n_groups; g += kAggThreads) {
+        const uint32_t k0 = gptr[g], k1 = gptr[g + 1];
+        if (k1 - k0 > kAggBig) continue;
+        Fr acc = Fr::zero();
+        for (uint32_t k = k0; k < k1; k++) acc = fp_add(acc, scalar_of(gcols[k]));
+        store_fr_raw(out + g, acc);
+    }
+    for (int i = 0; i < n_big; i++) {                       // the few big groups: block-wide sums
+        const uint32_t g = big[i];
+        const uint32_t k0 = gptr[g], k1 = gptr[g + 1];
+        Fr acc = Fr::zero();
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += kAggThreads) acc = fp_add(acc, scalar_of(gcols[k]));
+        for (int stride = kAggThreads >> 1; stride >= 1; stride >>= 1) {
+            sm[threadIdx.x] = acc;
+            __syncthreads();
+            if (threadIdx.x < stride) acc = fp_add(acc, sm[threadIdx.x + stride]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_fr_raw(out + g, acc);
+    }
+}
+
 static constexpr int kRankBins = 256;
 static constexpr int kMaxTaskCap = 255;
 

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "msm_kernels.cuh"
@@ -40,6 +41,7 @@ struct sbn_ctx {
     std::mutex mu;
     std::string last_error;
     long chunk_rows = 0;    // 0 = auto (see commit_chunk_rows)
+    long dedup_generators = 1;   // merge equal generators of a set created afterwards (k_aggregate_rows)
     long first_chunk_rows = 0;   // host path: rows of the short first chunk; 0 = auto (an eighth of a chunk, measured best)
     long window_bits = 0;
     long task_cap = 0;      // 0 = auto: 2.5 x the mean bucket occupancy
@@ -51,6 +53,7 @@ struct sbn_ctx {
     struct Slot {          // one in-flight chunk of rows: private workspace
         DevBuf entries, tstart, tasks, partials, heavy, pairs;
         DevBuf pts[3], prefix, other, wtot, winv;      // batched-affine rounds (ba_kernels.cuh)
+        DevBuf zagg;                                   // per-group scalar sums when the generator set has duplicates
     } slots[2];
     // Pipeline streams.  The latency-bound stages (sort, split-bucket fold, bucket reduction) run on a HIGH priority
     // stream and the IMAD-bound accumulation on LOW priority ones, so that while chunk i accumulates, the blocks of
@@ -76,6 +79,10 @@ struct sbn_bases {
     int n1 = 0;        // table columns: n + has_g1 + 1, h is the last one
     int c = 0, W = 0, nb = 0;
     Affine* table = nullptr;   // W * n1 affine points
+    Affine* orig = nullptr;    // the n + has_g1 + 1 generators as given (the explicit-folding bullet path reads them)
+    // duplicate generators merged (k_aggregate_rows): n1 counts DISTINCT non-identity points, n_cols the given columns
+    int dedup = 0, n_cols = 0, n_big = 0;
+    uint32_t *gptr = nullptr, *gcols = nullptr, *gbig = nullptr;
 };
 
 #define SBN_CUDA(ctx, call)                                                                      \
@@ -218,7 +225,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto& sl : ctx->slots)
         for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs, &sl.pts[0], &sl.pts[1], &sl.pts[2],
-                          &sl.prefix, &sl.other, &sl.wtot, &sl.winv})
+                          &sl.prefix, &sl.other, &sl.wtot, &sl.winv, &sl.zagg})
             release(*b);
     pool_flush(ctx);
     cudaEventDestroy(ctx->fork);
@@ -242,7 +249,9 @@ extern "C" int sbn_ctx_synchronize(sbn_ctx* ctx) {
 extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if (!strcmp(key, "first_chunk_rows")) {
+    if (!strcmp(key, "dedup_generators")) {
+        ctx->dedup_generators = value ? 1 : 0;
+    } else if (!strcmp(key, "first_chunk_rows")) {
         if (value < 0) return SBN_ERR_ARG;
         ctx->first_chunk_rows = value;
     } else if (!strcmp(key, "chunk_rows")) {
@@ -329,7 +338,43 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
     b->n = n;
     b->has_g1 = g1 ? 1 : 0;
     b->n1 = (int)n + 1 + b->has_g1;
-    b->c = ctx->window_bits ? (int)ctx->window_bits : choose_window(n + 1);
+    b->n_cols = b->n1;
+    // group equal points (byte-equal affine coordinates); identity points drop out
+    std::vector<uint32_t> gptr, gcols, gbig;
+    std::vector<sbn_g1a> distinct;
+    if (!g1 && ctx->dedup_generators) {
+        std::unordered_map<std::string, uint32_t> ids;
+        std::vector<std::vector<uint32_t>> members;
+        auto is_identity = [&](const sbn_g1a* p, size_t j) {
+            if (j < n && G_inf && G_inf[j]) return true;
+            static const sbn_g1a zero = {};
+            return memcmp(p, &zero, sizeof(sbn_g1a)) == 0;
+        };
+        for (size_t j = 0; j <= n; j++) {
+            const sbn_g1a* p = j < n ? &G[j] : h;
+            if (is_identity(p, j)) continue;
+            std::string key((const char*)p, sizeof(sbn_g1a));
+            auto it = ids.find(key);
+            if (it == ids.end()) {
+                it = ids.emplace(key, (uint32_t)members.size()).first;
+                members.emplace_back();
+                distinct.push_back(*p);
+            }
+            members[it->second].push_back((uint32_t)j);
+        }
+        if (!members.empty() && members.size() * 10 <= (size_t)b->n1 * 8) {       // at least a fifth of the columns merge away
+            b->dedup = 1;
+            gptr.push_back(0);
+            for (size_t gi = 0; gi < members.size(); gi++) {
+                for (uint32_t cidx : members[gi]) gcols.push_back(cidx);
+                gptr.push_back((uint32_t)gcols.size());
+                if (members[gi].size() > kAggBig) gbig.push_back((uint32_t)gi);
+            }
+            b->n1 = (int)members.size();
+            b->n_big = (int)gbig.size();
+        }
+    }
+    b->c = ctx->window_bits ? (int)ctx->window_bits : choose_window((size_t)b->n1);
     b->W = msm_num_windows(b->c);
     b->nb = 1 << (b->c - 1);
     if ((uint64_t)b->W * b->n1 >= (1ull << 31)) { delete b; return SBN_ERR_SHAPE; }
@@ -340,26 +385,56 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
         if (dbases) cudaFree(dbases);
         if (dinf) cudaFree(dinf);
         if (b->table) cudaFree(b->table);
+        if (b->orig) cudaFree(b->orig);
+        for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
         delete b;
         return code;
     };
     cudaError_t e;
+    if ((e = cudaMalloc(&b->orig, sizeof(Affine) * b->n_cols)) != cudaSuccess) {
+        ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
+        return fail(SBN_ERR_OOM);
+    }
     if ((e = cudaMalloc(&dbases, sizeof(Affine) * b->n1)) != cudaSuccess ||
         (e = cudaMalloc(&dinf, b->n1)) != cudaSuccess ||
         (e = cudaMalloc(&b->table, sizeof(Affine) * (size_t)b->W * b->n1)) != cudaSuccess) {
         ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
         return fail(SBN_ERR_OOM);
     }
-    std::vector<uint8_t> inf_host(b->n1, 0);
-    if (G_inf) memcpy(inf_host.data(), G_inf, n);
-    if ((e = cudaMemcpyAsync(dbases, G, sizeof(Affine) * n, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
+    std::vector<uint8_t> inf_host(std::max(b->n1, b->n_cols), 0);
+    if (G_inf && !b->dedup) memcpy(inf_host.data(), G_inf, n);
+    // the generators as given (identity flags folded into the (0, 0) encoding)
+    {
+        std::vector<sbn_g1a> given(b->n_cols);
+        memcpy(given.data(), G, sizeof(sbn_g1a) * n);
+        if (G_inf) for (size_t j = 0; j < n; j++) if (G_inf[j]) memset(&given[j], 0, sizeof(sbn_g1a));
+        if (g1) given[n] = *g1;
+        given[b->n_cols - 1] = *h;
+        if ((e = cudaMemcpy(b->orig, given.data(), sizeof(Affine) * b->n_cols, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            ctx->last_error = std::string("sbn_bases_create upload: ") + cudaGetErrorString(e);
+            return fail(SBN_ERR_CUDA);
+        }
+    }
+    if (b->dedup) {
+        if ((e = cudaMalloc(&b->gptr, gptr.size() * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&b->gcols, gcols.size() * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&b->gbig, std::max<size_t>(1, gbig.size()) * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMemcpy(b->gptr, gptr.data(), gptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(b->gcols, gcols.data(), gcols.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (gbig.size() && (e = cudaMemcpy(b->gbig, gbig.data(), gbig.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) ||
+            (e = cudaMemcpyAsync(dbases, distinct.data(), sizeof(Affine) * b->n1, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(dinf, inf_host.data(), b->n1, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess) {
+            ctx->last_error = std::string("sbn_bases_create upload: ") + cudaGetErrorString(e);
+            return fail(SBN_ERR_CUDA);
+        }
+    } else if ((e = cudaMemcpyAsync(dbases, G, sizeof(Affine) * n, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
         (g1 && (e = cudaMemcpyAsync(dbases + n, g1, sizeof(Affine), cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess) ||
         (e = cudaMemcpyAsync(dbases + (b->n1 - 1), h, sizeof(Affine), cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess ||
         (e = cudaMemcpyAsync(dinf, inf_host.data(), b->n1, cudaMemcpyHostToDevice, ctx->compute)) != cudaSuccess) {
         ctx->last_error = std::string("sbn_bases_create upload: ") + cudaGetErrorString(e);
         return fail(SBN_ERR_CUDA);
     }
-    ctx->h2d += sizeof(Affine) * b->n1 + b->n1;
+    ctx->h2d += sizeof(Affine) * (b->n1 + b->n_cols) + b->n1;
     k_build_tables<<<(b->n1 + 63) / 64, 64, 0, ctx->compute>>>(dbases, dinf, b->n1, b->c, b->W, b->table);
     ctx->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(ctx->compute)) != cudaSuccess) {
@@ -389,6 +464,8 @@ extern "C" int sbn_bases_destroy(sbn_bases* b) {
         cudaSetDevice(b->ctx->device);
         cudaStreamSynchronize(b->ctx->compute);
         if (b->table) cudaFree(b->table);
+        if (b->orig) cudaFree(b->orig);
+        for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
     }
     delete b;
     return SBN_OK;
@@ -493,6 +570,14 @@ static int stage_sort(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const
     const ChunkPlan p = chunk_plan(ctx, b, (size_t)rows);
     m.mark(-1, st);
     if (p.ba) SBN_CUDA(ctx, cudaMemsetAsync(sl.entries.p, 0xff, (size_t)rows * p.E * sizeof(uint32_t), st));   // NULL padding
+    if (b->dedup) {     // scalars of equal generators are summed first; the blind joins the group of h
+        k_aggregate_rows<<<rows, kAggThreads, 0, st>>>(dZ_chunk, dblinds_chunk, R, b->n_cols, b->gptr, b->gcols, b->n1, b->gbig,
+                                                       b->n_big, (Fr*)sl.zagg.p);
+        ctx->launches += 1;
+        dZ_chunk = (const Fr*)sl.zagg.p;
+        dblinds_chunk = nullptr;
+        R = b->n1;
+    }
     SBN_TRY(dispatch_sort(b->c, dZ_chunk, dblinds_chunk, R, b->n1, p.cap, p.ba, p.E, p.max_tasks, p.max_heavy,
                           (uint32_t*)sl.entries.p, (uint32_t*)sl.tstart.p, (Task*)sl.tasks.p, (uint32_t*)sl.heavy.p, rows, st));
     m.mark(0, st);
@@ -623,6 +708,7 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
         SBN_TRY(ensure(ctx, sl.partials, chunk * max_tasks * sizeof(XYZZ)));
         SBN_TRY(ensure(ctx, sl.heavy, chunk * (max_heavy + 1) * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.pairs, chunk * (size_t)(b->nb / std::max(4, b->nb / 256) + 1) * sizeof(LeafPair)));
+        if (b->dedup) SBN_TRY(ensure(ctx, sl.zagg, chunk * (size_t)b->n1 * sizeof(Fr)));
         const int ba = std::max(plan.ba, plain.ba);
         if (ba) {
             const size_t np1 = chunk * E / 2;                       // pairs of the first round
@@ -1147,11 +1233,11 @@ extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_
         if (rc != SBN_OK) return fail(rc);
     } else {
         // G <- the resident generators (window 0 of the tables), H = h
-        BCUDA(cudaMemcpyAsync(st->G, bases->table, n * sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+        BCUDA(cudaMemcpyAsync(st->G, bases->orig, n * sizeof(Affine), cudaMemcpyDeviceToDevice, s));
         BCUDA(cudaMemsetAsync(st->Ginf, 0, n, s));
         for (int k = 0; k < 2; k++) {
             BCUDA(cudaMemcpyAsync(st->QH + 2 * k, Q, sizeof(Affine), cudaMemcpyHostToDevice, s));
-            BCUDA(cudaMemcpyAsync(st->QH + 2 * k + 1, bases->table + (bases->n1 - 1), sizeof(Affine), cudaMemcpyDeviceToDevice, s));
+            BCUDA(cudaMemcpyAsync(st->QH + 2 * k + 1, bases->orig + (bases->n_cols - 1), sizeof(Affine), cudaMemcpyDeviceToDevice, s));
         }
         ctx->h2d += sizeof(Affine);
         // Gamma = MSM(a, G) + blind * H (one row through the table pipeline) + <a, b> * Q
