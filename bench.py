@@ -290,6 +290,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = points_per_step * args.steps / float(t.item())
 
+    # ---- the same commit on the REFERENCE's generator set (MultiCommitGens::new, commitments.rs:31-62): about two thirds of
+    #      those generators are the same point, which the library merges (k_aggregate_rows), so the real prover's commits
+    #      run faster than the distinct-generator headline above; reported separately, as SURVEY.md 8(d) asks
+    ref_gens = None
+    if args.gens == "distinct" and args.workload == "cfg1_1024x1024":
+        gref = MultiCommitGens.new(R, b"gens_r1cs_eval", ctx)
+        bases_ref = ctx.bases(gref.G, gref.h)
+        distinct_pts = len({bytes(p) for p in np.concatenate([gref.G, gref.h.reshape(1, 8)]).view(np.uint8).reshape(R + 1, 64)})
+        for i in range(args.warmup):
+            ctx.hyrax_commit_device(bases_ref, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=stream.cuda_stream)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for i in range(args.steps):
+            ctx.hyrax_commit_device(bases_ref, dev_bufs[(args.warmup + i) % nbuf].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(),
+                                    stream=stream.cuda_stream)
+        r1.record(stream)
+        barrier()
+        tref = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tref, op=dist.ReduceOp.MAX)
+        ref_gens = {"value": points_per_step * args.steps / (float(tref.item()) * 1e-3), "unit": UNIT,
+                    "ms_per_step": float(tref.item()) / args.steps, "generators": R + 1, "distinct_points": distinct_pts,
+                    "note": "MultiCommitGens::new(R, b\"gens_r1cs_eval\"): equal generators are merged by summing their scalars"}
+        bases_ref.close()
+
     # ---- "keyless prove time (s)": SNARK::prove of a synthetic keyless-shaped R1CS (2^20 constraints) through the GPU path,
     #      derefs commitment sharded by rows across the ranks (scripts/bench_snark.py).  The proof is not checked here -- the
     #      oracle is test infrastructure: tests/test_snark.py verifies the same keyless-scale proof with the CPU verifier.
@@ -358,6 +384,8 @@ def main():
             },
             "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_rows": prof_rows,
         }
+        if ref_gens is not None:
+            line["reference_generators"] = ref_gens
         if prove is not None:
             line["keyless_prove"] = prove
         if not args.no_cpu_baseline:

@@ -628,6 +628,8 @@ class Addrs:
                                                  C.c_size_t(ry.shape[0]), C.c_size_t(row0), C.c_size_t(L), _ptr(out), _ptr(inf),
                                                  C.byref(ph) if keep else None)
         self.ctx._check(st, "sbn_derefs_commit_rows")
+        if os.environ.get("SBN_DEBUG_TIMING"):
+            print("derefs_commit profile", self.ctx.last_commit_profile(), flush=True)
         poly = None
         if keep:
             poly = Poly.__new__(Poly)
