@@ -239,6 +239,16 @@ int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr /* n + 1 */, const uint32
 int sbn_spmat_destroy(sbn_spmat* m);
 int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* coeffs, size_t nm, const sbn_fr* vec,
                      size_t veclen, sbn_fr* out);
+/* The two sumcheck set-ups of R1CSProof::prove with the tables built in HBM from the resident matrices, so that only z,
+ * the challenge vector and three coefficients cross the bus:
+ *   begin_r1cs       r1csproof.rs:268-290: tables eq(tau), A z, B z, C z; mats = {A, B, C} by row, 2^n_tau rows each
+ *   begin_quad_r1cs  r1csproof.rs:378-410: tables z and r_A A^T e + r_B B^T e + r_C C^T e with e = eq(rx); mats_t = the
+ *                    column-sorted copies (zlen rows each), coeffs = (r_A, r_B, r_C)
+ * The states are driven by sbn_sumcheck_round_eval / _bind / _end / _destroy like the host-table ones. */
+int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, size_t zlen, const sbn_fr* tau,
+                            size_t n_tau, sbn_sumcheck** out);
+int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats_t, const sbn_fr* coeffs, const sbn_fr* rx,
+                                 size_t n_rx, const sbn_fr* z, size_t zlen, sbn_sumcheck** out);
 /* EqPolynomial::evals (hyrax.rs:355-369): the 2^n evaluations of eq(r, .), computed on the device. */
 int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out);
 
@@ -252,6 +262,10 @@ void sbn_merlin_init(void* state, const uint8_t* label, size_t label_len);
 void sbn_merlin_append(void* state, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
 void sbn_merlin_append_many(void* state, const uint8_t* label, size_t label_len, const uint8_t* msgs, size_t msg_len, size_t count);
 void sbn_merlin_challenge(void* state, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
+/* GroupElement::compress (group.rs:135-140) on the host: n affine Montgomery points -> n x 32 bytes of ark's compressed
+ * encoding; and the share loop of PolyCommitment::append_to_transcript (hyrax.rs:46-50): compress + append each point. */
+int sbn_g1_compress(const sbn_g1a* pts, const uint8_t* inf, size_t n, uint8_t* out);
+int sbn_merlin_append_points(void* state, const uint8_t* label, size_t label_len, const sbn_g1a* pts, const uint8_t* inf, size_t n);
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
 int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
 /* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for

@@ -18,7 +18,7 @@ from spartan_bn254_b200.transcript import Transcript
 
 
 
-def run(k=20, verify=False, quiet=False, ctx_in=None, keep=None):
+def run(k=20, verify=False, quiet=False, ctx_in=None, keep=None, keep_instance=False):
     """Builds the instance, encodes and proves (3 warm proofs, best; max over ranks); returns the result dict on rank 0 and None
     on the other ranks.  Under torchrun every rank must call it.  `keep` (dict) receives the proof and what a verifier needs
     (tests/test_snark.py checks the keyless-scale proof with the oracle's verifier that way); verify=True does the same check
@@ -141,6 +141,9 @@ def run(k=20, verify=False, quiet=False, ctx_in=None, keep=None):
         print(json.dumps(out, indent=1))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(out, open(os.path.join(ROOT, "gpurun_out", "snark_%d%s.json" % (k, "" if world == 1 else "_n%d" % world)), "w"), indent=1)
+    if keep_instance and keep is not None:      # scripts/profile_snark.py proves again on the warm instance
+        keep["instance"] = (inst, comm, decomm, vars_m, input_m, gens, ctx)
+        return out
     decomm.close()
     for m_ in inst.by_row + inst.by_col:
         m_.close()

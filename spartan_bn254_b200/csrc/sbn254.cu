@@ -17,6 +17,7 @@
 #include "msm_kernels.cuh"
 #include "opening_kernels.cuh"
 #include "ba_kernels.cuh"
+#include "small_kernels.cuh"
 #include "prodtree_kernels.cuh"
 #include "host/keccak.hpp"
 #include "host/merlin.hpp"
@@ -66,6 +67,10 @@ struct sbn_ctx {
     // Everything that touches them is ordered on `compute`, so a released buffer can be handed out again without a sync.
     std::vector<std::pair<size_t, void*>> mem_pool;
     size_t mem_pool_bytes = 0;
+    std::unordered_map<void*, size_t> pool_live;   // size class of every buffer handed out by pool_alloc
+    uint8_t* small_pin = nullptr;      // mapped pinned staging of the short-commitment path (scalars in, points out)
+    uint8_t* small_pin_dev = nullptr;
+    long small_commit_path = 1;        // 0: short generator sets go through the general pipeline (test hook)
     // last-commit profile
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[4] = {0, 0, 0, 0};
@@ -83,6 +88,7 @@ struct sbn_bases {
     // duplicate generators merged (k_aggregate_rows): n1 counts DISTINCT non-identity points, n_cols the given columns
     int dedup = 0, n_cols = 0, n_big = 0;
     uint32_t *gptr = nullptr, *gcols = nullptr, *gbig = nullptr;
+    Affine* small = nullptr;   // short sets (n_cols <= kSmallMaxCols): every digit multiple of every generator (small_kernels.cuh)
 };
 
 #define SBN_CUDA(ctx, call)                                                                      \
@@ -120,34 +126,55 @@ static void pool_flush(sbn_ctx* ctx) {
     ctx->mem_pool.clear();
     ctx->mem_pool_bytes = 0;
 }
+// Size class of a pooled buffer: table-sized requests recur with exact sizes (powers of two times 32 B); small ones (the
+// per-layer scratch of the sumchecks and the bullet reduction) are rounded up to a power of two so that they recur too --
+// a cudaMalloc / cudaFree pair costs about a millisecond next to several GB of live tables, and a proof makes hundreds.
+static size_t pool_class(size_t bytes) {
+    if (bytes >= kPoolMinBytes) return bytes;
+    size_t c = 256;
+    while (c < bytes) c <<= 1;
+    return c;
+}
 static cudaError_t pool_alloc(sbn_ctx* ctx, void** out, size_t bytes) {
-    if (bytes >= kPoolMinBytes)
-        for (size_t i = 0; i < ctx->mem_pool.size(); i++)
-            if (ctx->mem_pool[i].first == bytes) {
-                *out = ctx->mem_pool[i].second;
-                ctx->mem_pool_bytes -= bytes;
-                ctx->mem_pool.erase(ctx->mem_pool.begin() + i);
-                return cudaSuccess;
-            }
-    cudaError_t e = cudaMalloc(out, bytes);
+    const size_t cls = pool_class(bytes);
+    for (size_t i = ctx->mem_pool.size(); i-- > 0;)
+        if (ctx->mem_pool[i].first == cls) {
+            *out = ctx->mem_pool[i].second;
+            ctx->mem_pool_bytes -= cls;
+            ctx->mem_pool.erase(ctx->mem_pool.begin() + i);
+            ctx->pool_live[*out] = cls;
+            return cudaSuccess;
+        }
+    cudaError_t e = cudaMalloc(out, cls);
     if (e == cudaErrorMemoryAllocation && !ctx->mem_pool.empty()) {
         cudaGetLastError();
         cudaStreamSynchronize(ctx->compute);
         pool_flush(ctx);
-        e = cudaMalloc(out, bytes);
+        e = cudaMalloc(out, cls);
     }
+    if (e == cudaSuccess) ctx->pool_live[*out] = cls;
     return e;
 }
 template <class T>
 static cudaError_t pool_alloc(sbn_ctx* ctx, T** out, size_t bytes) { return pool_alloc(ctx, (void**)out, bytes); }
 static void pool_free(sbn_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
-    if (bytes >= kPoolMinBytes && ctx->mem_pool_bytes + bytes <= kPoolMaxBytes) {
-        ctx->mem_pool.emplace_back(bytes, p);
-        ctx->mem_pool_bytes += bytes;
+    const size_t cls = pool_class(bytes);
+    ctx->pool_live.erase(p);
+    if (ctx->mem_pool_bytes + cls <= kPoolMaxBytes) {
+        ctx->mem_pool.emplace_back(cls, p);
+        ctx->mem_pool_bytes += cls;
     } else {
         cudaFree(p);
     }
+}
+// Release of a pool_alloc'ed buffer whose size the owner did not keep.
+static void pool_release(sbn_ctx* ctx, void* p) {
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) { cudaFree(p); return; }
+    const size_t cls = it->second;
+    pool_free(ctx, p, cls);
 }
 
 static void release(DevBuf& b) {
@@ -181,6 +208,40 @@ extern "C" void sbn_merlin_append_many(void* state, const uint8_t* label, size_t
 }
 extern "C" void sbn_merlin_challenge(void* state, const uint8_t* label, size_t llen, uint8_t* out, size_t n) {
     sbn::merlin::challenge_bytes(*(sbn::merlin::State*)state, label, llen, out, n);
+}
+
+// host utility: GroupElement::compress (group.rs:135-140) of n affine Montgomery points -- ark's compressed short-Weierstrass
+// encoding: x as 32 little-endian bytes, bit 7 of byte 31 set when y > p - y, bit 6 (x = 0) for the identity
+extern "C" int sbn_g1_compress(const sbn_g1a* pts, const uint8_t* inf, size_t n, uint8_t* out) {
+    if ((n && !pts) || !out) return SBN_ERR_ARG;
+    for (size_t i = 0; i < n; i++) {
+        uint8_t* o = out + 32 * i;
+        Fq xm, ym;
+        memcpy(xm.l, pts[i].x, 32);
+        memcpy(ym.l, pts[i].y, 32);
+        if ((inf && inf[i]) || (xm.is_zero() && ym.is_zero())) {
+            memset(o, 0, 32);
+            o[31] = 0x40;
+            continue;
+        }
+        const Fq x = fp_from_mont(xm), y = fp_from_mont(ym), ny = fp_neg(y);    // y != 0 on a prime-order curve
+        memcpy(o, x.l, 32);
+        bool greater = false;
+        for (int k = 7; k >= 0; k--)
+            if (y.l[k] != ny.l[k]) { greater = y.l[k] > ny.l[k]; break; }
+        if (greater) o[31] |= 0x80;
+    }
+    return SBN_OK;
+}
+// PolyCommitment::append_to_transcript's share loop (hyrax.rs:46-50): compress and append n points under one label
+extern "C" int sbn_merlin_append_points(void* state, const uint8_t* label, size_t llen, const sbn_g1a* pts, const uint8_t* inf, size_t n) {
+    if (!state || !label || (n && !pts)) return SBN_ERR_ARG;
+    uint8_t buf[32];
+    for (size_t i = 0; i < n; i++) {
+        sbn_g1_compress(pts + i, inf ? inf + i : nullptr, 1, buf);
+        sbn::merlin::append_message(*(sbn::merlin::State*)state, label, llen, buf, 32);
+    }
+    return SBN_OK;
 }
 
 extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
@@ -233,6 +294,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
+    if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
     delete ctx;
     return SBN_OK;
 }
@@ -249,7 +311,9 @@ extern "C" int sbn_ctx_synchronize(sbn_ctx* ctx) {
 extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if (!strcmp(key, "dedup_generators")) {
+    if (!strcmp(key, "small_commit_path")) {
+        ctx->small_commit_path = value ? 1 : 0;
+    } else if (!strcmp(key, "dedup_generators")) {
         ctx->dedup_generators = value ? 1 : 0;
     } else if (!strcmp(key, "first_chunk_rows")) {
         if (value < 0) return SBN_ERR_ARG;
@@ -386,6 +450,7 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
         if (dinf) cudaFree(dinf);
         if (b->table) cudaFree(b->table);
         if (b->orig) cudaFree(b->orig);
+        if (b->small) cudaFree(b->small);
         for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
         delete b;
         return code;
@@ -443,6 +508,19 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
     }
     cudaFree(dbases);
     cudaFree(dinf);
+    if (b->n_cols <= kSmallMaxCols) {     // short set: tabulate every digit multiple (one-off, a few ms)
+        const size_t entries = (size_t)kSmallW * b->n_cols * kSmallD;
+        if ((e = cudaMalloc(&b->small, entries * sizeof(Affine))) != cudaSuccess) {
+            ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
+            return fail(SBN_ERR_OOM);
+        }
+        k_build_small_table<<<(kSmallW * b->n_cols + 31) / 32, 32, 0, ctx->compute>>>(b->orig, b->n_cols, b->small);
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(ctx->compute)) != cudaSuccess) {
+            ctx->last_error = std::string("k_build_small_table: ") + cudaGetErrorString(e);
+            return fail(SBN_ERR_CUDA);
+        }
+    }
     *out = b;
     return SBN_OK;
 }
@@ -465,6 +543,7 @@ extern "C" int sbn_bases_destroy(sbn_bases* b) {
         cudaStreamSynchronize(b->ctx->compute);
         if (b->table) cudaFree(b->table);
         if (b->orig) cudaFree(b->orig);
+        if (b->small) cudaFree(b->small);
         for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
     }
     delete b;
@@ -836,12 +915,39 @@ extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const v
     return SBN_OK;
 }
 
+// Short generator set, few rows: one launch over the tabulated digit multiples, operands through mapped pinned memory.
+static int small_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
+                        sbn_g1a* C_out, uint8_t* inf_out) {
+    const size_t off_blind = (size_t)kSmallMaxRows * kSmallMaxCols * sizeof(Fr), off_out = off_blind + kSmallMaxRows * sizeof(Fr),
+                 off_inf = off_out + kSmallMaxRows * sizeof(Affine), total = off_inf + kSmallMaxRows;
+    if (!ctx->small_pin) {
+        SBN_CUDA(ctx, cudaHostAlloc((void**)&ctx->small_pin, total, cudaHostAllocMapped));
+        SBN_CUDA(ctx, cudaHostGetDevicePointer((void**)&ctx->small_pin_dev, ctx->small_pin, 0));
+    }
+    memcpy(ctx->small_pin, Z, L * R * sizeof(Fr));
+    if (blinds) memcpy(ctx->small_pin + off_blind, blinds, L * sizeof(Fr));
+    uint8_t* d = ctx->small_pin_dev;
+    k_small_commit<<<(unsigned)L, 32 * ((unsigned)R + 1), 0, ctx->compute>>>((const Fr*)d, blinds ? (const Fr*)(d + off_blind) : nullptr,
+                                                                             (int)R, b->n_cols, b->small, (Affine*)(d + off_out),
+                                                                             d + off_inf);
+    ctx->launches += 1;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    memcpy(C_out, ctx->small_pin + off_out, L * sizeof(Affine));
+    memcpy(inf_out, ctx->small_pin + off_inf, L);
+    ctx->h2d += L * R * sizeof(Fr) + (blinds ? L * sizeof(Fr) : 0);
+    ctx->d2h += L * (sizeof(Affine) + 1);
+    for (int i = 0; i < 4; i++) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+    return SBN_OK;
+}
+
 extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
                                 sbn_g1a* C_out, uint8_t* inf_out) {
     if (!ctx || !b || !Z || !C_out || !inf_out || b->ctx != ctx) return SBN_ERR_ARG;
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (b->small && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     SBN_TRY(ensure(ctx, ctx->dZ, L * R * sizeof(Fr)));
@@ -1082,7 +1188,7 @@ extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_po
     if (pool_alloc(ctx, &p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_poly_upload: cudaMalloc failed"; return SBN_ERR_OOM; }
     if (cudaMemcpyAsync(p->Z, Z, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
         cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
-        cudaFree(p->Z);
+        pool_release(ctx, p->Z);
         delete p;
         ctx->last_error = "sbn_poly_upload: copy failed";
         return SBN_ERR_CUDA;
@@ -1170,7 +1276,7 @@ static void bullet_free(sbn_bullet* st) {
     for (void* p : {(void*)st->G, (void*)st->Ginf, (void*)st->a, (void*)st->b, (void*)st->QH, (void*)st->scal,
                     (void*)st->partial, (void*)st->terms, (void*)st->frpart, (void*)st->outp, (void*)st->outinf,
                     (void*)st->coef[0], (void*)st->coef[1], (void*)st->rows})
-        if (p) cudaFree(p);
+        pool_release(st->ctx, p);
     delete st;
 }
 
@@ -1195,18 +1301,18 @@ extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_
     st->n0 = st->n = n;
     st->fast = fast;
     st->max_blocks = (unsigned)((n / 2 + kSmallThreads - 1) / kSmallThreads) + 1;
-    bool ok = cudaMalloc(&st->a, n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->b, n * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->scal, 8 * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->frpart, 2 * (kBulletDotBlocks + 1) * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->outp, 2 * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->outinf, 2) == cudaSuccess;
+    bool ok = pool_alloc(ctx, &st->a, n * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->b, n * sizeof(Fr)) == cudaSuccess &&
+              pool_alloc(ctx, &st->scal, 8 * sizeof(Fr)) == cudaSuccess &&
+              pool_alloc(ctx, &st->frpart, 2 * (kBulletDotBlocks + 1) * sizeof(Fr)) == cudaSuccess &&
+              pool_alloc(ctx, &st->outp, 2 * sizeof(Affine)) == cudaSuccess && pool_alloc(ctx, &st->outinf, 2) == cudaSuccess;
     if (ok && fast)
-        ok = cudaMalloc(&st->coef[0], n * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->coef[1], n * sizeof(Fr)) == cudaSuccess &&
-             cudaMalloc(&st->rows, 2 * (n + 1) * sizeof(Fr)) == cudaSuccess;
+        ok = pool_alloc(ctx, &st->coef[0], n * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->coef[1], n * sizeof(Fr)) == cudaSuccess &&
+             pool_alloc(ctx, &st->rows, 2 * (n + 1) * sizeof(Fr)) == cudaSuccess;
     if (ok && !fast)
-        ok = cudaMalloc(&st->G, n * sizeof(Affine)) == cudaSuccess && cudaMalloc(&st->Ginf, n) == cudaSuccess &&
-             cudaMalloc(&st->QH, 4 * sizeof(Affine)) == cudaSuccess &&
-             cudaMalloc(&st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
-             cudaMalloc(&st->terms, 6 * sizeof(XYZZ)) == cudaSuccess;
+        ok = pool_alloc(ctx, &st->G, n * sizeof(Affine)) == cudaSuccess && pool_alloc(ctx, &st->Ginf, n) == cudaSuccess &&
+             pool_alloc(ctx, &st->QH, 4 * sizeof(Affine)) == cudaSuccess &&
+             pool_alloc(ctx, &st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
+             pool_alloc(ctx, &st->terms, 6 * sizeof(XYZZ)) == cudaSuccess;
     if (!ok) { bullet_free(st); ctx->last_error = "sbn_bullet_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
     auto fail = [&](int code) { bullet_free(st); return code; };
 #define BCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(SBN_ERR_CUDA); } } while (0)
@@ -1390,9 +1496,9 @@ struct sbn_sumcheck {
 };
 
 static void sumcheck_free(sbn_sumcheck* st) {
-    for (Fr* t : st->T) if (t) cudaFree(t);
-    if (st->partial) cudaFree(st->partial);
-    if (st->out) cudaFree(st->out);
+    for (Fr* t : st->T) pool_release(st->ctx, t);
+    pool_release(st->ctx, st->partial);
+    pool_release(st->ctx, st->out);
     delete st;
 }
 
@@ -1421,8 +1527,8 @@ static int sumcheck_begin(sbn_ctx* ctx, const sbn_fr* const* src, int ntables, s
     st->len = len;
     st->blocks = 592;
     st->ntables = ntables;
-    bool ok = cudaMalloc(&st->partial, 3 * st->blocks * sizeof(Fr)) == cudaSuccess && cudaMalloc(&st->out, 4 * sizeof(Fr)) == cudaSuccess;
-    for (int k = 0; k < ntables && ok; k++) ok = cudaMalloc(&st->T[k], len * sizeof(Fr)) == cudaSuccess;
+    bool ok = pool_alloc(ctx, &st->partial, 3 * st->blocks * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->out, 4 * sizeof(Fr)) == cudaSuccess;
+    for (int k = 0; k < ntables && ok; k++) ok = pool_alloc(ctx, &st->T[k], len * sizeof(Fr)) == cudaSuccess;
     if (!ok) { sumcheck_free(st); ctx->last_error = "sbn_sumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
     for (int k = 0; k < ntables; k++) {
         if (cudaMemcpyAsync(st->T[k], src[k], len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess) {
@@ -1596,7 +1702,7 @@ static void bsumcheck_free(sbn_bsumcheck* st) {
     pool_free(st->ctx, st->eq[1], st->T0 * sizeof(Fr));
     pool_free(st->ctx, st->seq, 3 * st->S * st->T0 * sizeof(Fr));
     for (void* p : {(void*)st->d_triples, (void*)st->d_tables, (void*)st->partial, (void*)st->out})
-        if (p) cudaFree(p);
+        pool_release(st->ctx, p);
     delete st;
 }
 
@@ -1626,10 +1732,10 @@ static int bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_
     st->max_blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((T / 2 + kDotThreads - 1) / kDotThreads, std::max<size_t>(16, 1184 / n)));
     st->T0 = T;
     bool ok = pool_alloc(ctx, &st->eq[0], T * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->eq[1], T * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->d_triples, n * sizeof(CubicTriple)) == cudaSuccess &&
-              cudaMalloc(&st->d_tables, (2 * P + 1 + 3 * S) * sizeof(Fr*)) == cudaSuccess &&
-              cudaMalloc(&st->partial, 3 * n * st->max_blocks * sizeof(Fr)) == cudaSuccess &&
-              cudaMalloc(&st->out, (3 * n + n_rand + 2) * sizeof(Fr)) == cudaSuccess &&
+              pool_alloc(ctx, &st->d_triples, n * sizeof(CubicTriple)) == cudaSuccess &&
+              pool_alloc(ctx, &st->d_tables, (2 * P + 1 + 3 * S) * sizeof(Fr*)) == cudaSuccess &&
+              pool_alloc(ctx, &st->partial, 3 * n * st->max_blocks * sizeof(Fr)) == cudaSuccess &&
+              pool_alloc(ctx, &st->out, (3 * n + n_rand + 2) * sizeof(Fr)) == cudaSuccess &&
               (S == 0 || pool_alloc(ctx, &st->seq, 3 * S * T * sizeof(Fr)) == cudaSuccess);
     if (!ok) { bsumcheck_free(st); ctx->last_error = "sbn_bsumcheck_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
     auto fail = [&](const char* what, cudaError_t e) {
@@ -2241,6 +2347,26 @@ extern "C" int sbn_spmat_destroy(sbn_spmat* m) {
 }
 
 // out[i] = sum_m coeffs[m] * (M_m vec)[i]   (coeffs == NULL: plain sum); 1 <= nm <= 3 matrices of equal shape
+// out = M vec (nm = 1, coeffs NULL) or sum_m coeffs[m] M_m vec, everything in HBM
+static void spmv_device(sbn_ctx* ctx, const sbn_spmat* const* mats, size_t nm, const sbn_fr* coeffs, const Fr* dvec, Fr* dout,
+                        cudaStream_t s) {
+    const size_t n = mats[0]->n;
+    SpMat sm[3];
+    Fr c[3];
+    for (size_t m = 0; m < 3; m++) {
+        const sbn_spmat* src = mats[m < nm ? m : 0];
+        sm[m] = SpMat{src->ptr, src->idx, src->val};
+        if (coeffs && m < nm) memcpy(&c[m], &coeffs[m], sizeof(Fr)); else c[m] = Fr::zero();
+    }
+    k_spmv<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sm[0], sm[1], sm[2], c[0], c[1], c[2], (int)nm, coeffs ? 1 : 0, dvec, n, dout);
+    ctx->launches++;
+    for (size_t m = 0; m < nm; m++)
+        if (mats[m]->nheavy) {
+            k_spmv_heavy<<<(unsigned)mats[m]->nheavy, kDotThreads, 0, s>>>(sm[m], mats[m]->heavy, c[m], coeffs ? 1 : 0, dvec, dout);
+            ctx->launches++;
+        }
+}
+
 extern "C" int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* coeffs, size_t nm, const sbn_fr* vec,
                                 size_t veclen, sbn_fr* out) {
     if (!ctx || !mats || !vec || !out || nm < 1 || nm > 3) return SBN_ERR_ARG;
@@ -2254,25 +2380,85 @@ extern "C" int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, cons
     const size_t n = mats[0]->n;
     SBN_TRY(upload(ctx, ctx->scratch0, vec, veclen * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->scratch1, n * sizeof(Fr)));
-    SpMat sm[3];
-    Fr c[3];
-    for (size_t m = 0; m < 3; m++) {
-        const sbn_spmat* src = mats[m < nm ? m : 0];
-        sm[m] = SpMat{src->ptr, src->idx, src->val};
-        if (coeffs && m < nm) memcpy(&c[m], &coeffs[m], sizeof(Fr)); else c[m] = Fr::zero();
-    }
-    k_spmv<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sm[0], sm[1], sm[2], c[0], c[1], c[2], (int)nm, coeffs ? 1 : 0,
-                                                        (const Fr*)ctx->scratch0.p, n, (Fr*)ctx->scratch1.p);
-    ctx->launches++;
-    for (size_t m = 0; m < nm; m++)
-        if (mats[m]->nheavy) {
-            k_spmv_heavy<<<(unsigned)mats[m]->nheavy, kDotThreads, 0, s>>>(sm[m], mats[m]->heavy, c[m], coeffs ? 1 : 0,
-                                                                          (const Fr*)ctx->scratch0.p, (Fr*)ctx->scratch1.p);
-            ctx->launches++;
-        }
+    spmv_device(ctx, mats, nm, coeffs, (const Fr*)ctx->scratch0.p, (Fr*)ctx->scratch1.p, s);
     SBN_CUDA(ctx, cudaGetLastError());
     SBN_TRY(download(ctx, out, ctx->scratch1.p, n * sizeof(Fr)));
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}
+
+// The table set-ups of the two R1CS-sat sumchecks with nothing but z, tau / rx and three coefficients crossing the bus:
+//   phase 1 (r1csproof.rs:268-290)  eq(tau), A z, B z, C z   -> the four tables of the cubic sumcheck
+//   phase 2 (r1csproof.rs:378-410)  z and r_A A^T eq(rx) + r_B B^T eq(rx) + r_C C^T eq(rx)   -> the two tables of the quadratic one
+// (the host-table variants copy 4 x 32 MB up after copying 3 x 32 MB down at 2^20 constraints).
+static sbn_sumcheck* sumcheck_alloc(sbn_ctx* ctx, int ntables, size_t len) {
+    sbn_sumcheck* st = new (std::nothrow) sbn_sumcheck();
+    if (!st) return nullptr;
+    st->ctx = ctx;
+    st->len = len;
+    st->blocks = 592;
+    st->ntables = ntables;
+    bool ok = pool_alloc(ctx, &st->partial, 3 * st->blocks * sizeof(Fr)) == cudaSuccess && pool_alloc(ctx, &st->out, 4 * sizeof(Fr)) == cudaSuccess;
+    for (int k = 0; k < ntables && ok; k++) ok = pool_alloc(ctx, &st->T[k], len * sizeof(Fr)) == cudaSuccess;
+    if (!ok) { sumcheck_free(st); ctx->last_error = "sbn_sumcheck_begin: cudaMalloc failed"; return nullptr; }
+    return st;
+}
+
+extern "C" int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, size_t zlen, const sbn_fr* tau,
+                                       size_t n_tau, sbn_sumcheck** out) {
+    if (!ctx || !mats || !z || !tau || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (n_tau == 0 || n_tau > 28) return SBN_ERR_SHAPE;
+    const size_t len = size_t(1) << n_tau;
+    for (int m = 0; m < 3; m++) {
+        if (!mats[m] || mats[m]->ctx != ctx) return SBN_ERR_ARG;
+        if (mats[m]->n != len || mats[m]->ncols > zlen) return SBN_ERR_SHAPE;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    SBN_TRY(ensure(ctx, ctx->scratch0, zlen * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, n_tau * sizeof(Fr)));
+    sbn_sumcheck* st = sumcheck_alloc(ctx, 4, len);
+    if (!st) return SBN_ERR_OOM;
+    auto fail = [&](cudaError_t e) { ctx->last_error = std::string("sbn_sumcheck_begin_r1cs: ") + cudaGetErrorString(e); sumcheck_free(st); return SBN_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(ctx->scratch0.p, z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(ctx->scratch2.p, tau, n_tau * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    ctx->h2d += (zlen + n_tau) * sizeof(Fr);
+    eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n_tau, st->T[0], st->T[1], s);      // T[1] is scratch until A z lands in it
+    for (int m = 0; m < 3; m++) spmv_device(ctx, mats + m, 1, nullptr, (const Fr*)ctx->scratch0.p, st->T[1 + m], s);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);
+    *out = st;
+    return SBN_OK;
+}
+
+extern "C" int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats_t, const sbn_fr* coeffs, const sbn_fr* rx,
+                                            size_t n_rx, const sbn_fr* z, size_t zlen, sbn_sumcheck** out) {
+    if (!ctx || !mats_t || !coeffs || !rx || !z || !out) return SBN_ERR_ARG;
+    *out = nullptr;
+    if (n_rx == 0 || n_rx > 28 || zlen < 2 || (zlen & (zlen - 1)) || zlen > (1u << 28)) return SBN_ERR_SHAPE;
+    const size_t veclen = size_t(1) << n_rx;
+    for (int m = 0; m < 3; m++) {
+        if (!mats_t[m] || mats_t[m]->ctx != ctx) return SBN_ERR_ARG;
+        if (mats_t[m]->n != zlen || mats_t[m]->ncols > veclen) return SBN_ERR_SHAPE;
+    }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    SBN_TRY(ensure(ctx, ctx->scratch0, 2 * veclen * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, n_rx * sizeof(Fr)));
+    sbn_sumcheck* st = sumcheck_alloc(ctx, 2, zlen);
+    if (!st) return SBN_ERR_OOM;
+    auto fail = [&](cudaError_t e) { ctx->last_error = std::string("sbn_sumcheck_begin_quad_r1cs: ") + cudaGetErrorString(e); sumcheck_free(st); return SBN_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(st->T[0], z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(ctx->scratch2.p, rx, n_rx * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    ctx->h2d += (zlen + n_rx) * sizeof(Fr);
+    const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n_rx, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + veclen, s);
+    spmv_device(ctx, mats_t, 3, coeffs, eq, st->T[1], s);
+    if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);
+    *out = st;
     return SBN_OK;
 }
 

@@ -176,8 +176,9 @@ class DotProductProofGens:
     def device_bases_ext(self):
         """gens_n (G, h) plus gens_1.G[0] resident with window tables: what the opening's bullet reduction uses."""
         if self._bases_ext is None:
+            # kept apart from gens_n's own tables: a commit merges equal generators (two thirds of the reference's set),
+            # the bullet reduction needs every generator as given
             self._bases_ext = self.gens_n.ctx.bases(self.gens_n.G, self.gens_n.h, g1=self.gens_1.G[0])
-            self.gens_n._bases = self._bases_ext        # commits reuse the same resident tables
         return self._bases_ext
 
 

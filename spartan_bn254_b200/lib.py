@@ -22,7 +22,7 @@ EXPORTS = [
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
-    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
+    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
@@ -230,6 +230,14 @@ class Context:
     def sumcheck_begin_quad(self, z, ABC):
         return SumcheckState(self, z, ABC)
 
+    def sumcheck_begin_r1cs(self, mats, z, tau):
+        """Phase-1 tables eq(tau), A z, B z, C z built on the device from the resident matrices (r1csproof.rs:268-290)."""
+        return SumcheckState._resident(self, 4, mats, z, tau, None)
+
+    def sumcheck_begin_quad_r1cs(self, mats_t, coeffs, rx, z):
+        """Phase-2 tables z and sum_m coeffs[m] M_m^T eq(rx) built on the device (r1csproof.rs:378-410)."""
+        return SumcheckState._resident(self, 2, mats_t, z, rx, coeffs)
+
     # ---- utilities
     def fr_from_canonical(self, canon):
         canon = _u64(canon, 4)
@@ -338,6 +346,26 @@ class BulletState:
 
 class SumcheckState:
     """sbn_sumcheck: the four tables of the R1CS-sat cubic sumcheck (sumcheck.rs:465-649) on the GPU."""
+
+    @staticmethod
+    def _resident(ctx, ntables, mats, z, point, coeffs):
+        self = SumcheckState.__new__(SumcheckState)
+        self.ctx, self.ntables = ctx, ntables
+        z, point = _u64(z, 4), _u64(point, 4)
+        hs = (C.c_void_p * 3)(*[m.h for m in mats])
+        h = C.c_void_p()
+        if ntables == 4:
+            self.len = 1 << point.shape[0]
+            st = ctx.lib.sbn_sumcheck_begin_r1cs(ctx.h, hs, _ptr(z), C.c_size_t(z.shape[0]), _ptr(point), C.c_size_t(point.shape[0]),
+                                                 C.byref(h))
+            ctx._check(st, "sbn_sumcheck_begin_r1cs")
+        else:
+            self.len = z.shape[0]
+            st = ctx.lib.sbn_sumcheck_begin_quad_r1cs(ctx.h, hs, _ptr(_u64(coeffs, 4)), _ptr(point), C.c_size_t(point.shape[0]),
+                                                      _ptr(z), C.c_size_t(z.shape[0]), C.byref(h))
+            ctx._check(st, "sbn_sumcheck_begin_quad_r1cs")
+        self.h = h
+        return self
 
     def __init__(self, ctx, *tables):
         self.ctx = ctx

@@ -112,13 +112,16 @@ class DotProductProof:
         self.delta, self.beta, self.z, self.z_delta, self.z_beta = delta, beta, z, z_delta, z_beta
 
     @staticmethod
-    def prove(gens_1, gens_n, transcript, tape, x_vec, blind_x, a_vec, y, blind_y):
+    def prove(gens_1, gens_n, transcript, tape, x_vec, blind_x, a_vec, y, blind_y, Cx=None):
+        """nizk/mod.rs:238-296.  Cx: the commitment to (x_vec, blind_x) when the caller already holds it (the sumcheck round
+        has just sent it as comm_poly); the reference recomputes the same point."""
         transcript.append_protocol_name(b"dot product proof")
         n = len(x_vec)
         assert len(a_vec) == n and gens_n.n == n and gens_1.n == 1
         d_vec = tape.random_vector(b"d_vec", n)
         r_delta, r_beta = tape.random_scalar(b"r_delta"), tape.random_scalar(b"r_beta")
-        Cx = commit_scalars(gens_n, x_vec, blind_x)
+        if Cx is None:
+            Cx = commit_scalars(gens_n, x_vec, blind_x)
         _append(transcript, b"Cx", Cx)
         Cy = commit_scalars(gens_1, [y], blind_y)
         _append(transcript, b"Cy", Cy)
@@ -169,7 +172,8 @@ class ZKSumcheckInstanceProof:
             for _ in range(deg):
                 a_eval.append(a_eval[-1] * r_j % R_MOD)
             a = [(w[0] * s + w[1] * e) % R_MOD for s, e in zip(a_sc, a_eval)]
-            proof, _, _ = DotProductProof.prove(gens_1, gens_n, transcript, tape, poly.coeffs, blinds_poly[j], a, target, blind)
+            proof, _, _ = DotProductProof.prove(gens_1, gens_n, transcript, tape, poly.coeffs, blinds_poly[j], a, target, blind,
+                                                Cx=comm_poly)
             proofs.append(proof)
             claim_per_round, comm_claim_per_round = ev_r, comm_eval
             r.append(r_j)
@@ -248,9 +252,8 @@ class R1CSProof:
         z[num_vars + 1: num_vars + 1 + input_m.shape[0]] = input_m
         num_rounds_x, num_rounds_y = log_2(inst.num_cons), log_2(2 * num_vars)
         tau = transcript.challenge_scalars(b"challenge_tau", num_rounds_x)
-        poly_tau = eq_evals(ctx, fr_vec_from_ints(tau))
-        Az, Bz, Cz = inst.multiply_vec(z)
-        st1 = ctx.sumcheck_begin(poly_tau, Az, Bz, Cz)
+        # eq(tau), A z, B z, C z (r1csproof.rs:268-290) are built in HBM from the resident matrices
+        st1 = ctx.sumcheck_begin_r1cs(inst.by_row, z, fr_vec_from_ints(tau))
         lap("sumcheck1_setup(eq(tau), Az, Bz, Cz)_ms")
         sc1, rx, claims1, blind_claim_postsc1 = ZKSumcheckInstanceProof._prove(
             st1, 3, 0, 0, num_rounds_x, gens.gens_sc.gens_1, gens.gens_sc.gens_4, transcript, tape)
@@ -275,9 +278,8 @@ class R1CSProof:
         claim_phase2 = (r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim) % R_MOD
         blind_claim_phase2 = (r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind) % R_MOD
         lap("sigma_protocols_phase1_ms")
-        evals_rx = eq_evals(ctx, fr_vec_from_ints(rx))
-        evals_ABC = inst.compute_eval_table_combined(evals_rx, [r_A, r_B, r_C])
-        st2 = ctx.sumcheck_begin_quad(z, evals_ABC)
+        # eq(rx) and r_A A^T eq(rx) + r_B B^T eq(rx) + r_C C^T eq(rx) (r1csproof.rs:378-410) likewise
+        st2 = ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints([r_A, r_B, r_C]), fr_vec_from_ints(rx), z)
         lap("sumcheck2_setup(eq(rx), eval tables)_ms")
         sc2, ry, claims2, blind_claim_postsc2 = ZKSumcheckInstanceProof._prove(
             st2, 2, claim_phase2, blind_claim_phase2, num_rounds_y, gens.gens_sc.gens_1, gens.gens_sc.gens_3, transcript, tape)

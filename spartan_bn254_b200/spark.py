@@ -137,8 +137,7 @@ def commit_dense(dense, gens):
 def append_poly_commitment(transcript, label, comm):
     """hyrax.rs:44-52."""
     transcript.append_message(label, b"poly_commitment_begin")
-    for c in comm.compressed():
-        transcript.append_point(b"poly_commitment_share", c)
+    transcript.append_points(b"poly_commitment_share", comm.C, comm.inf)
     transcript.append_message(label, b"poly_commitment_end")
 
 

@@ -107,6 +107,15 @@ class Transcript:
     def append_point(self, label, compressed32):
         self.append_message(label, compressed32)
 
+    def append_points(self, label, xy, inf):
+        """One append_point per affine Montgomery point (uint64[n, 8] + infinity bytes): the share loop of
+        PolyCommitment::append_to_transcript (hyrax.rs:46-50), compressed (group.rs:135-140) by the library's host code."""
+        import numpy as _np
+        xy = _np.ascontiguousarray(xy, dtype=_np.uint64).reshape(-1, 8)
+        inf = _np.ascontiguousarray(inf, dtype=_np.uint8).reshape(-1)
+        self._lib.sbn_merlin_append_points(self._st, label, _ctypes.c_size_t(len(label)), xy.ctypes.data_as(_ctypes.c_void_p),
+                                           inf.ctypes.data_as(_ctypes.c_void_p), _ctypes.c_size_t(xy.shape[0]))
+
     def challenge_scalar(self, label):
         return int.from_bytes(self.challenge_bytes(label, 64), "little") % R_MOD   # transcript.rs:56-67
 
@@ -215,6 +224,11 @@ class PyTranscript(Transcript):
 
     def append_point(self, label, compressed32):
         self.append_message(label, compressed32)
+
+    def append_points(self, label, xy, inf):
+        from .hyrax import GroupElement
+        for p, i in zip(xy.reshape(-1, 8), inf.reshape(-1)):
+            self.append_point(label, GroupElement(p, i).compress())
 
     def challenge_scalar(self, label):
         return int.from_bytes(self.challenge_bytes(label, 64), "little") % R_MOD   # transcript.rs:56-67

@@ -238,3 +238,43 @@ def _add256(a, b):
             out[:, k] = t2
             carry = c1 | c2
     return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 14, 15])
+def test_short_commitments_match_oracle(ctx, orc, n):
+    """The Sigma-protocols' short vectors (commitments.rs:118-154 over gens_1 / gens_3 / gens_4, sumcheck.rs:559-649):
+    generator sets of at most 16 points take the tabulated one-launch path (small_kernels.cuh).  Checked against the oracle
+    and against the general pipeline on random rows and on digit-boundary scalars (0, 1, r - 1, 0x80 / 0x7f / 0x81 bytes,
+    which sit on the signed-digit carry), with and without blinds, with the reference's duplicate generators."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.hyrax import DotProductProofGens, MultiCommitGens
+    rmod = h2i(GOLD["constants"]["r"])
+    gens = MultiCommitGens.new(n, b"gens_r1cs_sat", ctx)
+    edge = [0, 1, rmod - 1, rmod - 2, int.from_bytes(b"\x80" * 31, "little"), int.from_bytes(b"\x7f" * 31, "little"),
+            int.from_bytes(b"\x81" * 31, "little"), 128, 127, 129, 1 << 253, (1 << 253) + (1 << 8) - 128]
+    for L in (1, 2, 41, 64, 65):              # 65 rows fall back to the pipeline
+        Z = synth.uniform_scalars(11 + L, L * n)
+        ez = orc.to_mont([edge[(i * 5 + 3 * (i // n)) % len(edge)] for i in range(L * n)])
+        for Zm, bl in ((Z, synth.uniform_scalars(5, L)), (Z, None), (ez, orc.to_mont([edge[(7 * i) % len(edge)] for i in range(L)]))):
+            C, inf = ctx.hyrax_commit(gens.device_bases(), Zm, L, n, bl)
+            Co, info = orc.hyrax_commit(gens.G, gens.h, Zm, L, n, bl)
+            assert np.array_equal(inf, info) and np.array_equal(C, Co), (n, L)
+    # the same rows through the general pipeline, and through a set that carries gens_1's generator as well
+    c2 = Context(0)
+    c2.set("small_commit_path", 0)
+    b2 = c2.bases(gens.G, gens.h)
+    Z = synth.uniform_scalars(3, 8 * n)
+    bl = synth.uniform_scalars(4, 8)
+    C, inf = ctx.hyrax_commit(gens.device_bases(), Z, 8, n, bl)
+    C2, inf2 = c2.hyrax_commit(b2, Z, 8, n, bl)
+    assert np.array_equal(C, C2) and np.array_equal(inf, inf2)
+    b2.close()
+    c2.close()
+    d = DotProductProofGens(n, b"gens_r1cs_sat", ctx)
+    C3, inf3 = ctx.hyrax_commit(d.device_bases_ext(), Z, 8, n, bl)
+    Co, info = orc.hyrax_commit(d.gens_n.G, d.gens_n.h, Z, 8, n, bl)
+    assert np.array_equal(C3, Co) and np.array_equal(inf3, info)
+    # a single scalar that cancels against the blind: x G + (r - x) G when h equals the generator
+    one = MultiCommitGens.from_generators(gens.G[:1].reshape(1, 8), gens.G[0], ctx)
+    C, inf = ctx.hyrax_commit(one.device_bases(), orc.to_mont([5]), 1, 1, orc.to_mont([rmod - 5]))
+    assert inf[0] == 1

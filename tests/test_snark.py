@@ -112,6 +112,58 @@ def test_sparse_matvec_with_heavy_rows(ctx):
         s_.close()
 
 
+@pytest.mark.parametrize("num_cons,num_vars", [(16, 8), (64, 64), (32, 256)])
+def test_resident_sumcheck_setups_match_host_tables(ctx, num_cons, num_vars):
+    """sbn_sumcheck_begin_r1cs / _begin_quad_r1cs (tables built in HBM from the resident matrices, r1csproof.rs:268-290 and
+    :378-410) against host integers: every round's evaluations and the final table values equal those of the host-table
+    set-ups fed with eq(tau), A z, B z, C z (resp. z and the combined evaluation table) computed in Python."""
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints, fr_vec_to_ints, fr_to_int, fr_from_int
+    from spartan_bn254_b200.r1csproof import R1CSShape
+    rnd = random.Random(11)
+    vars_, inputs, A, B, Cm = synthetic_r1cs(5, num_cons, num_vars, 1)
+    inst = R1CSShape(ctx, num_cons, num_vars, 1, _arrays(A), _arrays(B), _arrays(Cm))
+    z = vars_ + [1] + inputs + [0] * (num_vars - 2)
+    zm = fr_vec_from_ints(z)
+
+    def eq(point):
+        t = [1]
+        for r in point:
+            t = [v for x in t for v in (x * (1 - r) % R, x * r % R)]
+        return t
+
+    def drive(st, n):
+        out = []
+        for _ in range(n):
+            out.append([fr_to_int(e) for e in st.round_eval()])
+            st.bind(fr_from_int(rnd.randrange(R)))
+        out.append(fr_vec_to_ints(st.end()))
+        st.close()
+        return out
+
+    lx, ly = num_cons.bit_length() - 1, (2 * num_vars).bit_length() - 1
+    tau = [rnd.randrange(R) for _ in range(lx)]
+    mv = lambda ent: [sum(v * z[c] for r, c, v in ent if r == i) % R for i in range(num_cons)]
+    host = ctx.sumcheck_begin(fr_vec_from_ints(eq(tau)), fr_vec_from_ints(mv(A)), fr_vec_from_ints(mv(B)), fr_vec_from_ints(mv(Cm)))
+    state = rnd.getstate()
+    want = drive(host, lx)
+    rnd.setstate(state)
+    assert drive(ctx.sumcheck_begin_r1cs(inst.by_row, zm, fr_vec_from_ints(tau)), lx) == want
+    rx = [rnd.randrange(R) for _ in range(lx)]
+    co = [rnd.randrange(R) for _ in range(3)]
+    e = eq(rx)
+    table = [0] * (2 * num_vars)
+    for k, ent in enumerate((A, B, Cm)):
+        for r, c, v in ent:
+            table[c] = (table[c] + co[k] * v % R * e[r]) % R
+    host = ctx.sumcheck_begin_quad(zm, fr_vec_from_ints(table))
+    state = rnd.getstate()
+    want = drive(host, ly)
+    rnd.setstate(state)
+    assert drive(ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints(co), fr_vec_from_ints(rx), zm), ly) == want
+    for m_ in inst.by_row + inst.by_col:
+        m_.close()
+
+
 def test_keyless_scale_proof_is_accepted(ctx, orc):
     """BASELINE configs[4] at full size: the proof scripts/bench_snark.py times (2^20 constraints, nnz padded to 2^22) is
     accepted by the oracle's CPU restatement of SNARK::verify."""

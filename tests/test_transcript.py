@@ -46,3 +46,40 @@ def test_native_and_python_transcripts_agree():
         else:
             n = rnd.randrange(1, 200)
             assert a.challenge_bytes(b"cb", n) == b.challenge_bytes(b"cb", n)
+
+
+def test_native_point_compression_and_append_points(orc):
+    """sbn_g1_compress / sbn_merlin_append_points (host code of the library) against GroupElement::compress restated in
+    Python (group.rs:135-140) and against the oracle's transcript fed point by point: multiples of G (both signs of y occur),
+    the identity by flag and by the (0, 0) encoding."""
+    import ctypes as C
+    import numpy as np
+    from spartan_bn254_b200.hyrax import GroupElement
+    from spartan_bn254_b200.lib import load_library
+    from spartan_bn254_b200.transcript import Transcript, PyTranscript
+    lib = load_library()
+    G, h = orc.multi_commit_gens(b"gens_r1cs_eval", 24)
+    pts = np.concatenate([G, h.reshape(1, 8), np.zeros((2, 8), dtype=np.uint64)])
+    neg = pts[:6].copy()                         # -P: y -> p - y flips the sign bit
+    P = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    for row in neg:
+        y = sum(int(v) << (64 * i) for i, v in enumerate(row[4:]))
+        ny = (P - y) % P
+        row[4:] = [(ny >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+    pts = np.ascontiguousarray(np.concatenate([pts, neg]))
+    inf = np.zeros(pts.shape[0], dtype=np.uint8)
+    inf[25] = 1                                  # flagged identity; row 26 is the (0, 0) encoding without a flag
+    out = np.zeros((pts.shape[0], 32), dtype=np.uint8)
+    assert lib.sbn_g1_compress(pts.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p), C.c_size_t(pts.shape[0]),
+                               out.ctypes.data_as(C.c_void_p)) == 0
+    exp = [GroupElement(p, i or not p.any()).compress() for p, i in zip(pts, inf)]
+    assert [bytes(o) for o in out] == exp
+    assert {e[31] >> 7 for e in exp} == {0, 1} and exp[25][31] == 0x40 and exp[26][31] == 0x40
+    inf[26] = 1
+    a, b, c = Transcript(b"pts"), PyTranscript(b"pts"), orc.Transcript(b"pts")
+    a.append_points(b"poly_commitment_share", pts, inf)
+    b.append_points(b"poly_commitment_share", pts, inf)
+    for e in exp:
+        c.append_message(b"poly_commitment_share", e)
+    ch = a.challenge_bytes(b"c", 64)
+    assert ch == b.challenge_bytes(b"c", 64) == c.challenge_bytes(b"c", 64)
