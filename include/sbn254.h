@@ -143,6 +143,11 @@ int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn_fr* blind_
                      sbn_g1a* L_out, uint8_t* L_inf, sbn_g1a* R_out, uint8_t* R_inf);
 int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_inv);
 int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_g1a* g_hat, uint8_t* g_hat_inf);
+/* sbn_bullet_end together with DotProductProofLog::prove's delta = d * g_hat + r_delta * h (nizk/mod.rs:497-500), computed
+ * as a second row over the resident tables (g_hat = <coef, G>).  Table path only (begin with q_scalar): SBN_ERR_UNSUPPORTED
+ * otherwise. */
+int sbn_bullet_end_delta(sbn_bullet* st, const sbn_fr* d, const sbn_fr* r_delta, sbn_fr* a_hat, sbn_fr* b_hat, sbn_g1a* g_hat,
+                         uint8_t* g_hat_inf, sbn_g1a* delta, uint8_t* delta_inf);
 int sbn_bullet_destroy(sbn_bullet* st);
 
 /* ---- a16: R1CS-sat sumcheck round (sumcheck.rs:501-530 evaluation, :551-554 + hyrax.rs:195-203 bind).
@@ -268,6 +273,9 @@ int sbn_g1_compress(const sbn_g1a* pts, const uint8_t* inf, size_t n, uint8_t* o
 int sbn_merlin_append_points(void* state, const uint8_t* label, size_t label_len, const sbn_g1a* pts, const uint8_t* inf, size_t n);
 int sbn_fr_from_canonical(sbn_ctx* ctx, const uint64_t* canon /* n x 4 */, size_t n, sbn_fr* out);
 int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uint64_t* canon);
+/* the same conversions on the host, for the handful of scalars a sumcheck round exchanges */
+int sbn_fr_to_canonical_host(const sbn_fr* in, size_t n, uint64_t* canon);
+int sbn_fr_from_canonical_host(const uint64_t* canon, size_t n, sbn_fr* out);
 /* integer-multiply microbenchmark: returns achieved 32-bit multiply-add results per second for
  * kind 0 = IMAD (mad.lo), 1 = IMAD.HI, 2 = IMAD.WIDE (a 64-bit result counted as 2), 3 = Montgomery Fq
  * multiplications per second (not x264). */

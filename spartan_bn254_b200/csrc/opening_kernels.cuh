@@ -236,6 +236,12 @@ __global__ void k_bullet_row_single(const Fr* __restrict__ vec, int n, const Fr*
     else if (dot) v = fr_mul_call(load_fr(dot), load_fr(qs));
     store_fr(row + k, v);
 }
+// row[k < n] = vec[k] * scale; row[n] = 0
+__global__ void k_bullet_row_scaled(const Fr* __restrict__ vec, int n, const Fr* __restrict__ scale, Fr* __restrict__ row) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n) return;
+    store_fr(row + k, k < n ? fr_mul_call(load_fr(vec + k), load_fr(scale)) : Fr::zero());
+}
 // out[2t] = in[t] * u^-1, out[2t + 1] = in[t] * u
 __global__ void k_coef_update(const Fr* __restrict__ in, int len, const Fr* __restrict__ uu, Fr* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

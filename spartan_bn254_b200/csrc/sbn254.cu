@@ -233,6 +233,28 @@ extern "C" int sbn_g1_compress(const sbn_g1a* pts, const uint8_t* inf, size_t n,
     }
     return SBN_OK;
 }
+// host utilities: Scalar <-> canonical little-endian integers for short vectors (scalar.rs:75-95); long ones change form
+// on the device (sbn_fr_to_canonical / sbn_fr_from_canonical)
+extern "C" int sbn_fr_to_canonical_host(const sbn_fr* in, size_t n, uint64_t* canon) {
+    if (n && (!in || !canon)) return SBN_ERR_ARG;
+    for (size_t i = 0; i < n; i++) {
+        Fr v;
+        memcpy(v.l, &in[i], 32);
+        v = fp_from_mont(v);
+        memcpy(canon + 4 * i, v.l, 32);
+    }
+    return SBN_OK;
+}
+extern "C" int sbn_fr_from_canonical_host(const uint64_t* canon, size_t n, sbn_fr* out) {
+    if (n && (!canon || !out)) return SBN_ERR_ARG;
+    for (size_t i = 0; i < n; i++) {
+        Fr v;
+        memcpy(v.l, canon + 4 * i, 32);
+        v = fp_to_mont(v);             // any 256-bit value: the product with R^2 reduces it
+        memcpy(&out[i], v.l, 32);
+    }
+    return SBN_OK;
+}
 // PolyCommitment::append_to_transcript's share loop (hyrax.rs:46-50): compress and append n points under one label
 extern "C" int sbn_merlin_append_points(void* state, const uint8_t* label, size_t llen, const sbn_g1a* pts, const uint8_t* inf, size_t n) {
     if (!state || !label || (n && !pts)) return SBN_ERR_ARG;
@@ -1468,6 +1490,48 @@ extern "C" int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_
     SBN_CUDA(ctx, cudaStreamSynchronize(s));
     ctx->d2h += 2 * sizeof(Fr) + sizeof(Affine) + 1;
     if (*g_hat_inf) memset(g_hat, 0, sizeof(*g_hat));
+    return SBN_OK;
+}
+
+// sbn_bullet_end plus DotProductProofLog's delta = d * g_hat + r_delta * h (nizk/mod.rs:497-500).  On the table path
+// g_hat = <coef, G>, so delta = <d * coef, G> + r_delta * h is a second row of the same commit over the resident tables
+// instead of a 254-step double-and-add chain on the one-off point g_hat (~3 ms).
+extern "C" int sbn_bullet_end_delta(sbn_bullet* st, const sbn_fr* d, const sbn_fr* r_delta, sbn_fr* a_hat, sbn_fr* b_hat,
+                                    sbn_g1a* g_hat, uint8_t* g_hat_inf, sbn_g1a* delta, uint8_t* delta_inf) {
+    if (!st || !d || !r_delta || !a_hat || !b_hat || !g_hat || !g_hat_inf || !delta || !delta_inf) return SBN_ERR_ARG;
+    if (st->n != 1) return SBN_ERR_SHAPE;                      // bullet.rs:110-112 asserts
+    if (!st->fast) return SBN_ERR_UNSUPPORTED;                 // the explicit-folding path holds no coefficients
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const size_t n0 = st->n0;
+    Fr blinds[2];
+    blinds[0] = Fr::zero();
+    memcpy(&blinds[1], r_delta, sizeof(Fr));
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 2, blinds, 2 * sizeof(Fr), cudaMemcpyHostToDevice, s));   // the rounds' blind slots
+    SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 7, d, sizeof(Fr), cudaMemcpyHostToDevice, s));
+    const unsigned blocks = (unsigned)((n0 + 128) / 128);
+    k_bullet_row_single<<<blocks, 128, 0, s>>>(st->coef[st->coef_cur], (int)n0, nullptr, nullptr, st->rows);
+    k_bullet_row_scaled<<<blocks, 128, 0, s>>>(st->coef[st->coef_cur], (int)n0, st->scal + 7, st->rows + (n0 + 1));
+    ctx->launches += 2;
+    std::vector<int> ev_stage;
+    SBN_TRY(ensure_commit_workspace(ctx, st->bases, 2, 2));
+    SBN_TRY(run_commit(ctx, st->bases, st->rows, nullptr, 2, n0 + 1, st->scal + 2, st->outp, st->outinf, s, ev_stage));
+    Affine pts[2];
+    uint8_t infs[2];
+    SBN_CUDA(ctx, cudaMemcpyAsync(a_hat, st->a, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(b_hat, st->b, sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(pts, st->outp, 2 * sizeof(Affine), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaMemcpyAsync(infs, st->outinf, 2, cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += 2 * sizeof(Fr) + 2 * (sizeof(Affine) + 1);
+    memcpy(g_hat, &pts[0], sizeof(Affine));
+    memcpy(delta, &pts[1], sizeof(Affine));
+    *g_hat_inf = infs[0];
+    *delta_inf = infs[1];
+    if (*g_hat_inf) memset(g_hat, 0, sizeof(*g_hat));
+    if (*delta_inf) memset(delta, 0, sizeof(*delta));
     return SBN_OK;
 }
 

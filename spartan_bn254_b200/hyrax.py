@@ -9,6 +9,7 @@ the reference's own tests; every heavy operation goes through the libsbn254 C AB
   DensePolynomial      reference hyrax.rs:155-324  (commit, commit_inner, bound)
   GroupElement         reference group.rs:20,98-175 (compress, msm_affine, vartime_multiscalar_mul)
 """
+import ctypes as _C
 import hashlib
 
 import numpy as np
@@ -288,24 +289,53 @@ def _bulk_ctx():
     return _lib._live_contexts[-1] if _lib._live_contexts else None
 
 
+_hostlib = None
+
+
+def _host_lib():
+    """libsbn254's host-side conversions (sbn_fr_{to,from}_canonical_host) when the library has been built."""
+    global _hostlib
+    if _hostlib is None:
+        try:
+            from .lib import load_library
+            _hostlib = load_library()
+        except Exception:
+            _hostlib = False
+    return _hostlib or None
+
+
 def fr_vec_to_ints(arr):
     arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
-    ctx = _bulk_ctx() if arr.shape[0] >= _BULK else None
-    if ctx is None:
-        return [fr_to_int(a) for a in arr]
-    data = ctx.fr_to_canonical(arr).tobytes()
-    return [int.from_bytes(data[32 * i: 32 * i + 32], "little") for i in range(arr.shape[0])]
+    n = arr.shape[0]
+    ctx = _bulk_ctx() if n >= _BULK else None
+    if ctx is not None:
+        canon = ctx.fr_to_canonical(arr)
+    else:
+        lib = _host_lib()
+        if lib is None or n == 0:
+            return [fr_to_int(a) for a in arr]
+        canon = np.empty_like(arr)
+        lib.sbn_fr_to_canonical_host(arr.ctypes.data_as(_C.c_void_p), _C.c_size_t(n), canon.ctypes.data_as(_C.c_void_p))
+    data = canon.tobytes()
+    return [int.from_bytes(data[32 * i: 32 * i + 32], "little") for i in range(n)]
 
 
 def fr_vec_from_ints(vals):
-    ctx = _bulk_ctx() if len(vals) >= _BULK else None
-    if ctx is None:
-        out = np.zeros((len(vals), 4), dtype=np.uint64)
+    n = len(vals)
+    ctx = _bulk_ctx() if n >= _BULK else None
+    lib = _host_lib() if ctx is None else None
+    if (ctx is None and lib is None) or n == 0:
+        out = np.zeros((n, 4), dtype=np.uint64)
         for i, v in enumerate(vals):
             out[i] = fr_from_int(v)
         return out
     data = b"".join((int(v) % R_MOD).to_bytes(32, "little") for v in vals)
-    return ctx.fr_from_canonical(np.frombuffer(data, dtype=np.uint64).reshape(-1, 4))
+    canon = np.frombuffer(data, dtype=np.uint64).reshape(-1, 4)
+    if ctx is not None:
+        return ctx.fr_from_canonical(canon)
+    out = np.empty((n, 4), dtype=np.uint64)
+    lib.sbn_fr_from_canonical_host(canon.ctypes.data_as(_C.c_void_p), _C.c_size_t(n), out.ctypes.data_as(_C.c_void_p))
+    return out
 
 
 class EqPolynomial:
@@ -316,6 +346,10 @@ class EqPolynomial:
 
     def evals(self):
         ell = len(self.r)
+        ctx = _bulk_ctx() if (1 << ell) >= _BULK else None
+        if ctx is not None:         # the doubling runs on the device (sbn_eq_evals); only the canonical values come back
+            from .lib import eq_evals as _eq_evals
+            return fr_vec_to_ints(_eq_evals(ctx, fr_vec_from_ints(self.r)))
         ev = [1] * (1 << ell)
         size = 1
         for j in range(ell):
@@ -359,14 +393,12 @@ class DotProductProofLog:
         x_m = fr_vec_from_ints(x_vec)
         Cx = gens.gens_n.commit(x_m, fr_from_int(blind_x))                  # (n+1)-point MSM, mod.rs:470
         transcript.append_point(b"Cx", Cx.compress())
-        h = gens.gens_n.h
-        G1 = gens.gens_1.G[0]
-        Cy = DotProductProofLog._commit2(ctx, G1, y, h, blind_y)            # mod.rs:473
+        Cy = gens.gens_1.commit(fr_vec_from_ints([y]), fr_from_int(blind_y))   # mod.rs:473, over gens_1's resident tables
         transcript.append_point(b"Cy", Cy.compress())
         transcript.append_scalars(b"a", a_vec)
         r = transcript.challenge_scalar(b"r")
-        gens_1_scaled = gens.gens_1.scale(fr_from_int(r))                   # mod.rs:481
-        Q = gens_1_scaled.G[0]
+        # gens_1.scale(r) (mod.rs:481): Q = r * gens_1.G[0] never leaves the device -- the reduction takes r (q_scalar below)
+        # and beta = d * Q + r_beta * h is committed as (d r) * gens_1.G[0] + r_beta * h, the same group element
         blind_Gamma = (blind_x + r * blind_y) % R_MOD
         # BulletReductionProof::prove (bullet.rs:24-126): G, a, b stay on the device; L, R and u cross the boundary
         # Q = r * gens_1.G[0]: handed over as the scalar r so every MSM of the reduction runs on the window tables
@@ -385,14 +417,15 @@ class DotProductProofLog:
             rhat = (u * u * v1[i] + rhat + u_inv * u_inv * v2[i]) % R_MOD
             L_vec.append(L)
             R_vec.append(R)
-        a_hat_m, b_hat_m, g_hat, g_inf = st.end()
+        # delta = d * g_hat + r_delta * h (mod.rs:497-500) comes back with g_hat: a second row over the resident tables
+        a_hat_m, b_hat_m, g_hat, g_inf, delta_xy, delta_inf = st.end_delta(fr_from_int(d), fr_from_int(r_delta))
         st.close()
         x_hat, a_hat = fr_to_int(a_hat_m), fr_to_int(b_hat_m)
         y_hat = x_hat * a_hat % R_MOD
         assert not g_inf
-        delta = DotProductProofLog._commit2(ctx, g_hat, d, h, r_delta)      # mod.rs:497-500
+        delta = GroupElement(delta_xy, delta_inf)
         transcript.append_point(b"delta", delta.compress())
-        beta = DotProductProofLog._commit2(ctx, Q, d, h, r_beta)            # mod.rs:503
+        beta = gens.gens_1.commit(fr_vec_from_ints([d * r % R_MOD]), fr_from_int(r_beta))   # mod.rs:503
         transcript.append_point(b"beta", beta.compress())
         c = transcript.challenge_scalar(b"c")
         z1 = (d + c * y_hat) % R_MOD

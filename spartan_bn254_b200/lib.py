@@ -16,13 +16,13 @@ EXPORTS = [
     "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
     "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
-    "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_destroy",
+    "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_end_delta", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
-    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
+    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_fr_to_canonical_host", "sbn_fr_from_canonical_host", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
 ]
@@ -331,6 +331,15 @@ class BulletState:
         g = np.zeros(8, dtype=np.uint64); gi = np.zeros(1, dtype=np.uint8)
         self.ctx._check(self.ctx.lib.sbn_bullet_end(self.h, _ptr(a), _ptr(b), _ptr(g), _ptr(gi)), "sbn_bullet_end")
         return a, b, g, int(gi[0])
+
+    def end_delta(self, d, r_delta):
+        """end() plus delta = d * g_hat + r_delta * h (nizk/mod.rs:497-500) as a second row over the resident tables."""
+        a = np.zeros(4, dtype=np.uint64); b = np.zeros(4, dtype=np.uint64)
+        g = np.zeros(8, dtype=np.uint64); gi = np.zeros(1, dtype=np.uint8)
+        dl = np.zeros(8, dtype=np.uint64); di = np.zeros(1, dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.sbn_bullet_end_delta(self.h, _ptr(_u64(d, 4)), _ptr(_u64(r_delta, 4)), _ptr(a), _ptr(b), _ptr(g),
+                                                          _ptr(gi), _ptr(dl), _ptr(di)), "sbn_bullet_end_delta")
+        return a, b, g, int(gi[0]), dl, int(di[0])
 
     def close(self):
         if self.h and self.ctx.h:

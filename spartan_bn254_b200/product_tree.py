@@ -103,11 +103,8 @@ class SumcheckInstanceProof:
         e, r, polys = claim, [], []
         P, S = state.P, state.S
         for _ in range(num_rounds):
-            ev = state.round_eval()                                 # (P + S) x 3: e0, e2, e3 per instance (:201-271)
-            comb = [0, 0, 0]
-            for i in range(P + S):
-                for k in range(3):
-                    comb[k] = (comb[k] + fr_to_int(ev[i, k]) * coeffs[i]) % R_MOD
+            ev = fr_vec_to_ints(state.round_eval().reshape(-1, 4))  # (P + S) x 3: e0, e2, e3 per instance (:201-271)
+            comb = [sum(ev[3 * i + k] * coeffs[i] for i in range(P + S)) % R_MOD for k in range(3)]
             poly = UniPoly.from_evals([comb[0], (e - comb[0]) % R_MOD, comb[1], comb[2]])   # :273-284
             poly.append_to_transcript(b"poly", transcript)
             r_j = transcript.challenge_scalar(b"challenge_nextround")
