@@ -188,6 +188,13 @@ int sbn_bsumcheck_begin_resident(sbn_ctx* ctx, sbn_prodcircuit* const* circuits,
 int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals /* (P + S) x 3 */);
 int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r);
 int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final);
+/* One layer's whole round loop inside the library (SumcheckInstanceProof::prove_cubic_batched, sumcheck.rs:165-330): per
+ * round the batched evaluation, the combination with `coeffs` (P + S scalars, :273-275), UniPoly::from_evals
+ * (unipoly.rs:28-59), the transcript append (unipoly.rs:119-127), the challenge "challenge_nextround"
+ * (transcript.rs:56-67) and the bind; then the final values as sbn_bsumcheck_end returns them.  `merlin` is the transcript
+ * state of the sbn_merlin_* calls.  polys: num_rounds x 4 coefficients, lowest degree first; r_out: the challenges. */
+int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr* claim, const sbn_fr* coeffs, size_t num_rounds,
+                        sbn_fr* polys, sbn_fr* r_out, sbn_fr* claim_out, sbn_fr* A_final, sbn_fr* B_final, sbn_fr* C_final);
 int sbn_bsumcheck_destroy(sbn_bsumcheck* st);
 
 /* ---- f2: the derefs polynomial built on the device.

@@ -48,6 +48,9 @@ extern "C" {
     pub fn sbn_bullet_fold(st: *mut sbn_bullet, u: *const SbnFr, u_inv: *const SbnFr) -> c_int;
     pub fn sbn_bullet_end(st: *mut sbn_bullet, a_hat: *mut SbnFr, b_hat: *mut SbnFr, g_hat: *mut SbnG1a,
                           g_hat_inf: *mut u8) -> c_int;
+    // nizk/mod.rs:497-500: delta = d * g_hat + r_delta * h returned with g_hat (a second row over the resident tables)
+    pub fn sbn_bullet_end_delta(st: *mut sbn_bullet, d: *const SbnFr, r_delta: *const SbnFr, a_hat: *mut SbnFr, b_hat: *mut SbnFr,
+                                g_hat: *mut SbnG1a, g_hat_inf: *mut u8, delta: *mut SbnG1a, delta_inf: *mut u8) -> c_int;
     pub fn sbn_bullet_destroy(st: *mut sbn_bullet) -> c_int;
     // resident polynomials (hyrax.rs:217-222, 283-324)
     pub fn sbn_poly_upload(ctx: *mut sbn_ctx, z: *const SbnFr, len: usize, out: *mut *mut sbn_poly) -> c_int;
@@ -62,6 +65,11 @@ extern "C" {
     pub fn sbn_sumcheck_begin(ctx: *mut sbn_ctx, tau: *const SbnFr, az: *const SbnFr, bz: *const SbnFr, cz: *const SbnFr,
                               len: usize, out: *mut *mut sbn_sumcheck) -> c_int;
     pub fn sbn_sumcheck_begin_quad(ctx: *mut sbn_ctx, z: *const SbnFr, abc: *const SbnFr, len: usize, out: *mut *mut sbn_sumcheck) -> c_int;
+    // the same two set-ups with the tables built in HBM from the resident matrices (r1csproof.rs:268-290, 378-410)
+    pub fn sbn_sumcheck_begin_r1cs(ctx: *mut sbn_ctx, mats: *const *const sbn_spmat, z: *const SbnFr, zlen: usize, tau: *const SbnFr,
+                                   n_tau: usize, out: *mut *mut sbn_sumcheck) -> c_int;
+    pub fn sbn_sumcheck_begin_quad_r1cs(ctx: *mut sbn_ctx, mats_t: *const *const sbn_spmat, coeffs: *const SbnFr, rx: *const SbnFr,
+                                        n_rx: usize, z: *const SbnFr, zlen: usize, out: *mut *mut sbn_sumcheck) -> c_int;
     pub fn sbn_sumcheck_round_eval(st: *mut sbn_sumcheck, e0: *mut SbnFr, e2: *mut SbnFr, e3: *mut SbnFr) -> c_int;
     pub fn sbn_sumcheck_bind(st: *mut sbn_sumcheck, r: *const SbnFr) -> c_int;
     pub fn sbn_sumcheck_end(st: *mut sbn_sumcheck, finals: *mut SbnFr) -> c_int;

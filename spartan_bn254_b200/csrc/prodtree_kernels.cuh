@@ -73,6 +73,12 @@ __global__ void k_bind_top_batched(Fr* const* __restrict__ tables, size_t half, 
     store_fr(T + i, fp_add(lo, fp_mul(load_fr(r), fp_sub(hi, lo))));
 }
 
+// out[t] = tables[t][0]: the final values of a sumcheck whose tables have been bound down to one entry (sumcheck.rs:309-327)
+__global__ void k_gather_first(Fr* const* __restrict__ tables, int ntables, Fr* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntables) store_fr(out + t, load_fr(tables[t]));
+}
+
 // Derefs (sparse_mlpoly_full.rs:245-257 deref_mem, :292-297 Derefs::new, hyrax.rs:237-247 merge): segment s < batch gathers
 // mem_rx[row_addr[s][i]], segment batch + s gathers mem_ry[col_addr[s][i]]; the tail up to the next power of two is zero.
 __global__ void k_derefs_gather(const Fr* __restrict__ mem_rx, const Fr* __restrict__ mem_ry, const uint32_t* __restrict__ row_addr,

@@ -1936,6 +1936,114 @@ extern "C" int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_f
     return SBN_OK;
 }
 
+// ---- host-side field helpers of the round loop below (Montgomery Fr; the same fp.cuh code compiled for the host)
+namespace {
+struct FrHost {
+    static Fr small(uint32_t v) { Fr x = Fr::zero(); x.l[0] = v; return fp_to_mont(x); }
+    static Fr mul_small(const Fr& a, int k) { Fr r = a; for (int i = 1; i < k; i++) r = fp_add(r, a); return r; }
+    // from_le_bytes_mod_order of 64 bytes (transcript.rs:56-67): lo + hi * 2^256, the Montgomery form of 2^256 being R^2 mod r
+    static Fr from_wide(const uint8_t* b) {
+        Fr lo, hi, r2;
+        memcpy(lo.l, b, 32);
+        memcpy(hi.l, b + 32, 32);
+        for (int i = 0; i < 8; i++) r2.l[i] = FrParams::R2(i);
+        return fp_add(fp_to_mont(lo), fp_mul(fp_to_mont(hi), r2));
+    }
+};
+}  // namespace
+
+// SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:165-330) for one layer with the round loop inside the library:
+// per round the batched evaluation (:201-271), the combination with `coeffs` (:273-275), UniPoly::from_evals
+// (unipoly.rs:28-59), the transcript append (unipoly.rs:119-127), the challenge (transcript.rs:56-67) and the bind
+// (:293-306); then the final values (:309-327).  `merlin` is the 203-byte transcript state the sbn_merlin_* calls drive.
+// polys: num_rounds x 4 coefficients, lowest degree first; r_out: the challenges; claim_out: the claim after the last round.
+extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr* claim, const sbn_fr* coeffs, size_t num_rounds,
+                                   sbn_fr* polys, sbn_fr* r_out, sbn_fr* claim_out, sbn_fr* A_final, sbn_fr* B_final,
+                                   sbn_fr* C_final) {
+    if (!st || !merlin || !claim || !coeffs || !polys || !r_out || !claim_out || !A_final || !B_final || !C_final) return SBN_ERR_ARG;
+    if (st->len != (size_t(1) << num_rounds)) return SBN_ERR_SHAPE;
+    sbn_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    sbn::merlin::State& tr = *(sbn::merlin::State*)merlin;
+    const size_t n = st->P + st->S;
+    static const Fr two_inv = fp_inv(FrHost::small(2)), six_inv = fp_inv(FrHost::small(6));
+    std::vector<Fr> ev(3 * n), cf(n);
+    memcpy(cf.data(), coeffs, n * sizeof(Fr));
+    Fr e;
+    memcpy(e.l, claim, sizeof(Fr));
+    Fr* rdev = st->out + 3 * n;
+    auto append_scalar = [&](const Fr& v) {
+        const Fr c = fp_from_mont(v);
+        sbn::merlin::append_message(tr, (const uint8_t*)"coeff", 5, (const uint8_t*)c.l, 32);
+    };
+    for (size_t j = 0; j < num_rounds; j++) {
+        const size_t half = st->len / 2;
+        const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
+        k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
+        k_fr_sum<<<(unsigned)(3 * n), kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
+        ctx->launches += 2;
+        SBN_CUDA(ctx, cudaGetLastError());
+        SBN_CUDA(ctx, cudaMemcpyAsync(ev.data(), st->out, 3 * n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+        SBN_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->d2h += 3 * n * sizeof(Fr);
+        Fr comb[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+        for (size_t i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) comb[k] = fp_add(comb[k], fp_mul(ev[3 * i + k], cf[i]));
+        // evaluations at 0, 1, 2, 3 -> coefficients (unipoly.rs:28-59, the cubic branch)
+        const Fr e0 = comb[0], e1 = fp_sub(e, comb[0]), e2 = comb[1], e3 = comb[2];
+        const Fr d = e0;
+        const Fr a = fp_mul(six_inv, fp_sub(fp_add(fp_sub(e3, FrHost::mul_small(e2, 3)), FrHost::mul_small(e1, 3)), e0));
+        const Fr b = fp_mul(two_inv, fp_sub(fp_add(fp_sub(FrHost::mul_small(e0, 2), FrHost::mul_small(e1, 5)), FrHost::mul_small(e2, 4)), e3));
+        const Fr c = fp_sub(fp_sub(fp_sub(e1, d), a), b);
+        const Fr poly[4] = {d, c, b, a};
+        sbn::merlin::append_message(tr, (const uint8_t*)"poly", 4, (const uint8_t*)"UniPoly_begin", 13);
+        for (int k = 0; k < 4; k++) append_scalar(poly[k]);
+        sbn::merlin::append_message(tr, (const uint8_t*)"poly", 4, (const uint8_t*)"UniPoly_end", 11);
+        uint8_t wide[64];
+        sbn::merlin::challenge_bytes(tr, (const uint8_t*)"challenge_nextround", 19, wide, 64);
+        const Fr r = FrHost::from_wide(wide);
+        SBN_CUDA(ctx, cudaMemcpyAsync(rdev, &r, sizeof(Fr), cudaMemcpyHostToDevice, s));
+        k_bind_top_batched<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, rdev);
+        ctx->launches += 1;
+        ctx->h2d += sizeof(Fr);
+        SBN_CUDA(ctx, cudaGetLastError());
+        st->len = half;
+        // e = poly(r)
+        Fr acc = poly[0], power = r;
+        for (int k = 1; k < 4; k++) {
+            acc = fp_add(acc, fp_mul(power, poly[k]));
+            power = fp_mul(power, r);
+        }
+        e = acc;
+        memcpy(polys + 4 * j, poly, 4 * sizeof(Fr));
+        memcpy(r_out + j, &r, sizeof(Fr));
+    }
+    memcpy(claim_out, &e, sizeof(Fr));
+    // final values: element 0 of every table, gathered by one kernel and one copy
+    std::vector<Fr> fin(st->ntables);
+    Fr* gbuf = st->partial;              // scratch of 3 * n * max_blocks >= ntables scalars
+    k_gather_first<<<(unsigned)((st->ntables + 127) / 128), 128, 0, s>>>(st->d_tables, st->ntables, gbuf);
+    ctx->launches += 1;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_CUDA(ctx, cudaMemcpyAsync(fin.data(), gbuf, st->ntables * sizeof(Fr), cudaMemcpyDeviceToHost, s));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->d2h += st->ntables * sizeof(Fr);
+    // table order: (A_i, B_i) per parallel instance, eq, then (A, B, C) per sequential instance
+    for (size_t i = 0; i < st->P; i++) {
+        memcpy(A_final + i, &fin[2 * i], sizeof(Fr));
+        memcpy(B_final + i, &fin[2 * i + 1], sizeof(Fr));
+    }
+    memcpy(C_final, &fin[2 * st->P], sizeof(Fr));
+    for (size_t k = 0; k < st->S; k++) {
+        memcpy(A_final + st->P + k, &fin[2 * st->P + 1 + 3 * k], sizeof(Fr));
+        memcpy(B_final + st->P + k, &fin[2 * st->P + 2 + 3 * k], sizeof(Fr));
+        memcpy(C_final + 1 + k, &fin[2 * st->P + 3 + 3 * k], sizeof(Fr));
+    }
+    return SBN_OK;
+}
+
 extern "C" int sbn_bsumcheck_destroy(sbn_bsumcheck* st) {
     if (!st) return SBN_ERR_ARG;
     {

@@ -24,7 +24,7 @@ EXPORTS = [
     "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_fr_to_canonical_host", "sbn_fr_from_canonical_host", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
-    "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_destroy",
+    "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_prove", "sbn_bsumcheck_destroy",
 ]
 
 
@@ -576,6 +576,21 @@ class BatchedSumcheckState:
         c = np.zeros((1 + self.S, 4), dtype=np.uint64)
         self.ctx._check(self.ctx.lib.sbn_bsumcheck_end(self.h, _ptr(a), _ptr(b), _ptr(c)), "sbn_bsumcheck_end")
         return a, b, c
+
+    def prove(self, merlin_state, claim, coeffs, num_rounds):
+        """The layer's whole round loop inside the library (sbn_bsumcheck_prove) against the native Merlin state: returns
+        (polys uint64[num_rounds, 4, 4], r uint64[num_rounds, 4], final claim, A_final, B_final, C_final), all Montgomery."""
+        n = self.P + self.S
+        polys = np.zeros((max(1, num_rounds), 4, 4), dtype=np.uint64)
+        r = np.zeros((max(1, num_rounds), 4), dtype=np.uint64)
+        e = np.zeros(4, dtype=np.uint64)
+        a = np.zeros((n, 4), dtype=np.uint64); b = np.zeros((n, 4), dtype=np.uint64)
+        c = np.zeros((1 + self.S, 4), dtype=np.uint64)
+        st = self.ctx.lib.sbn_bsumcheck_prove(self.h, merlin_state, _ptr(_u64(claim, 4)), _ptr(_u64(coeffs, 4)), C.c_size_t(num_rounds),
+                                              _ptr(polys), _ptr(r), _ptr(e), _ptr(a), _ptr(b), _ptr(c))
+        self.ctx._check(st, "sbn_bsumcheck_prove")
+        self.len = 1
+        return polys[:num_rounds], r[:num_rounds], e, a, b, c
 
     def close(self):
         if self.h and self.ctx.h:

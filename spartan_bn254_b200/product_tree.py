@@ -100,8 +100,16 @@ class SumcheckInstanceProof:
     def prove_cubic_batched(claim, num_rounds, state, coeffs, transcript):
         """sumcheck.rs:165-330 with the tables behind `state` (BatchedSumcheckState); returns
         (proof, r, (A_par, B_par, C_par0), (A_seq, B_seq, C_seq)) as canonical ints."""
-        e, r, polys = claim, [], []
         P, S = state.P, state.S
+        if getattr(transcript, "_st", None) is not None:
+            # native Merlin state: the round loop runs inside the library (sbn_bsumcheck_prove), one call per layer
+            pm, rm, _e, a, b, c = state.prove(transcript._st, fr_from_int(claim), fr_vec_from_ints(list(coeffs)), num_rounds)
+            co = fr_vec_to_ints(pm.reshape(-1, 4))
+            polys = [UniPoly(co[4 * j: 4 * j + 4]).compress() for j in range(num_rounds)]
+            r = fr_vec_to_ints(rm)
+            a, b, c = fr_vec_to_ints(a), fr_vec_to_ints(b), fr_vec_to_ints(c)
+            return (SumcheckInstanceProof(polys), r, (a[:P], b[:P], c[0]), (a[P:], b[P:], c[1:]))
+        e, r, polys = claim, [], []
         for _ in range(num_rounds):
             ev = fr_vec_to_ints(state.round_eval().reshape(-1, 4))  # (P + S) x 3: e0, e2, e3 per instance (:201-271)
             comb = [sum(ev[3 * i + k] * coeffs[i] for i in range(P + S)) % R_MOD for k in range(3)]
