@@ -62,8 +62,12 @@ def test_unipoly_matches_reference_kats():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("n,P,S", [(2, 1, 0), (8, 2, 1), (64, 3, 2), (1024, 2, 0), (4096, 1, 2)])
-def test_gpu_prover_matches_oracle(ctx, orc, n, P, S):
+def test_gpu_prover_matches_oracle(ctx, orc, n, P, S, native):
+    """native: the layer's round loop runs inside the library against the native Merlin state (sbn_bsumcheck_prove);
+    otherwise round by round from Python over the pure-Python transcript (sbn_bsumcheck_round_eval / _bind / _end).  Both
+    must reproduce the oracle's proof integer for integer."""
     import product_model as pm
     from spartan_bn254_b200.hyrax import fr_vec_from_ints
     from spartan_bn254_b200.product_tree import ProductCircuit, DotProductCircuit, ProductCircuitEvalProofBatched
@@ -73,7 +77,7 @@ def test_gpu_prover_matches_oracle(ctx, orc, n, P, S):
     circuits = [ProductCircuit(ctx, fr_vec_from_ints(p)) for p in prod]
     assert [c.evaluate() for c in circuits] == want["claims_prod"]
     dcs = [DotProductCircuit(*[fr_vec_from_ints(t) for t in d]) for d in dotp]
-    proof, rand = ProductCircuitEvalProofBatched.prove(ctx, circuits, dcs, Transcript(b"prodtest"))
+    proof, rand = ProductCircuitEvalProofBatched.prove(ctx, circuits, dcs, Transcript(b"prodtest", native=native))
     assert rand == want["rand"]
     assert len(proof.proof) == len(want["layers"])
     for got, (polys, left, right) in zip(proof.proof, want["layers"]):
@@ -153,3 +157,56 @@ def test_prover_entry_points_reject_bad_shapes(ctx):
         a.num_cells = 8
         a.hashlayer(0, synth.uniform_scalars(7, 3), synth.uniform_scalars(8, 1)[0], synth.uniform_scalars(9, 1)[0])
     a.close()
+
+
+@pytest.mark.gpu
+def test_round1h_entry_points_reject_bad_shapes(ctx):
+    """sbn_bsumcheck_prove with the wrong number of rounds, sbn_sumcheck_begin_r1cs / _begin_quad_r1cs with matrices that do
+    not fit the vectors, sbn_bullet_end_delta on the explicit-folding path: status codes, never a crash."""
+    import ctypes as C
+    from spartan_bn254_b200 import SbnError, synth
+    from spartan_bn254_b200.hyrax import DotProductProofGens
+    from spartan_bn254_b200.lib import ProdCircuit, BatchedSumcheckState, SpMat
+    from spartan_bn254_b200.transcript import Transcript
+    pc = ProdCircuit(ctx, synth.uniform_scalars(1, 16))
+    st = BatchedSumcheckState(ctx, [pc], 0, synth.uniform_scalars(2, 3))
+    tr = Transcript(b"x")
+    with pytest.raises(SbnError) as e:
+        st.prove(tr._st, synth.uniform_scalars(3, 1)[0], synth.uniform_scalars(4, 1), 2)     # the tables hold 2^3 entries
+    assert e.value.status == -2
+    st.len = 8
+    polys, r, claim, a, b, c = st.prove(tr._st, synth.uniform_scalars(3, 1)[0], synth.uniform_scalars(4, 1), 3)
+    assert polys.shape == (3, 4, 4) and r.shape == (3, 4)
+    with pytest.raises(SbnError):
+        st.round_eval()                                                                      # no round left
+    st.close()
+    pc.close()
+    n = 8
+    mats = [SpMat(ctx, n, 16, [0, 1], [0, 3], synth.uniform_scalars(5 + i, 2)) for i in range(3)]
+    z = synth.uniform_scalars(9, 16)
+    with pytest.raises(SbnError) as e:
+        ctx.sumcheck_begin_r1cs(mats, z, synth.uniform_scalars(10, 2))        # 2^2 != 8 rows
+    assert e.value.status == -2
+    with pytest.raises(SbnError):
+        ctx.sumcheck_begin_r1cs(mats, z[:8], synth.uniform_scalars(10, 3))    # z shorter than the matrices are wide
+    with pytest.raises(SbnError):
+        ctx.sumcheck_begin_quad_r1cs(mats, synth.uniform_scalars(11, 3), synth.uniform_scalars(12, 3), z)   # rows != len(z)
+    ctx.sumcheck_begin_r1cs(mats, z, synth.uniform_scalars(10, 3)).close()
+    for m in mats:
+        m.close()
+    # explicit-folding bullet path (Q given as a point): end_delta is unsupported there, end still works
+    d = DotProductProofGens(2, b"test", ctx)
+    bases = d.device_bases_ext()
+    av, bv = synth.uniform_scalars(13, 2), synth.uniform_scalars(14, 2)
+    bl = synth.uniform_scalars(15, 3)
+    st = ctx.bullet_begin(bases, d.gens_1.G[0], av, bv, bl[0])
+    st.round(bl[1], bl[2])
+    u = synth.uniform_scalars(16, 1)[0]
+    from spartan_bn254_b200.hyrax import fr_to_int, fr_from_int
+    R = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+    st.fold(u, fr_from_int(pow(fr_to_int(u), -1, R)))
+    with pytest.raises(SbnError) as e:
+        st.end_delta(bl[1], bl[2])
+    assert e.value.status == -5
+    st.end()
+    st.close()
