@@ -62,6 +62,8 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    DevBuf tabpart;                    // per-block partial sums of the tabulated few-row commit (small_kernels.cuh)
+    long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
     // allocates and releases ~5 GB of them, and cudaFree costs ~35 ms per 268 MB buffer (574 ms per keyless-scale proof).
     // Everything that touches them is ordered on `compute`, so a released buffer can be handed out again without a sync.
@@ -302,7 +304,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2})
+                      &ctx->scratch2, &ctx->tabpart})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -335,6 +337,9 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!strcmp(key, "small_commit_path")) {
         ctx->small_commit_path = value ? 1 : 0;
+    } else if (!strcmp(key, "tab_max_mb")) {
+        if (value < 0) return SBN_ERR_ARG;
+        ctx->tab_max_mb = value;
     } else if (!strcmp(key, "dedup_generators")) {
         ctx->dedup_generators = value ? 1 : 0;
     } else if (!strcmp(key, "first_chunk_rows")) {
@@ -530,7 +535,11 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
     }
     cudaFree(dbases);
     cudaFree(dinf);
-    if (b->n_cols <= kSmallMaxCols) {     // short set: tabulate every digit multiple (one-off, a few ms)
+    // Digit-multiple tables (small_kernels.cuh): always for a short set (a few ms, <= 4 MiB); for an opening's set (the one
+    // created with gens_1's generator, whose commits are single rows and row pairs on the Fiat-Shamir critical path) up to
+    // tab_max_mb -- 2 GiB at 8192 generators, built once per generator set in ~0.1 s.
+    const size_t tab_bytes = (size_t)kSmallW * b->n_cols * kSmallD * sizeof(Affine);
+    if (b->n_cols <= kSmallMaxCols || (b->has_g1 && tab_bytes <= ((size_t)ctx->tab_max_mb << 20))) {
         const size_t entries = (size_t)kSmallW * b->n_cols * kSmallD;
         if ((e = cudaMalloc(&b->small, entries * sizeof(Affine))) != cudaSuccess) {
             ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
@@ -851,9 +860,34 @@ static int check_commit_shape(const sbn_bases* b, size_t L, size_t R) {
 // so reduce(i-1) and sort(i+1) run underneath acc(i).  When `host_Z` is given each chunk's H2D copy is issued on the
 // copy stream and handed to the sort by an event.  `main` is the stream the caller's inputs are ordered on and on which
 // the normalisation runs.
+// Few rows over a tabulated generator set: two launches on the caller's stream (small_kernels.cuh).
+static int tab_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R, const Fr* dblinds,
+                      Affine* dC, uint8_t* dinf, cudaStream_t main, bool normalize) {
+    const unsigned nblk = (unsigned)((R + 1 + kTabScalarsPerBlock - 1) / kTabScalarsPerBlock);
+    SBN_TRY(ensure(ctx, ctx->tabpart, L * nblk * sizeof(XYZZ)));
+    SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
+    if (host_Z) {
+        SBN_CUDA(ctx, cudaMemcpyAsync((void*)dZ, host_Z, L * R * sizeof(Fr), cudaMemcpyHostToDevice, main));
+        ctx->h2d += L * R * sizeof(Fr);
+    }
+    XYZZ* totals = (XYZZ*)ctx->totals.p;
+    k_tab_commit_partial<<<dim3(nblk, (unsigned)L), kTabThreads, 0, main>>>(dZ, dblinds, (int)R, b->n_cols, b->small,
+                                                                           (XYZZ*)ctx->tabpart.p);
+    k_tab_commit_final<<<(unsigned)L, kTabThreads, 0, main>>>((const XYZZ*)ctx->tabpart.p, (int)nblk, totals);
+    ctx->launches += 2;
+    if (normalize) {
+        k_normalize<<<1, 64, 0, main>>>(totals, (int)L, dC, dinf);
+        ctx->launches++;
+    }
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
 static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                       const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                       bool normalize = true) {
+    if (b->small && ctx->small_commit_path && L <= (size_t)kTabMaxRows && R + 1 <= (size_t)b->n_cols)
+        return tab_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, normalize);
     const size_t chunk = commit_chunk_rows(ctx, L);
     // chunk schedule: equal chunks; when the scalars come from the host the first chunk is a short one (an eighth: 4.85 ms
     // end to end at 1024 x 1024 against 5.06 with a quarter and 5.08 with none) so the kernels start after a short copy and
@@ -969,7 +1003,7 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (b->small && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
+    if (b->small && b->n_cols <= kSmallMaxCols && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     SBN_TRY(ensure(ctx, ctx->dZ, L * R * sizeof(Fr)));

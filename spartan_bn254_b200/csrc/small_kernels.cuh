@@ -85,4 +85,86 @@ k_small_commit(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Few rows over a LONG tabulated generator set (the opening's Cx, the two rows of every bullet round, delta).
+// One or two rows through the bucket pipeline are a chain of ~110 dependent point additions (the longest bucket, then the
+// two-level bucket reduction) that no amount of SMs shortens: ~1 ms per call, ~60 calls per proof.  With every digit
+// multiple in HBM (2 GiB at 8192 generators -- this is what 180 GB are for) a row is a plain SUM of 32 table points per
+// scalar, and sums parallelise: stage 1, thread = 4 windows of one scalar (3 mixed additions), shuffle tree over the warp,
+// shared-memory tree over the block's 16 warps -> one partial per 64 scalars; stage 2, one block per row adds the
+// partials.  Critical path ~20 additions; ~7 M products per row.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTabThreads = 512;
+static constexpr int kTabWinPerThread = 4;                                   // 8 lanes per scalar
+static constexpr int kTabScalarsPerBlock = kTabThreads * kTabWinPerThread / kSmallW;   // 64
+static constexpr int kTabMaxRows = 4;
+
+__device__ __noinline__ void xyzz_add_mixed_call(XYZZ* acc, const Affine* q) { xyzz_add_mixed<MulCall>(*acc, *q); }
+
+// block tree: every warp's lane-0 value -> value of the whole block in thread 0 (blockDim.x = kTabThreads)
+__device__ __forceinline__ XYZZ tab_block_sum(XYZZ acc, XYZZ* part /* shared, kTabThreads / 32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
+        if (lane >= stride) o = XYZZ::identity();
+        xyzz_add_call(&acc, &o);
+    }
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (warp != 0) return XYZZ::identity();
+    XYZZ v = lane < kTabThreads / 32 ? part[lane] : XYZZ::identity();
+    for (int stride = kTabThreads / 64; stride >= 1; stride >>= 1) {
+        XYZZ o = shfl_xyzz(v, (lane + stride) & 31);
+        if (lane >= stride) o = XYZZ::identity();
+        xyzz_add_call(&v, &o);
+    }
+    return v;
+}
+
+// grid = (ceil((R + 1) / 64), rows).  partial[row * gridDim.x + blockIdx.x] = sum over the block's 64 scalars.
+__global__ void __launch_bounds__(kTabThreads)
+k_tab_commit_partial(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n_cols, const Affine* __restrict__ table,
+                     XYZZ* __restrict__ partial) {
+    __shared__ XYZZ part[kTabThreads / 32];
+    const int row = blockIdx.y;
+    constexpr int lanes_per_scalar = kSmallW / kTabWinPerThread;              // 8
+    const int sidx = blockIdx.x * kTabScalarsPerBlock + threadIdx.x / lanes_per_scalar;
+    const int q = threadIdx.x % lanes_per_scalar;                             // windows 4q .. 4q + 3
+    XYZZ acc = XYZZ::identity();
+    if (sidx < R || (sidx == R && blinds)) {
+        const Fr s = fp_from_mont(sidx < R ? load_fr(Z + (size_t)row * R + sidx) : load_fr(blinds + row));
+        const int col = sidx < R ? sidx : n_cols - 1;
+        int dig[kTabWinPerThread] = {0, 0, 0, 0};
+        for_each_digit<kSmallC>(s, [&](int k, uint32_t dm1, bool negative) {
+            if ((k / kTabWinPerThread) == q) dig[k % kTabWinPerThread] = negative ? -(int)(dm1 + 1) : (int)(dm1 + 1);
+        });
+#pragma unroll 1
+        for (int i = 0; i < kTabWinPerThread; i++) {
+            if (dig[i] == 0) continue;
+            const int k = q * kTabWinPerThread + i;
+            const int d = dig[i] < 0 ? -dig[i] : dig[i];
+            Affine p = load_affine(table + ((size_t)(k * n_cols + col) * kSmallD + (d - 1)));
+            if (p.is_identity()) continue;
+            if (dig[i] < 0) p = affine_neg(p);
+            xyzz_add_mixed_call(&acc, &p);
+        }
+    }
+    const XYZZ v = tab_block_sum(acc, part);
+    if (threadIdx.x == 0) store_xyzz(partial + (size_t)row * gridDim.x + blockIdx.x, v);
+}
+
+// grid = rows: totals[row] = sum of the row's nblk partials
+__global__ void __launch_bounds__(kTabThreads)
+k_tab_commit_final(const XYZZ* __restrict__ partial, int nblk, XYZZ* __restrict__ totals) {
+    __shared__ XYZZ part[kTabThreads / 32];
+    const int row = blockIdx.x;
+    XYZZ acc = XYZZ::identity();
+    for (int i = threadIdx.x; i < nblk; i += kTabThreads) {
+        const XYZZ v = load_xyzz(partial + (size_t)row * nblk + i);
+        xyzz_add_call(&acc, &v);
+    }
+    const XYZZ v = tab_block_sum(acc, part);
+    if (threadIdx.x == 0) store_xyzz(totals + row, v);
+}
+
 }  // namespace sbn

@@ -391,7 +391,9 @@ class DotProductProofLog:
         v1 = random_tape.random_vector(b"blinds_vec_1", lg_n)
         v2 = random_tape.random_vector(b"blinds_vec_2", lg_n)
         x_m = fr_vec_from_ints(x_vec)
-        Cx = gens.gens_n.commit(x_m, fr_from_int(blind_x))                  # (n+1)-point MSM, mod.rs:470
+        # (n+1)-point MSM, mod.rs:470: a single row, over the opening's tabulated set (the g1 column takes no scalar)
+        out, inf = ctx.commit(gens.device_bases_ext(), x_m, fr_from_int(blind_x))
+        Cx = GroupElement(out, inf)
         transcript.append_point(b"Cx", Cx.compress())
         Cy = gens.gens_1.commit(fr_vec_from_ints([y]), fr_from_int(blind_y))   # mod.rs:473, over gens_1's resident tables
         transcript.append_point(b"Cy", Cy.compress())

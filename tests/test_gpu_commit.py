@@ -278,3 +278,32 @@ def test_short_commitments_match_oracle(ctx, orc, n):
     one = MultiCommitGens.from_generators(gens.G[:1].reshape(1, 8), gens.G[0], ctx)
     C, inf = ctx.hyrax_commit(one.device_bases(), orc.to_mont([5]), 1, 1, orc.to_mont([rmod - 5]))
     assert inf[0] == 1
+
+
+@pytest.mark.parametrize("n", [16, 63, 64, 65, 200, 1024])
+def test_tabulated_few_row_commits_match_oracle(ctx, orc, n):
+    """Single rows and row pairs over an opening's generator set (Cx of nizk/mod.rs:470, the L / R rows of bullet.rs:75-76)
+    take the tabulated sum-of-table-points path (small_kernels.cuh, k_tab_commit_*): checked against the oracle and against
+    the bucket pipeline for 1..5 rows (5 rows fall back to the pipeline), random and digit-boundary scalars, with and
+    without blinds, row lengths n and n + 1 (the extra column is gens_1's generator)."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.hyrax import DotProductProofGens
+    rmod = h2i(GOLD["constants"]["r"])
+    d = DotProductProofGens(n, b"gens_r1cs_eval", ctx)
+    bases = d.device_bases_ext()
+    edge = [0, 1, rmod - 1, rmod - 2, int.from_bytes(b"\x80" * 31, "little"), int.from_bytes(b"\x7f" * 31, "little"),
+            int.from_bytes(b"\x81" * 31, "little"), 128, 127, 129, 1 << 253, (1 << 253) + (1 << 8) - 128]
+    c2 = Context(0)
+    c2.set("small_commit_path", 0)
+    b2 = c2.bases(d.gens_n.G, d.gens_n.h, g1=d.gens_1.G[0])
+    for L in (1, 2, 3, 4, 5):
+        Z = synth.uniform_scalars(20 + L, L * n)
+        ez = orc.to_mont([edge[(i * 7 + 5 * (i // n)) % len(edge)] for i in range(L * n)])
+        for Zm, bl in ((Z, synth.uniform_scalars(6, L)), (Z, None), (ez, orc.to_mont([edge[(3 * i + 1) % len(edge)] for i in range(L)]))):
+            C, inf = ctx.hyrax_commit(bases, Zm, L, n, bl)
+            Co, info = orc.hyrax_commit(d.gens_n.G, d.gens_n.h, Zm, L, n, bl)
+            assert np.array_equal(inf, info) and np.array_equal(C, Co), (n, L)
+            C2, inf2 = c2.hyrax_commit(b2, Zm, L, n, bl)
+            assert np.array_equal(C, C2) and np.array_equal(inf, inf2), (n, L)
+    b2.close()
+    c2.close()
