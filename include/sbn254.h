@@ -256,6 +256,7 @@ int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* c
  *   begin_r1cs       r1csproof.rs:268-290: tables eq(tau), A z, B z, C z; mats = {A, B, C} by row, 2^n_tau rows each
  *   begin_quad_r1cs  r1csproof.rs:378-410: tables z and r_A A^T e + r_B B^T e + r_C C^T e with e = eq(rx); mats_t = the
  *                    column-sorted copies (zlen rows each), coeffs = (r_A, r_B, r_C)
+ * begin_quad_r1cs accepts z = NULL: the z of the preceding begin_r1cs on this context (same zlen) is still resident.
  * The states are driven by sbn_sumcheck_round_eval / _bind / _end / _destroy like the host-table ones. */
 int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, size_t zlen, const sbn_fr* tau,
                             size_t n_tau, sbn_sumcheck** out);

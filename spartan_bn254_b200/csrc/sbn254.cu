@@ -62,6 +62,8 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
+    size_t zkeep_len = 0;
     DevBuf tabpart;                    // per-block partial sums of the tabulated few-row commit (small_kernels.cuh)
     long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
@@ -304,7 +306,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -2623,26 +2625,29 @@ extern "C" int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mat
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->compute;
-    SBN_TRY(ensure(ctx, ctx->scratch0, zlen * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->zkeep, zlen * sizeof(Fr)));
+    ctx->zkeep_len = 0;
     SBN_TRY(ensure(ctx, ctx->scratch2, n_tau * sizeof(Fr)));
     sbn_sumcheck* st = sumcheck_alloc(ctx, 4, len);
     if (!st) return SBN_ERR_OOM;
     auto fail = [&](cudaError_t e) { ctx->last_error = std::string("sbn_sumcheck_begin_r1cs: ") + cudaGetErrorString(e); sumcheck_free(st); return SBN_ERR_CUDA; };
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(ctx->scratch0.p, z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(ctx->zkeep.p, z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
     if ((e = cudaMemcpyAsync(ctx->scratch2.p, tau, n_tau * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
     ctx->h2d += (zlen + n_tau) * sizeof(Fr);
     eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n_tau, st->T[0], st->T[1], s);      // T[1] is scratch until A z lands in it
-    for (int m = 0; m < 3; m++) spmv_device(ctx, mats + m, 1, nullptr, (const Fr*)ctx->scratch0.p, st->T[1 + m], s);
+    for (int m = 0; m < 3; m++) spmv_device(ctx, mats + m, 1, nullptr, (const Fr*)ctx->zkeep.p, st->T[1 + m], s);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);
+    ctx->zkeep_len = zlen;             // phase 2 of the same proof takes z from here (z = NULL)
     *out = st;
     return SBN_OK;
 }
 
 extern "C" int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats_t, const sbn_fr* coeffs, const sbn_fr* rx,
                                             size_t n_rx, const sbn_fr* z, size_t zlen, sbn_sumcheck** out) {
-    if (!ctx || !mats_t || !coeffs || !rx || !z || !out) return SBN_ERR_ARG;
+    if (!ctx || !mats_t || !coeffs || !rx || !out) return SBN_ERR_ARG;
     *out = nullptr;
+    if (!z && ctx->zkeep_len != zlen) return SBN_ERR_ARG;      // z = NULL: the z of the preceding sbn_sumcheck_begin_r1cs
     if (n_rx == 0 || n_rx > 28 || zlen < 2 || (zlen & (zlen - 1)) || zlen > (1u << 28)) return SBN_ERR_SHAPE;
     const size_t veclen = size_t(1) << n_rx;
     for (int m = 0; m < 3; m++) {
@@ -2658,9 +2663,10 @@ extern "C" int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const
     if (!st) return SBN_ERR_OOM;
     auto fail = [&](cudaError_t e) { ctx->last_error = std::string("sbn_sumcheck_begin_quad_r1cs: ") + cudaGetErrorString(e); sumcheck_free(st); return SBN_ERR_CUDA; };
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(st->T[0], z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if ((e = cudaMemcpyAsync(st->T[0], z ? (const void*)z : (const void*)ctx->zkeep.p, zlen * sizeof(Fr),
+                             z ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return fail(e);
     if ((e = cudaMemcpyAsync(ctx->scratch2.p, rx, n_rx * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
-    ctx->h2d += (zlen + n_rx) * sizeof(Fr);
+    ctx->h2d += ((z ? zlen : 0) + n_rx) * sizeof(Fr);
     const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n_rx, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + veclen, s);
     spmv_device(ctx, mats_t, 3, coeffs, eq, st->T[1], s);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);

@@ -234,9 +234,10 @@ class Context:
         """Phase-1 tables eq(tau), A z, B z, C z built on the device from the resident matrices (r1csproof.rs:268-290)."""
         return SumcheckState._resident(self, 4, mats, z, tau, None)
 
-    def sumcheck_begin_quad_r1cs(self, mats_t, coeffs, rx, z):
-        """Phase-2 tables z and sum_m coeffs[m] M_m^T eq(rx) built on the device (r1csproof.rs:378-410)."""
-        return SumcheckState._resident(self, 2, mats_t, z, rx, coeffs)
+    def sumcheck_begin_quad_r1cs(self, mats_t, coeffs, rx, z, z_len=None):
+        """Phase-2 tables z and sum_m coeffs[m] M_m^T eq(rx) built on the device (r1csproof.rs:378-410).  z=None with z_len:
+        the z uploaded by the preceding sumcheck_begin_r1cs is still resident."""
+        return SumcheckState._resident(self, 2, mats_t, z, rx, coeffs, z_len)
 
     # ---- utilities
     def fr_from_canonical(self, canon):
@@ -357,10 +358,12 @@ class SumcheckState:
     """sbn_sumcheck: the four tables of the R1CS-sat cubic sumcheck (sumcheck.rs:465-649) on the GPU."""
 
     @staticmethod
-    def _resident(ctx, ntables, mats, z, point, coeffs):
+    def _resident(ctx, ntables, mats, z, point, coeffs, z_len=None):
         self = SumcheckState.__new__(SumcheckState)
         self.ctx, self.ntables = ctx, ntables
-        z, point = _u64(z, 4), _u64(point, 4)
+        point = _u64(point, 4)
+        z = None if z is None else _u64(z, 4)
+        z_len = z.shape[0] if z is not None else int(z_len)
         hs = (C.c_void_p * 3)(*[m.h for m in mats])
         h = C.c_void_p()
         if ntables == 4:
@@ -369,9 +372,9 @@ class SumcheckState:
                                                  C.byref(h))
             ctx._check(st, "sbn_sumcheck_begin_r1cs")
         else:
-            self.len = z.shape[0]
+            self.len = z_len
             st = ctx.lib.sbn_sumcheck_begin_quad_r1cs(ctx.h, hs, _ptr(_u64(coeffs, 4)), _ptr(point), C.c_size_t(point.shape[0]),
-                                                      _ptr(z), C.c_size_t(z.shape[0]), C.byref(h))
+                                                      _ptr(z), C.c_size_t(z_len), C.byref(h))
             ctx._check(st, "sbn_sumcheck_begin_quad_r1cs")
         self.h = h
         return self

@@ -37,6 +37,15 @@ def commit_scalars(gens, scalars, blind, resident=True):
     return GroupElement(out, inf)
 
 
+def commit_rows(gens, rows, blinds):
+    """Several commitments over the same short generator set in one call (one CTA per row on the tabulated path)."""
+    n = len(rows[0])
+    assert gens.n == n and all(len(r) == n for r in rows), "assert_eq!(gens_n.n, self.len())"
+    Z = fr_vec_from_ints([v for r in rows for v in r])
+    C, inf = gens.ctx.hyrax_commit(gens.device_bases(), Z, len(rows), n, fr_vec_from_ints(list(blinds)))
+    return [GroupElement(C[i], inf[i]) for i in range(len(rows))]
+
+
 def _scalar_mul(ctx, point, s):
     out, inf = ctx.msm(point.reshape(1, 8), None, fr_vec_from_ints([s]))
     return GroupElement(out, inf)
@@ -74,7 +83,9 @@ class EqualityProof:
         _append(transcript, b"C1", C1)
         C2 = commit_scalars(gens_n, [v2], s2)
         _append(transcript, b"C2", C2)
-        alpha = _scalar_mul(gens_n.ctx, gens_n.h, r)
+        # alpha = r * h (mod.rs:117): the commitment to 0 with blind r over the resident tables -- the same group element as
+        # the reference's scalar multiplication, without a 254-step double-and-add chain
+        alpha = commit_scalars(gens_n, [0], r)
         _append(transcript, b"alpha", alpha)
         c = transcript.challenge_scalar(b"c")
         return EqualityProof(alpha, (c * (s1 - s2) + r) % R_MOD), C1, C2
@@ -98,8 +109,9 @@ class ProductProof:
         _append(transcript, b"alpha", alpha)
         beta = commit_scalars(gens_n, [b3], b4)
         _append(transcript, b"beta", beta)
-        gens_X = MultiCommitGens.from_generators(X.xy.reshape(1, 8), gens_n.h, gens_n.ctx)      # mod.rs:203-206
-        delta = commit_scalars(gens_X, [b3], b5, resident=False)    # one-off generator X: variable-base MSM
+        # delta = b3 * X + b5 * h over the one-off generator X (mod.rs:203-206).  X = x * G + rX * h was committed above, so
+        # delta = (b3 x) * G + (b3 rX + b5) * h: the same group element, as a commitment over the resident tables
+        delta = commit_scalars(gens_n, [b3 * x % R_MOD], (b3 * rX + b5) % R_MOD)
         _append(transcript, b"delta", delta)
         c = transcript.challenge_scalar(b"c")
         zs = [(b1 + c * x) % R_MOD, (b2 + c * rX) % R_MOD, (b3 + c * y) % R_MOD, (b4 + c * rY) % R_MOD,
@@ -112,24 +124,33 @@ class DotProductProof:
         self.delta, self.beta, self.z, self.z_delta, self.z_beta = delta, beta, z, z_delta, z_beta
 
     @staticmethod
-    def prove(gens_1, gens_n, transcript, tape, x_vec, blind_x, a_vec, y, blind_y, Cx=None):
+    def draw(tape, n):
+        """The prover's randomness in the order the reference draws it (nizk/mod.rs:252-258)."""
+        d_vec = tape.random_vector(b"d_vec", n)
+        return d_vec, tape.random_scalar(b"r_delta"), tape.random_scalar(b"r_beta")
+
+    @staticmethod
+    def prove(gens_1, gens_n, transcript, tape, x_vec, blind_x, a_vec, y, blind_y, Cx=None, pre=None):
         """nizk/mod.rs:238-296.  Cx: the commitment to (x_vec, blind_x) when the caller already holds it (the sumcheck round
-        has just sent it as comm_poly); the reference recomputes the same point."""
+        has just sent it as comm_poly); the reference recomputes the same point.  pre = (d_vec, r_delta, r_beta, delta) when
+        the caller drew the randomness ahead (in tape order) and committed delta with the other rounds' in one call.  Cy and
+        beta have no challenge between them and are committed as two rows of one call."""
         transcript.append_protocol_name(b"dot product proof")
         n = len(x_vec)
         assert len(a_vec) == n and gens_n.n == n and gens_1.n == 1
-        d_vec = tape.random_vector(b"d_vec", n)
-        r_delta, r_beta = tape.random_scalar(b"r_delta"), tape.random_scalar(b"r_beta")
+        if pre is None:
+            d_vec, r_delta, r_beta = DotProductProof.draw(tape, n)
+            delta = commit_scalars(gens_n, d_vec, r_delta)
+        else:
+            d_vec, r_delta, r_beta, delta = pre
         if Cx is None:
             Cx = commit_scalars(gens_n, x_vec, blind_x)
         _append(transcript, b"Cx", Cx)
-        Cy = commit_scalars(gens_1, [y], blind_y)
+        dot = sum(a * d for a, d in zip(a_vec, d_vec)) % R_MOD
+        Cy, beta = commit_rows(gens_1, [[y], [dot]], [blind_y, r_beta])
         _append(transcript, b"Cy", Cy)
         transcript.append_scalars(b"a", a_vec)
-        delta = commit_scalars(gens_n, d_vec, r_delta)
         _append(transcript, b"delta", delta)
-        dot = sum(a * d for a, d in zip(a_vec, d_vec)) % R_MOD
-        beta = commit_scalars(gens_1, [dot], r_beta)
         _append(transcript, b"beta", beta)
         c = transcript.challenge_scalar(b"c")
         z = [(c * x + d) % R_MOD for x, d in zip(x_vec, d_vec)]
@@ -148,6 +169,10 @@ class ZKSumcheckInstanceProof:
         blinds_evals = tape.random_vector(b"blinds_evals", num_rounds)
         claim_per_round = claim
         comm_claim_per_round = commit_scalars(gens_1, [claim_per_round], blind_claim)
+        # the dot-product proofs' randomness of every round, drawn in the reference's tape order (nothing else draws from the
+        # tape inside the loop), so that the rounds' delta commitments are one call of num_rounds rows
+        drawn = [DotProductProof.draw(tape, nevals + 1) for _ in range(num_rounds)]
+        deltas = commit_rows(gens_n, [d[0] for d in drawn], [d[1] for d in drawn]) if num_rounds else []
         r, comm_polys, comm_evals, proofs = [], [], [], []
         for j in range(num_rounds):
             ev = [fr_to_int(e) for e in state.round_eval()]                   # e0, e2(, e3)
@@ -173,7 +198,7 @@ class ZKSumcheckInstanceProof:
                 a_eval.append(a_eval[-1] * r_j % R_MOD)
             a = [(w[0] * s + w[1] * e) % R_MOD for s, e in zip(a_sc, a_eval)]
             proof, _, _ = DotProductProof.prove(gens_1, gens_n, transcript, tape, poly.coeffs, blinds_poly[j], a, target, blind,
-                                                Cx=comm_poly)
+                                                Cx=comm_poly, pre=drawn[j] + (deltas[j],))
             proofs.append(proof)
             claim_per_round, comm_claim_per_round = ev_r, comm_eval
             r.append(r_j)
@@ -279,7 +304,8 @@ class R1CSProof:
         blind_claim_phase2 = (r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind) % R_MOD
         lap("sigma_protocols_phase1_ms")
         # eq(rx) and r_A A^T eq(rx) + r_B B^T eq(rx) + r_C C^T eq(rx) (r1csproof.rs:378-410) likewise
-        st2 = ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints([r_A, r_B, r_C]), fr_vec_from_ints(rx), z)
+        st2 = ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints([r_A, r_B, r_C]), fr_vec_from_ints(rx), None,
+                                           z_len=z.shape[0])       # z is still resident from phase 1
         lap("sumcheck2_setup(eq(rx), eval tables)_ms")
         sc2, ry, claims2, blind_claim_postsc2 = ZKSumcheckInstanceProof._prove(
             st2, 2, claim_phase2, blind_claim_phase2, num_rounds_y, gens.gens_sc.gens_1, gens.gens_sc.gens_3, transcript, tape)

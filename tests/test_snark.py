@@ -160,6 +160,12 @@ def test_resident_sumcheck_setups_match_host_tables(ctx, num_cons, num_vars):
     want = drive(host, ly)
     rnd.setstate(state)
     assert drive(ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints(co), fr_vec_from_ints(rx), zm), ly) == want
+    # z = None: the z uploaded by the phase-1 set-up above is still resident
+    rnd.setstate(state)
+    assert drive(ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints(co), fr_vec_from_ints(rx), None, z_len=len(z)), ly) == want
+    from spartan_bn254_b200 import SbnError
+    with pytest.raises(SbnError):
+        ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints(co), fr_vec_from_ints(rx), None, z_len=len(z) * 2)
     for m_ in inst.by_row + inst.by_col:
         m_.close()
 
