@@ -188,7 +188,15 @@ class PolyCommitmentGens:
 
     def __init__(self, num_vars, label, ctx=None):
         _, right = compute_factored_lens(num_vars)
-        self.gens = DotProductProofGens(1 << right, label, ctx)
+        # The generators are a function of (n, label) alone (commitments.rs:31-62), and the Spark prover derives gens_ops,
+        # gens_mem and gens_derefs from ONE label (sparse_mlpoly_full.rs:625-627): sets of equal n are the same points, so
+        # they share one derivation and one resident copy (tables included) per context.
+        ctx = ctx or default_context()
+        cache = ctx.__dict__.setdefault("_gens_cache", {})
+        key = (1 << right, bytes(label))
+        if key not in cache:
+            cache[key] = DotProductProofGens(1 << right, label, ctx)
+        self.gens = cache[key]
 
 
 class PolyCommitment:
@@ -304,6 +312,16 @@ def _host_lib():
     return _hostlib or None
 
 
+def _to_canonical_host(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    lib = _host_lib()
+    if lib is None:
+        return np.frombuffer(b"".join(fr_to_int(a).to_bytes(32, "little") for a in arr), dtype=np.uint64).reshape(-1, 4)
+    canon = np.empty_like(arr)
+    lib.sbn_fr_to_canonical_host(arr.ctypes.data_as(_C.c_void_p), _C.c_size_t(arr.shape[0]), canon.ctypes.data_as(_C.c_void_p))
+    return canon
+
+
 def fr_vec_to_ints(arr):
     arr = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
     n = arr.shape[0]
@@ -380,6 +398,8 @@ class DotProductProofLog:
 
     @staticmethod
     def prove(gens, transcript, random_tape, x_vec, blind_x, a_vec, y, blind_y):
+        """x_vec, a_vec: lists of canonical ints, or Montgomery uint64[n, 4] arrays (what `bound` and the device eq tables
+        hand over: the vectors then never pass through Python integers)."""
         ctx = gens.gens_n.ctx
         transcript.append_protocol_name(b"dot product proof (log)")
         n = len(x_vec)
@@ -390,21 +410,25 @@ class DotProductProofLog:
         r_beta = random_tape.random_scalar(b"r_delta")                      # sic (mod.rs:459)
         v1 = random_tape.random_vector(b"blinds_vec_1", lg_n)
         v2 = random_tape.random_vector(b"blinds_vec_2", lg_n)
-        x_m = fr_vec_from_ints(x_vec)
+        x_m = x_vec if isinstance(x_vec, np.ndarray) else fr_vec_from_ints(x_vec)
+        a_m = a_vec if isinstance(a_vec, np.ndarray) else fr_vec_from_ints(a_vec)
         # (n+1)-point MSM, mod.rs:470: a single row, over the opening's tabulated set (the g1 column takes no scalar)
         out, inf = ctx.commit(gens.device_bases_ext(), x_m, fr_from_int(blind_x))
         Cx = GroupElement(out, inf)
         transcript.append_point(b"Cx", Cx.compress())
         Cy = gens.gens_1.commit(fr_vec_from_ints([y]), fr_from_int(blind_y))   # mod.rs:473, over gens_1's resident tables
         transcript.append_point(b"Cy", Cy.compress())
-        transcript.append_scalars(b"a", a_vec)
+        if isinstance(a_vec, np.ndarray):
+            transcript.append_scalars_canonical(b"a", ctx.fr_to_canonical(a_m) if n >= _BULK else _to_canonical_host(a_m))
+        else:
+            transcript.append_scalars(b"a", a_vec)
         r = transcript.challenge_scalar(b"r")
         # gens_1.scale(r) (mod.rs:481): Q = r * gens_1.G[0] never leaves the device -- the reduction takes r (q_scalar below)
         # and beta = d * Q + r_beta * h is committed as (d r) * gens_1.G[0] + r_beta * h, the same group element
         blind_Gamma = (blind_x + r * blind_y) % R_MOD
         # BulletReductionProof::prove (bullet.rs:24-126): G, a, b stay on the device; L, R and u cross the boundary
         # Q = r * gens_1.G[0]: handed over as the scalar r so every MSM of the reduction runs on the window tables
-        st = ctx.bullet_begin(gens.device_bases_ext(), None, x_m, fr_vec_from_ints(a_vec), fr_from_int(blind_Gamma),
+        st = ctx.bullet_begin(gens.device_bases_ext(), None, x_m, a_m, fr_from_int(blind_Gamma),
                               q_scalar=fr_from_int(r))
         L_vec, R_vec = [], []
         rhat = blind_Gamma
@@ -449,15 +473,18 @@ class PolyEvalProof:
         assert poly.get_num_vars() == len(r)                                 # hyrax.rs:77
         left, right = compute_factored_lens(len(r))
         L_size, R_size = 1 << left, 1 << right
-        Lv, Rv = EqPolynomial(r).compute_factored_evals()
-        LZ = poly.bound(fr_vec_from_ints(Lv), ctx)                           # GPU, hyrax.rs:100
+        # EqPolynomial::compute_factored_evals (hyrax.rs:375-383) on the device; L, R, LZ stay Montgomery arrays
+        from .lib import eq_evals as _eq_evals
+        L_m = _eq_evals(ctx, fr_vec_from_ints(list(r[:left])))
+        R_m = _eq_evals(ctx, fr_vec_from_ints(list(r[left:])))
+        LZ = poly.bound(L_m, ctx)                                            # GPU, hyrax.rs:100
         LZ_blind = 0
         if blinds is not None:
             bl = fr_vec_to_ints(blinds)
             assert len(bl) == L_size                                         # hyrax.rs:88
-            LZ_blind = sum(b * l for b, l in zip(bl, Lv)) % R_MOD
-        proof, _C_LR, C_Zr_prime = DotProductProofLog.prove(gens.gens, transcript, random_tape, fr_vec_to_ints(LZ),
-                                                            LZ_blind, Rv, Zr, blind_Zr or 0)
+            LZ_blind = sum(b * l for b, l in zip(bl, fr_vec_to_ints(L_m))) % R_MOD
+        proof, _C_LR, C_Zr_prime = DotProductProofLog.prove(gens.gens, transcript, random_tape, LZ, LZ_blind, R_m, Zr,
+                                                            blind_Zr or 0)
         return PolyEvalProof(proof), C_Zr_prime
 
 

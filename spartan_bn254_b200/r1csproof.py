@@ -339,6 +339,16 @@ class SNARKGens:
         # R1CSCommitmentGens::new (r1cs.rs:275-288)
         self.gens_r1cs_eval = SparseMatPolyCommitmentGens(b"gens_r1cs_eval", log_2(num_cons), log_2(2 * num_vars),
                                                           num_nz_entries, 3, ctx)
+        # the resident copies the prover commits and opens over (window tables, digit-multiple tables), built here once
+        # rather than inside the first proof
+        ev = self.gens_r1cs_eval
+        for pc in (self.gens_r1cs_sat.gens_pc, ev.gens_ops, ev.gens_mem, ev.gens_derefs):
+            pc.gens.gens_n.device_bases()
+            pc.gens.device_bases_ext()
+            pc.gens.gens_1.device_bases()
+        sc = self.gens_r1cs_sat.gens_sc
+        for g in (sc.gens_1, sc.gens_3, sc.gens_4):
+            g.device_bases()
 
 
 class R1CSCommitment:

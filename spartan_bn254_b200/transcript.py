@@ -104,6 +104,12 @@ class Transcript:
         self._lib.sbn_merlin_append_many(self._st, label, _ctypes.c_size_t(len(label)), data, _ctypes.c_size_t(32),
                                          _ctypes.c_size_t(len(data) // 32))
 
+    def append_scalars_canonical(self, label, canon):
+        """append_scalars for a uint64[n, 4] array of canonical little-endian values (no Python integers in between)."""
+        data = canon.tobytes()
+        self._lib.sbn_merlin_append_many(self._st, label, _ctypes.c_size_t(len(label)), data, _ctypes.c_size_t(32),
+                                         _ctypes.c_size_t(len(data) // 32))
+
     def append_point(self, label, compressed32):
         self.append_message(label, compressed32)
 
@@ -224,6 +230,11 @@ class PyTranscript(Transcript):
 
     def append_point(self, label, compressed32):
         self.append_message(label, compressed32)
+
+    def append_scalars_canonical(self, label, canon):
+        data = canon.tobytes()
+        for i in range(len(data) // 32):
+            self.append_message(label, data[32 * i: 32 * i + 32])
 
     def append_points(self, label, xy, inf):
         from .hyrax import GroupElement
