@@ -85,6 +85,9 @@ int sbn_bases_create_ext(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, s
 int sbn_bases_destroy(sbn_bases* bases);
 size_t sbn_bases_len(const sbn_bases* bases);                 /* n (without h) */
 int sbn_bases_window_bits(const sbn_bases* bases);
+/* Window width and size of the digit-multiple table that commits of many rows sum over (0 / 0 when none has been built:
+ * the table is built by the first commit of at least `mult_min_rows` rows, within `mult_max_mb` -- sbn_ctx_set). */
+int sbn_bases_mult_table(const sbn_bases* b, int* window_bits, uint64_t* bytes);
 
 /* ---- a7/a9: DensePolynomial::commit_inner (hyrax.rs:253-281), R1CSProof::commit_poly
  *      (r1csproof.rs:210-237).  C_i = sum_j Z[i*R_size + j] * G_j + blinds[i] * h  for i < L_size.

@@ -18,6 +18,7 @@
 #include "opening_kernels.cuh"
 #include "ba_kernels.cuh"
 #include "small_kernels.cuh"
+#include "mult_kernels.cuh"
 #include "prodtree_kernels.cuh"
 #include "host/keccak.hpp"
 #include "host/merlin.hpp"
@@ -65,6 +66,8 @@ struct sbn_ctx {
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
     size_t zkeep_len = 0;
     DevBuf tabpart;                    // per-block partial sums of the tabulated few-row commit (small_kernels.cuh)
+    long mult_max_mb = 6144;           // largest digit-multiple table built for a commit's generator set (MiB); 0 = none
+    long mult_min_rows = 256;          // commits of at least this many rows take the tabulated-sum path
     long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
     // allocates and releases ~5 GB of them, and cudaFree costs ~35 ms per 268 MB buffer (574 ms per keyless-scale proof).
@@ -93,6 +96,9 @@ struct sbn_bases {
     int dedup = 0, n_cols = 0, n_big = 0;
     uint32_t *gptr = nullptr, *gcols = nullptr, *gbig = nullptr;
     Affine* small = nullptr;   // short sets (n_cols <= kSmallMaxCols): every digit multiple of every generator (small_kernels.cuh)
+    // every digit multiple of the n1 table columns for many-row commits (mult_kernels.cuh), built on the first such commit
+    Affine* mult = nullptr;
+    int mc = 0, mW = 0, mult_tried = 0;
 };
 
 #define SBN_CUDA(ctx, call)                                                                      \
@@ -292,6 +298,7 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
         delete ctx;
         return SBN_ERR_CUDA;
     }
+    if (const char* e = getenv("SBN_MULT_MAX_MB")) ctx->mult_max_mb = atol(e);      // bench / test hook: budget of the digit-multiple tables
     if (const char* e = getenv("SBN_BA_ROUNDS")) {     // test hook: default number of batched-affine rounds
         long v = atol(e);
         if (v >= -1 && v <= 3) ctx->ba_rounds = v;
@@ -339,6 +346,12 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     std::lock_guard<std::mutex> g(ctx->mu);
     if (!strcmp(key, "small_commit_path")) {
         ctx->small_commit_path = value ? 1 : 0;
+    } else if (!strcmp(key, "mult_max_mb")) {
+        if (value < 0) return SBN_ERR_ARG;
+        ctx->mult_max_mb = value;
+    } else if (!strcmp(key, "mult_min_rows")) {
+        if (value < 1) return SBN_ERR_ARG;
+        ctx->mult_min_rows = value;
     } else if (!strcmp(key, "tab_max_mb")) {
         if (value < 0) return SBN_ERR_ARG;
         ctx->tab_max_mb = value;
@@ -577,6 +590,7 @@ extern "C" int sbn_bases_destroy(sbn_bases* b) {
         if (b->table) cudaFree(b->table);
         if (b->orig) cudaFree(b->orig);
         if (b->small) cudaFree(b->small);
+        if (b->mult) cudaFree(b->mult);
         for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
     }
     delete b;
@@ -584,6 +598,13 @@ extern "C" int sbn_bases_destroy(sbn_bases* b) {
 }
 extern "C" size_t sbn_bases_len(const sbn_bases* b) { return b ? b->n : 0; }
 extern "C" int sbn_bases_window_bits(const sbn_bases* b) { return b ? b->c : 0; }
+// window width and size of the digit-multiple table many-row commits sum over (0 when none has been built, mult_kernels.cuh)
+extern "C" int sbn_bases_mult_table(const sbn_bases* b, int* window_bits, uint64_t* bytes) {
+    if (!b) return SBN_ERR_ARG;
+    if (window_bits) *window_bits = b->mult ? b->mc : 0;
+    if (bytes) *bytes = b->mult ? ((uint64_t)b->mW * b->n1 << (b->mc - 1)) * sizeof(Affine) : 0;
+    return SBN_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // commit pipeline
@@ -885,9 +906,157 @@ static int tab_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
     return SBN_OK;
 }
 
+// Digit-multiple table of a commit's generator set (mult_kernels.cuh), built on the first commit of many rows: the largest
+// window width whose table fits mult_max_mb, provided the tabulated sum then costs clearly less than the bucket method
+// (W_m batched-affine additions of ~6.5 products against W additions of ~8 plus the bucket reduction).
+static void mult_try_build(sbn_ctx* ctx, sbn_bases* b) {
+    b->mult_tried = 1;
+    if (ctx->mult_max_mb <= 0) return;
+    const double cost_cur = b->W * 8.0 + 2.0 * b->nb / double(b->n1) * 14.0;
+    for (int c = kMultMaxBits; c >= 8; c--) {
+        const int W = msm_num_windows(c);
+        const uint64_t entries = (uint64_t)W * b->n1 << (c - 1);
+        if (entries >= (1ull << 31) || entries * sizeof(Affine) > ((uint64_t)ctx->mult_max_mb << 20)) continue;
+        if (W * 6.5 >= 0.9 * cost_cur) return;          // smaller windows only cost more
+        if (cudaMalloc(&b->mult, entries * sizeof(Affine)) != cudaSuccess) { cudaGetLastError(); b->mult = nullptr; return; }
+        const uint64_t threads = (uint64_t)W * b->n1 * ((1u << (c - 1)) / kMultChunk);
+        k_mult_fill<<<(unsigned)((threads + 63) / 64), 64, 0, ctx->compute>>>(b->table, b->n1, c, W, b->mult);   // window 0 of the tables = the bases
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+            cudaFree(b->mult);
+            b->mult = nullptr;
+            return;
+        }
+        b->mc = c;
+        b->mW = W;
+        return;
+    }
+}
+
+static int mult_rounds_for(uint32_t used) {
+    int r = 1;
+    while (r < 10 && (used >> (r + 1)) >= 192) r++;      // leave a few hundred points per row to the XYZZ sum
+    return r;
+}
+
+// Many rows as sums of tabulated digit multiples.  Chunks of rows run one after the other on `main`; with host scalars
+// the copy of chunk i + 1 is issued on the copy stream before the kernels of chunk i.
+static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R, const Fr* dblinds,
+                       Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage, bool normalize) {
+    const size_t chunk = commit_chunk_rows(ctx, L);
+    std::vector<size_t> sched;
+    {
+        size_t done = 0;
+        const size_t first = ctx->first_chunk_rows > 0 ? std::min<size_t>((size_t)ctx->first_chunk_rows, chunk) : chunk / 8;
+        if (host_Z && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
+        while (done < L) { size_t cr = std::min(chunk, L - done); sched.push_back(cr); done += cr; }
+    }
+    const size_t nchunks = sched.size();
+    const int c = b->mc, W = b->mW;
+    const int Rk = b->dedup ? b->n1 : (int)R;              // scalars per row the entries kernel sees
+    const uint32_t used = (uint32_t)W * (uint32_t)(Rk + 1);
+    const int rounds = mult_rounds_for(used);
+    const uint32_t stride = (used + (1u << rounds) - 1) >> rounds << rounds;
+    auto& sl = ctx->slots[0];
+    const size_t np1 = chunk * (size_t)stride / 2;
+    SBN_TRY(ensure(ctx, sl.entries, chunk * (size_t)stride * sizeof(uint32_t)));
+    SBN_TRY(ensure(ctx, sl.pts[0], np1 * sizeof(Affine)));
+    SBN_TRY(ensure(ctx, sl.pts[1], (np1 / 2 + 1) * sizeof(Affine)));
+    SBN_TRY(ensure(ctx, sl.prefix, np1 * sizeof(Fq)));
+    {
+        const size_t nthreads = np1 / 4 + 2 * kBaThreads;
+        SBN_TRY(ensure(ctx, sl.other, nthreads * sizeof(Fq)));
+        SBN_TRY(ensure(ctx, sl.wtot, (nthreads / 32 + 1) * sizeof(Fq)));
+        SBN_TRY(ensure(ctx, sl.winv, (nthreads / 32 + 1) * sizeof(Fq)));
+    }
+    if (b->dedup) SBN_TRY(ensure(ctx, sl.zagg, chunk * (size_t)b->n1 * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
+    XYZZ* totals = (XYZZ*)ctx->totals.p;
+    size_t ev_idx = 0;
+    StageMarks marks{ctx, ev_idx, ev_stage};
+    const size_t sync_base = 3 * nchunks + 8;
+    if (!get_event(ctx, sync_base + nchunks)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
+    std::vector<size_t> row0(nchunks, 0);
+    for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
+    auto issue_copy = [&](size_t ci) -> int {
+        SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0[ci] * R), host_Z + row0[ci] * R, sched[ci] * R * sizeof(Fr),
+                                      cudaMemcpyHostToDevice, ctx->copy));
+        ctx->h2d += sched[ci] * R * sizeof(Fr);
+        SBN_CUDA(ctx, cudaEventRecord(get_event(ctx, sync_base + ci), ctx->copy));
+        return SBN_OK;
+    };
+    if (host_Z) {
+        SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
+        SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
+        SBN_TRY(issue_copy(0));
+    }
+    for (size_t ci = 0; ci < nchunks; ci++) {
+        const int rows = (int)sched[ci];
+        if (host_Z) {
+            if (ci + 1 < nchunks) SBN_TRY(issue_copy(ci + 1));
+            SBN_CUDA(ctx, cudaStreamWaitEvent(main, get_event(ctx, sync_base + ci), 0));
+        }
+        const Fr* zc = dZ + row0[ci] * R;
+        const Fr* bc = dblinds ? dblinds + row0[ci] : nullptr;
+        marks.mark(-1, main);
+        if (b->dedup) {
+            k_aggregate_rows<<<rows, kAggThreads, 0, main>>>(zc, bc, (int)R, b->n_cols, b->gptr, b->gcols, b->n1, b->gbig, b->n_big,
+                                                             (Fr*)sl.zagg.p);
+            ctx->launches++;
+            zc = (const Fr*)sl.zagg.p;
+            bc = nullptr;
+        }
+        const unsigned ethreads = (unsigned)(Rk + 1) + (stride - used);
+        k_mult_entries<<<dim3((ethreads + 255) / 256, (unsigned)rows), 256, 0, main>>>(zc, bc, Rk, b->n1, c, W, stride,
+                                                                                      (uint32_t*)sl.entries.p);
+        ctx->launches++;
+        marks.mark(0, main);
+        const Affine* in = nullptr;
+        for (int k = 0; k < rounds; k++) {
+            const size_t npairs = ((size_t)rows * stride) >> (k + 1);
+            const int B = ba_pairs_per_thread(ctx, npairs);
+            const unsigned blocks = (unsigned)((npairs + (size_t)kBaThreads * B - 1) / ((size_t)kBaThreads * B));
+            const size_t nwarps = (size_t)blocks * kBaThreads / 32;
+            Affine* out = (Affine*)sl.pts[k & 1].p;
+            if (k == 0) {
+                k_ba_prefix<true><<<blocks, kBaThreads, 0, main>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
+                                                                   (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, main>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<true><<<blocks, kBaThreads, 0, main>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
+                                                                   (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
+                                                                   (const Fq*)sl.winv.p, out);
+            } else {
+                k_ba_prefix<false><<<blocks, kBaThreads, 0, main>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
+                                                                    (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, main>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<false><<<blocks, kBaThreads, 0, main>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p,
+                                                                    (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
+            }
+            in = out;
+            ctx->launches += 3;
+        }
+        k_mult_sum_rows<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, main>>>(
+            in, stride >> rounds, rows, totals + row0[ci]);
+        ctx->launches++;
+        marks.mark(1, main);
+        SBN_CUDA(ctx, cudaGetLastError());
+    }
+    if (!normalize) return SBN_OK;
+    marks.mark(-1, main);
+    k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, main>>>(totals, (int)L, dC, dinf);
+    ctx->launches++;
+    marks.mark(3, main);
+    SBN_CUDA(ctx, cudaGetLastError());
+    return SBN_OK;
+}
+
 static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                       const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                       bool normalize = true) {
+    if (L >= (size_t)ctx->mult_min_rows && !b->has_g1 && ctx->mult_max_mb > 0) {
+        if (!b->mult_tried) mult_try_build(ctx, const_cast<sbn_bases*>(b));
+        if (b->mult) return mult_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
+    }
     if (b->small && ctx->small_commit_path && L <= (size_t)kTabMaxRows && R + 1 <= (size_t)b->n_cols)
         return tab_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, normalize);
     const size_t chunk = commit_chunk_rows(ctx, L);

@@ -12,7 +12,7 @@ EXPORTS = [
     "sbn_strerror", "sbn_last_cuda_error", "sbn_version",
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
     "sbn_ctx_last_commit_profile", "sbn_host_alloc", "sbn_host_free",
-    "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits",
+    "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
     "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
     "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
@@ -281,6 +281,12 @@ class Bases:
     @property
     def window_bits(self):
         return self.ctx.lib.sbn_bases_window_bits(self.h)
+
+    def mult_table(self):
+        """(window bits, bytes) of the digit-multiple table many-row commits sum over; (0, 0) when none has been built."""
+        c, nbytes = C.c_int(), C.c_uint64()
+        self.ctx._check(self.ctx.lib.sbn_bases_mult_table(self.h, C.byref(c), C.byref(nbytes)), "sbn_bases_mult_table")
+        return int(c.value), int(nbytes.value)
 
     def close(self):
         if self.h and self.ctx.h:

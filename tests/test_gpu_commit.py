@@ -307,3 +307,48 @@ def test_tabulated_few_row_commits_match_oracle(ctx, orc, n):
             assert np.array_equal(C, C2) and np.array_equal(inf, inf2), (n, L)
     b2.close()
     c2.close()
+
+
+@pytest.mark.parametrize("gens_kind,L,R,chunk", [("ref", 4, 32, 0), ("ref", 64, 64, 24), ("distinct", 32, 16, 0), ("distinct", 8, 200, 3),
+                                                 ("ref", 16, 1024, 0), ("distinct", 300, 33, 128)])
+def test_tabulated_sum_commits_match_oracle(orc, gens_kind, L, R, chunk):
+    """Many-row commits as sums of tabulated digit multiples (mult_kernels.cuh), forced on small shapes with
+    mult_min_rows = 1: against the oracle and against the bucket pipeline (mult_max_mb = 0), on the reference's generators
+    (duplicates merged first) and on distinct ones, with blinds, zero rows, digit-boundary scalars, odd chunking, and through
+    both the host-pointer and the resident-polynomial entry points."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.hyrax import MultiCommitGens
+    from spartan_bn254_b200.lib import Poly
+    rmod = h2i(GOLD["constants"]["r"])
+    cm, cp = Context(0), Context(0)
+    cm.set("mult_min_rows", 1)
+    cp.set("mult_max_mb", 0)
+    if chunk:
+        cm.set("chunk_rows", chunk)
+    if gens_kind == "ref":
+        g = MultiCommitGens.new(R, b"gens_r1cs_eval", cm)
+        G, h = g.G, g.h
+    else:
+        G, h = synth.distinct_generators(cm, R)
+    bm, bp = cm.bases(G, h), cp.bases(G, h)
+    edge = [0, 1, rmod - 1, rmod - 2, int.from_bytes(b"\x80" * 31, "little"), int.from_bytes(b"\x7f" * 31, "little"),
+            int.from_bytes(b"\x81" * 31, "little"), 1 << 12, (1 << 12) - 1, (1 << 12) + 1, 1 << 253, (1 << 15) + 1, 1 << 15]
+    Z = synth.uniform_scalars(31, L * R)
+    Z[R: 2 * R] = 0                                   # an all-zero row -> identity
+    Z[2 * R: 3 * R] = orc.to_mont([edge[i % len(edge)] for i in range(R)])
+    for bl in (synth.uniform_scalars(32, L), None):
+        C, inf = cm.hyrax_commit(bm, Z, L, R, bl)
+        Co, info = orc.hyrax_commit(G, h, Z, L, R, bl)
+        assert np.array_equal(inf, info) and np.array_equal(C, Co)
+        C2, inf2 = cp.hyrax_commit(bp, Z, L, R, bl)
+        assert np.array_equal(C, C2) and np.array_equal(inf, inf2)
+    assert inf[1] == 1                                # the zero row without a blind
+    assert cm.last_commit_profile()["reduce"]["launches"] == 0 and cp.last_commit_profile()["reduce"]["launches"] > 0
+    poly = Poly(cm, Z)
+    C3, inf3 = poly.commit(bm, L, R, None)
+    assert np.array_equal(C3, C) and np.array_equal(inf3, inf)
+    poly.close()
+    for b in (bm, bp):
+        b.close()
+    cm.close()
+    cp.close()
