@@ -939,15 +939,18 @@ static int mult_rounds_for(uint32_t used) {
     return r;
 }
 
-// Many rows as sums of tabulated digit multiples.  Chunks of rows run one after the other on `main`; with host scalars
-// the copy of chunk i + 1 is issued on the copy stream before the kernels of chunk i.
+// Many rows as sums of tabulated digit multiples.  Chunks of rows alternate between the two workspaces and the two
+// low-priority streams, so that one chunk's inversion launches (a 27 us dependency per round) and kernel tails run under
+// the other chunk's additions; a commit that would be one chunk is cut in two for the same reason.  With host scalars the
+// copy of chunk i + 1 is issued on the copy stream before the kernels of chunk i.
 static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R, const Fr* dblinds,
                        Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage, bool normalize) {
-    const size_t chunk = commit_chunk_rows(ctx, L);
+    size_t chunk = commit_chunk_rows(ctx, L);
+    if (ctx->chunk_rows <= 0 && L >= 512 && L <= chunk) chunk = (L + 1) / 2;
     std::vector<size_t> sched;
     {
         size_t done = 0;
-        const size_t first = ctx->first_chunk_rows > 0 ? std::min<size_t>((size_t)ctx->first_chunk_rows, chunk) : chunk / 8;
+        const size_t first = ctx->first_chunk_rows > 0 ? std::min<size_t>((size_t)ctx->first_chunk_rows, chunk) : chunk / 4;
         if (host_Z && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
         while (done < L) { size_t cr = std::min(chunk, L - done); sched.push_back(cr); done += cr; }
     }
@@ -957,25 +960,25 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
     const uint32_t used = (uint32_t)W * (uint32_t)(Rk + 1);
     const int rounds = mult_rounds_for(used);
     const uint32_t stride = (used + (1u << rounds) - 1) >> rounds << rounds;
-    auto& sl = ctx->slots[0];
     const size_t np1 = chunk * (size_t)stride / 2;
-    SBN_TRY(ensure(ctx, sl.entries, chunk * (size_t)stride * sizeof(uint32_t)));
-    SBN_TRY(ensure(ctx, sl.pts[0], np1 * sizeof(Affine)));
-    SBN_TRY(ensure(ctx, sl.pts[1], (np1 / 2 + 1) * sizeof(Affine)));
-    SBN_TRY(ensure(ctx, sl.prefix, np1 * sizeof(Fq)));
-    {
+    for (size_t k = 0; k < std::min<size_t>(2, nchunks); k++) {
+        auto& sl = ctx->slots[k];
+        SBN_TRY(ensure(ctx, sl.entries, chunk * (size_t)stride * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.pts[0], np1 * sizeof(Affine)));
+        SBN_TRY(ensure(ctx, sl.pts[1], (np1 / 2 + 1) * sizeof(Affine)));
+        SBN_TRY(ensure(ctx, sl.prefix, np1 * sizeof(Fq)));
         const size_t nthreads = np1 / 4 + 2 * kBaThreads;
         SBN_TRY(ensure(ctx, sl.other, nthreads * sizeof(Fq)));
         SBN_TRY(ensure(ctx, sl.wtot, (nthreads / 32 + 1) * sizeof(Fq)));
         SBN_TRY(ensure(ctx, sl.winv, (nthreads / 32 + 1) * sizeof(Fq)));
+        if (b->dedup) SBN_TRY(ensure(ctx, sl.zagg, chunk * (size_t)b->n1 * sizeof(Fr)));
     }
-    if (b->dedup) SBN_TRY(ensure(ctx, sl.zagg, chunk * (size_t)b->n1 * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
     XYZZ* totals = (XYZZ*)ctx->totals.p;
     size_t ev_idx = 0;
     StageMarks marks{ctx, ev_idx, ev_stage};
-    const size_t sync_base = 3 * nchunks + 8;
-    if (!get_event(ctx, sync_base + nchunks)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
+    const size_t sync_base = 3 * nchunks + 8;              // hand-off events live after the profiling events
+    if (!get_event(ctx, sync_base + nchunks + 2)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
     std::vector<size_t> row0(nchunks, 0);
     for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
     auto issue_copy = [&](size_t ci) -> int {
@@ -985,32 +988,35 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
         SBN_CUDA(ctx, cudaEventRecord(get_event(ctx, sync_base + ci), ctx->copy));
         return SBN_OK;
     };
+    SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
+    for (cudaStream_t st : {ctx->lo[0], ctx->lo[1]}) SBN_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork, 0));
     if (host_Z) {
-        SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
         SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
         SBN_TRY(issue_copy(0));
     }
     for (size_t ci = 0; ci < nchunks; ci++) {
         const int rows = (int)sched[ci];
+        auto& sl = ctx->slots[ci & 1];
+        cudaStream_t st = ctx->lo[ci & 1];
         if (host_Z) {
             if (ci + 1 < nchunks) SBN_TRY(issue_copy(ci + 1));
-            SBN_CUDA(ctx, cudaStreamWaitEvent(main, get_event(ctx, sync_base + ci), 0));
+            SBN_CUDA(ctx, cudaStreamWaitEvent(st, get_event(ctx, sync_base + ci), 0));
         }
         const Fr* zc = dZ + row0[ci] * R;
         const Fr* bc = dblinds ? dblinds + row0[ci] : nullptr;
-        marks.mark(-1, main);
+        marks.mark(-1, st);
         if (b->dedup) {
-            k_aggregate_rows<<<rows, kAggThreads, 0, main>>>(zc, bc, (int)R, b->n_cols, b->gptr, b->gcols, b->n1, b->gbig, b->n_big,
-                                                             (Fr*)sl.zagg.p);
+            k_aggregate_rows<<<rows, kAggThreads, 0, st>>>(zc, bc, (int)R, b->n_cols, b->gptr, b->gcols, b->n1, b->gbig, b->n_big,
+                                                           (Fr*)sl.zagg.p);
             ctx->launches++;
             zc = (const Fr*)sl.zagg.p;
             bc = nullptr;
         }
         const unsigned ethreads = (unsigned)(Rk + 1) + (stride - used);
-        k_mult_entries<<<dim3((ethreads + 255) / 256, (unsigned)rows), 256, 0, main>>>(zc, bc, Rk, b->n1, c, W, stride,
-                                                                                      (uint32_t*)sl.entries.p);
+        k_mult_entries<<<dim3((ethreads + 255) / 256, (unsigned)rows), 256, 0, st>>>(zc, bc, Rk, b->n1, c, W, stride,
+                                                                                    (uint32_t*)sl.entries.p);
         ctx->launches++;
-        marks.mark(0, main);
+        marks.mark(0, st);
         const Affine* in = nullptr;
         for (int k = 0; k < rounds; k++) {
             const size_t npairs = ((size_t)rows * stride) >> (k + 1);
@@ -1019,27 +1025,32 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
             const size_t nwarps = (size_t)blocks * kBaThreads / 32;
             Affine* out = (Affine*)sl.pts[k & 1].p;
             if (k == 0) {
-                k_ba_prefix<true><<<blocks, kBaThreads, 0, main>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
-                                                                   (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
-                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, main>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
-                k_ba_finish<true><<<blocks, kBaThreads, 0, main>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
-                                                                   (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
-                                                                   (const Fq*)sl.winv.p, out);
+                k_ba_prefix<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
+                                                                 (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
+                                                                 (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
+                                                                 (const Fq*)sl.winv.p, out);
             } else {
-                k_ba_prefix<false><<<blocks, kBaThreads, 0, main>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
-                                                                    (Fq*)sl.other.p, (Fq*)sl.wtot.p);
-                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, main>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
-                k_ba_finish<false><<<blocks, kBaThreads, 0, main>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p,
-                                                                    (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
+                k_ba_prefix<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
+                                                                  (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
+                k_ba_finish<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p,
+                                                                  (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
             }
             in = out;
             ctx->launches += 3;
         }
-        k_mult_sum_rows<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, main>>>(
+        k_mult_sum_rows<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, st>>>(
             in, stride >> rounds, rows, totals + row0[ci]);
         ctx->launches++;
-        marks.mark(1, main);
+        marks.mark(1, st);
         SBN_CUDA(ctx, cudaGetLastError());
+    }
+    for (int k = 0; k < 2; k++) {
+        cudaEvent_t e = get_event(ctx, sync_base + nchunks + k);
+        SBN_CUDA(ctx, cudaEventRecord(e, ctx->lo[k]));
+        SBN_CUDA(ctx, cudaStreamWaitEvent(main, e, 0));
     }
     if (!normalize) return SBN_OK;
     marks.mark(-1, main);
