@@ -4,7 +4,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_s3.log 2>&
 python bench.py > gpurun_out/bench_s3.json 2> gpurun_out/bench_s3.err; tail -c 600 gpurun_out/bench_s3.json
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_s3_ref.json 2> gpurun_out/bench_s3_ref.err; tail -c 400 gpurun_out/bench_s3_ref.json
 python scripts/bench_small_commit.py > gpurun_out/small_commit.log 2>&1; tail -1 gpurun_out/small_commit.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_s3_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prove > gpurun_out/ncu_bench_s3.log 2>&1
-ncu --set full --clock-control none --import-source on -k k_small_commit --launch-skip 50 -c 2 -o gpurun_out/small_s3 -f python scripts/bench_small_commit.py 60 > gpurun_out/ncu_small_s3.log 2>&1
-ncu -i gpurun_out/small_s3.ncu-rep --page raw --csv > gpurun_out/small_s3_raw.csv 2>/dev/null
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_s3_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prove > gpurun_out/ncu_bench_s3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_ba_finish|k_ba_prefix" --launch-skip 72 -c 4 -o gpurun_out/ba_s3 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prove > gpurun_out/ncu_ba_s3.log 2>&1
+ncu -i gpurun_out/ba_s3.ncu-rep --page raw --csv > gpurun_out/ba_s3_raw.csv 2>/dev/null
 ls -la gpurun_out | tail -5
