@@ -9,6 +9,10 @@ of an (N*1024) x 1024 polynomial (rows are independent -- weak scaling, no data-
 commitment vector is all-gathered over NCCL at the end of every step, reference hyrax.rs:259-265 collects
 the rows the same way).
 
+The generators' digit-multiple table (mult_kernels.cuh: every d * 2^(kc) * G_j, built once per generator set and kept in
+HBM like the bases themselves) is sized by --table-mb (default 36000 MiB: c = 16 at 1025 generators); --table-mb 0 times
+the bucket pipeline instead.
+
   value  points/s with scalars already resident in HBM (device-pointer C-ABI entry point)
   e2e    the same metric through sbn_hyrax_commit with PINNED HOST buffers: H2D of the scalars and D2H
          of the commitments inside the timed region
