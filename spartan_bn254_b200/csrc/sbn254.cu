@@ -67,6 +67,7 @@ struct sbn_ctx {
     size_t zkeep_len = 0;
     DevBuf tabpart;                    // per-block partial sums of the tabulated few-row commit (small_kernels.cuh)
     long mult_max_mb = 6144;           // largest digit-multiple table built for a commit's generator set (MiB); 0 = none
+    long mult_rounds = 0;              // batched-affine rounds of the tabulated-sum path; 0 = auto (mult_rounds_for)
     long mult_min_rows = 256;          // commits of at least this many rows take the tabulated-sum path
     long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
@@ -299,6 +300,8 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
         return SBN_ERR_CUDA;
     }
     if (const char* e = getenv("SBN_MULT_MAX_MB")) ctx->mult_max_mb = atol(e);      // bench / test hook: budget of the digit-multiple tables
+    if (const char* e = getenv("SBN_MULT_ROUNDS")) ctx->mult_rounds = atol(e);      // tuning hooks (scripts/sweep_mult.sh)
+    if (const char* e = getenv("SBN_BA_BATCH")) ctx->ba_batch = atol(e);
     if (const char* e = getenv("SBN_BA_ROUNDS")) {     // test hook: default number of batched-affine rounds
         long v = atol(e);
         if (v >= -1 && v <= 3) ctx->ba_rounds = v;
@@ -958,7 +961,9 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
     const int c = b->mc, W = b->mW;
     const int Rk = b->dedup ? b->n1 : (int)R;              // scalars per row the entries kernel sees
     const uint32_t used = (uint32_t)W * (uint32_t)(Rk + 1);
-    const int rounds = mult_rounds_for(used);
+    int rounds = mult_rounds_for(used);
+    if (ctx->mult_rounds > 0) rounds = (int)std::min<long>(ctx->mult_rounds, 12);
+    while (rounds > 1 && (used >> rounds) == 0) rounds--;
     const uint32_t stride = (used + (1u << rounds) - 1) >> rounds << rounds;
     const size_t np1 = chunk * (size_t)stride / 2;
     for (size_t k = 0; k < std::min<size_t>(2, nchunks); k++) {
