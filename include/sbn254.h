@@ -59,7 +59,16 @@ int sbn_ctx_destroy(sbn_ctx* ctx);
 int sbn_ctx_synchronize(sbn_ctx* ctx);
 /* Tunables: "chunk_rows" (rows per pipeline chunk; 0 = auto), "window_bits" (0 = auto, applies to bases created
  * afterwards), "task_cap" (max entries one accumulation thread sums; fuller buckets are split; 0 = auto), "leaf_m"
- * (buckets per leaf thread of the two-level bucket reduction; 0 = auto). */
+ * (buckets per leaf thread of the two-level bucket reduction; 0 = auto), "ba_rounds" / "ba_batch" (batched-affine rounds of
+ * the bucket pipeline and pairs per thread; -1 / 0 = auto), "dedup_generators" (merge equal generators of sets created
+ * afterwards; default 1).
+ * Resident tables of digit multiples (HBM for speed; all results are identical with or without them):
+ *   "mult_max_mb"   budget (MiB, default 6144) of the table d * 2^(k c) * G_j that commits of many rows sum over instead of
+ *                   sorting into buckets; the widest window that fits is used, 0 disables the path
+ *   "mult_min_rows" commits of at least this many rows (default 256) take that path and build the table on first use
+ *   "tab_max_mb"    budget (MiB, default 3072) of the 8-bit-window table of an opening's generator set
+ *                   (sbn_bases_create_ext): single rows and row pairs become sums of table points; 0 disables
+ *   "small_commit_path" 0 sends short generator sets and few-row commits through the general pipeline (test hook) */
 int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
 /* Counters since creation / last reset: kernels launched by this library, bytes copied H2D / D2H. */
 int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
