@@ -21,6 +21,7 @@
 // generators).  The table is read at random (64 B per entry): HBM traffic the bucket method did not have, 1-2 GB per commit.
 #pragma once
 #include "ba_kernels.cuh"
+#include "digits.cuh"
 #include "small_kernels.cuh"
 
 namespace sbn {
@@ -81,20 +82,13 @@ k_mult_entries(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
     if (have && s.is_zero()) have = false;
     if (have) s = fp_from_mont(s);
     const uint32_t col = j < (uint32_t)R ? j : (uint32_t)(n1 - 1);
-    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     uint32_t carry = 0;
 #pragma unroll 1
     for (int k = 0; k < W; k++) {
         uint32_t e = kNullEntry;
         if (have) {
-            const int bit = k * c, limb = bit >> 5, off = bit & 31;
-            uint32_t raw = s.l[limb] >> off;
-            if (off + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - off);
-            uint32_t d = (raw & mask) + carry;
-            carry = 0;
-            uint32_t neg = 0;
-            if (d > half) { d = (1u << c) - d; carry = 1; neg = 1; }
-            if (d) e = ((((uint32_t)k * (uint32_t)n1 + col) << (c - 1)) + (d - 1)) | (neg << 31);
+            const uint32_t d = signed_window_digit(s.l, k, c, carry);      // |d| with the sign in bit 31, 0 for a zero digit
+            if (d) e = ((((uint32_t)k * (uint32_t)n1 + col) << (c - 1)) + ((d & 0x7fffffffu) - 1)) | (d & 0x80000000u);
         }
         erow[(size_t)k * (R + 1) + j] = e;
     }
