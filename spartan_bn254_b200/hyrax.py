@@ -391,12 +391,6 @@ class DotProductProofLog:
         self.L_vec, self.R_vec, self.delta, self.beta, self.z1, self.z2 = L_vec, R_vec, delta, beta, z1, z2
 
     @staticmethod
-    def _commit2(ctx, g, s, h, blind):
-        """Scalar::commit (commitments.rs:122-130): s * g + blind * h as a 2-point MSM."""
-        out, inf = ctx.msm(np.stack([g, h]), None, np.stack([fr_from_int(s), fr_from_int(blind)]))
-        return GroupElement(out, inf)
-
-    @staticmethod
     def prove(gens, transcript, random_tape, x_vec, blind_x, a_vec, y, blind_y):
         """x_vec, a_vec: lists of canonical ints, or Montgomery uint64[n, 4] arrays (what `bound` and the device eq tables
         hand over: the vectors then never pass through Python integers)."""

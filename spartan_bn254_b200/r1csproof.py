@@ -17,23 +17,19 @@ import numpy as np
 
 from .hyrax import (R_MOD, DensePolynomial, GroupElement, MultiCommitGens, PolyCommitmentGens, PolyEvalProof, fr_from_int,
                     fr_to_int, fr_vec_from_ints, fr_vec_to_ints, log_2)
-from .lib import SpMat, eq_evals
+from .lib import SpMat
 from .product_tree import UniPoly
 from .spark import (MultiSparseMatPolynomialAsDense, SparseMatPolyCommitmentGens, SparseMatPolyEvalProof,
                     append_poly_commitment, commit_dense, equalize)
 
 
-def commit_scalars(gens, scalars, blind, resident=True):
+def commit_scalars(gens, scalars, blind):
     """Commitments::commit (commitments.rs:118-154) for the short vectors of the Sigma-protocols: sum s_i G_i + blind h.
-    The generator sets of the sumchecks are fixed, so the commitment runs over their resident window tables (one row of the
-    commit pipeline, ~0.2 ms) rather than as a variable-base MSM (a 254-step double-and-add chain, ~2.4 ms)."""
+    The generator sets of the sumchecks are fixed, so the commitment runs over their resident digit-multiple tables (one
+    launch, ~0.1 ms) rather than as a variable-base MSM (a 254-step double-and-add chain, ~2.4 ms)."""
     n = len(scalars)
     assert gens.n == n, "assert_eq!(gens_n.n, self.len())"
-    if resident:
-        out, inf = gens.ctx.commit(gens.device_bases(), fr_vec_from_ints(list(scalars)), fr_from_int(blind))
-        return GroupElement(out, inf)
-    pts = np.concatenate([gens.G[:n].reshape(n, 8), gens.h.reshape(1, 8)])
-    out, inf = gens.ctx.msm(pts, None, fr_vec_from_ints(list(scalars) + [blind]))
+    out, inf = gens.ctx.commit(gens.device_bases(), fr_vec_from_ints(list(scalars)), fr_from_int(blind))
     return GroupElement(out, inf)
 
 
@@ -44,11 +40,6 @@ def commit_rows(gens, rows, blinds):
     Z = fr_vec_from_ints([v for r in rows for v in r])
     C, inf = gens.ctx.hyrax_commit(gens.device_bases(), Z, len(rows), n, fr_vec_from_ints(list(blinds)))
     return [GroupElement(C[i], inf[i]) for i in range(len(rows))]
-
-
-def _scalar_mul(ctx, point, s):
-    out, inf = ctx.msm(point.reshape(1, 8), None, fr_vec_from_ints([s]))
-    return GroupElement(out, inf)
 
 
 def _append(transcript, label, g):
