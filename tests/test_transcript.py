@@ -83,3 +83,27 @@ def test_native_point_compression_and_append_points(orc):
         c.append_message(b"poly_commitment_share", e)
     ch = a.challenge_bytes(b"c", 64)
     assert ch == b.challenge_bytes(b"c", 64) == c.challenge_bytes(b"c", 64)
+
+
+def test_host_side_scalar_conversions_and_canonical_append(orc):
+    """sbn_fr_{to,from}_canonical_host (the library's host code behind fr_vec_to_ints / fr_vec_from_ints for short vectors)
+    against the Python big-int forms and the oracle's Montgomery conversion; append_scalars_canonical feeds the transcript
+    the same bytes as append_scalars."""
+    import random
+    import numpy as np
+    from spartan_bn254_b200.hyrax import (R_MOD, _to_canonical_host, fr_from_int, fr_to_int, fr_vec_from_ints, fr_vec_to_ints)
+    from spartan_bn254_b200.transcript import Transcript, PyTranscript
+    rnd = random.Random(9)
+    vals = [0, 1, 2, R_MOD - 1, R_MOD - 2, 1 << 253] + [rnd.randrange(R_MOD) for _ in range(60)]
+    m = fr_vec_from_ints(vals)                                   # 66 < 128 elements: host path of the library
+    assert np.array_equal(m, orc.to_mont(vals))
+    assert all(np.array_equal(m[i], fr_from_int(v)) for i, v in enumerate(vals))
+    assert fr_vec_to_ints(m) == vals == [fr_to_int(x) for x in m]
+    canon = _to_canonical_host(m)
+    assert [int.from_bytes(canon[i].tobytes(), "little") for i in range(len(vals))] == vals
+    a, b, c = Transcript(b"sc"), Transcript(b"sc"), PyTranscript(b"sc")
+    a.append_scalars(b"a", vals)
+    b.append_scalars_canonical(b"a", canon)
+    c.append_scalars_canonical(b"a", canon)
+    ch = a.challenge_bytes(b"c", 64)
+    assert ch == b.challenge_bytes(b"c", 64) == c.challenge_bytes(b"c", 64)
