@@ -234,6 +234,10 @@ int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* addrs, int side, const sb
 int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer, sbn_fr* out /* len >> layer scalars */);
 /* DensePolynomial::evaluate (hyrax.rs:217-222) of the 2^nr evaluations poly[offset .. offset + 2^nr) at the point r. */
 int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offset, const sbn_fr* r, size_t nr, sbn_fr* out);
+/* The same for `count` equally long segments starting at offset0 + i * stride, at one point: one eq table, one launch
+ * (the evaluations of HashLayerProof::prove, sparse_mlpoly_full.rs:935-976).  out: count scalars. */
+int sbn_poly_evaluate_strided(sbn_ctx* ctx, const sbn_poly* poly, size_t offset0, size_t stride, size_t count, const sbn_fr* r,
+                              size_t nr, sbn_fr* out);
 /* comb_ops = merge(row.ops_addr, row.read_ts, col.ops_addr, col.read_ts, val) (zero-padded to a power of two) and
  * comb_mem = row.audit_ts ++ col.audit_ts (sparse_mlpoly_full.rs:155-170) as resident polynomials, built from the
  * resident addresses / timestamps and the host `val` (batch x N Montgomery scalars). */

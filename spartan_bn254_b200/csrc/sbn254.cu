@@ -2570,6 +2570,37 @@ extern "C" int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offs
     return SBN_OK;
 }
 
+// `count` evaluations at the same point of the equally long segments starting at offset0 + i * stride: the eq table is
+// built once and the dot products run as one launch (HashLayerProof::prove evaluates the 2 b segments of derefs, the 5 b
+// of comb_ops and the 2 of comb_mem at one point each, sparse_mlpoly_full.rs:935-976)
+extern "C" int sbn_poly_evaluate_strided(sbn_ctx* ctx, const sbn_poly* poly, size_t offset0, size_t stride, size_t count,
+                                         const sbn_fr* r, size_t nr, sbn_fr* out) {
+    if (!ctx || !poly || !r || !out || poly->ctx != ctx) return SBN_ERR_ARG;
+    if (nr == 0 || nr > 30 || count == 0 || count > 4096) return SBN_ERR_SHAPE;
+    const size_t n = size_t(1) << nr;
+    if (offset0 > poly->len || n > poly->len - offset0 || (count > 1 && (stride == 0 || (count - 1) > (poly->len - offset0 - n) / stride)))
+        return SBN_ERR_SHAPE;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->compute;
+    const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(1, 1184 / count), (n + kDotThreads - 1) / kDotThreads);
+    SBN_TRY(ensure(ctx, ctx->scratch0, 2 * n * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch1, ((size_t)blocks * count + count) * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, ctx->scratch2, nr * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaMemcpyAsync(ctx->scratch2.p, r, nr * sizeof(Fr), cudaMemcpyHostToDevice, s));
+    ctx->h2d += nr * sizeof(Fr);
+    const Fr* eq = eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, nr, (Fr*)ctx->scratch0.p, (Fr*)ctx->scratch0.p + n, s);
+    Fr* partial = (Fr*)ctx->scratch1.p;
+    Fr* res = partial + (size_t)blocks * count;
+    k_fr_dot<<<dim3(blocks, (unsigned)count), kDotThreads, 0, s>>>(poly->Z + offset0, (long)stride, eq, 0, (int)n, partial);
+    k_fr_sum<<<(unsigned)count, kDotThreads, 0, s>>>(partial, (int)blocks, res, 1);
+    ctx->launches += 2;
+    SBN_CUDA(ctx, cudaGetLastError());
+    SBN_TRY(download(ctx, out, res, count * sizeof(Fr)));
+    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    return SBN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // f4 building blocks: the dense representation of a multi-sparse-matrix commitment, resident
 // ------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ EXPORTS = [
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
-    "sbn_poly_evaluate", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
+    "sbn_poly_evaluate", "sbn_poly_evaluate_strided", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
     "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_fr_to_canonical_host", "sbn_fr_from_canonical_host", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_prove", "sbn_bsumcheck_destroy",
@@ -448,6 +448,16 @@ class Poly:
                                           _ptr(out), _ptr(inf))
         self.ctx._check(st, "sbn_poly_commit")
         return out, inf
+
+    def evaluate_strided(self, r, offset0, stride, count):
+        """DensePolynomial::evaluate of `count` segments of 2^len(r) evaluations starting at offset0 + i * stride, at one point:
+        uint64[count, 4]."""
+        r = _u64(r, 4)
+        out = np.zeros((count, 4), dtype=np.uint64)
+        st = self.ctx.lib.sbn_poly_evaluate_strided(self.ctx.h, self.h, C.c_size_t(offset0), C.c_size_t(stride), C.c_size_t(count),
+                                                    _ptr(r), C.c_size_t(r.shape[0]), _ptr(out))
+        self.ctx._check(st, "sbn_poly_evaluate_strided")
+        return out
 
     def evaluate(self, r, offset=0):
         """DensePolynomial::evaluate of the 2^len(r) evaluations starting at `offset`."""

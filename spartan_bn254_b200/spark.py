@@ -16,7 +16,7 @@ and the few dozen field elements per round; proofs are plain Python objects hold
 import numpy as np
 
 from .hyrax import (R_MOD, PolyCommitment, PolyCommitmentGens, PolyEvalProof, fr_from_int, fr_to_int,
-                    fr_vec_from_ints, log_2)
+                    fr_vec_from_ints, fr_vec_to_ints, log_2)
 from .lib import Poly
 from .product_tree import ProductCircuitEvalProofBatched
 from .sparse_mlpoly import PolyEvalNetwork, SparkAddresses
@@ -236,24 +236,21 @@ class HashLayerProof:
         b, N, M = dense.batch_size, dense.N, dense.num_mem_cells
         r_ops_m, r_mem_m = fr_vec_from_ints(rand_ops), fr_vec_from_ints(rand_mem)
 
-        def ev(poly, r_m, off):
-            return fr_to_int(poly.evaluate(r_m, offset=off))
+        def evs(poly, r_m, stride, count):
+            """The evaluations at one point of `count` consecutive segments: one eq table and one launch for all of them."""
+            return fr_vec_to_ints(poly.evaluate_strided(r_m, 0, stride, count))
 
-        eval_row_ops_val = [ev(derefs_poly, r_ops_m, i * N) for i in range(b)]
-        eval_col_ops_val = [ev(derefs_poly, r_ops_m, (b + i) * N) for i in range(b)]
+        d = evs(derefs_poly, r_ops_m, N, 2 * b)
+        eval_row_ops_val, eval_col_ops_val = d[:b], d[b:]
         # DerefsEvalProof::prove (:412-432)
         transcript.append_protocol_name(b"Derefs evaluation proof")
         proof_derefs = _joint_opening(derefs_poly, eval_row_ops_val + eval_col_ops_val, rand_ops, gens.gens_derefs,
                                       (b"evals_ops_val", b"challenge_combine_n_to_one", b"joint_claim_eval"), transcript,
                                       random_tape)
         ops = dense.comb_ops
-        row_addr = [ev(ops, r_ops_m, i * N) for i in range(b)]
-        row_read = [ev(ops, r_ops_m, (b + i) * N) for i in range(b)]
-        row_audit = ev(dense.comb_mem, r_mem_m, 0)
-        col_addr = [ev(ops, r_ops_m, (2 * b + i) * N) for i in range(b)]
-        col_read = [ev(ops, r_ops_m, (3 * b + i) * N) for i in range(b)]
-        col_audit = ev(dense.comb_mem, r_mem_m, M)
-        eval_val = [ev(ops, r_ops_m, (4 * b + i) * N) for i in range(b)]
+        o = evs(ops, r_ops_m, N, 5 * b)
+        row_addr, row_read, col_addr, col_read, eval_val = (o[k * b: (k + 1) * b] for k in range(5))
+        row_audit, col_audit = evs(dense.comb_mem, r_mem_m, M, 2)
         proof_ops = _joint_opening(ops, row_addr + row_read + col_addr + col_read + eval_val, rand_ops, gens.gens_ops,
                                    (b"claim_evals_ops", b"challenge_combine_n_to_one", b"joint_claim_eval_ops"), transcript,
                                    random_tape)
