@@ -30,6 +30,7 @@ extern "C" {
     pub fn sbn_bases_create(ctx: *mut sbn_ctx, g: *const SbnG1a, g_inf: *const u8, n: usize, h: *const SbnG1a,
                             out: *mut *mut sbn_bases) -> c_int;
     pub fn sbn_bases_destroy(b: *mut sbn_bases) -> c_int;
+    pub fn sbn_bases_mult_table(b: *const sbn_bases, window_bits: *mut c_int, bytes: *mut u64) -> c_int;
     pub fn sbn_hyrax_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, z: *const SbnFr, l_size: usize, r_size: usize,
                             blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_msm(ctx: *mut sbn_ctx, pts: *const SbnG1a, inf: *const u8, s: *const SbnFr, n: usize,
@@ -59,6 +60,8 @@ extern "C" {
                            blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_poly_bound(ctx: *mut sbn_ctx, p: *const sbn_poly, l: *const SbnFr, l_size: usize, r_size: usize, lz_out: *mut SbnFr) -> c_int;
     pub fn sbn_poly_evaluate(ctx: *mut sbn_ctx, p: *const sbn_poly, offset: usize, r: *const SbnFr, nr: usize, out: *mut SbnFr) -> c_int;
+    pub fn sbn_poly_evaluate_strided(ctx: *mut sbn_ctx, p: *const sbn_poly, offset0: usize, stride: usize, count: usize,
+                                     r: *const SbnFr, nr: usize, out: *mut SbnFr) -> c_int;
     pub fn sbn_poly_triple_dot(ctx: *mut sbn_ctx, a: *const sbn_poly, off_a: usize, b: *const sbn_poly, off_b: usize,
                                c: *const sbn_poly, off_c: usize, n: usize, out: *mut SbnFr) -> c_int;
     // R1CS-sat sumcheck rounds (sumcheck.rs:501-530, 690-699) and their inputs (r1csproof.rs:285, 380)
@@ -105,6 +108,11 @@ extern "C" {
     pub fn sbn_bsumcheck_round_eval(st: *mut sbn_bsumcheck, evals: *mut SbnFr) -> c_int;
     pub fn sbn_bsumcheck_bind(st: *mut sbn_bsumcheck, r: *const SbnFr) -> c_int;
     pub fn sbn_bsumcheck_end(st: *mut sbn_bsumcheck, a_final: *mut SbnFr, b_final: *mut SbnFr, c_final: *mut SbnFr) -> c_int;
+    // one layer's whole round loop against the caller's Merlin state (only meaningful when the transcript is the
+    // library's own sbn_merlin_* state; a Rust prover keeps merlin::Transcript and drives round_eval / bind instead)
+    pub fn sbn_bsumcheck_prove(st: *mut sbn_bsumcheck, merlin: *mut c_void, claim: *const SbnFr, coeffs: *const SbnFr,
+                               num_rounds: usize, polys: *mut SbnFr, r_out: *mut SbnFr, claim_out: *mut SbnFr,
+                               a_final: *mut SbnFr, b_final: *mut SbnFr, c_final: *mut SbnFr) -> c_int;
     pub fn sbn_bsumcheck_destroy(st: *mut sbn_bsumcheck) -> c_int;
 }
 
