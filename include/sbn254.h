@@ -68,10 +68,24 @@ int sbn_ctx_synchronize(sbn_ctx* ctx);
  *   "mult_min_rows" commits of at least this many rows (default 256) take that path and build the table on first use
  *   "tab_max_mb"    budget (MiB, default 3072) of the 8-bit-window table of an opening's generator set
  *                   (sbn_bases_create_ext): single rows and row pairs become sums of table points; 0 disables
- *   "small_commit_path" 0 sends short generator sets and few-row commits through the general pipeline (test hook) */
+ *   "small_commit_path" 0 sends short generator sets and few-row commits through the general pipeline (test hook)
+ * Tuning of the tabulated-sum path (mult_kernels.cuh; every setting gives identical results):
+ *   "mult_layout"   1 (default) position-major entry lists -- a warp is 32 rows at one table column; 0 row-major (round 1)
+ *   "mult_streams"  chunks in flight, 1..4 (default 2);  "mult_rounds" batched-affine rounds, 0 = auto
+ *   "ba_minb"       register target of the finish pass: 3 (80 registers, default) or 4 (64) resident blocks per SM
+ *   "ba_prefetch"   round 1 reads its entries two pairs ahead and prefetches the table points into L2 (default 0: loses)
+ *   "finish_smem_kb" / "prefix_smem_kb"  dynamic shared memory requested per block to cap co-residency (default 0)
+ *   "l2_fetch"      cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured to change nothing on B200)
+ *   "ablate"        PROFILING ONLY: bit mask of skipped launches (1 prefix round 1, 2 prefix rounds >= 2, 4 inversions,
+ *                   8 row sums, 16 finish round 1, 32 finish rounds >= 2); results are WRONG when non-zero */
 int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
 /* Counters since creation / last reset: kernels launched by this library, bytes copied H2D / D2H. */
 int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
+/* Memory behaviour since creation: out[0] bytes of released device buffers held by the context's pool, out[1] times an
+ * allocation failure emptied that pool and retried, out[2] digit-multiple tables ("mult_max_mb") the device could not hold
+ * -- those generator sets ran through the bucket pipeline and sbn_last_cuda_error says so --, out[3] buffers in the pool.
+ * (No reference counterpart: the Rust prover's Vec allocations cannot fail softly; a GPU backend's can.) */
+int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[4]);
 /* Device time (ms, CUDA events on the library's compute stream) of the kernels of the last
  * sbn_hyrax_commit* call, per stage: [0] digit decomposition + bucket sort, [1] bucket accumulation,
  * [2] bucket reduction, [3] affine normalisation; and the number of launches per stage. */

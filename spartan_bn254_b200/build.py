@@ -16,8 +16,11 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
-        os.path.join(HERE, "..", "include", "sbn254.h")]
+    """Every file under csrc/ (the host headers in csrc/host/ are compiled into the library too) plus the C-ABI header."""
+    out = [os.path.join(HERE, "..", "include", "sbn254.h")]
+    for d, _, files in os.walk(CSRC):
+        out += [os.path.join(d, f) for f in sorted(files)]
+    return out
 
 
 def needs_build():

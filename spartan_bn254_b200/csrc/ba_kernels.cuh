@@ -136,17 +136,34 @@ k_ba_invert(const Fq* __restrict__ warp_tot, size_t n, Fq* __restrict__ inv) {
     store_fq(inv + i, fp_inv_fast(load_fq(warp_tot + i)));
 }
 
-template <bool FIRST>
-__global__ void __launch_bounds__(kBaThreads)
+// L2 prefetch of the two table points the next pair of this thread will gather (round 1 only): the gathers are random 64 B
+// reads over a table of tens of GB, and a warp that waits for them holds 80 registers per thread doing nothing.
+__device__ __forceinline__ void ba_prefetch_pair(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, size_t g) {
+    const uint2 e = __ldg(reinterpret_cast<const uint2*>(entries) + g);
+    if (e.x != kNullEntry) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + (e.x & 0x7fffffffu)));
+    if (e.y != kNullEntry) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + (e.y & 0x7fffffffu)));
+}
+
+// MINB = resident CTAs per SM the register allocation aims at (3: 80 registers, 4: 64 with a few spilled words);
+// PF = prefetch the next pair's table points (round 1).
+template <bool FIRST, int MINB = 3, bool PF = false>
+__global__ void __launch_bounds__(kBaThreads, MINB)
 k_ba_finish(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, const Affine* __restrict__ in,
             size_t npairs, int B, const Fq* __restrict__ prefix, const Fq* __restrict__ other,
             const Fq* __restrict__ warp_inv, Affine* __restrict__ out) {
     const size_t base = (size_t)blockIdx.x * kBaThreads * B;
     const size_t tid_global = (size_t)blockIdx.x * kBaThreads + threadIdx.x;
+    if (FIRST && PF) {
+        const size_t g = base + (size_t)(B - 1) * kBaThreads + threadIdx.x;
+        if (g < npairs) ba_prefetch_pair(entries, table, g);
+    }
     Fq run = fp_mul(load_fq(warp_inv + (tid_global >> 5)), load_fq(other + tid_global));   // (own total)^-1
 #pragma unroll 1
     for (int j = B - 1; j >= 0; j--) {
         const size_t g = base + (size_t)j * kBaThreads + threadIdx.x;
+        if (FIRST && PF) {
+            if (j > 0 && g - kBaThreads < npairs) ba_prefetch_pair(entries, table, g - kBaThreads);
+        }
         if (g >= npairs) continue;
         Affine P, Q;
         ba_load_pair<FIRST>(entries, table, in, g, P, Q);

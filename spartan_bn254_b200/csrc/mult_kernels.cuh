@@ -27,7 +27,7 @@
 namespace sbn {
 
 static constexpr int kMultChunk = 128;       // multiples filled by one thread of the table builder
-static constexpr int kMultMaxBits = 16;
+static constexpr int kMultMaxBits = 17;      // 64 GB at 1025 generators; the entry index stays below 2^31
 static constexpr int kMultSumThreads = 128;
 
 // thread per (k, j, chunk): B = 2^(k c) * base_j, S = (chunk * 128) * B, then 128 times S += B, each stored in affine form
@@ -92,6 +92,299 @@ k_mult_entries(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
         }
         erow[(size_t)k * (R + 1) + j] = e;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Position-major ("transposed") layout of the sum tree (round 2).
+//
+// Measured on B200 (microbench/gather_bench.cu, profiles/r2_gather_microbench.txt): 64 B gathers at random over a 32 GiB
+// table run at 22.7 G points/s however few bytes each one moves (the 128 B DRAM fetch per point halves with the L2::64B
+// qualifier and the rate stays), but at 49-55 G points/s when the 32 lanes of a warp read from ONE 2 MiB region.  Round 1
+// of the sum tree is 2 x 16 gathers per scalar, so with the row-major entry list (a warp = 32 neighbouring (window,
+// generator) columns of one row = 32 regions) its two kernels sat at 74 % and 85 % of the random-gather rate, not on the
+// multiplier.  A column (k, j) of the table -- the 2^(c-1) multiples of 2^(kc) G_j -- IS one such region (2 MiB at c = 16),
+// so the lists are now stored position-major:
+//
+//     entries[p * rp + r]       p = k (R + 1) + j  the (window, generator) position, r the row, rp = rows padded to 32
+//     round t:  pair g = q * rp + r  adds the points at positions 2q and 2q + 1 of row r:  in[2g - r], in[2g - r + rp]
+//
+// and the 32 lanes of a warp are 32 ROWS at the same position: one table column per operand and warp instruction, and
+// every other load and store of the rounds is a contiguous run of 32 elements.  Intermediate points are kept as separate
+// x and y arrays so that the prefix pass of rounds >= 2 streams x only.
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fq load_fq_tab(const Fq* p) {      // table gather: 64 B DRAM fetch instead of the default 128 B
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a, b;
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(q));
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(q + 1));
+    Fq r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_mult_entries_t(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n1, int c, int W, uint32_t stride, int rows,
+                 uint32_t rp, uint32_t* __restrict__ entries) {
+    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t r = (uint32_t)(t % rp);
+    const uint32_t j = (uint32_t)(t / rp);                             // 0 .. R: scalar index (R = the blind); above: padding
+    const uint32_t used = (uint32_t)W * (uint32_t)(R + 1);
+    if (j > (uint32_t)R) {
+        const uint32_t p = used + (j - (uint32_t)R - 1);
+        if (p < stride) entries[(size_t)p * rp + r] = kNullEntry;
+        return;
+    }
+    Fr s;
+    bool have = r < (uint32_t)rows;
+    if (have) {
+        if (j < (uint32_t)R) s = load_fr(Z + (size_t)r * R + j);
+        else if (blinds) s = load_fr(blinds + r);
+        else have = false;
+    }
+    if (have && s.is_zero()) have = false;
+    if (have) s = fp_from_mont(s);
+    const uint32_t col = j < (uint32_t)R ? j : (uint32_t)(n1 - 1);
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int k = 0; k < W; k++) {
+        uint32_t e = kNullEntry;
+        if (have) {
+            const uint32_t d = signed_window_digit(s.l, k, c, carry);
+            if (d) e = ((((uint32_t)k * (uint32_t)n1 + col) << (c - 1)) + ((d & 0x7fffffffu) - 1)) | (d & 0x80000000u);
+        }
+        entries[((size_t)k * (R + 1) + j) * rp + r] = e;
+    }
+}
+
+// Denominator of pair g (operands at iP and iP + rp) from the x coordinates alone; y only on the rare path.
+template <bool FIRST>
+__device__ __forceinline__ bool bat_denominator(uint32_t ex, uint32_t ey, const Affine* __restrict__ table,
+                                                const Fq* __restrict__ inx, const Fq* __restrict__ iny, size_t iP, uint32_t rp,
+                                                Fq& d) {
+    Fq px, qx;
+    if (FIRST) {
+        if (ex == kNullEntry || ey == kNullEntry) return false;
+        px = load_fq_tab(&table[ex & 0x7fffffffu].x);
+        qx = load_fq_tab(&table[ey & 0x7fffffffu].x);
+    } else {
+        px = load_fq(inx + iP);
+        qx = load_fq(inx + iP + rp);
+    }
+    if (px != qx && !px.is_zero() && !qx.is_zero()) { d = fp_sub(qx, px); return true; }
+    Affine P, Q;
+    P.x = px; Q.x = qx;
+    if (FIRST) {
+        P.y = load_fq_tab(&table[ex & 0x7fffffffu].y);
+        Q.y = load_fq_tab(&table[ey & 0x7fffffffu].y);
+        if ((ex >> 31) && !P.is_identity()) P.y = fp_neg(P.y);
+        if ((ey >> 31) && !Q.is_identity()) Q.y = fp_neg(Q.y);
+    } else {
+        P.y = load_fq(iny + iP);
+        Q.y = load_fq(iny + iP + rp);
+    }
+    return ba_classify(P, Q, d) != BA_NONE;
+}
+
+// The entry pair of pair g (NULL, NULL past the end)
+__device__ __forceinline__ uint2 bat_entries(const uint32_t* __restrict__ entries, size_t g, size_t npairs, uint32_t rp) {
+    if (g >= npairs) return make_uint2(kNullEntry, kNullEntry);
+    const size_t iP = 2 * g - g % rp;
+    return make_uint2(__ldg(entries + iP), __ldg(entries + iP + rp));
+}
+// L2 prefetch of the table bytes a pair will gather (YTOO: the whole point, else the x coordinate's sector)
+template <bool YTOO>
+__device__ __forceinline__ void bat_prefetch(const Affine* __restrict__ table, uint2 e) {
+    if (e.x != kNullEntry) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&table[e.x & 0x7fffffffu].x));
+        if (YTOO) asm volatile("prefetch.global.L2 [%0];" ::"l"(&table[e.x & 0x7fffffffu].y));
+    }
+    if (e.y != kNullEntry) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&table[e.y & 0x7fffffffu].x));
+        if (YTOO) asm volatile("prefetch.global.L2 [%0];" ::"l"(&table[e.y & 0x7fffffffu].y));
+    }
+}
+
+// PF (round 1): the entries of a thread's pairs are read two iterations ahead and their table points prefetched into L2 one
+// iteration ahead, so that three gathers per operand are in flight instead of one -- the pass is bound by the latency of
+// its gathers, not by the multiplier (ncu: 21 % issue, 36 % DRAM at 47 % occupancy).
+template <bool FIRST, bool PF = false>
+__global__ void __launch_bounds__(kBaThreads)
+k_bat_prefix(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, const Fq* __restrict__ inx,
+             const Fq* __restrict__ iny, size_t npairs, uint32_t rp, int B, Fq* __restrict__ prefix, Fq* __restrict__ other,
+             Fq* __restrict__ warp_tot) {
+    const size_t base = (size_t)blockIdx.x * kBaThreads * B;
+    Fq run = fq_one();
+    uint2 e0 = make_uint2(kNullEntry, kNullEntry), e1 = e0, e2 = e0;       // entries of iterations j, j + 1, j + 2
+    if (FIRST) {
+        e0 = bat_entries(entries, base + threadIdx.x, npairs, rp);
+        if (PF) {
+            if (B > 1) e1 = bat_entries(entries, base + kBaThreads + threadIdx.x, npairs, rp);
+            bat_prefetch<false>(table, e1);
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        const size_t g = base + (size_t)j * kBaThreads + threadIdx.x;
+        if (FIRST && PF) {
+            if (j + 2 < B) e2 = bat_entries(entries, g + 2 * kBaThreads, npairs, rp);
+            else e2 = make_uint2(kNullEntry, kNullEntry);
+        }
+        if (g < npairs) {
+            Fq d;
+            if (bat_denominator<FIRST>(e0.x, e0.y, table, inx, iny, 2 * g - g % rp, rp, d)) run = fp_mul(run, d);
+            store_fq(prefix + g, run);
+        }
+        if (FIRST) {
+            if (PF) {
+                e0 = e1; e1 = e2;
+                bat_prefetch<false>(table, e1);
+            } else if (j + 1 < B) {
+                e0 = bat_entries(entries, g + kBaThreads, npairs, rp);
+            }
+        }
+    }
+    // Every thread needs the product of the OTHER threads' totals of its block (times the inverse of the block total, that
+    // is its own total's inverse).  One warp computes all 256 of them through shared memory -- lane l owns the totals of
+    // threads l, l + 32, ..., l + 224: 8 running products forward, a shuffle scan over the 32 lane totals, 16 products
+    // backward -- 35 multiplications of one warp per block instead of 12 of every warp, and one inversion per block instead
+    // of one per warp.
+    __shared__ uint4 s_tot[kBaThreads * 2], s_exc[kBaThreads * 2];
+    s_tot[2 * threadIdx.x] = make_uint4(run.l[0], run.l[1], run.l[2], run.l[3]);
+    s_tot[2 * threadIdx.x + 1] = make_uint4(run.l[4], run.l[5], run.l[6], run.l[7]);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    auto lds = [](const uint4* a, int i) {
+        const uint4 u = a[2 * i], v = a[2 * i + 1];
+        Fq r;
+        r.l[0] = u.x; r.l[1] = u.y; r.l[2] = u.z; r.l[3] = u.w; r.l[4] = v.x; r.l[5] = v.y; r.l[6] = v.z; r.l[7] = v.w;
+        return r;
+    };
+    Fq acc = fq_one();
+#pragma unroll 1
+    for (int i = 0; i < kBaThreads / 32; i++) {
+        const int t = i * 32 + lane;
+        s_exc[2 * t] = make_uint4(acc.l[0], acc.l[1], acc.l[2], acc.l[3]);           // product of this lane's totals before t
+        s_exc[2 * t + 1] = make_uint4(acc.l[4], acc.l[5], acc.l[6], acc.l[7]);
+        acc = fp_mul(acc, lds(s_tot, t));
+    }
+    Fq pre = acc, suf = acc;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        Fq a = shfl_fq(pre, (lane - off) & 31), b = shfl_fq(suf, (lane + off) & 31);
+        if (lane < off) a = fq_one();
+        if (lane + off >= 32) b = fq_one();
+        pre = fp_mul(pre, a);
+        suf = fp_mul(suf, b);
+    }
+    Fq pe = shfl_fq(pre, (lane - 1) & 31), se = shfl_fq(suf, (lane + 1) & 31);
+    if (lane == 0) pe = fq_one();
+    if (lane == 31) se = fq_one();
+    acc = fp_mul(pe, se);                                                          // the other lanes' totals
+    Fq* oth = other + (size_t)blockIdx.x * kBaThreads;
+#pragma unroll 1
+    for (int i = kBaThreads / 32 - 1; i >= 0; i--) {
+        const int t = i * 32 + lane;
+        store_fq(oth + t, fp_mul(acc, lds(s_exc, t)));                             // others of thread t
+        acc = fp_mul(acc, lds(s_tot, t));
+    }
+    if (lane == 31) store_fq(warp_tot + blockIdx.x, pre);                          // the block's total
+}
+
+// Round 1 walks the blocks in reverse: the prefix pass has just pulled the table points of the LAST blocks through L2, so
+// the finish pass meets them there before they are evicted.
+template <bool FIRST, int MINB = 3, bool PF = false>
+__global__ void __launch_bounds__(kBaThreads, MINB)
+k_bat_finish(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, const Fq* __restrict__ inx,
+             const Fq* __restrict__ iny, size_t npairs, uint32_t rp, int B, const Fq* __restrict__ prefix,
+             const Fq* __restrict__ other, const Fq* __restrict__ warp_inv, Fq* __restrict__ outx, Fq* __restrict__ outy) {
+    const size_t blk = FIRST ? (size_t)(gridDim.x - 1 - blockIdx.x) : (size_t)blockIdx.x;
+    const size_t base = blk * kBaThreads * B;
+    const size_t tid_global = blk * kBaThreads + threadIdx.x;
+    uint2 e0 = make_uint2(kNullEntry, kNullEntry), e1 = e0;                // entries of iterations j and j - 1
+    if (FIRST) {
+        e0 = bat_entries(entries, base + (size_t)(B - 1) * kBaThreads + threadIdx.x, npairs, rp);
+        if (PF && B > 1) e1 = bat_entries(entries, base + (size_t)(B - 2) * kBaThreads + threadIdx.x, npairs, rp);
+    }
+    Fq run = fp_mul(load_fq(warp_inv + blk), load_fq(other + tid_global));   // (own total)^-1: block total^-1 x the others
+#pragma unroll 1
+    for (int j = B - 1; j >= 0; j--) {
+        const size_t g = base + (size_t)j * kBaThreads + threadIdx.x;
+        const uint32_t ex = e0.x, ey = e0.y;
+        if (FIRST) {       // rotate the entry pipeline before the long body: loads issued here return under the additions
+            if (PF) {       // entries of j - 1 arrived an iteration ago: their table points start towards L2 now
+                e0 = e1;
+                bat_prefetch<true>(table, e0);
+                e1 = j >= 2 ? bat_entries(entries, g - 2 * kBaThreads, npairs, rp) : make_uint2(kNullEntry, kNullEntry);
+            } else if (j >= 1) {
+                e0 = bat_entries(entries, g - kBaThreads, npairs, rp);
+            }
+        }
+        if (g >= npairs) continue;
+        const size_t iP = 2 * g - g % rp;
+        Affine P, Q;
+        if (FIRST) {
+            if (ex == kNullEntry) P = Affine::identity();
+            else { P.x = load_fq_tab(&table[ex & 0x7fffffffu].x); P.y = load_fq_tab(&table[ex & 0x7fffffffu].y); }
+            if (ey == kNullEntry) Q = Affine::identity();
+            else { Q.x = load_fq_tab(&table[ey & 0x7fffffffu].x); Q.y = load_fq_tab(&table[ey & 0x7fffffffu].y); }
+            if (ex != kNullEntry && (ex >> 31) && !P.is_identity()) P.y = fp_neg(P.y);
+            if (ey != kNullEntry && (ey >> 31) && !Q.is_identity()) Q.y = fp_neg(Q.y);
+        } else {
+            P.x = load_fq(inx + iP); P.y = load_fq(iny + iP);
+            Q.x = load_fq(inx + iP + rp); Q.y = load_fq(iny + iP + rp);
+        }
+        Fq d;
+        const int kind = ba_classify(P, Q, d);
+        Affine S;
+        if (kind == BA_NONE) {
+            if (P.is_identity()) S = Q;
+            else if (Q.is_identity()) S = P;
+            else S = Affine::identity();
+        } else {
+            Fq inv_d = run;
+            if (j > 0) inv_d = fp_mul(run, load_fq(prefix + (g - kBaThreads)));
+            run = fp_mul(run, d);
+            Fq num;
+            if (kind == BA_ADD) {
+                num = fp_sub(Q.y, P.y);
+            } else {
+                const Fq xx = fp_mul(P.x, P.x);
+                num = fp_add(fp_dbl(xx), xx);
+            }
+            const Fq lambda = fp_mul(num, inv_d);
+            const Fq x3 = fp_sub(fp_sub(fp_mul(lambda, lambda), P.x), Q.x);
+            S.x = x3;
+            S.y = fp_sub(fp_mul(lambda, fp_sub(P.x, x3)), P.y);
+        }
+        store_fq(outx + g, S.x);
+        store_fq(outy + g, S.y);
+    }
+}
+
+// warp per row: totals[row] = sum of the row's `cnt` points, point i of row r at [i * rp + r] of the x and y arrays.
+// (A block per row with a shared-memory tree -- 9 additions deep instead of 13 -- was measured and is slower, 2.66 against
+// 2.62 ms per cfg1 commit: the kernel's cost is the ~256 XYZZ additions per row, not their depth.)
+__global__ void __launch_bounds__(kMultSumThreads)
+k_mult_sum_rows_t(const Fq* __restrict__ ptsx, const Fq* __restrict__ ptsy, uint32_t cnt, uint32_t rp, int rows,
+                  XYZZ* __restrict__ totals) {
+    const int lane = threadIdx.x & 31;
+    const int row = (int)((blockIdx.x * (unsigned)kMultSumThreads + threadIdx.x) >> 5);
+    if (row >= rows) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        Affine p;
+        p.x = load_fq(ptsx + (size_t)i * rp + row);
+        p.y = load_fq(ptsy + (size_t)i * rp + row);
+        if (!p.is_identity()) xyzz_add_mixed_call(&acc, &p);
+    }
+    for (int stride = 16; stride >= 1; stride >>= 1) {
+        XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
+        if (lane >= stride) o = XYZZ::identity();
+        xyzz_add_call(&acc, &o);
+    }
+    if (lane == 0) store_xyzz(totals + row, acc);
 }
 
 // warp per row: totals[row] = sum of the row's `cnt` affine points.  Lanes add cnt / 32 points each (mixed additions), a

@@ -51,16 +51,18 @@ struct sbn_ctx {
     long ba_batch = 0;      // pairs per thread in a round; 0 = auto
     long leaf_m = 0;        // buckets per leaf thread of the two-level reduction; 0 = auto
     uint64_t launches = 0, h2d = 0, d2h = 0;
+    uint64_t pool_flushes = 0;         // times an allocation failure emptied the buffer pool (dev_malloc)
+    uint64_t mult_fallbacks = 0;       // digit-multiple tables that could not be allocated: those sets use the bucket pipeline
     // grow-only workspaces
     struct Slot {          // one in-flight chunk of rows: private workspace
         DevBuf entries, tstart, tasks, partials, heavy, pairs;
         DevBuf pts[3], prefix, other, wtot, winv;      // batched-affine rounds (ba_kernels.cuh)
         DevBuf zagg;                                   // per-group scalar sums when the generator set has duplicates
-    } slots[2];
+    } slots[4];
     // Pipeline streams.  The latency-bound stages (sort, split-bucket fold, bucket reduction) run on a HIGH priority
     // stream and the IMAD-bound accumulation on LOW priority ones, so that while chunk i accumulates, the blocks of
     // sort(i+1) and reduce(i-1) are placed first as accumulation blocks retire and fill its idle issue slots.
-    cudaStream_t hi = nullptr, lo[2] = {nullptr, nullptr};
+    cudaStream_t hi = nullptr, lo[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
@@ -69,6 +71,13 @@ struct sbn_ctx {
     long mult_max_mb = 6144;           // largest digit-multiple table built for a commit's generator set (MiB); 0 = none
     long mult_rounds = 0;              // batched-affine rounds of the tabulated-sum path; 0 = auto (mult_rounds_for)
     long mult_min_rows = 256;          // commits of at least this many rows take the tabulated-sum path
+    long mult_streams = 2;             // chunks of the tabulated-sum path in flight (streams / workspaces), 1..4
+    long ba_minb = 3;                  // finish pass register target: resident CTAs per SM (3: 80 registers, 4: 64)
+    long ba_prefetch = 0;              // round 1 (measured: loses 5 %): entries read two pairs ahead, table points prefetched into L2 one pair ahead
+    long finish_smem_kb = 0;           // dynamic shared memory requested by the finish pass: caps its resident blocks so that a prefix pass of the other stream co-resides
+    long prefix_smem_kb = 0;
+    long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
+    long mult_layout = 1;              // 1: position-major lists (a warp = 32 rows at one table column); 0: row-major (round 1)
     long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
     // allocates and releases ~5 GB of them, and cudaFree costs ~35 ms per 268 MB buffer (574 ms per keyless-scale proof).
@@ -99,7 +108,7 @@ struct sbn_bases {
     Affine* small = nullptr;   // short sets (n_cols <= kSmallMaxCols): every digit multiple of every generator (small_kernels.cuh)
     // every digit multiple of the n1 table columns for many-row commits (mult_kernels.cuh), built on the first such commit
     Affine* mult = nullptr;
-    int mc = 0, mW = 0, mult_tried = 0;
+    int mc = 0, mW = 0, mult_tried = 0, mult_fails = 0;
 };
 
 #define SBN_CUDA(ctx, call)                                                                      \
@@ -117,6 +126,34 @@ struct sbn_bases {
         if (_s != SBN_OK) return _s; \
     } while (0)
 
+static constexpr size_t kPoolMinBytes = size_t(1) << 20, kPoolMaxBytes = size_t(48) << 30;
+
+static void pool_flush(sbn_ctx* ctx) {
+    for (auto& e : ctx->mem_pool) cudaFree(e.second);
+    ctx->mem_pool.clear();
+    ctx->mem_pool_bytes = 0;
+}
+// cudaMalloc for everything that is not pooled.  The pool may be sitting on tens of GB of released buffers: when the
+// allocator says no, the sticky error is cleared, the pool is emptied (after the work that may still read its buffers has
+// drained) and the allocation is tried once more, so that a long-lived prover does not see a spurious SBN_ERR_OOM.
+static cudaError_t dev_malloc(sbn_ctx* ctx, void** out, size_t bytes) {
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        if (!ctx->mem_pool.empty()) {
+            cudaDeviceSynchronize();
+            pool_flush(ctx);
+            ctx->pool_flushes++;
+            e = cudaMalloc(out, bytes);
+            if (e == cudaErrorMemoryAllocation) cudaGetLastError();
+        }
+    }
+    if (e != cudaSuccess) *out = nullptr;
+    return e;
+}
+template <class T>
+static cudaError_t dev_malloc(sbn_ctx* ctx, T** out, size_t bytes) { return dev_malloc(ctx, (void**)out, bytes); }
+
 static int ensure(sbn_ctx* ctx, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return SBN_OK;
     if (b.p) {
@@ -126,16 +163,9 @@ static int ensure(sbn_ctx* ctx, DevBuf& b, size_t bytes) {
         b.cap = 0;
     }
     size_t want = bytes + bytes / 8;
-    SBN_CUDA(ctx, cudaMalloc(&b.p, want));
+    SBN_CUDA(ctx, dev_malloc(ctx, &b.p, want));
     b.cap = want;
     return SBN_OK;
-}
-static constexpr size_t kPoolMinBytes = size_t(1) << 20, kPoolMaxBytes = size_t(48) << 30;
-
-static void pool_flush(sbn_ctx* ctx) {
-    for (auto& e : ctx->mem_pool) cudaFree(e.second);
-    ctx->mem_pool.clear();
-    ctx->mem_pool_bytes = 0;
 }
 // Size class of a pooled buffer: table-sized requests recur with exact sizes (powers of two times 32 B); small ones (the
 // per-layer scratch of the sumchecks and the bullet reduction) are rounded up to a power of two so that they recur too --
@@ -156,13 +186,7 @@ static cudaError_t pool_alloc(sbn_ctx* ctx, void** out, size_t bytes) {
             ctx->pool_live[*out] = cls;
             return cudaSuccess;
         }
-    cudaError_t e = cudaMalloc(out, cls);
-    if (e == cudaErrorMemoryAllocation && !ctx->mem_pool.empty()) {
-        cudaGetLastError();
-        cudaStreamSynchronize(ctx->compute);
-        pool_flush(ctx);
-        e = cudaMalloc(out, cls);
-    }
+    cudaError_t e = dev_malloc(ctx, out, cls);
     if (e == cudaSuccess) ctx->pool_live[*out] = cls;
     return e;
 }
@@ -294,18 +318,20 @@ extern "C" int sbn_ctx_create(int device, sbn_ctx** out) {
          cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
          cudaStreamCreateWithPriority(&ctx->lo[0], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
          cudaStreamCreateWithPriority(&ctx->lo[1], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&ctx->lo[2], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&ctx->lo[3], cudaStreamNonBlocking, prio_least) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->join_hi, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         delete ctx;
         return SBN_ERR_CUDA;
     }
-    if (const char* e = getenv("SBN_MULT_MAX_MB")) ctx->mult_max_mb = atol(e);      // bench / test hook: budget of the digit-multiple tables
-    if (const char* e = getenv("SBN_MULT_ROUNDS")) ctx->mult_rounds = atol(e);      // tuning hooks (scripts/sweep_mult.sh)
-    if (const char* e = getenv("SBN_BA_BATCH")) ctx->ba_batch = atol(e);
-    if (const char* e = getenv("SBN_BA_ROUNDS")) {     // test hook: default number of batched-affine rounds
-        long v = atol(e);
-        if (v >= -1 && v <= 3) ctx->ba_rounds = v;
-    }
+    // Bench / test / tuning hooks (scripts/sweep_mult.sh).  They go through sbn_ctx_set, so an out-of-range value is
+    // ignored exactly as the call would reject it (the batched-affine workspaces are sized for >= 4 pairs per thread).
+    static const char* const kEnvHooks[][2] = {{"SBN_MULT_MAX_MB", "mult_max_mb"}, {"SBN_MULT_ROUNDS", "mult_rounds"},
+                                               {"SBN_BA_BATCH", "ba_batch"},       {"SBN_BA_ROUNDS", "ba_rounds"},
+                                               {"SBN_MULT_STREAMS", "mult_streams"}};
+    for (auto& hk : kEnvHooks)
+        if (const char* e = getenv(hk[0])) sbn_ctx_set(ctx, hk[1], atol(e));
     *out = ctx;
     return SBN_OK;
 }
@@ -318,7 +344,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
                       &ctx->scratch2, &ctx->tabpart, &ctx->zkeep})
         release(*b);
-    for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1]})
+    for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto& sl : ctx->slots)
         for (DevBuf* b : {&sl.entries, &sl.tstart, &sl.tasks, &sl.partials, &sl.heavy, &sl.pairs, &sl.pts[0], &sl.pts[1], &sl.pts[2],
@@ -352,9 +378,49 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     } else if (!strcmp(key, "mult_max_mb")) {
         if (value < 0) return SBN_ERR_ARG;
         ctx->mult_max_mb = value;
+    } else if (!strcmp(key, "mult_rounds")) {
+        if (value < 0 || value > 12) return SBN_ERR_ARG;
+        ctx->mult_rounds = value;
     } else if (!strcmp(key, "mult_min_rows")) {
         if (value < 1) return SBN_ERR_ARG;
         ctx->mult_min_rows = value;
+    } else if (!strcmp(key, "mult_streams")) {
+        if (value < 1 || value > 4) return SBN_ERR_ARG;
+        ctx->mult_streams = value;
+    } else if (!strcmp(key, "ba_minb")) {
+        if (value != 3 && value != 4) return SBN_ERR_ARG;
+        ctx->ba_minb = value;
+    } else if (!strcmp(key, "finish_smem_kb") || !strcmp(key, "prefix_smem_kb")) {
+        if (value < 0 || value > 200) return SBN_ERR_ARG;
+        (key[0] == 'f' ? ctx->finish_smem_kb : ctx->prefix_smem_kb) = value;
+        const int bytes = (int)value << 10;
+        cudaSetDevice(ctx->device);
+        if (key[0] == 'f') {
+            cudaFuncSetAttribute(k_bat_finish<true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_finish<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_finish<true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_finish<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_finish<false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_finish<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        } else {
+            cudaFuncSetAttribute(k_bat_prefix<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_prefix<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            cudaFuncSetAttribute(k_bat_prefix<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        }
+        if (cudaGetLastError() != cudaSuccess) return SBN_ERR_CUDA;
+    } else if (!strcmp(key, "ablate")) {
+        ctx->ablate = value;
+    } else if (!strcmp(key, "mult_layout")) {
+        ctx->mult_layout = value ? 1 : 0;
+    } else if (!strcmp(key, "ba_prefetch")) {
+        ctx->ba_prefetch = value ? 1 : 0;
+    } else if (!strcmp(key, "l2_fetch")) {      // cudaLimitMaxL2FetchGranularity: the table gathers are random 64 B reads
+        if (value != 32 && value != 64 && value != 128) return SBN_ERR_ARG;
+        if (cudaSetDevice(ctx->device) != cudaSuccess ||
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value) != cudaSuccess) {
+            cudaGetLastError();
+            return SBN_ERR_CUDA;
+        }
     } else if (!strcmp(key, "tab_max_mb")) {
         if (value < 0) return SBN_ERR_ARG;
         ctx->tab_max_mb = value;
@@ -394,6 +460,16 @@ extern "C" int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* launches, uint64_t* h2d,
     if (h2d) *h2d = ctx->h2d;
     if (d2h) *d2h = ctx->d2h;
     if (reset) ctx->launches = ctx->h2d = ctx->d2h = 0;
+    return SBN_OK;
+}
+
+extern "C" int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return SBN_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    out[0] = ctx->mem_pool_bytes;
+    out[1] = ctx->pool_flushes;
+    out[2] = ctx->mult_fallbacks;
+    out[3] = ctx->mem_pool.size();
     return SBN_OK;
 }
 
@@ -501,13 +577,13 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
         return code;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&b->orig, sizeof(Affine) * b->n_cols)) != cudaSuccess) {
+    if ((e = dev_malloc(ctx, &b->orig, sizeof(Affine) * b->n_cols)) != cudaSuccess) {
         ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
         return fail(SBN_ERR_OOM);
     }
-    if ((e = cudaMalloc(&dbases, sizeof(Affine) * b->n1)) != cudaSuccess ||
-        (e = cudaMalloc(&dinf, b->n1)) != cudaSuccess ||
-        (e = cudaMalloc(&b->table, sizeof(Affine) * (size_t)b->W * b->n1)) != cudaSuccess) {
+    if ((e = dev_malloc(ctx, &dbases, sizeof(Affine) * b->n1)) != cudaSuccess ||
+        (e = dev_malloc(ctx, &dinf, b->n1)) != cudaSuccess ||
+        (e = dev_malloc(ctx, &b->table, sizeof(Affine) * (size_t)b->W * b->n1)) != cudaSuccess) {
         ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
         return fail(SBN_ERR_OOM);
     }
@@ -526,9 +602,9 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
         }
     }
     if (b->dedup) {
-        if ((e = cudaMalloc(&b->gptr, gptr.size() * sizeof(uint32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&b->gcols, gcols.size() * sizeof(uint32_t))) != cudaSuccess ||
-            (e = cudaMalloc(&b->gbig, std::max<size_t>(1, gbig.size()) * sizeof(uint32_t))) != cudaSuccess ||
+        if ((e = dev_malloc(ctx, &b->gptr, gptr.size() * sizeof(uint32_t))) != cudaSuccess ||
+            (e = dev_malloc(ctx, &b->gcols, gcols.size() * sizeof(uint32_t))) != cudaSuccess ||
+            (e = dev_malloc(ctx, &b->gbig, std::max<size_t>(1, gbig.size()) * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMemcpy(b->gptr, gptr.data(), gptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
             (e = cudaMemcpy(b->gcols, gcols.data(), gcols.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess ||
             (gbig.size() && (e = cudaMemcpy(b->gbig, gbig.data(), gbig.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) ||
@@ -559,7 +635,7 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
     const size_t tab_bytes = (size_t)kSmallW * b->n_cols * kSmallD * sizeof(Affine);
     if (b->n_cols <= kSmallMaxCols || (b->has_g1 && tab_bytes <= ((size_t)ctx->tab_max_mb << 20))) {
         const size_t entries = (size_t)kSmallW * b->n_cols * kSmallD;
-        if ((e = cudaMalloc(&b->small, entries * sizeof(Affine))) != cudaSuccess) {
+        if ((e = dev_malloc(ctx, &b->small, entries * sizeof(Affine))) != cudaSuccess) {
             ctx->last_error = std::string("sbn_bases_create cudaMalloc: ") + cudaGetErrorString(e);
             return fail(SBN_ERR_OOM);
         }
@@ -725,6 +801,18 @@ static int stage_sort(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, const
 static int ba_pairs_per_thread(const sbn_ctx* ctx, size_t npairs) {
     if (ctx->ba_batch) return (int)ctx->ba_batch;
     return (int)std::max<size_t>(4, std::min<size_t>(32, npairs / 150000));   // keep >= ~150k threads in a round
+}
+
+// Pairs per thread of a round of the tabulated-sum path.  Both passes of a round hold kBatSlots = 148 SMs x 4 resident
+// blocks (k_bat_prefix: 58 registers; k_bat_finish at its 64-register target); the grid is sized to fill a whole number of
+// such waves -- a 1.3-wave grid leaves a third of the machine idle for the length of a block -- with at most ~20 pairs per
+// thread (longer chains lose more to the tail than they save on the per-thread inversion bookkeeping) and at least 4.
+static int bat_pairs_per_thread(const sbn_ctx* ctx, size_t npairs) {
+    if (ctx->ba_batch) return (int)ctx->ba_batch;
+    const size_t wave = (size_t)148 * (ctx->ba_minb == 4 ? 4 : 3) * kBaThreads;     // pairs of one wave at one pair per thread
+    const size_t waves = std::max<size_t>(1, (npairs + wave * 20 - 1) / (wave * 20));
+    const size_t B = (npairs + wave * waves - 1) / (wave * waves);
+    return (int)std::max<size_t>(4, B);
 }
 
 static int stage_accumulate(sbn_ctx* ctx, const sbn_bases* b, sbn_ctx::Slot& sl, int rows, cudaStream_t st, StageMarks& m) {
@@ -913,27 +1001,42 @@ static int tab_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
 // window width whose table fits mult_max_mb, provided the tabulated sum then costs clearly less than the bucket method
 // (W_m batched-affine additions of ~6.5 products against W additions of ~8 plus the bucket reduction).
 static void mult_try_build(sbn_ctx* ctx, sbn_bases* b) {
-    b->mult_tried = 1;
-    if (ctx->mult_max_mb <= 0) return;
+    if (ctx->mult_max_mb <= 0) return;     // not a decision about this set: a later, larger budget may still build one
     const double cost_cur = b->W * 8.0 + 2.0 * b->nb / double(b->n1) * 14.0;
     for (int c = kMultMaxBits; c >= 8; c--) {
         const int W = msm_num_windows(c);
         const uint64_t entries = (uint64_t)W * b->n1 << (c - 1);
         if (entries >= (1ull << 31) || entries * sizeof(Affine) > ((uint64_t)ctx->mult_max_mb << 20)) continue;
-        if (W * 6.5 >= 0.9 * cost_cur) return;          // smaller windows only cost more
-        if (cudaMalloc(&b->mult, entries * sizeof(Affine)) != cudaSuccess) { cudaGetLastError(); b->mult = nullptr; return; }
+        if (W * 6.5 >= 0.9 * cost_cur) { b->mult_tried = 1; return; }      // smaller windows only cost more: deliberate "no table"
+        if (dev_malloc(ctx, &b->mult, entries * sizeof(Affine)) != cudaSuccess) {
+            // The budget allowed the table but the device could not hold it (dev_malloc has already emptied the pool and
+            // retried).  Not remembered in mult_tried: the next many-row commit tries again.  Visible to the caller
+            // through sbn_ctx_counters2 / sbn_last_cuda_error instead of a silent switch to the slower pipeline.
+            b->mult = nullptr;
+            ctx->mult_fallbacks++;
+            if (++b->mult_fails >= 3) b->mult_tried = 1;      // stop asking for tens of GB on every commit
+            ctx->last_error = "digit-multiple table: cudaMalloc of " + std::to_string(entries * sizeof(Affine)) +
+                              " bytes failed; this commit runs through the bucket pipeline";
+            return;
+        }
         const uint64_t threads = (uint64_t)W * b->n1 * ((1u << (c - 1)) / kMultChunk);
         k_mult_fill<<<(unsigned)((threads + 63) / 64), 64, 0, ctx->compute>>>(b->table, b->n1, c, W, b->mult);   // window 0 of the tables = the bases
         ctx->launches++;
-        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute);
+        if (e != cudaSuccess) {
             cudaFree(b->mult);
             b->mult = nullptr;
+            ctx->mult_fallbacks++;
+            ctx->last_error = std::string("digit-multiple table build: ") + cudaGetErrorString(e);
             return;
         }
         b->mc = c;
         b->mW = W;
+        b->mult_tried = 1;
         return;
     }
+    b->mult_tried = 1;       // no window width fits the budget
 }
 
 static int mult_rounds_for(uint32_t used) {
@@ -949,12 +1052,13 @@ static int mult_rounds_for(uint32_t used) {
 static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R, const Fr* dblinds,
                        Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage, bool normalize) {
     size_t chunk = commit_chunk_rows(ctx, L);
-    if (ctx->chunk_rows <= 0 && L >= 512 && L <= chunk) chunk = (L + 1) / 2;
+    const size_t ns_max = (size_t)ctx->mult_streams;
+    if (ctx->chunk_rows <= 0 && L >= 512 && L <= chunk) chunk = (L + ns_max - 1) / ns_max;    // at least one chunk per stream
     std::vector<size_t> sched;
     {
         size_t done = 0;
         const size_t first = ctx->first_chunk_rows > 0 ? std::min<size_t>((size_t)ctx->first_chunk_rows, chunk) : chunk / 4;
-        if (host_Z && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
+        if ((host_Z || ctx->first_chunk_rows > 0) && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
         while (done < L) { size_t cr = std::min(chunk, L - done); sched.push_back(cr); done += cr; }
     }
     const size_t nchunks = sched.size();
@@ -965,10 +1069,13 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
     if (ctx->mult_rounds > 0) rounds = (int)std::min<long>(ctx->mult_rounds, 12);
     while (rounds > 1 && (used >> rounds) == 0) rounds--;
     const uint32_t stride = (used + (1u << rounds) - 1) >> rounds << rounds;
-    const size_t np1 = chunk * (size_t)stride / 2;
-    for (size_t k = 0; k < std::min<size_t>(2, nchunks); k++) {
+    const bool tr = ctx->mult_layout != 0;                 // position-major lists: rows padded to a multiple of 32
+    const size_t chunk_pad = tr ? (chunk + 31) / 32 * 32 : chunk;
+    const size_t np1 = chunk_pad * (size_t)stride / 2;
+    const size_t ns = std::max<size_t>(1, std::min(ns_max, nchunks));
+    for (size_t k = 0; k < ns; k++) {
         auto& sl = ctx->slots[k];
-        SBN_TRY(ensure(ctx, sl.entries, chunk * (size_t)stride * sizeof(uint32_t)));
+        SBN_TRY(ensure(ctx, sl.entries, chunk_pad * (size_t)stride * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.pts[0], np1 * sizeof(Affine)));
         SBN_TRY(ensure(ctx, sl.pts[1], (np1 / 2 + 1) * sizeof(Affine)));
         SBN_TRY(ensure(ctx, sl.prefix, np1 * sizeof(Fq)));
@@ -983,7 +1090,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
     size_t ev_idx = 0;
     StageMarks marks{ctx, ev_idx, ev_stage};
     const size_t sync_base = 3 * nchunks + 8;              // hand-off events live after the profiling events
-    if (!get_event(ctx, sync_base + nchunks + 2)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
+    if (!get_event(ctx, sync_base + nchunks + 4)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
     std::vector<size_t> row0(nchunks, 0);
     for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
     auto issue_copy = [&](size_t ci) -> int {
@@ -994,15 +1101,15 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
         return SBN_OK;
     };
     SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
-    for (cudaStream_t st : {ctx->lo[0], ctx->lo[1]}) SBN_CUDA(ctx, cudaStreamWaitEvent(st, ctx->fork, 0));
+    for (size_t k = 0; k < ns; k++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[k], ctx->fork, 0));
     if (host_Z) {
         SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
         SBN_TRY(issue_copy(0));
     }
     for (size_t ci = 0; ci < nchunks; ci++) {
         const int rows = (int)sched[ci];
-        auto& sl = ctx->slots[ci & 1];
-        cudaStream_t st = ctx->lo[ci & 1];
+        auto& sl = ctx->slots[ci % ns];
+        cudaStream_t st = ctx->lo[ci % ns];
         if (host_Z) {
             if (ci + 1 < nchunks) SBN_TRY(issue_copy(ci + 1));
             SBN_CUDA(ctx, cudaStreamWaitEvent(st, get_event(ctx, sync_base + ci), 0));
@@ -1016,6 +1123,56 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
             ctx->launches++;
             zc = (const Fr*)sl.zagg.p;
             bc = nullptr;
+        }
+        if (tr) {
+            const uint32_t rp = (uint32_t)((rows + 31) / 32 * 32);
+            const size_t ethreads = (size_t)rp * ((size_t)(Rk + 1) + (stride - used));
+            k_mult_entries_t<<<(unsigned)((ethreads + 255) / 256), 256, 0, st>>>(zc, bc, Rk, b->n1, c, W, stride, rows, rp,
+                                                                                 (uint32_t*)sl.entries.p);
+            ctx->launches++;
+            marks.mark(0, st);
+            const Fq *inx = nullptr, *iny = nullptr;
+            for (int k = 0; k < rounds; k++) {
+                const size_t npairs = ((size_t)rp * stride) >> (k + 1);
+                const int B = bat_pairs_per_thread(ctx, npairs);
+                const unsigned blocks = (unsigned)((npairs + (size_t)kBaThreads * B - 1) / ((size_t)kBaThreads * B));
+                Fq* outx = (Fq*)sl.pts[k & 1].p;
+                Fq* outy = outx + npairs;
+                const bool pf = ctx->ba_prefetch != 0, m4 = ctx->ba_minb == 4;
+                const long ab = ctx->ablate;
+                const size_t fsm = (size_t)ctx->finish_smem_kb << 10, psm = (size_t)ctx->prefix_smem_kb << 10;
+                if (k == 0) {
+                    auto pre = pf ? k_bat_prefix<true, true> : k_bat_prefix<true, false>;
+                    if (!(ab & 1))
+                        pre<<<blocks, kBaThreads, psm, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, nullptr, npairs, rp, B,
+                                                           (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                    if (!(ab & 4)) k_ba_invert<<<(blocks + 63) / 64, 64, 0, st>>>((const Fq*)sl.wtot.p, blocks, (Fq*)sl.winv.p);
+                    auto fin = m4 ? (pf ? k_bat_finish<true, 4, true> : k_bat_finish<true, 4, false>)
+                                  : (pf ? k_bat_finish<true, 3, true> : k_bat_finish<true, 3, false>);
+                    if (!(ab & 16))
+                        fin<<<blocks, kBaThreads, fsm, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, nullptr, npairs, rp, B,
+                                                           (const Fq*)sl.prefix.p, (const Fq*)sl.other.p, (const Fq*)sl.winv.p, outx, outy);
+                } else {
+                    if (!(ab & 2))
+                        k_bat_prefix<false><<<blocks, kBaThreads, psm, st>>>(nullptr, nullptr, inx, iny, npairs, rp, B, (Fq*)sl.prefix.p,
+                                                                           (Fq*)sl.other.p, (Fq*)sl.wtot.p);
+                    if (!(ab & 4)) k_ba_invert<<<(blocks + 63) / 64, 64, 0, st>>>((const Fq*)sl.wtot.p, blocks, (Fq*)sl.winv.p);
+                    auto fin = m4 ? k_bat_finish<false, 4> : k_bat_finish<false, 3>;
+                    if (!(ab & 32))
+                        fin<<<blocks, kBaThreads, fsm, st>>>(nullptr, nullptr, inx, iny, npairs, rp, B, (const Fq*)sl.prefix.p,
+                                                           (const Fq*)sl.other.p, (const Fq*)sl.winv.p, outx, outy);
+                }
+                inx = outx;
+                iny = outy;
+                ctx->launches += 3;
+            }
+            if (!(ctx->ablate & 8))
+                k_mult_sum_rows_t<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, st>>>(
+                    inx, iny, stride >> rounds, rp, rows, totals + row0[ci]);
+            ctx->launches++;
+            marks.mark(1, st);
+            SBN_CUDA(ctx, cudaGetLastError());
+            continue;
         }
         const unsigned ethreads = (unsigned)(Rk + 1) + (stride - used);
         k_mult_entries<<<dim3((ethreads + 255) / 256, (unsigned)rows), 256, 0, st>>>(zc, bc, Rk, b->n1, c, W, stride,
@@ -1033,15 +1190,17 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
                 k_ba_prefix<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
                                                                  (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
                 k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
-                k_ba_finish<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
-                                                                 (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
-                                                                 (const Fq*)sl.winv.p, out);
+                auto fin = ctx->ba_minb == 4 ? (ctx->ba_prefetch ? k_ba_finish<true, 4, true> : k_ba_finish<true, 4, false>)
+                                             : (ctx->ba_prefetch ? k_ba_finish<true, 3, true> : k_ba_finish<true, 3, false>);
+                fin<<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B, (const Fq*)sl.prefix.p,
+                                                   (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
             } else {
                 k_ba_prefix<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
                                                                   (Fq*)sl.other.p, (Fq*)sl.wtot.p);
                 k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
-                k_ba_finish<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p,
-                                                                  (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
+                auto fin = ctx->ba_minb == 4 ? k_ba_finish<false, 4, false> : k_ba_finish<false, 3, false>;
+                fin<<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (const Fq*)sl.prefix.p, (const Fq*)sl.other.p,
+                                                   (const Fq*)sl.winv.p, out);
             }
             in = out;
             ctx->launches += 3;
@@ -1052,7 +1211,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
         marks.mark(1, st);
         SBN_CUDA(ctx, cudaGetLastError());
     }
-    for (int k = 0; k < 2; k++) {
+    for (size_t k = 0; k < ns; k++) {
         cudaEvent_t e = get_event(ctx, sync_base + nchunks + k);
         SBN_CUDA(ctx, cudaEventRecord(e, ctx->lo[k]));
         SBN_CUDA(ctx, cudaStreamWaitEvent(main, e, 0));
@@ -1066,9 +1225,25 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
     return SBN_OK;
 }
 
+static int run_commit_inner(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
+                            const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
+                            bool normalize);
+// Every commit goes through here.  The pipeline forks `main` into the copy / hi / lo streams and joins them at the very
+// end; an early error return skips that join, so the streams are drained here before the caller releases or reuses the
+// buffers they may still be reading (the pool hands buffers out again in `compute` order only).
 static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                       const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                       bool normalize = true) {
+    const int rc = run_commit_inner(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
+    if (rc != SBN_OK) {
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+    }
+    return rc;
+}
+static int run_commit_inner(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
+                            const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
+                            bool normalize) {
     if (L >= (size_t)ctx->mult_min_rows && !b->has_g1 && ctx->mult_max_mb > 0) {
         if (!b->mult_tried) mult_try_build(ctx, const_cast<sbn_bases*>(b));
         if (b->mult) return mult_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
@@ -1557,7 +1732,8 @@ extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_
              pool_alloc(ctx, &st->partial, 2 * (st->max_blocks + 1) * sizeof(XYZZ)) == cudaSuccess &&
              pool_alloc(ctx, &st->terms, 6 * sizeof(XYZZ)) == cudaSuccess;
     if (!ok) { bullet_free(st); ctx->last_error = "sbn_bullet_begin: cudaMalloc failed"; return SBN_ERR_OOM; }
-    auto fail = [&](int code) { bullet_free(st); return code; };
+    // a failed commit may leave kernels of the pipeline streams in flight: drain them before the buffers return to the pool
+    auto fail = [&](int code) { cudaDeviceSynchronize(); cudaGetLastError(); bullet_free(st); return code; };
 #define BCUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e); return fail(SBN_ERR_CUDA); } } while (0)
     BCUDA(cudaMemcpyAsync(st->a, a, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
     BCUDA(cudaMemcpyAsync(st->b, b, n * sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -2306,7 +2482,7 @@ extern "C" int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const u
         a->max_col = std::max(a->max_col, col_addrs[i]);
     }
     const size_t bytes = batch * N * sizeof(uint32_t);
-    if (cudaMalloc(&a->row, bytes) != cudaSuccess || cudaMalloc(&a->col, bytes) != cudaSuccess ||
+    if (dev_malloc(ctx, &a->row, bytes) != cudaSuccess || dev_malloc(ctx, &a->col, bytes) != cudaSuccess ||
         cudaMemcpyAsync(a->row, row_addrs, bytes, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
         cudaMemcpyAsync(a->col, col_addrs, bytes, cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
         cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
@@ -2349,9 +2525,9 @@ extern "C" int sbn_addrs_set_timestamps(sbn_addrs* a, const uint32_t* row_read_t
     const uint32_t* src_a[2] = {row_audit_ts, col_audit_ts};
     const size_t ops_bytes = a->batch * a->N * sizeof(uint32_t), mem_bytes = num_cells * sizeof(uint32_t);
     for (int k = 0; k < 2; k++) {
-        if (!a->read_ts[k]) SBN_CUDA(ctx, cudaMalloc(&a->read_ts[k], ops_bytes));
+        if (!a->read_ts[k]) SBN_CUDA(ctx, dev_malloc(ctx, &a->read_ts[k], ops_bytes));
         if (a->audit_ts[k] && a->num_cells != num_cells) { cudaFree(a->audit_ts[k]); a->audit_ts[k] = nullptr; }
-        if (!a->audit_ts[k]) SBN_CUDA(ctx, cudaMalloc(&a->audit_ts[k], mem_bytes));
+        if (!a->audit_ts[k]) SBN_CUDA(ctx, dev_malloc(ctx, &a->audit_ts[k], mem_bytes));
         SBN_CUDA(ctx, cudaMemcpyAsync(a->read_ts[k], src_r[k], ops_bytes, cudaMemcpyHostToDevice, ctx->compute));
         SBN_CUDA(ctx, cudaMemcpyAsync(a->audit_ts[k], src_a[k], mem_bytes, cudaMemcpyHostToDevice, ctx->compute));
     }
@@ -2400,7 +2576,8 @@ static int derefs_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs*
     p->ctx = ctx;
     p->len = len;
     if (pool_alloc(ctx, &p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_derefs_commit: cudaMalloc failed"; return SBN_ERR_OOM; }
-    auto fail = [&](int code) { pool_free(ctx, p->Z, len * sizeof(Fr)); delete p; return code; };
+    // the commit reads p->Z on the pipeline streams, which join `compute` only at its end: drain them before the release
+    auto fail = [&](int code) { cudaDeviceSynchronize(); cudaGetLastError(); pool_free(ctx, p->Z, len * sizeof(Fr)); delete p; return code; };
     const size_t tx = size_t(1) << nx, ty = size_t(1) << ny;
     int rc;
     if ((rc = ensure(ctx, ctx->scratch0, 2 * tx * sizeof(Fr))) != SBN_OK || (rc = ensure(ctx, ctx->scratch1, 2 * ty * sizeof(Fr))) != SBN_OK ||
@@ -2731,16 +2908,16 @@ extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_
     if (!m) return SBN_ERR_OOM;
     m->ctx = ctx; m->n = n; m->nnz = nnz; m->ncols = ncols;
     cudaStream_t s = ctx->compute;
-    bool ok = cudaMalloc(&m->ptr, (n + 1) * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&m->idx, std::max<size_t>(1, nnz) * sizeof(uint32_t)) == cudaSuccess &&
-              cudaMalloc(&m->val, std::max<size_t>(1, nnz) * sizeof(Fr)) == cudaSuccess &&
+    bool ok = dev_malloc(ctx, &m->ptr, (n + 1) * sizeof(uint32_t)) == cudaSuccess &&
+              dev_malloc(ctx, &m->idx, std::max<size_t>(1, nnz) * sizeof(uint32_t)) == cudaSuccess &&
+              dev_malloc(ctx, &m->val, std::max<size_t>(1, nnz) * sizeof(Fr)) == cudaSuccess &&
               cudaMemcpyAsync(m->ptr, ptr, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
               (nnz == 0 || (cudaMemcpyAsync(m->idx, idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s) == cudaSuccess &&
                             cudaMemcpyAsync(m->val, val, nnz * sizeof(Fr), cudaMemcpyHostToDevice, s) == cudaSuccess)) &&
               cudaStreamSynchronize(s) == cudaSuccess;
     if (ok && !heavy_rows.empty()) {
         m->nheavy = heavy_rows.size();
-        ok = cudaMalloc(&m->heavy, m->nheavy * sizeof(uint32_t)) == cudaSuccess &&
+        ok = dev_malloc(ctx, &m->heavy, m->nheavy * sizeof(uint32_t)) == cudaSuccess &&
              cudaMemcpy(m->heavy, heavy_rows.data(), m->nheavy * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) {

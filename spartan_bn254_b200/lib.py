@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsbn254.so")
 EXPORTS = [
     "sbn_strerror", "sbn_last_cuda_error", "sbn_version",
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
-    "sbn_ctx_last_commit_profile", "sbn_host_alloc", "sbn_host_free",
+    "sbn_ctx_last_commit_profile", "sbn_ctx_memory_stats", "sbn_host_alloc", "sbn_host_free",
     "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
     "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
@@ -118,6 +118,11 @@ class Context:
         self._check(self.lib.sbn_ctx_counters(self.h, C.byref(a), C.byref(b), C.byref(c), C.c_int(int(reset))),
                     "sbn_ctx_counters")
         return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
+
+    def memory_stats(self):
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.sbn_ctx_memory_stats(self.h, out), "sbn_ctx_memory_stats")
+        return dict(pool_bytes=int(out[0]), pool_flushes=int(out[1]), mult_table_fallbacks=int(out[2]), pool_buffers=int(out[3]))
 
     def last_commit_profile(self):
         ms = (C.c_float * 4)()
