@@ -47,7 +47,7 @@ FQMUL_PER_MIXED_ADD = 10   # XYZZ madd-2008-s: 8M + 2S
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg1_1024x1024", choices=sorted(WORKLOADS))
@@ -63,6 +63,9 @@ def parse():
                          "window whose table fits is tabulated once and kept resident; 0 = bucket pipeline only; the "
                          "library's own default is 6144")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="skip the strong-scaling leg (BASELINE configs[2]: 4096 x 8192 derefs-shaped commit divided by rows across the GPUs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing check of sampled commitments against the oracle")
     ap.add_argument("--no-prove", action="store_true",
                     help="skip the second half of BASELINE.json's metric: the keyless-shaped end-to-end prove time")
     return ap.parse_args()
@@ -124,17 +127,29 @@ def run_reference(args, rank, world):
     orc.build()
     rows_per_gpu, R = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_rows = max(cores, min(rows_per_gpu, 8 * cores))     # bounded sample of the same workload
     G, h = orc.multi_commit_gens(b"bench-gens", R)              # any valid generators: cost is scalar-driven
-    Z = synth.uniform_scalars(1, sample_rows * R)
+    Z = synth.uniform_scalars(1, rows_per_gpu * R)
+    # one untimed pass over `cores` rows sizes the step: every row of the workload when K steps of that fit ~150 s,
+    # otherwise the largest whole multiple of the thread count that does (stated in `sample`)
+    t0 = time.perf_counter()
+    orc.hyrax_commit(G, h, Z[: cores * R], cores, R, None, threads=0)
+    t_row = time.perf_counter() - t0                            # seconds per batch of `cores` rows (one per thread)
+    per_full = t_row * rows_per_gpu / cores
+    sample_rows = rows_per_gpu
+    if per_full * (args.steps + min(args.warmup, 1)) > 150.0:
+        sample_rows = max(cores, int(150.0 / (args.steps + 1) / t_row) * cores)
+        sample_rows = min(sample_rows, rows_per_gpu)
+    Z = Z[: sample_rows * R]
     for _ in range(min(args.warmup, 1)):
-        orc.hyrax_commit(G, h, Z[: cores * R], cores, R, None, threads=0)
+        orc.hyrax_commit(G, h, Z, sample_rows, R, None, threads=0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         orc.hyrax_commit(G, h, Z, sample_rows, R, None, threads=0)
     dt = time.perf_counter() - t0
     value = args.steps * sample_rows * R / dt
-    sample = f"{sample_rows} of {rows_per_gpu} rows x {R} generators per step, uniform scalars, zero blinds"
+    sample = (f"{sample_rows} of {rows_per_gpu} rows x {R} generators per step" +
+              (" (every row of the workload)" if sample_rows == rows_per_gpu else " (bounded sample)") +
+              ", uniform scalars, zero blinds")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -142,7 +157,12 @@ def run_reference(args, rank, world):
         "config": {"workload": args.workload, "rows_per_gpu": rows_per_gpu, "generators": R,
                    "note": "CPU restatement of hyrax.rs:253-267 -> commitments.rs:144-154 -> signed-window Pippenger; "
                            "the Rust reference cannot be built offline (no cargo, arkworks not vendored)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "points_per_s_per_thread": value / cores,
+                         "reference_published_points_per_s_per_thread": 2.0e5,
+                         "published_note": "arkworks on ONE M2-Max thread (BASELINE.md 1: 166.2 s for the keyless derefs commitment); "
+                                           "the C port is slower per thread than arkworks -- quote any GPU/CPU ratio beside both"},
+        "same_config": sample_rows == rows_per_gpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -212,7 +232,7 @@ def main():
     nbuf = min(nbuf, 8)
     if L * R * 32 > (1 << 30):
         nbuf = 1                                            # one 2 GiB input already exceeds L2 many times over
-    host_bufs, dev_bufs = [], []
+    host_bufs, dev_bufs, page_bufs = [], [], []
     for i in range(nbuf):
         seed = 1 + 131 * rank + i
         if args.scalars == "uniform":
@@ -221,21 +241,35 @@ def main():
             z = ctx.fr_from_canonical(synth.small_scalars_canonical(seed, L * R))
         else:
             z = synth.derefs_scalars((L * R).bit_length() - 1, seed_table=2 + seed, seed_addr=3 + seed)
+        page_bufs.append(z)                                 # pageable numpy memory: what a Rust Vec<Scalar> is
         t = torch.from_numpy(z.view(np.int64)).pin_memory()
         host_bufs.append(t)
         dev_bufs.append(t.to(dev, non_blocking=False))
-    dC = torch.empty((L, 8), dtype=torch.int64, device=dev)
-    dinf = torch.empty((L,), dtype=torch.uint8, device=dev)
-    gather = [torch.empty_like(dC) for _ in range(world)] if world > 1 else None
+    # two output buffers: with N > 1 the all-gather of step i runs on NCCL's stream underneath the commit of step i + 1
+    dCs = [torch.empty((L, 8), dtype=torch.int64, device=dev) for _ in range(2)]
+    dinfs = [torch.empty((L,), dtype=torch.uint8, device=dev) for _ in range(2)]
+    dC, dinf = dCs[0], dinfs[0]
+    gathers = [[torch.empty_like(dCs[0]) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    pending = [None, None]
     hC = torch.empty((L, 8), dtype=torch.int64).pin_memory()
     hinf = torch.empty((L,), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.current_stream()
 
-    def step_device(i):
-        ctx.hyrax_commit_device(bases, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(),
+    def step_device(i, b=None):
+        k = i & 1
+        if pending[k] is not None:          # the gather of step i - 2 still reads this output buffer
+            pending[k].wait()
+            pending[k] = None
+        ctx.hyrax_commit_device(b or bases, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dCs[k].data_ptr(), dinfs[k].data_ptr(),
                                 stream=stream.cuda_stream)
         if world > 1:
-            dist.all_gather(gather, dC)
+            pending[k] = dist.all_gather(gathers[k], dCs[k], async_op=True)
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()            # the timed stream waits for the collective: it is inside the timed region
+                pending[k] = None
 
     def step_e2e(i):
         ctx.hyrax_commit_raw(bases, host_bufs[i % nbuf].data_ptr(), L, R, 0, hC.data_ptr(), hinf.data_ptr())
@@ -245,12 +279,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_device(steps, warm, b=None):
+        for i in range(warm):
+            step_device(i, b)
+        drain()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for i in range(steps):
+            step_device(warm + i, b)
+        drain()
+        a1.record(stream)
+        barrier()
+        tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     # ---- integer roofline denominator, measured live (MEASURED_PEAKS.json has no integer-pipe figure)
     peak_imad = ctx.microbench(0)
 
-    # ---- device-resident timing (library defaults: chunks of 1024 rows, two pipeline slots)
+    # ---- the first commit builds the digit-multiple table of the generator set (one-off, outside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    step_device(0)
+    drain()
+    barrier()
+    first_call_s = time.perf_counter() - t0
+
+    # ---- device-resident timing (library defaults: two chunks on two streams)
     for i in range(args.warmup):
         step_device(i)
+    drain()
     barrier()
     ctx.counters(reset=True)
     sampler = ClockSampler(local_rank)
@@ -262,6 +322,7 @@ def main():
     e0.record(stream)
     for i in range(args.steps):
         step_device(args.warmup + i)
+    drain()
     e1.record(stream)
     barrier()
     w1 = time.time()
@@ -274,30 +335,82 @@ def main():
     ms_max = float(t.item())
     points_per_step = L * R * world
     value = points_per_step * args.steps / (ms_max * 1e-3)
+    last_buf = (args.warmup + args.steps - 1) % nbuf
+    dC, dinf = dCs[(args.warmup + args.steps - 1) & 1], dinfs[(args.warmup + args.steps - 1) & 1]
+    table_build_s = max(0.0, first_call_s - ms_max / args.steps * 1e-3)
+
+    # ---- parity of the TIMED configuration: sampled rows of the last timed commit against the CPU oracle (the oracle is the
+    #      checker here, never the thing measured; rank 0 only)
+    parity = None
+    if not args.no_parity and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as orc
+        orc.build()
+        nchk = min(L, 32)
+        rows = sorted(set(int(x) for x in np.linspace(0, L - 1, nchk)))
+        zs = page_bufs[last_buf].reshape(L, R, 4)[rows].reshape(-1, 4)
+        C_ref, inf_ref = orc.hyrax_commit(G, h, np.ascontiguousarray(zs), len(rows), R, None, threads=0)
+        C_gpu = dC.cpu().numpy().view(np.uint64)[rows]
+        inf_gpu = dinf.cpu().numpy()[rows]
+        ok = bool(np.array_equal(C_gpu, C_ref) and np.array_equal(inf_gpu, inf_ref))
+        parity = {"parity_checked": ok, "rows_checked": len(rows),
+                  "what": "rows of the last timed commit (device-resident path, this table budget) vs oracle.hyrax_commit, bit-exact affine limbs + infinity flags"}
+        if not ok:
+            raise SystemExit("bench.py: the timed commit differs from the oracle on sampled rows -- refusing to print a number")
 
     # ---- stage profile on the library's own stream (CUDA events inside the library): the first `prof_rows` rows as ONE
     #      chunk, so the stages run back to back and each event pair brackets exactly one launch set of that stage
     #      (a single chunk of every row would need > 100 GB of workspace at 8192 x 8192)
     prof_rows = L if L * R <= (1 << 24) else max(1024, (1 << 24) // R)
     ctx.set("chunk_rows", prof_rows)
-    ctx.hyrax_commit_device(bases, dev_bufs[0].data_ptr(), prof_rows, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=0)
-    prof = ctx.last_commit_profile()
-
-    # ---- end to end: pinned host buffers through the host-pointer C ABI (library defaults: a short first chunk, then
-    #      chunks of 1024 rows; the H2D copy of chunk i+1 overlaps the kernels of chunk i)
+    ctx.set("mult_streams", 1)
+    prof_ms = []
+    for _ in range(5):
+        ctx.hyrax_commit_device(bases, dev_bufs[0].data_ptr(), prof_rows, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=0)
+        prof_ms.append(ctx.last_commit_profile())
+    prof = prof_ms[-1]
+    acc_ms = sorted(p["accumulate"]["ms"] for p in prof_ms[1:])[len(prof_ms[1:]) // 2]      # median of the warm ones
+    ctx.set("mult_streams", 2)
     ctx.set("chunk_rows", 0)      # back to the library default (auto)
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = points_per_step * args.steps / float(t.item())
+
+    # ---- end to end: host buffers through the host-pointer C ABI (library defaults: a short first chunk, then chunks; the
+    #      H2D copy of chunk i+1 overlaps the kernels of chunk i).  Pinned buffers first, then PAGEABLE ones (what an
+    #      unmodified Rust caller's Vec<Scalar> is; sbn_host_alloc exists for callers that can allocate pinned)
+    def timed_e2e(fn, steps):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        tt0 = time.perf_counter()
+        for i in range(steps):
+            fn(args.warmup + i)
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - tt0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return points_per_step * steps / float(tt.item())
+
+    e2e_value = timed_e2e(step_e2e, args.steps)
+    pC = np.empty((L, 8), dtype=np.uint64)
+    pinf = np.empty((L,), dtype=np.uint8)
+
+    def step_pageable(i):
+        ctx.hyrax_commit_raw(bases, page_bufs[i % nbuf].ctypes.data, L, R, 0, pC.ctypes.data, pinf.ctypes.data)
+
+    e2e_pageable = timed_e2e(step_pageable, max(3, min(args.steps, 50)))
+
+    # ---- the same commit under the LIBRARY's default table budget (6144 MiB: c = 13 at 1025 generators) -- the headline above
+    #      uses --table-mb; a deployment that cannot spare that much HBM gets this number
+    default_budget = None
+    if args.table_mb != 6144 and L * R <= (1 << 24):
+        ctx.set("mult_max_mb", 6144)
+        bases_d = ctx.bases(G, h)
+        nd = max(3, min(args.steps, 50))
+        ms_d = timed_device(nd, args.warmup, bases_d)
+        bits_d, bytes_d = bases_d.mult_table()
+        default_budget = {"value": points_per_step * nd / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / nd,
+                          "table_budget_mb": 6144, "table_window_bits": bits_d, "table_bytes": bytes_d, "steps": nd}
+        bases_d.close()
+        ctx.set("mult_max_mb", args.table_mb)
 
     # ---- the same commit on the REFERENCE's generator set (MultiCommitGens::new, commitments.rs:31-62): about two thirds of
     #      those generators are the same point, which the library merges (k_aggregate_rows), so the real prover's commits
@@ -307,23 +420,19 @@ def main():
         gref = MultiCommitGens.new(R, b"gens_r1cs_eval", ctx)
         bases_ref = ctx.bases(gref.G, gref.h)
         distinct_pts = len({bytes(p) for p in np.concatenate([gref.G, gref.h.reshape(1, 8)]).view(np.uint8).reshape(R + 1, 64)})
-        for i in range(args.warmup):
-            ctx.hyrax_commit_device(bases_ref, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(), stream=stream.cuda_stream)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(stream)
-        for i in range(args.steps):
-            ctx.hyrax_commit_device(bases_ref, dev_bufs[(args.warmup + i) % nbuf].data_ptr(), L, R, 0, dC.data_ptr(), dinf.data_ptr(),
-                                    stream=stream.cuda_stream)
-        r1.record(stream)
-        barrier()
-        tref = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tref, op=dist.ReduceOp.MAX)
-        ref_gens = {"value": points_per_step * args.steps / (float(tref.item()) * 1e-3), "unit": UNIT,
-                    "ms_per_step": float(tref.item()) / args.steps, "generators": R + 1, "distinct_points": distinct_pts,
+        nr = max(3, min(args.steps, 50))
+        tref = timed_device(nr, args.warmup, bases_ref)
+        ref_gens = {"value": points_per_step * nr / (tref * 1e-3), "unit": UNIT,
+                    "ms_per_step": tref / nr, "generators": R + 1, "distinct_points": distinct_pts,
                     "note": "MultiCommitGens::new(R, b\"gens_r1cs_eval\"): equal generators are merged by summing their scalars"}
         bases_ref.close()
+
+    # ---- BASELINE configs[2], strong scaling: the keyless derefs shape (4096 rows x 8192 generators) divided by rows across
+    #      the GPUs, every rank commits its block and the blocks are all-gathered.  Run at every N (N = 1 is the efficiency
+    #      denominator), so the driver's --gpus N sweep carries it.
+    strong = None
+    if not args.no_strong and args.workload == "cfg1_1024x1024" and args.scaling == "weak" and 4096 % world == 0:
+        strong = run_strong(ctx, synth, torch, dist, dev, stream, rank, world, args)
 
     # ---- "keyless prove time (s)": SNARK::prove of a synthetic keyless-shaped R1CS (2^20 constraints) through the GPU path,
     #      derefs commitment sharded by rows across the ranks (scripts/bench_snark.py).  The proof is not checked here -- the
@@ -343,74 +452,91 @@ def main():
                      "reference_published_s": 208.8}
 
     if rank == 0:
-        acc = prof["accumulate"]
-        W = (254 + bases.window_bits) // bases.window_bits
-        if args.scalars == "small":     # 21-bit values: only the windows that can hold a non-zero digit count as work
-            W = min(W, -(-22 // bases.window_bits))
-        # algorithmic integer work of the dominant kernel (bucket accumulation): one XYZZ mixed addition per
-        # (scalar, window) pair = W * 10 * 264 32-bit multiply-adds per point, all launches of a commit
-        alg_imad_acc = float(prof_rows) * R * W * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
-        achieved = alg_imad_acc / (acc["ms"] * 1e-3) if acc["ms"] > 0 else 0.0
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get(args.workload, {}).get("accumulate_stage_dram_bytes_per_commit")
-            except Exception:
-                traffic = None
-        # tabulated-sum path (mult_kernels.cuh): what the stage EXECUTES is one batched-affine addition (6 products) per
-        # (scalar, window) entry of the table's own window width, plus the short XYZZ tail
         mult_bits, mult_bytes = bases.mult_table()
-        executed = None
-        if mult_bits:
-            Wm = (254 + mult_bits) // mult_bits
-            executed = float(prof_rows) * (R + 1) * Wm * 6 * IMAD_PER_FQMUL / (acc["ms"] * 1e-3) if acc["ms"] > 0 else 0.0
+        path_bits = mult_bits or bases.window_bits            # window width of the path that was TIMED
+        W = (254 + path_bits) // path_bits
+        Wb = (254 + bases.window_bits) // bases.window_bits    # the bucket method's window count (SURVEY 8(d) accounting)
+        if args.scalars == "small":     # 21-bit values: only the windows that can hold a non-zero digit count as work
+            W = min(W, -(-22 // path_bits))
+            Wb = min(Wb, -(-22 // bases.window_bits))
+        # one XYZZ mixed addition per (scalar, window) pair of the BUCKET method = Wb * 10 * 264 IMAD per point
+        alg_imad_acc = float(prof_rows) * R * Wb * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
+        formula = alg_imad_acc / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
+        # what the timed path EXECUTES: tabulated sum = one batched-affine addition (6 products) per (scalar, window) entry of
+        # the table's own window width; bucket pipeline = one XYZZ mixed addition (10 products) per entry
+        per_entry = 6 if mult_bits else FQMUL_PER_MIXED_ADD
+        exec_imad_stage = float(prof_rows) * (R + 1) * W * per_entry * IMAD_PER_FQMUL
+        executed = exec_imad_stage / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
+        exec_imad_step = float(L) * (R + 1) * W * per_entry * IMAD_PER_FQMUL
+        step_s = ms_max / args.steps * 1e-3
+        traffic, traffic_note = stage_traffic(args.workload, mult_bits)
+        hbm_peak, hbm_src = hbm_peak_gbs()
         step_alg = A_ADDS_PER_POINT.get(R, 26.0) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         if args.scalars == "small":
-            step_alg = (W + 2.0 * (1 << (bases.window_bits - 1)) / R) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
+            step_alg = (Wb + 2.0 * (1 << (bases.window_bits - 1)) / R) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32x8 Montgomery (integer, IMAD.WIDE carry chains)", "data": "synthetic",
-            "config": {"workload": args.workload, "rows_per_gpu": L, "generators": R, "window_bits": bases.window_bits,
+            "config": {"workload": args.workload, "rows_per_gpu": L, "generators": R, "window_bits": path_bits,
+                       "path": "tabulated sum over the resident digit-multiple table" if mult_bits else "bucket pipeline",
+                       "bucket_pipeline_window_bits": bases.window_bits,
+                       "table_budget_mb": args.table_mb, "table_bytes": mult_bytes, "table_build_s": table_build_s,
+                       "table_note": "built once per generator set by the first commit of >= 256 rows, outside the timed region; "
+                                     "value_default_budget is the same commit under the library's default 6144 MiB",
                        "gens": args.gens, "scalars": args.scalars, "blinds": "zero (derefs-style, hyrax.rs:301-305)",
                        "l2": f"inputs rotated over {nbuf} buffers ({nbuf * L * R * 32 >> 20} MiB > 126 MiB L2)",
                        "points_counted": "L x R scalar-base pairs per GPU per step",
-                       "collective": "NCCL all_gather of the commitment vector per step" if world > 1 else "none (1 GPU)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": L * R * 32, "d2h_bytes_per_step": L * 65},
+                       "collective": ("NCCL all_gather of the commitment vector per step, issued asynchronously: it runs under the "
+                                      "next step's commit (two output buffers) and is waited for inside the timed region")
+                       if world > 1 else "none (1 GPU)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": L * R * 32, "d2h_bytes_per_step": L * 65,
+                    "host_memory": "pinned", "pageable_value": e2e_pageable,
+                    "pageable_note": "the same call from pageable numpy buffers (a Rust Vec<Scalar>); sbn_host_alloc gives callers pinned memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
                 "bound": "int32 multiply-add (IMAD pipe); not hbm, not tensor: modular integer arithmetic",
-                "kernel": ("accumulation stage as a batched-affine sum tree over tabulated digit multiples (k_ba_prefix / "
-                           "k_ba_invert / k_ba_finish per round + k_mult_sum_rows)") if mult_bits else
+                "kernel": ("accumulation stage as a batched-affine sum tree over tabulated digit multiples (k_bat_prefix / "
+                           "k_ba_invert / k_bat_finish per round + k_mult_sum_rows_t)") if mult_bits else
                           ("bucket accumulation stage (k_accumulate; with batched-affine rounds: k_ba_prefix / k_ba_invert / "
                            "k_ba_finish + k_accumulate_pts)"),
-                "achieved": achieved / 1e12, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
-                "frac": achieved / peak_imad if peak_imad else None, "traffic": traffic,
-                "frac_note": "algorithmic work is counted as SURVEY 8(d) defines it (W x 10 x 264 IMAD per point at the bucket "
-                             "method's window width, i.e. XYZZ mixed additions); the path does LESS than that -- a wider "
-                             "window (fewer entries per scalar) because the digit multiples are tabulated, and 6-product "
-                             "batched-affine additions -- so the algorithmic rate exceeds the pipe's peak; executed_frac is "
-                             "what the multiplier actually sustains",
-                "executed_frac": executed / peak_imad if (executed and peak_imad) else None,
-                "executed_note": "entries x 6 products x 264 IMAD over the stage time / peak" if executed else None,
+                "achieved": executed / 1e12, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
+                "frac": executed / peak_imad if peak_imad else None,
+                "frac_note": f"EXECUTED work of the stage: entries x {per_entry} Fq products x 264 IMAD / stage time / peak "
+                             f"(entries = rows x (R + 1) x {W} windows of {path_bits} bits)",
+                "executed_imad_per_launch_set": exec_imad_stage,
+                "kernel_ms_per_launch_set": acc_ms, "rows_per_launch_set": prof_rows,
+                "launch_set_note": "median of 4 warm commits of prof_rows rows as ONE chunk on ONE stream, CUDA events inside the "
+                                   "library around the stage's launches",
+                "whole_step_executed_frac": exec_imad_step / step_s / peak_imad if peak_imad else None,
+                "algorithmic_vs_formula": formula / peak_imad if peak_imad else None,
+                "algorithmic_vs_formula_note": "SURVEY 8(d)'s accounting (bucket method: W x 10 x 264 IMAD per point at the bucket "
+                                               "window width) over the stage time; NOT a utilisation -- the path does less work than "
+                                               "the formula assumes (wider window, 6-product additions), so this can exceed 1",
+                "whole_step_vs_formula": (value / world) * step_alg / peak_imad if peak_imad else None,
+                "traffic": traffic, "traffic_note": traffic_note,
+                "hbm_frac": (traffic / (acc_ms * 1e-3) / 1e9 / hbm_peak) if (traffic and acc_ms > 0 and hbm_peak) else None,
+                "hbm_peak_GBps": hbm_peak, "hbm_peak_source": hbm_src,
                 "digit_multiple_table": {"window_bits": mult_bits, "bytes": mult_bytes,
                                          "note": "d * 2^(k c) * G_j for every window k, generator j and digit d <= 2^(c-1), "
                                                  "resident in HBM, built once per generator set"} if mult_bits else None,
                 "peak_source": "measured live on this GPU: independent mad.lo.u32 streams (sbn_microbench kind 0); "
                                "MEASURED_PEAKS.json has no integer-pipe figure",
-                "algorithmic_imad_per_launch_set": alg_imad_acc,
-                "kernel_ms_per_launch_set": acc["ms"], "rows_per_launch_set": prof_rows,
-                "whole_step_frac": (value / world) * step_alg / peak_imad if peak_imad else None,
-                "whole_step_imad_alg_per_point": step_alg,
                 "hbm": {"algorithmic_bytes_per_step": L * R * 32 + L * 64,
-                        "achieved_GBps": (L * R * 32 + L * 64) / (ms_max / args.steps * 1e-3) / 1e9},
+                        "achieved_GBps": (L * R * 32 + L * 64) / step_s / 1e9},
             },
             "stage_ms": {k: v["ms"] for k, v in prof.items()}, "stage_rows": prof_rows,
+            "memory": ctx.memory_stats(),
         }
+        if parity is not None:
+            line.update(parity)
+        if default_budget is not None:
+            line["value_default_budget"] = default_budget
         if ref_gens is not None:
             line["reference_generators"] = ref_gens
+        if strong is not None:
+            line["strong_cfg2_4096x8192"] = strong
         if prove is not None:
             line["keyless_prove"] = prove
         if not args.no_cpu_baseline:
@@ -419,6 +545,83 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def source_sha16():
+    """Hash of the CUDA sources: profiles/roofline_traffic.json is stamped with it, so a DRAM-traffic figure measured on other
+    kernels is never printed as if it were current."""
+    import hashlib
+    hsh = hashlib.sha256()
+    csrc = os.path.join(ROOT, "spartan_bn254_b200", "csrc")
+    for d, _, files in sorted(os.walk(csrc)):
+        for f in sorted(files):
+            hsh.update(open(os.path.join(d, f), "rb").read())
+    return hsh.hexdigest()[:16]
+
+
+def stage_traffic(workload, mult_bits):
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        rec = json.load(open(tp)).get(workload, {})
+    except Exception:
+        return None, "profiles/roofline_traffic.json missing"
+    if rec.get("source_sha16") != source_sha16():
+        return None, ("stale: profiles/roofline_traffic.json was measured on other kernel sources (sha16 %s, now %s); re-run "
+                      "scripts/update_traffic.py on an ncu launch list" % (rec.get("source_sha16"), source_sha16()))
+    if rec.get("table_window_bits") != mult_bits:
+        return None, "profiles/roofline_traffic.json was measured with another table width"
+    return rec.get("accumulate_stage_dram_bytes_per_commit"), rec.get("source")
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (driver-written copy bandwidth)"
+    except Exception:
+        return 6459.0, "fallback: the pool's measured copy bandwidth as recorded in round 1 (MEASURED_PEAKS.json absent)"
+
+
+def run_strong(ctx, synth, torch, dist, dev, stream, rank, world, args):
+    import numpy as np
+    Ls, Rs = 4096 // world, 8192
+    Gs, hs = synth.distinct_generators(ctx, Rs)
+    ctx.set("mult_max_mb", max(args.table_mb, 50000) if args.table_mb else 0)     # c = 13 over 8193 generators is 43 GB
+    bs = ctx.bases(Gs, hs)
+    z = torch.from_numpy(synth.uniform_scalars(77 + rank, Ls * Rs).view(np.int64)).to(dev)
+    dCs = torch.empty((Ls, 8), dtype=torch.int64, device=dev)
+    dis = torch.empty((Ls,), dtype=torch.uint8, device=dev)
+    gat = [torch.empty_like(dCs) for _ in range(world)] if world > 1 else None
+
+    def step():
+        ctx.hyrax_commit_device(bs, z.data_ptr(), Ls, Rs, 0, dCs.data_ptr(), dis.data_ptr(), stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather(gat, dCs)
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n = 5
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(n):
+        step()
+    a1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tt = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item()) / n
+    bits, nbytes = bs.mult_table()
+    bs.close()
+    ctx.set("mult_max_mb", args.table_mb)
+    return {"ms_per_commit": ms, "value": 4096 * Rs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "rows_per_gpu": Ls,
+            "generators": Rs, "scaling": "strong", "steps": n, "table_window_bits": bits, "table_bytes": nbytes,
+            "inputs": "2 GiB / n_gpus of uniform scalars per GPU: larger than L2, not rotated",
+            "note": "BASELINE configs[2] (keyless derefs shape) divided by rows across the GPUs + all_gather of the blocks; "
+                    "time is the max over ranks"}
 
 
 if __name__ == "__main__":

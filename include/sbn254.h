@@ -123,6 +123,14 @@ int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size
 int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* bases, const void* dZ, size_t L_size, size_t R_size,
                             const void* dblinds, void* dC_out, void* dinf_out, void* stream);
 
+/* a7 on k GPUs of one process (sbn_ctx_create(n_gpus) became one context per device plus this call).
+ * Replaces the Rayon fan-out of reference hyrax.rs:259-265: the L rows are cut into k contiguous blocks, block i is
+ * committed by ctxs[i] over bases[i] (the same generators, created once per context) from its own host thread, and the
+ * blocks are written side by side into C_out / inf_out -- no inter-GPU exchange.  Same arguments, results and errors as
+ * sbn_hyrax_commit; the first non-zero status of any block is returned. */
+int sbn_hyrax_commit_multi(sbn_ctx* const* ctxs, const sbn_bases* const* bases, size_t k, const sbn_fr* Z, size_t L_size,
+                           size_t R_size, const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);
+
 /* ---- a6: GroupElement::msm_affine / vartime_multiscalar_mul (group.rs:143-175).
  * One variable-base MSM over caller-supplied points.  The reference swallows a length mismatch into
  * the identity (`unwrap_or_default`); here the caller passes one n, so that case cannot arise. */

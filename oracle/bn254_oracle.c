@@ -112,49 +112,49 @@ static inline uint64_t add4(uint64_t r[4], const uint64_t a[4], const uint64_t b
 }
 static inline int is_zero4(const uint64_t a[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
 
-static void fp_mul(int m, const ofp* a, const ofp* b, ofp* out) {
+/* Montgomery product, CIOS (the same word-serial algorithm as before) with the accumulator in five named words so that the
+ * compiler keeps it in registers and emits mul / adc chains. */
+#define ORC_MAC(lo, hi, a, b, c, d) do { u128 _t = (u128)(a) * (b) + (c) + (d); lo = (uint64_t)_t; hi = (uint64_t)(_t >> 64); } while (0)
+static inline __attribute__((always_inline)) void fp_mul(int m, const ofp* a, const ofp* b, ofp* out) {
     const field_t* F = &FIELDS[m];
-    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    const uint64_t p0 = F->p[0], p1 = F->p[1], p2 = F->p[2], p3 = F->p[3], inv = F->inv;
+    const uint64_t a0 = a->l[0], a1 = a->l[1], a2 = a->l[2], a3 = a->l[3];
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
     for (int i = 0; i < 4; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 4; j++) {
-            c += (u128)a->l[j] * b->l[i] + t[j];
-            t[j] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[4] = (uint64_t)c;
-        t[5] = (uint64_t)(c >> 64);
-        uint64_t mm = t[0] * F->inv;
-        c = (u128)mm * F->p[0] + t[0];
-        c >>= 64;
-        for (int j = 1; j < 4; j++) {
-            c += (u128)mm * F->p[j] + t[j];
-            t[j - 1] = (uint64_t)c;
-            c >>= 64;
-        }
-        c += t[4];
-        t[3] = (uint64_t)c;
-        t[4] = t[5] + (uint64_t)(c >> 64);
+        const uint64_t bi = b->l[i];
+        uint64_t c, t5;
+        ORC_MAC(t0, c, a0, bi, t0, 0);
+        ORC_MAC(t1, c, a1, bi, t1, c);
+        ORC_MAC(t2, c, a2, bi, t2, c);
+        ORC_MAC(t3, c, a3, bi, t3, c);
+        { u128 s = (u128)t4 + c; t4 = (uint64_t)s; t5 = (uint64_t)(s >> 64); }
+        const uint64_t mm = t0 * inv;
+        uint64_t dump;
+        ORC_MAC(dump, c, mm, p0, t0, 0);
+        (void)dump;
+        ORC_MAC(t0, c, mm, p1, t1, c);
+        ORC_MAC(t1, c, mm, p2, t2, c);
+        ORC_MAC(t2, c, mm, p3, t3, c);
+        { u128 s = (u128)t4 + c; t3 = (uint64_t)s; t4 = t5 + (uint64_t)(s >> 64); }
     }
-    uint64_t r[4] = {t[0], t[1], t[2], t[3]};
-    if (t[4] || geq(r, F->p)) sub4(r, r, F->p);
+    uint64_t r[4] = {t0, t1, t2, t3};
+    if (t4 || geq(r, F->p)) sub4(r, r, F->p);
     memcpy(out->l, r, 32);
 }
-static void fp_add(int m, const ofp* a, const ofp* b, ofp* out) {
+static inline __attribute__((always_inline)) void fp_add(int m, const ofp* a, const ofp* b, ofp* out) {
     const field_t* F = &FIELDS[m];
     uint64_t r[4];
     uint64_t c = add4(r, a->l, b->l);
     if (c || geq(r, F->p)) sub4(r, r, F->p);
     memcpy(out->l, r, 32);
 }
-static void fp_sub(int m, const ofp* a, const ofp* b, ofp* out) {
+static inline __attribute__((always_inline)) void fp_sub(int m, const ofp* a, const ofp* b, ofp* out) {
     const field_t* F = &FIELDS[m];
     uint64_t r[4];
     if (sub4(r, a->l, b->l)) add4(r, r, F->p);
     memcpy(out->l, r, 32);
 }
-static void fp_neg(int m, const ofp* a, ofp* out) {
+static inline __attribute__((always_inline)) void fp_neg(int m, const ofp* a, ofp* out) {
     ofp z = {{0, 0, 0, 0}};
     fp_sub(m, &z, a, out);
 }
@@ -560,7 +560,7 @@ static void gens_body(long i, void* vc) {
 void orc_multi_commit_gens(const uint8_t* label, size_t label_len, size_t n, og1a* out) {
     ofp* sc = (ofp*)malloc(sizeof(ofp) * (n + 1));
     orc_gen_scalars(label, label_len, n, sc, NULL);
-    gens_ctx c = {sc, out};
+    gens_ctx c = {sc, out, {{{0}}, {{0}}}};
     orc_g1_generator(&c.g);
     parallel_for((long)n + 1, 16, 0, gens_body, &c);
     free(sc);

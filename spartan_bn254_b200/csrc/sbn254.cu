@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1386,6 +1387,34 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
     ctx->d2h += L * sizeof(Affine) + L;
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     collect_profile(ctx, ev_stage);
+    return SBN_OK;
+}
+
+// One process, k GPUs: the rows of one commit divided into k contiguous blocks, block i committed by context i (one
+// context per device, each with its own resident copy of the generator set) from a host thread of its own -- the calls
+// run concurrently, the blocks land in the caller's C_out / inf_out side by side, and there is no inter-GPU traffic at
+// all (hyrax.rs:259-265: rows are independent; the Rayon fan-out of the reference becomes a fan-out over devices).
+extern "C" int sbn_hyrax_commit_multi(sbn_ctx* const* ctxs, const sbn_bases* const* bases, size_t k, const sbn_fr* Z, size_t L,
+                                      size_t R, const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out) {
+    if (!ctxs || !bases || k == 0 || !Z || !C_out || !inf_out) return SBN_ERR_ARG;
+    for (size_t i = 0; i < k; i++)
+        if (!ctxs[i] || !bases[i] || bases[i]->ctx != ctxs[i]) return SBN_ERR_ARG;
+    if (L == 0 || R == 0) return SBN_ERR_SHAPE;
+    const size_t kk = std::min(k, L);
+    std::vector<int> rc(kk, SBN_OK);
+    std::vector<std::thread> workers;
+    size_t row0 = 0;
+    for (size_t i = 0; i < kk; i++) {
+        const size_t n = L / kk + (i < L % kk ? 1 : 0);
+        workers.emplace_back([=, &rc] {
+            rc[i] = sbn_hyrax_commit(ctxs[i], bases[i], Z + row0 * R, n, R, blinds ? blinds + row0 : nullptr, C_out + row0,
+                                     inf_out + row0);
+        });
+        row0 += n;
+    }
+    for (auto& w : workers) w.join();
+    for (size_t i = 0; i < kk; i++)
+        if (rc[i] != SBN_OK) return rc[i];
     return SBN_OK;
 }
 

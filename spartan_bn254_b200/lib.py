@@ -13,7 +13,7 @@ EXPORTS = [
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
     "sbn_ctx_last_commit_profile", "sbn_ctx_memory_stats", "sbn_host_alloc", "sbn_host_free",
     "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
-    "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_msm", "sbn_commit",
+    "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_hyrax_commit_multi", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
     "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_end_delta", "sbn_bullet_destroy",
@@ -762,6 +762,23 @@ class SpMat:
             self.close()
         except Exception:
             pass
+
+
+def hyrax_commit_multi(ctxs, bases, Z, L_size, R_size, blinds=None):
+    """sbn_hyrax_commit_multi: one commit over len(ctxs) devices of this process (contiguous row blocks, no exchange)."""
+    Z = _u64(Z, 4)
+    k = len(ctxs)
+    if Z.shape[0] != L_size * R_size:
+        raise AssertionError("assert_eq!(L_size * R_size, self.Z.len())")
+    bl = _u64(blinds, 4) if blinds is not None else None
+    out = np.zeros((L_size, 8), dtype=np.uint64)
+    inf = np.zeros(L_size, dtype=np.uint8)
+    ca = (C.c_void_p * k)(*[c.h for c in ctxs])
+    ba = (C.c_void_p * k)(*[b.h for b in bases])
+    st = ctxs[0].lib.sbn_hyrax_commit_multi(ca, ba, C.c_size_t(k), _ptr(Z), C.c_size_t(L_size), C.c_size_t(R_size),
+                                            _ptr(bl) if bl is not None else None, _ptr(out), _ptr(inf))
+    ctxs[0]._check(st, "sbn_hyrax_commit_multi")
+    return out, inf
 
 
 def eq_evals(ctx, r):

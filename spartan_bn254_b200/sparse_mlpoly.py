@@ -8,6 +8,8 @@ points: the address / timestamp vectors fixed at encode time, the derefs commitm
 """
 import numpy as np
 
+from .parallel import shard_rows
+
 from .lib import Addrs
 from .product_tree import ProductCircuit
 
@@ -52,9 +54,27 @@ class SparkAddresses:
             return self.gpu.derefs_commit(gens_n.device_bases(), rx, ry)
         rank, world, all_gather = shard
         L = self.gpu.derefs_rows()
-        assert L % world == 0
-        C, inf, poly = self.gpu.derefs_commit(gens_n.device_bases(), rx, ry, rows=(rank * (L // world), L // world))
-        return np.concatenate(all_gather(C)), np.concatenate(all_gather(inf)), poly
+        # Only the rows that hold values are divided: the merged polynomial is zero-padded to a power of two
+        # (sparse_mlpoly_full.rs:295), so with three matrices the last quarter of the rows is all-zero and commits to the
+        # identity -- contiguous blocks of ALL rows would hand the last ranks nothing to do.
+        used = 2 * self.gpu.batch * self.gpu.N
+        R = (1 << (max(0, (used - 1).bit_length()))) // L
+        live = min(L, -(-used // R))
+        first, n = shard_rows(live, world, rank)
+        n_max = -(-live // world)
+        C = np.zeros((n_max, 8), dtype=np.uint64)
+        inf = np.ones(n_max, dtype=np.uint8)
+        poly = None
+        if n:
+            Cb, infb, poly = self.gpu.derefs_commit(gens_n.device_bases(), rx, ry, rows=(first, n))
+            C[:n], inf[:n] = Cb, infb
+        Cs, infs = all_gather(C), all_gather(inf)
+        C_all = np.zeros((L, 8), dtype=np.uint64)
+        inf_all = np.ones(L, dtype=np.uint8)                 # rows past `live`: identity
+        for r in range(world):
+            f, m = shard_rows(live, world, r)
+            C_all[f:f + m], inf_all[f:f + m] = Cs[r][:m], infs[r][:m]
+        return C_all, inf_all, poly
 
     def close(self):
         self.gpu.close()
