@@ -69,6 +69,9 @@ int sbn_ctx_synchronize(sbn_ctx* ctx);
  *   "tab_max_mb"    budget (MiB, default 3072) of the 8-bit-window table of an opening's generator set
  *                   (sbn_bases_create_ext): single rows and row pairs become sums of table points; 0 disables
  *   "small_commit_path" 0 sends short generator sets and few-row commits through the general pipeline (test hook)
+ *   "small_scalar_path" 1 (default): a commit without blinds classifies its rows by the bit length of their largest scalar
+ *                   and commits runs of small rows (comb_ops' addresses and timestamps, sparse_mlpoly_full.rs:176-196) over
+ *                   a table of just the windows that cover them; 0 disables the scan
  * Tuning of the tabulated-sum path (mult_kernels.cuh; every setting gives identical results):
  *   "mult_layout"   1 (default) position-major entry lists -- a warp is 32 rows at one table column; 0 row-major (round 1)
  *   "mult_streams"  chunks in flight, 1..4 (default 2);  "mult_rounds" batched-affine rounds, 0 = auto
@@ -83,9 +86,10 @@ int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value);
 int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes, int reset);
 /* Memory behaviour since creation: out[0] bytes of released device buffers held by the context's pool, out[1] times an
  * allocation failure emptied that pool and retried, out[2] digit-multiple tables ("mult_max_mb") the device could not hold
- * -- those generator sets ran through the bucket pipeline and sbn_last_cuda_error says so --, out[3] buffers in the pool.
+ * -- those generator sets ran through the bucket pipeline and sbn_last_cuda_error says so --, out[3] buffers in the pool,
+ * out[4] commits that took the small-scalar schedule ("small_scalar_path"), out[5..7] reserved (0).
  * (No reference counterpart: the Rust prover's Vec allocations cannot fail softly; a GPU backend's can.) */
-int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[4]);
+int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[8]);
 /* Device time (ms, CUDA events on the library's compute stream) of the kernels of the last
  * sbn_hyrax_commit* call, per stage: [0] digit decomposition + bucket sort, [1] bucket accumulation,
  * [2] bucket reduction, [3] affine normalisation; and the number of launches per stage. */

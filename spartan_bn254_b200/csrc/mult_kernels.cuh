@@ -94,6 +94,42 @@ k_mult_entries(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
     }
 }
 
+// Bit lengths of canonical scalar values, for the small-scalar schedule: the encode-time polynomials (comb_ops: addresses,
+// timestamps -- sparse_mlpoly_full.rs:155-196) hold values below 2^21 in most of their rows, and a commit over W windows
+// costs W additions per scalar whatever the values are.
+__device__ __forceinline__ uint32_t fr_bit_length(const Fr* p) {
+    Fr s = load_fr(p);
+    if (s.is_zero()) return 0;
+    s = fp_from_mont(s);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (s.l[k]) bits = 32 * k + (32 - __clz(s.l[k]));
+    return bits;
+}
+// out[0] = the SMALLEST bit length among `count` scalars sampled at a fixed stride (full-size inputs show none below ~240)
+__global__ void __launch_bounds__(256)
+k_min_bits_sample(const Fr* __restrict__ Z, size_t stride, size_t count, uint32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t bits = i < count ? fr_bit_length(Z + i * stride) : 0xffffffffu;
+    bits = __reduce_min_sync(0xffffffffu, bits);
+    if ((threadIdx.x & 31) == 0) atomicMin(out, bits);
+}
+// block per row: out[row] = the largest bit length of the row's R scalars
+__global__ void __launch_bounds__(256)
+k_row_max_bits(const Fr* __restrict__ Z, int R, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_best;
+    if (threadIdx.x == 0) s_best = 0;
+    __syncthreads();
+    const Fr* row = Z + (size_t)blockIdx.x * R;
+    uint32_t best = 0;
+    for (int j = threadIdx.x; j < R; j += 256) best = max(best, fr_bit_length(row + j));
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(&s_best, best);
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = s_best;
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // Position-major ("transposed") layout of the sum tree (round 2).
 //

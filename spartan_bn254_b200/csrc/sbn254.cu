@@ -66,6 +66,7 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
     size_t zkeep_len = 0;
     DevBuf tabpart;                    // per-block partial sums of the tabulated few-row commit (small_kernels.cuh)
@@ -78,6 +79,8 @@ struct sbn_ctx {
     long finish_smem_kb = 0;           // dynamic shared memory requested by the finish pass: caps its resident blocks so that a prefix pass of the other stream co-resides
     long prefix_smem_kb = 0;
     long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
+    long small_scalar_path = 1;        // commits without blinds scan their scalars' bit length and use a short window schedule when it is small
+    long small_scalar_hits = 0;        // commits that took it
     long mult_layout = 1;              // 1: position-major lists (a warp = 32 rows at one table column); 0: row-major (round 1)
     long tab_max_mb = 3072;            // largest digit-multiple table built for an opening's generator set (MiB); 0 = none
     // Pool of released table-sized device buffers (product circuits, resident polynomials, sumcheck tables): a proof
@@ -110,6 +113,9 @@ struct sbn_bases {
     // every digit multiple of the n1 table columns for many-row commits (mult_kernels.cuh), built on the first such commit
     Affine* mult = nullptr;
     int mc = 0, mW = 0, mult_tried = 0, mult_fails = 0;
+    // the same kind of table for SMALL scalars: msW windows of msc bits cover values below 2^(msW * msc - 1) (encode-time commits)
+    Affine* mult_s = nullptr;
+    int msc = 0, msW = 0, max_group = 1;
 };
 
 #define SBN_CUDA(ctx, call)                                                                      \
@@ -119,6 +125,15 @@ struct sbn_bases {
             (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);              \
             return _e == cudaErrorMemoryAllocation ? SBN_ERR_OOM : SBN_ERR_CUDA;                 \
         }                                                                                        \
+    } while (0)
+
+// Entry of an API call: this thread talks to the context's device, and whatever non-sticky error an earlier runtime call of
+// this thread left behind (another context's teardown, the caller's own CUDA code) is dropped, so that the
+// cudaGetLastError() after this call's launches reports this call's errors only.
+#define SBN_ENTER(ctx)                                  \
+    do {                                                \
+        SBN_CUDA(ctx, cudaSetDevice((ctx)->device));    \
+        cudaGetLastError();                             \
     } while (0)
 
 #define SBN_TRY(expr)            \
@@ -343,7 +358,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -359,13 +374,14 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamDestroy(ctx->copy);
     if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
     delete ctx;
+    cudaGetLastError();
     return SBN_OK;
 }
 
 extern "C" int sbn_ctx_synchronize(sbn_ctx* ctx) {
     if (!ctx) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
@@ -411,6 +427,8 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
         if (cudaGetLastError() != cudaSuccess) return SBN_ERR_CUDA;
     } else if (!strcmp(key, "ablate")) {
         ctx->ablate = value;
+    } else if (!strcmp(key, "small_scalar_path")) {
+        ctx->small_scalar_path = value ? 1 : 0;
     } else if (!strcmp(key, "mult_layout")) {
         ctx->mult_layout = value ? 1 : 0;
     } else if (!strcmp(key, "ba_prefetch")) {
@@ -464,13 +482,15 @@ extern "C" int sbn_ctx_counters(sbn_ctx* ctx, uint64_t* launches, uint64_t* h2d,
     return SBN_OK;
 }
 
-extern "C" int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[4]) {
+extern "C" int sbn_ctx_memory_stats(sbn_ctx* ctx, uint64_t out[8]) {
     if (!ctx || !out) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
     out[0] = ctx->mem_pool_bytes;
     out[1] = ctx->pool_flushes;
     out[2] = ctx->mult_fallbacks;
     out[3] = ctx->mem_pool.size();
+    out[4] = (uint64_t)ctx->small_scalar_hits;
+    out[5] = out[6] = out[7] = 0;
     return SBN_OK;
 }
 
@@ -517,7 +537,7 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
     *out = nullptr;
     if (n == 0 || n > (1u << 24)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_bases* b = new (std::nothrow) sbn_bases();
     if (!b) return SBN_ERR_OOM;
     b->ctx = ctx;
@@ -558,6 +578,7 @@ static int bases_create(sbn_ctx* ctx, const sbn_g1a* G, const uint8_t* G_inf, si
             }
             b->n1 = (int)members.size();
             b->n_big = (int)gbig.size();
+            for (auto& mv : members) b->max_group = std::max<int>(b->max_group, (int)mv.size());
         }
     }
     b->c = ctx->window_bits ? (int)ctx->window_bits : choose_window((size_t)b->n1);
@@ -671,6 +692,7 @@ extern "C" int sbn_bases_destroy(sbn_bases* b) {
         if (b->orig) cudaFree(b->orig);
         if (b->small) cudaFree(b->small);
         if (b->mult) cudaFree(b->mult);
+        if (b->mult_s) cudaFree(b->mult_s);
         for (uint32_t* p : {b->gptr, b->gcols, b->gbig}) if (p) cudaFree(p);
     }
     delete b;
@@ -951,7 +973,7 @@ static int ensure_commit_workspace(sbn_ctx* ctx, const sbn_bases* b, size_t chun
 
 static void collect_profile(sbn_ctx* ctx, const std::vector<int>& ev_stage) {
     for (int i = 0; i < 4; i++) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
-    for (size_t i = 1; i < ev_stage.size(); i++) {
+    for (size_t i = 1; i < ev_stage.size() && i < ctx->ev_pool.size(); i++) {
         int st = ev_stage[i];
         if (st < 0) continue;
         float ms = 0;
@@ -1040,6 +1062,65 @@ static void mult_try_build(sbn_ctx* ctx, sbn_bases* b) {
     b->mult_tried = 1;       // no window width fits the budget
 }
 
+// Per-row bit lengths of an L x R matrix of device scalars; `rowbits` stays empty when a strided sample of the scalars shows
+// none that is small -- every prove-time commit (eq-table values, witnesses) leaves after one tiny launch and a 4-byte copy.
+static constexpr int kSmallScalarBits = 64;
+static int scan_row_bits(sbn_ctx* ctx, const Fr* dZ, size_t L, size_t R, cudaStream_t st, std::vector<uint32_t>& rowbits) {
+    rowbits.clear();
+    const size_t n = L * R, count = std::min<size_t>(n, 8192), stride = n / count;
+    SBN_TRY(ensure(ctx, ctx->scan, (L + 1) * sizeof(uint32_t)));
+    uint32_t* d = (uint32_t*)ctx->scan.p;
+    uint32_t lo = 0xffffffffu;
+    SBN_CUDA(ctx, cudaMemsetAsync(d, 0xff, sizeof(uint32_t), st));
+    k_min_bits_sample<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dZ, stride, count, d);
+    ctx->launches++;
+    SBN_CUDA(ctx, cudaMemcpyAsync(&lo, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SBN_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d2h += 4;
+    if (lo > (uint32_t)kSmallScalarBits) return SBN_OK;
+    k_row_max_bits<<<(unsigned)L, 256, 0, st>>>(dZ, (int)R, d + 1);
+    ctx->launches++;
+    rowbits.resize(L);
+    SBN_CUDA(ctx, cudaMemcpyAsync(rowbits.data(), d + 1, L * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SBN_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->d2h += L * 4;
+    return SBN_OK;
+}
+
+// Table of the digit multiples of the first few windows only: Ws windows of cs bits with Ws * cs - 1 >= bits (signed digits:
+// the top window must not carry out), the fewest windows whose table fits the budget.  Kept per generator set and rebuilt only
+// when a later commit needs more bits than it covers.
+static const Affine* mult_small_table(sbn_ctx* ctx, sbn_bases* b, int bits) {
+    bits = std::max(bits, 1);
+    if (b->mult_s && b->msW * b->msc - 1 >= bits) return b->mult_s;
+    for (int Ws = 1; Ws <= 6; Ws++) {
+        int cs = (bits + 1 + Ws - 1) / Ws;
+        if (cs < 8) cs = 8;                                   // k_mult_fill works in runs of 128 multiples
+        if (cs > kMultMaxBits) continue;
+        const uint64_t entries = (uint64_t)Ws * b->n1 << (cs - 1);
+        if (entries >= (1ull << 31) || entries * sizeof(Affine) > ((uint64_t)ctx->mult_max_mb << 20)) continue;
+        if (b->mult && Ws * 2 > b->mW) return nullptr;        // the full table's schedule is not much longer: keep to it
+        if (b->mult_s) {
+            cudaStreamSynchronize(ctx->compute);
+            cudaFree(b->mult_s);
+            b->mult_s = nullptr;
+        }
+        if (dev_malloc(ctx, &b->mult_s, entries * sizeof(Affine)) != cudaSuccess) { b->mult_s = nullptr; return nullptr; }
+        const uint64_t threads = (uint64_t)Ws * b->n1 * ((1u << (cs - 1)) / kMultChunk);
+        k_mult_fill<<<(unsigned)((threads + 63) / 64), 64, 0, ctx->compute>>>(b->table, b->n1, cs, Ws, b->mult_s);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+            cudaFree(b->mult_s);
+            b->mult_s = nullptr;
+            return nullptr;
+        }
+        b->msc = cs;
+        b->msW = Ws;
+        return b->mult_s;
+    }
+    return nullptr;
+}
+
 static int mult_rounds_for(uint32_t used) {
     int r = 1;
     while (r < 10 && (used >> (r + 1)) >= 192) r++;      // leave a few hundred points per row to the XYZZ sum
@@ -1050,8 +1131,9 @@ static int mult_rounds_for(uint32_t used) {
 // low-priority streams, so that one chunk's inversion launches (a 27 us dependency per round) and kernel tails run under
 // the other chunk's additions; a commit that would be one chunk is cut in two for the same reason.  With host scalars the
 // copy of chunk i + 1 is issued on the copy stream before the kernels of chunk i.
-static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R, const Fr* dblinds,
-                       Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage, bool normalize) {
+static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, int mtc, int mtW, const Fr* dZ, const Fr* host_Z,
+                       size_t L, size_t R, const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main,
+                       std::vector<int>& ev_stage, bool normalize) {
     size_t chunk = commit_chunk_rows(ctx, L);
     const size_t ns_max = (size_t)ctx->mult_streams;
     if (ctx->chunk_rows <= 0 && L >= 512 && L <= chunk) chunk = (L + ns_max - 1) / ns_max;    // at least one chunk per stream
@@ -1063,7 +1145,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
         while (done < L) { size_t cr = std::min(chunk, L - done); sched.push_back(cr); done += cr; }
     }
     const size_t nchunks = sched.size();
-    const int c = b->mc, W = b->mW;
+    const int c = mtc, W = mtW;
     const int Rk = b->dedup ? b->n1 : (int)R;              // scalars per row the entries kernel sees
     const uint32_t used = (uint32_t)W * (uint32_t)(Rk + 1);
     int rounds = mult_rounds_for(used);
@@ -1145,13 +1227,13 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
                 if (k == 0) {
                     auto pre = pf ? k_bat_prefix<true, true> : k_bat_prefix<true, false>;
                     if (!(ab & 1))
-                        pre<<<blocks, kBaThreads, psm, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, nullptr, npairs, rp, B,
+                        pre<<<blocks, kBaThreads, psm, st>>>((const uint32_t*)sl.entries.p, mtable, nullptr, nullptr, npairs, rp, B,
                                                            (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
                     if (!(ab & 4)) k_ba_invert<<<(blocks + 63) / 64, 64, 0, st>>>((const Fq*)sl.wtot.p, blocks, (Fq*)sl.winv.p);
                     auto fin = m4 ? (pf ? k_bat_finish<true, 4, true> : k_bat_finish<true, 4, false>)
                                   : (pf ? k_bat_finish<true, 3, true> : k_bat_finish<true, 3, false>);
                     if (!(ab & 16))
-                        fin<<<blocks, kBaThreads, fsm, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, nullptr, npairs, rp, B,
+                        fin<<<blocks, kBaThreads, fsm, st>>>((const uint32_t*)sl.entries.p, mtable, nullptr, nullptr, npairs, rp, B,
                                                            (const Fq*)sl.prefix.p, (const Fq*)sl.other.p, (const Fq*)sl.winv.p, outx, outy);
                 } else {
                     if (!(ab & 2))
@@ -1188,12 +1270,12 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
             const size_t nwarps = (size_t)blocks * kBaThreads / 32;
             Affine* out = (Affine*)sl.pts[k & 1].p;
             if (k == 0) {
-                k_ba_prefix<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B,
+                k_ba_prefix<true><<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, mtable, nullptr, npairs, B,
                                                                  (Fq*)sl.prefix.p, (Fq*)sl.other.p, (Fq*)sl.wtot.p);
                 k_ba_invert<<<(unsigned)((nwarps + 63) / 64), 64, 0, st>>>((const Fq*)sl.wtot.p, nwarps, (Fq*)sl.winv.p);
                 auto fin = ctx->ba_minb == 4 ? (ctx->ba_prefetch ? k_ba_finish<true, 4, true> : k_ba_finish<true, 4, false>)
                                              : (ctx->ba_prefetch ? k_ba_finish<true, 3, true> : k_ba_finish<true, 3, false>);
-                fin<<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, b->mult, nullptr, npairs, B, (const Fq*)sl.prefix.p,
+                fin<<<blocks, kBaThreads, 0, st>>>((const uint32_t*)sl.entries.p, mtable, nullptr, npairs, B, (const Fq*)sl.prefix.p,
                                                    (const Fq*)sl.other.p, (const Fq*)sl.winv.p, out);
             } else {
                 k_ba_prefix<false><<<blocks, kBaThreads, 0, st>>>(nullptr, nullptr, in, npairs, B, (Fq*)sl.prefix.p,
@@ -1229,6 +1311,9 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr*
 static int run_commit_inner(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                             const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                             bool normalize);
+static int run_commit_general(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
+                              const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
+                              bool normalize);
 // Every commit goes through here.  The pipeline forks `main` into the copy / hi / lo streams and joins them at the very
 // end; an early error return skips that join, so the streams are drained here before the caller releases or reuses the
 // buffers they may still be reading (the pool hands buffers out again in `compute` order only).
@@ -1245,9 +1330,61 @@ static int run_commit(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* 
 static int run_commit_inner(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
                             const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
                             bool normalize) {
+    // Small scalars (no blinds, scalars already on the device).  The rows are classified by the bit length of their largest
+    // scalar; runs of at least mult_min_rows small rows are committed over a table of just the few windows that cover them,
+    // the other runs through the general path -- comb_ops is four fifths addresses and timestamps below 2^21 and one fifth
+    // matrix coefficients of any size (sparse_mlpoly_full.rs:176-196).
+    if (ctx->small_scalar_path && !dblinds && !host_Z && !b->has_g1 && ctx->mult_max_mb > 0 && L >= (size_t)ctx->mult_min_rows &&
+        L * R >= (size_t(1) << 16)) {
+        std::vector<uint32_t> rowbits;
+        SBN_TRY(scan_row_bits(ctx, dZ, L, R, main, rowbits));
+        if (!rowbits.empty()) {
+            int extra = 0;
+            while ((1 << extra) < b->max_group) extra++;                      // merged generators add their scalars
+            std::vector<uint8_t> small(L);
+            for (size_t i = 0; i < L; i++) small[i] = rowbits[i] + (uint32_t)extra <= (uint32_t)kSmallScalarBits;
+            struct Run { size_t row0, n; bool small; };
+            std::vector<Run> runs;
+            for (size_t i = 0; i < L;) {
+                size_t j = i;
+                while (j < L && small[j] == small[i]) j++;
+                bool sm = small[i] && (j - i) >= (size_t)ctx->mult_min_rows;   // short small runs join their neighbours
+                if (!runs.empty() && runs.back().small == sm) runs.back().n += j - i;
+                else runs.push_back({i, j - i, sm});
+                i = j;
+            }
+            uint32_t bits = 0;
+            bool any = false;
+            for (auto& r : runs)
+                if (r.small) { any = true; for (size_t i = r.row0; i < r.row0 + r.n; i++) bits = std::max(bits, rowbits[i]); }
+            const Affine* t = any ? mult_small_table(ctx, const_cast<sbn_bases*>(b), (int)bits + extra) : nullptr;
+            if (t) {
+                ctx->small_scalar_hits++;
+                for (auto& r : runs) {
+                    const Fr* z = dZ + r.row0 * R;
+                    // every run re-uses the profiling events from index 0: its marks go to a scratch list, and a commit that
+                    // was split into runs reports no stage profile (ev_stage stays empty)
+                    std::vector<int> scratch_marks;
+                    if (r.small)
+                        SBN_TRY(mult_commit(ctx, b, t, b->msc, b->msW, z, nullptr, r.n, R, nullptr, dC + r.row0, dinf + r.row0, main,
+                                            scratch_marks, normalize));
+                    else
+                        SBN_TRY(run_commit_general(ctx, b, z, nullptr, r.n, R, nullptr, dC + r.row0, dinf + r.row0, main,
+                                                   scratch_marks, normalize));
+                }
+                return SBN_OK;
+            }
+        }
+    }
+    return run_commit_general(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
+}
+
+static int run_commit_general(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
+                              const Fr* dblinds, Affine* dC, uint8_t* dinf, cudaStream_t main, std::vector<int>& ev_stage,
+                              bool normalize) {
     if (L >= (size_t)ctx->mult_min_rows && !b->has_g1 && ctx->mult_max_mb > 0) {
         if (!b->mult_tried) mult_try_build(ctx, const_cast<sbn_bases*>(b));
-        if (b->mult) return mult_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
+        if (b->mult) return mult_commit(ctx, b, b->mult, b->mc, b->mW, dZ, host_Z, L, R, dblinds, dC, dinf, main, ev_stage, normalize);
     }
     if (b->small && ctx->small_commit_path && L <= (size_t)kTabMaxRows && R + 1 <= (size_t)b->n_cols)
         return tab_commit(ctx, b, dZ, host_Z, L, R, dblinds, dC, dinf, main, normalize);
@@ -1318,7 +1455,7 @@ extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const v
     if (!ctx || !b || !dZ || !dC_out || b->ctx != ctx) return SBN_ERR_ARG;
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->compute;
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
@@ -1365,7 +1502,7 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
     if (!ctx || !b || !Z || !C_out || !inf_out || b->ctx != ctx) return SBN_ERR_ARG;
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     if (b->small && b->n_cols <= kSmallMaxCols && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
@@ -1379,8 +1516,27 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
         SBN_CUDA(ctx, cudaMemcpyAsync(dbl, blinds, L * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute));
         ctx->h2d += L * sizeof(Fr);
     }
+    // Host scalars that look small (a strided sample on the host) are uploaded in one piece, so that the device-side row
+    // classification of the small-scalar schedule sees them; everything else streams chunk by chunk under the kernels.
+    const Fr* host_Z = (const Fr*)Z;
+    if (ctx->small_scalar_path && !blinds && L >= (size_t)ctx->mult_min_rows && L * R >= (size_t(1) << 16) && ctx->mult_max_mb > 0 &&
+        !b->has_g1) {
+        const size_t n = L * R, count = 256, stride = n / count;
+        bool any_small = false;
+        for (size_t i = 0; i < count && !any_small; i++) {
+            Fr v;
+            memcpy(v.l, &Z[i * stride], 32);
+            v = fp_from_mont(v);
+            any_small = (v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) == 0;
+        }
+        if (any_small) {
+            SBN_CUDA(ctx, cudaMemcpyAsync(ctx->dZ.p, Z, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute));
+            ctx->h2d += n * sizeof(Fr);
+            host_Z = nullptr;
+        }
+    }
     std::vector<int> ev_stage;
-    SBN_TRY(run_commit(ctx, b, (const Fr*)ctx->dZ.p, (const Fr*)Z, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p,
+    SBN_TRY(run_commit(ctx, b, (const Fr*)ctx->dZ.p, host_Z, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p,
                        ctx->compute, ev_stage));
     SBN_CUDA(ctx, cudaMemcpyAsync(C_out, ctx->dC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, ctx->compute));
     SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, ctx->dinf.p, L, cudaMemcpyDeviceToHost, ctx->compute));
@@ -1438,7 +1594,7 @@ extern "C" int sbn_g1_scalar_mul_batch(sbn_ctx* ctx, const sbn_g1a* P, const sbn
     if (!ctx || !P || !s || !out || !inf_out) return SBN_ERR_ARG;
     if (n == 0) return SBN_OK;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(upload(ctx, ctx->scratch0, P, sizeof(Affine)));
     SBN_TRY(upload(ctx, ctx->scratch1, s, n * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->dC, n * sizeof(Affine)));
@@ -1459,7 +1615,7 @@ extern "C" int sbn_g1_scale_points(sbn_ctx* ctx, const sbn_g1a* P, const uint8_t
     if (!ctx || !P || !s || !out || !inf_out) return SBN_ERR_ARG;
     if (n == 0) return SBN_OK;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(upload(ctx, ctx->scratch0, P, n * sizeof(Affine)));
     SBN_TRY(upload(ctx, ctx->scratch1, s, sizeof(Fr)));
     const uint8_t* dinf_in = nullptr;
@@ -1484,7 +1640,7 @@ static int fr_convert(sbn_ctx* ctx, const void* in, size_t n, int to_mont, void*
     if (!ctx || !in || !out) return SBN_ERR_ARG;
     if (n == 0) return SBN_OK;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(upload(ctx, ctx->scratch0, in, n * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->scratch1, n * sizeof(Fr)));
     k_fr_convert<<<(unsigned)((n + 127) / 128), 128, 0, ctx->compute>>>((const Fr*)ctx->scratch0.p, (int)n, to_mont,
@@ -1505,7 +1661,7 @@ extern "C" int sbn_fr_to_canonical(sbn_ctx* ctx, const sbn_fr* in, size_t n, uin
 extern "C" int sbn_microbench(sbn_ctx* ctx, int kind, double* per_second) {
     if (!ctx || !per_second) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(ensure(ctx, ctx->scratch0, 4096));
     cudaDeviceProp prop;
     SBN_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
@@ -1546,7 +1702,7 @@ extern "C" int sbn_msm(sbn_ctx* ctx, const sbn_g1a* points, const uint8_t* inf, 
     if (!ctx || !out || !inf_out || (n && (!points || !scalars))) return SBN_ERR_ARG;
     if (n > (1u << 26)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     if (n == 0) {   // empty sum = identity
         memset(out, 0, sizeof(*out));
         *inf_out = 1;
@@ -1603,7 +1759,7 @@ extern "C" int sbn_bound(sbn_ctx* ctx, const sbn_fr* Z, const sbn_fr* Lv, size_t
     if (!ctx || !Z || !Lv || !LZ_out) return SBN_ERR_ARG;
     if (L == 0 || R == 0 || L > (1u << 24) || R > (1u << 24)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(upload(ctx, ctx->dZ, Z, L * R * sizeof(Fr)));
     SBN_TRY(upload(ctx, ctx->scratch0, Lv, L * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->scratch1, R * sizeof(Fr)));
@@ -1627,7 +1783,7 @@ extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_po
     *out = nullptr;
     if (len == 0 || len > (size_t(1) << 32)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_poly* p = new (std::nothrow) sbn_poly();
     if (!p) return SBN_ERR_OOM;
     p->ctx = ctx;
@@ -1662,7 +1818,7 @@ extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly*
     SBN_TRY(check_commit_shape(b, L, R));
     if (L * R != poly->len) return SBN_ERR_SHAPE;               // hyrax.rs:258
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
     SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
@@ -1685,7 +1841,7 @@ extern "C" int sbn_poly_bound(sbn_ctx* ctx, const sbn_poly* poly, const sbn_fr* 
     if (!ctx || !poly || !Lv || !LZ_out || poly->ctx != ctx) return SBN_ERR_ARG;
     if (L == 0 || R == 0 || L * R != poly->len) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(upload(ctx, ctx->scratch0, Lv, L * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->scratch1, R * sizeof(Fr)));
     SBN_TRY(bound_device(ctx, poly->Z, (const Fr*)ctx->scratch0.p, L, R, (Fr*)ctx->scratch1.p, ctx->compute));
@@ -1739,7 +1895,7 @@ extern "C" int sbn_bullet_begin(sbn_ctx* ctx, const sbn_bases* bases, const sbn_
     const bool fast = q_scalar != nullptr;
     if (fast && !bases->has_g1) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     sbn_bullet* st = new (std::nothrow) sbn_bullet();
     if (!st) return SBN_ERR_OOM;
@@ -1819,7 +1975,7 @@ extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn
     if (st->n < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const long n2 = (long)(st->n / 2);
     const unsigned dot_blocks = (unsigned)std::min<long>(kBulletDotBlocks, (n2 + kDotThreads - 1) / kDotThreads);
@@ -1869,7 +2025,7 @@ extern "C" int sbn_bullet_fold(sbn_bullet* st, const sbn_fr* u, const sbn_fr* u_
     if (st->n < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const int n2 = (int)(st->n / 2);
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 4, u, sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -1895,7 +2051,7 @@ extern "C" int sbn_bullet_end(sbn_bullet* st, sbn_fr* a_hat, sbn_fr* b_hat, sbn_
     if (st->n != 1) return SBN_ERR_SHAPE;                      // bullet.rs:110-112 asserts
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const Affine* gsrc = st->G;
     const uint8_t* gisrc = st->Ginf;
@@ -1929,7 +2085,7 @@ extern "C" int sbn_bullet_end_delta(sbn_bullet* st, const sbn_fr* d, const sbn_f
     if (!st->fast) return SBN_ERR_UNSUPPORTED;                 // the explicit-folding path holds no coefficients
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t n0 = st->n0;
     Fr blinds[2];
@@ -2010,7 +2166,7 @@ static int sumcheck_begin(sbn_ctx* ctx, const sbn_fr* const* src, int ntables, s
     *out = nullptr;
     if (len < 1 || (len & (len - 1)) || len > (1u << 28)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_sumcheck* st = new (std::nothrow) sbn_sumcheck();
     if (!st) return SBN_ERR_OOM;
     st->ctx = ctx;
@@ -2038,7 +2194,7 @@ extern "C" int sbn_sumcheck_round_eval(sbn_sumcheck* st, sbn_fr* e0, sbn_fr* e2,
     if (st->len < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const int half = (int)(st->len / 2);
     const unsigned blocks = (unsigned)std::min<size_t>(st->blocks, (half + kDotThreads - 1) / kDotThreads);
@@ -2062,7 +2218,7 @@ extern "C" int sbn_sumcheck_bind(sbn_sumcheck* st, const sbn_fr* r) {
     if (st->len < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const int half = (int)(st->len / 2);
     SBN_CUDA(ctx, cudaMemcpyAsync(st->out + 3, r, sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -2080,7 +2236,7 @@ extern "C" int sbn_sumcheck_end(sbn_sumcheck* st, sbn_fr finals[4]) {
     if (st->len != 1) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     for (int k = 0; k < 4; k++) {
         if (k < st->ntables) SBN_CUDA(ctx, cudaMemcpyAsync(&finals[k], st->T[k], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
         else memset(&finals[k], 0, sizeof(sbn_fr));
@@ -2117,7 +2273,7 @@ extern "C" int sbn_prodcircuit_create(sbn_ctx* ctx, const sbn_fr* poly, size_t l
     *out = nullptr;
     if (len < 2 || (len & (len - 1)) || len > (size_t(1) << 30)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_prodcircuit* pc = new (std::nothrow) sbn_prodcircuit();
     if (!pc) return SBN_ERR_OOM;
     pc->ctx = ctx;
@@ -2149,7 +2305,7 @@ extern "C" int sbn_prodcircuit_evaluate(sbn_prodcircuit* pc, sbn_fr* out) {
     if (!pc || !out) return SBN_ERR_ARG;
     sbn_ctx* ctx = pc->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     Fr top[2];
     SBN_CUDA(ctx, cudaMemcpyAsync(top, pc->buf + pc->off[pc->num_layers - 1], 2 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->compute));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
@@ -2210,7 +2366,7 @@ static int bsumcheck_begin(sbn_ctx* ctx, sbn_prodcircuit* const* circuits, size_
         if ((circuits[i]->len >> layer_id) != 2 * T) return SBN_ERR_SHAPE;      // product_tree.rs:272 assert_eq!(poly_C_par.len(), len / 2)
     }
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     sbn_bsumcheck* st = new (std::nothrow) sbn_bsumcheck();
     if (!st) return SBN_ERR_OOM;
@@ -2309,7 +2465,7 @@ extern "C" int sbn_bsumcheck_round_eval(sbn_bsumcheck* st, sbn_fr* evals) {
     if (st->len < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t half = st->len / 2, n = st->P + st->S;
     const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
@@ -2328,7 +2484,7 @@ extern "C" int sbn_bsumcheck_bind(sbn_bsumcheck* st, const sbn_fr* r) {
     if (st->len < 2) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t half = st->len / 2, n = st->P + st->S;
     Fr* rdev = st->out + 3 * n;
@@ -2346,7 +2502,7 @@ extern "C" int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_f
     if (st->len != 1) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t n = st->P + st->S;
     for (size_t i = 0; i < n; i++) {
@@ -2390,7 +2546,7 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
     if (st->len != (size_t(1) << num_rounds)) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     sbn::merlin::State& tr = *(sbn::merlin::State*)merlin;
     const size_t n = st->P + st->S;
@@ -2500,7 +2656,7 @@ extern "C" int sbn_addrs_upload(sbn_ctx* ctx, const uint32_t* row_addrs, const u
     *out = nullptr;
     if (batch == 0 || N == 0 || batch * N > (size_t(1) << 31)) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_addrs* a = new (std::nothrow) sbn_addrs();
     if (!a) return SBN_ERR_OOM;
     a->ctx = ctx;
@@ -2549,7 +2705,7 @@ extern "C" int sbn_addrs_set_timestamps(sbn_addrs* a, const uint32_t* row_read_t
     if (num_cells == 0 || (num_cells & (num_cells - 1)) || a->max_row >= num_cells || a->max_col >= num_cells) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = a->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     const uint32_t* src_r[2] = {row_read_ts, col_read_ts};
     const uint32_t* src_a[2] = {row_audit_ts, col_audit_ts};
     const size_t ops_bytes = a->batch * a->N * sizeof(uint32_t), mem_bytes = num_cells * sizeof(uint32_t);
@@ -2598,7 +2754,7 @@ static int derefs_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_addrs*
     const size_t L = nrows;                               // rows committed by this call (a rank's block of the Hyrax matrix)
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     sbn_poly* p = new (std::nothrow) sbn_poly();
     if (!p) return SBN_ERR_OOM;
@@ -2657,7 +2813,7 @@ extern "C" size_t sbn_poly_len(const sbn_poly* p) { return p ? p->len : 0; }
 extern "C" int sbn_poly_download(sbn_ctx* ctx, const sbn_poly* p, sbn_fr* out) {
     if (!ctx || !p || !out || p->ctx != ctx) return SBN_ERR_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(download(ctx, out, p->Z, p->len * sizeof(Fr)));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
@@ -2691,7 +2847,7 @@ extern "C" int sbn_hashlayer_build(sbn_ctx* ctx, const sbn_addrs* a, int side, c
     if (!a->read_ts[side] || !a->audit_ts[side]) return SBN_ERR_ARG;                 // sbn_addrs_set_timestamps first
     if (nr == 0 || nr > 30 || (size_t(1) << nr) != a->num_cells || a->N < 2 || (a->N & (a->N - 1)) || a->num_cells < 2) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t M = a->num_cells, N = a->N, B = a->batch, ncirc = 2 + 2 * B;
     for (size_t i = 0; i < ncirc; i++) circuits_out[i] = nullptr;
@@ -2742,7 +2898,7 @@ extern "C" int sbn_prodcircuit_download_layer(sbn_prodcircuit* pc, size_t layer,
     if (layer >= (size_t)pc->num_layers) return SBN_ERR_SHAPE;
     sbn_ctx* ctx = pc->ctx;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     SBN_TRY(download(ctx, out, pc->buf + pc->off[layer], (pc->len >> layer) * sizeof(Fr)));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return SBN_OK;
@@ -2757,7 +2913,7 @@ extern "C" int sbn_poly_evaluate(sbn_ctx* ctx, const sbn_poly* poly, size_t offs
     const size_t n = size_t(1) << nr;
     if (offset > poly->len || n > poly->len - offset) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const unsigned blocks = (unsigned)std::min<size_t>(592, (n + kDotThreads - 1) / kDotThreads);
     SBN_TRY(ensure(ctx, ctx->scratch0, 2 * n * sizeof(Fr)));
@@ -2787,7 +2943,7 @@ extern "C" int sbn_poly_evaluate_strided(sbn_ctx* ctx, const sbn_poly* poly, siz
     if (offset0 > poly->len || n > poly->len - offset0 || (count > 1 && (stride == 0 || (count - 1) > (poly->len - offset0 - n) / stride)))
         return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const unsigned blocks = (unsigned)std::min<size_t>(std::max<size_t>(1, 1184 / count), (n + kDotThreads - 1) / kDotThreads);
     SBN_TRY(ensure(ctx, ctx->scratch0, 2 * n * sizeof(Fr)));
@@ -2817,7 +2973,7 @@ extern "C" int sbn_spark_comb_polys(sbn_ctx* ctx, const sbn_addrs* a, const sbn_
     if (!a->read_ts[0] || !a->audit_ts[0]) return SBN_ERR_ARG;
     *comb_ops = *comb_mem = nullptr;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t seg = a->batch * a->N, used = 5 * seg;
     size_t len = 1;
@@ -2863,7 +3019,7 @@ extern "C" int sbn_poly_triple_dot(sbn_ctx* ctx, const sbn_poly* A, size_t offA,
     if (n == 0 || offA > A->len || n > A->len - offA || offB > B->len || n > B->len - offB || offC > Cp->len || n > Cp->len - offC)
         return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const unsigned blocks = (unsigned)std::min<size_t>(592, (n + kDotThreads - 1) / kDotThreads);
     SBN_TRY(ensure(ctx, ctx->scratch1, (blocks + 1) * sizeof(Fr)));
@@ -2885,7 +3041,7 @@ extern "C" int sbn_spark_evaluate(sbn_ctx* ctx, const sbn_addrs* a, const sbn_po
     if (nx == 0 || ny == 0 || nx > 30 || ny > 30) return SBN_ERR_SHAPE;
     if (a->max_row >= (size_t(1) << nx) || a->max_col >= (size_t(1) << ny) || comb_ops->len < 5 * a->batch * a->N) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t tx = size_t(1) << nx, ty = size_t(1) << ny, N = a->N, B = a->batch;
     const unsigned blocks = (unsigned)std::min<size_t>(592, (N + kDotThreads - 1) / kDotThreads);
@@ -2932,7 +3088,7 @@ extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_
     std::vector<uint32_t> heavy_rows;
     for (size_t i = 0; i < n; i++) if (ptr[i + 1] - ptr[i] > kSpmvHeavy) heavy_rows.push_back((uint32_t)i);
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     sbn_spmat* m = new (std::nothrow) sbn_spmat();
     if (!m) return SBN_ERR_OOM;
     m->ctx = ctx; m->n = n; m->nnz = nnz; m->ncols = ncols;
@@ -3005,7 +3161,7 @@ extern "C" int sbn_spmat_mulvec(sbn_ctx* ctx, const sbn_spmat* const* mats, cons
         if (mats[m]->n != mats[0]->n || mats[m]->ncols > veclen) return SBN_ERR_SHAPE;
     }
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t n = mats[0]->n;
     SBN_TRY(upload(ctx, ctx->scratch0, vec, veclen * sizeof(Fr)));
@@ -3045,7 +3201,7 @@ extern "C" int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mat
         if (mats[m]->n != len || mats[m]->ncols > zlen) return SBN_ERR_SHAPE;
     }
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     SBN_TRY(ensure(ctx, ctx->zkeep, zlen * sizeof(Fr)));
     ctx->zkeep_len = 0;
@@ -3077,7 +3233,7 @@ extern "C" int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const
         if (mats_t[m]->n != zlen || mats_t[m]->ncols > veclen) return SBN_ERR_SHAPE;
     }
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     SBN_TRY(ensure(ctx, ctx->scratch0, 2 * veclen * sizeof(Fr)));
     SBN_TRY(ensure(ctx, ctx->scratch2, n_rx * sizeof(Fr)));
@@ -3101,7 +3257,7 @@ extern "C" int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out
     if (!ctx || !out || (n && !r)) return SBN_ERR_ARG;
     if (n > 28) return SBN_ERR_SHAPE;
     std::lock_guard<std::mutex> g(ctx->mu);
-    SBN_CUDA(ctx, cudaSetDevice(ctx->device));
+    SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const size_t len = size_t(1) << n;
     SBN_TRY(ensure(ctx, ctx->scratch0, 2 * len * sizeof(Fr)));

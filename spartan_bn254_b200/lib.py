@@ -120,9 +120,10 @@ class Context:
         return dict(kernel_launches=a.value, h2d_bytes=b.value, d2h_bytes=c.value)
 
     def memory_stats(self):
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 8)()
         self._check(self.lib.sbn_ctx_memory_stats(self.h, out), "sbn_ctx_memory_stats")
-        return dict(pool_bytes=int(out[0]), pool_flushes=int(out[1]), mult_table_fallbacks=int(out[2]), pool_buffers=int(out[3]))
+        return dict(pool_bytes=int(out[0]), pool_flushes=int(out[1]), mult_table_fallbacks=int(out[2]), pool_buffers=int(out[3]),
+                    small_scalar_commits=int(out[4]))
 
     def last_commit_profile(self):
         ms = (C.c_float * 4)()

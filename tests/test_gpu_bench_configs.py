@@ -96,6 +96,44 @@ def test_enc_8192x8192_small_scalars(orc):
         Z = ctx.fr_from_canonical(synth.small_scalars_canonical(8, L * R))
         C, inf = _commit_device(ctx, bases, Z, L, R)
         _check_rows(orc, G, h, Z, L, R, C, inf, 64)
+        assert ctx.memory_stats()["small_scalar_commits"] == 1, "21-bit scalars must take the short window schedule"
+        ctx.set("small_scalar_path", 0)                    # and the general path gives the same points
+        C2, inf2 = _commit_device(ctx, bases, Z, L, R)
+        assert np.array_equal(C, C2) and np.array_equal(inf, inf2)
+        bases.close()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("gens_kind", ["distinct", "ref"])
+def test_mixed_small_and_full_rows(orc, gens_kind):
+    """comb_ops-like layout (sparse_mlpoly_full.rs:176-196): runs of rows of small values (addresses, timestamps) around a
+    run of full-size ones (matrix coefficients), plus an isolated small row and an all-zero row; the row classification must
+    send each run through its own schedule and reproduce the oracle everywhere.  With the reference's generators two thirds of
+    the columns merge into one point, whose scalars add up (the schedule must allow for the extra bits)."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.hyrax import MultiCommitGens
+    ctx = Context(0)
+    try:
+        L, R = 1024, 512
+        if gens_kind == "distinct":
+            G, h = synth.distinct_generators(ctx, R)
+        else:
+            g = MultiCommitGens.new(R, b"gens_r1cs_eval", ctx)
+            G, h = g.G, g.h
+        bases = ctx.bases(G, h)
+        small = ctx.fr_from_canonical(synth.small_scalars_canonical(3, L * R)).reshape(L, R, 4)
+        full = synth.uniform_scalars(4, L * R).reshape(L, R, 4)
+        Z = small.copy()
+        Z[400:700] = full[400:700]          # a run of full-size rows
+        Z[100] = full[100]                  # one full-size row inside a small run
+        Z[800] = 0
+        Z[900, 7] = full[900, 7]            # a single large scalar makes its row large
+        Z = np.ascontiguousarray(Z.reshape(L * R, 4))
+        C, inf = _commit_device(ctx, bases, Z, L, R)
+        assert ctx.memory_stats()["small_scalar_commits"] == 1
+        rows = _check_rows(orc, G, h, Z, L, R, C, inf, 96, must_include=(99, 100, 101, 399, 400, 699, 700, 800, 899, 900, 901, 1023))
+        assert inf[800] == 1 and len(rows) >= 96
         bases.close()
     finally:
         ctx.close()
