@@ -33,6 +33,11 @@ extern "C" {
     pub fn sbn_bases_mult_table(b: *const sbn_bases, window_bits: *mut c_int, bytes: *mut u64) -> c_int;
     pub fn sbn_hyrax_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, z: *const SbnFr, l_size: usize, r_size: usize,
                             blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_hyrax_commit_multi(ctxs: *const *mut sbn_ctx, bases: *const *const sbn_bases, k: usize, z: *const SbnFr,
+                                  l_size: usize, r_size: usize, blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_ctx_memory_stats(ctx: *mut sbn_ctx, out: *mut u64) -> c_int;
+    pub fn sbn_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    pub fn sbn_host_free(p: *mut c_void) -> c_int;
     pub fn sbn_msm(ctx: *mut sbn_ctx, pts: *const SbnG1a, inf: *const u8, s: *const SbnFr, n: usize,
                    out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, s: *const SbnFr, n: usize, blind: *const SbnFr,
@@ -171,6 +176,131 @@ pub fn hyrax_commit(ctx: &Context, bases: &Bases, z: &[Fr], blinds: &[Fr]) -> Ve
           "sbn_hyrax_commit");
     c.iter().zip(inf.iter()).map(|(p, i)| from_abi(p, *i)).collect()
 }
+
+/// The same commit over several GPUs of this process (`Context` per device, `Bases` per context): contiguous row blocks,
+/// one host thread per device inside the library, no inter-GPU traffic (the Rayon fan-out of hyrax.rs:259-265).
+pub fn hyrax_commit_multi(ctxs: &[&Context], bases: &[&Bases], z: &[Fr], blinds: &[Fr]) -> Vec<G1Affine> {
+    assert_eq!(ctxs.len(), bases.len());
+    let l_size = blinds.len();
+    let r_size = z.len() / l_size;
+    assert_eq!(l_size * r_size, z.len());
+    let cp: Vec<*mut sbn_ctx> = ctxs.iter().map(|c| c.0).collect();
+    let bp: Vec<*const sbn_bases> = bases.iter().map(|b| b.h as *const sbn_bases).collect();
+    let mut c = vec![SbnG1a::default(); l_size];
+    let mut inf = vec![0u8; l_size];
+    let zero_blinds = blinds.iter().all(|b| b.is_zero_vartime());
+    let blp = if zero_blinds { std::ptr::null() } else { blinds.as_ptr() as *const SbnFr };
+    check(unsafe { sbn_hyrax_commit_multi(cp.as_ptr(), bp.as_ptr(), cp.len(), z.as_ptr() as *const SbnFr, l_size, r_size, blp,
+                                          c.as_mut_ptr(), inf.as_mut_ptr()) }, "sbn_hyrax_commit_multi");
+    c.iter().zip(inf.iter()).map(|(p, i)| from_abi(p, *i)).collect()
+}
+
+/// Drop-in body of `GroupElement::msm_affine` (group.rs:171-175).  arkworks' `G1Projective::msm` returns `Err` when the
+/// slices differ in length and the reference swallows it with `unwrap_or_default()` (group.rs:156,173): the identity.  The
+/// same here, without touching the GPU.  An empty MSM is the identity too.
+pub fn msm_affine(ctx: &Context, scalars: &[Fr], points: &[G1Affine]) -> G1Affine {
+    if scalars.len() != points.len() || scalars.is_empty() {
+        return G1Affine::identity();
+    }
+    let (pts, inf): (Vec<_>, Vec<_>) = points.iter().map(to_abi).unzip();
+    let mut out = SbnG1a::default();
+    let mut out_inf = 0u8;
+    check(unsafe { sbn_msm(ctx.0, pts.as_ptr(), inf.as_ptr(), scalars.as_ptr() as *const SbnFr, scalars.len(), &mut out, &mut out_inf) },
+          "sbn_msm");
+    from_abi(&out, out_inf)
+}
+
+/// `<[Scalar] as Commitments>::commit` (commitments.rs:144-154) over a resident generator set.
+pub fn commit(ctx: &Context, bases: &Bases, scalars: &[Fr], blind: &Fr) -> G1Affine {
+    assert_eq!(bases.n, scalars.len());                                  // commitments.rs:146
+    let mut out = SbnG1a::default();
+    let mut out_inf = 0u8;
+    check(unsafe { sbn_commit(ctx.0, bases.h, scalars.as_ptr() as *const SbnFr, scalars.len(), blind as *const Fr as *const SbnFr,
+                              &mut out, &mut out_inf) }, "sbn_commit");
+    from_abi(&out, out_inf)
+}
+
+/// Drop-in body of `DensePolynomial::bound` (hyrax.rs:311-324): LZ[i] = sum_j L[j] * Z[j * R_size + i].
+pub fn bound(ctx: &Context, z: &[Fr], l: &[Fr]) -> Vec<Fr> {
+    let l_size = l.len();
+    let r_size = z.len() / l_size;
+    assert_eq!(l_size * r_size, z.len());
+    let mut out = vec![SbnFr::default(); r_size];
+    check(unsafe { sbn_bound(ctx.0, z.as_ptr() as *const SbnFr, l.as_ptr() as *const SbnFr, l_size, r_size, out.as_mut_ptr()) },
+          "sbn_bound");
+    out.into_iter().map(|v| ark_ff::Fp(BigInt(v.l), core::marker::PhantomData)).collect()
+}
+
+/// `BulletReductionProof::prove` (nizk/bullet.rs:24-126) with a, b, the folding coefficients and the generator tables
+/// resident on the GPU.  The caller keeps the transcript: per round it appends L, R, draws u and hands it back.
+///
+/// ```ignore
+/// let mut red = BulletReduction::begin(&ctx, &bases_ext, &q, None, a, b, &blind);   // Gamma = red.gamma (bullet.rs:57)
+/// for (bl, br) in blinds_vec {                                                      // bullet.rs:63
+///     let (l, r) = red.round(bl, br);                                               // :75-76
+///     transcript.append_point(b"L", &l.compress()); transcript.append_point(b"R", &r.compress());
+///     let u = transcript.challenge_scalar(b"u");                                    // :81-83
+///     red.fold(&u, &u.invert().unwrap());                                           // :85-104
+/// }
+/// let (a_hat, b_hat, g_hat) = red.end();                                            // :108-125
+/// ```
+pub struct BulletReduction { st: *mut sbn_bullet, pub gamma: G1Affine }
+impl BulletReduction {
+    pub fn begin(ctx: &Context, bases_ext: &Bases, q: &G1Affine, q_scalar: Option<&Fr>, a: &[Fr], b: &[Fr], blind: &Fr) -> Self {
+        assert_eq!(a.len(), b.len());                                    // bullet.rs:42-47
+        assert!(a.len().is_power_of_two());
+        let (qa, _) = to_abi(q);
+        let mut st = std::ptr::null_mut();
+        let mut gamma = SbnG1a::default();
+        let mut ginf = 0u8;
+        let qs = q_scalar.map(|s| s as *const Fr as *const SbnFr).unwrap_or(std::ptr::null());
+        check(unsafe { sbn_bullet_begin(ctx.0, bases_ext.h, &qa, qs, a.as_ptr() as *const SbnFr, b.as_ptr() as *const SbnFr, a.len(),
+                                        blind as *const Fr as *const SbnFr, &mut gamma, &mut ginf, &mut st) }, "sbn_bullet_begin");
+        BulletReduction { st, gamma: from_abi(&gamma, ginf) }
+    }
+    pub fn round(&mut self, blind_l: &Fr, blind_r: &Fr) -> (G1Affine, G1Affine) {
+        let (mut l, mut r, mut li, mut ri) = (SbnG1a::default(), SbnG1a::default(), 0u8, 0u8);
+        check(unsafe { sbn_bullet_round(self.st, blind_l as *const Fr as *const SbnFr, blind_r as *const Fr as *const SbnFr,
+                                        &mut l, &mut li, &mut r, &mut ri) }, "sbn_bullet_round");
+        (from_abi(&l, li), from_abi(&r, ri))
+    }
+    pub fn fold(&mut self, u: &Fr, u_inv: &Fr) {
+        check(unsafe { sbn_bullet_fold(self.st, u as *const Fr as *const SbnFr, u_inv as *const Fr as *const SbnFr) }, "sbn_bullet_fold");
+    }
+    pub fn end(self) -> (Fr, Fr, G1Affine) {
+        let (mut a, mut b, mut g, mut gi) = (SbnFr::default(), SbnFr::default(), SbnG1a::default(), 0u8);
+        check(unsafe { sbn_bullet_end(self.st, &mut a, &mut b, &mut g, &mut gi) }, "sbn_bullet_end");
+        (ark_ff::Fp(BigInt(a.l), core::marker::PhantomData), ark_ff::Fp(BigInt(b.l), core::marker::PhantomData), from_abi(&g, gi))
+    }
+}
+impl Drop for BulletReduction { fn drop(&mut self) { unsafe { sbn_bullet_destroy(self.st) }; } }
+
+/// A generator set with gens_1's point addressable (DotProductProofGens, nizk/mod.rs:412-415): what the opening uses.
+impl Bases {
+    pub fn new_ext(ctx: &Context, g_affine: &[G1Affine], g1: &G1Affine, h_affine: &G1Affine) -> Self {
+        let (pts, inf): (Vec<_>, Vec<_>) = g_affine.iter().map(to_abi).unzip();
+        let (h, _) = to_abi(h_affine);
+        let (g1a, _) = to_abi(g1);
+        let mut out = std::ptr::null_mut();
+        check(unsafe { sbn_bases_create_ext(ctx.0, pts.as_ptr(), inf.as_ptr(), pts.len(), &g1a, &h, &mut out) }, "sbn_bases_create_ext");
+        Bases { h: out, n: pts.len() }
+    }
+}
+
+/// Pinned host memory for a polynomial's evaluations: `sbn_hyrax_commit` copies from pageable memory at roughly half the rate
+/// (bench.py `e2e.pageable_value`); a prover that builds its Z vectors in this buffer gets the pinned figure.
+pub struct PinnedScalars { ptr: *mut Fr, len: usize }
+impl PinnedScalars {
+    pub fn new(len: usize) -> Self {
+        let mut p: *mut c_void = std::ptr::null_mut();
+        check(unsafe { sbn_host_alloc(&mut p, len * std::mem::size_of::<Fr>()) }, "sbn_host_alloc");
+        unsafe { std::ptr::write_bytes(p as *mut u8, 0, len * std::mem::size_of::<Fr>()) };       // all-zero limbs = Fr::zero()
+        PinnedScalars { ptr: p as *mut Fr, len }
+    }
+    pub fn as_mut_slice(&mut self) -> &mut [Fr] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) } }
+    pub fn as_slice(&self) -> &[Fr] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
+}
+impl Drop for PinnedScalars { fn drop(&mut self) { unsafe { sbn_host_free(self.ptr as *mut c_void) }; } }
 
 trait IsZeroVartime { fn is_zero_vartime(&self) -> bool; }
 impl IsZeroVartime for Fr { fn is_zero_vartime(&self) -> bool { self.into_bigint().0 == [0u64; 4] } }
