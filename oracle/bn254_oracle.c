@@ -25,6 +25,7 @@
 #include <string.h>
 #include <pthread.h>
 #include <unistd.h>
+#include <time.h>
 
 /* minimal parallel-for over [0,n) with dynamic chunking (the image's gcc has no libgomp) */
 typedef void (*pf_body)(long i, void* ctx);
@@ -1068,4 +1069,405 @@ int orc_poly_eval_verify(const orc_eval_proof* proof, size_t ell, const ofp* r, 
     }
     free(Lv); free(Rv); free(s);
     return result;
+}
+
+/* ==================================================================================================================
+ * CPU BASELINE of the end-to-end prove (bench.py's cpu_baseline leg for the second half of BASELINE.json's metric).
+ *
+ * orc_prove_workload() runs, on the host threads, the table-sized phases of SNARK::prove (snark.rs:428-484) for a synthetic
+ * R1CS of the keyless shape -- n = 2^s constraints and variables, 3 + 2 + 1 non-zeros per row so that every matrix pads to
+ * 4 n entries (the shape bench.py's GPU prove uses) -- in the reference's order, with the reference's algorithms (file:line
+ * at every phase), the real field and group arithmetic of this file, and every round's challenge drawn from a Merlin
+ * transcript fed with that round's evaluations, so the rounds are as sequential as the prover's.  It is a RESTATEMENT OF THE
+ * WORK, not a prover: tables are seeded pseudo-random values (a satisfying assignment changes no operation count), the
+ * Sigma-protocols of the ZK sumchecks are represented by their commitments (four short MSMs per round), and nothing is
+ * assembled into a proof or verified -- tests/test_snark.py does that for the GPU prover.  The reference itself runs these
+ * phases with Rayon over rows / table entries; threads here play that role.
+ * ================================================================================================================== */
+static double wall_now(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static inline uint64_t wl_mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static inline void wl_scalar(uint64_t seed, uint64_t i, ofp* out) {      /* a valid Montgomery representative (< 2^253 < r) */
+    for (int k = 0; k < 4; k++) out->l[k] = wl_mix(seed * 0x100000001B3ULL + 4 * i + (uint64_t)k);
+    out->l[3] &= (1ULL << 61) - 1;
+}
+typedef struct { ofp* v; uint64_t seed; } wl_fill_ctx;
+static void wl_fill_body(long i, void* vc) { wl_fill_ctx* c = (wl_fill_ctx*)vc; wl_scalar(c->seed, (uint64_t)i, &c->v[i]); }
+static ofp* wl_table(size_t n, uint64_t seed, int threads) {
+    ofp* v = (ofp*)malloc(sizeof(ofp) * n);
+    wl_fill_ctx c = {v, seed};
+    parallel_for((long)n, 4096, threads, wl_fill_body, &c);
+    return v;
+}
+
+/* --- threaded forms of the table passes (the serial ones above are the oracle's; these split the index range) */
+#define WL_MAX_THREADS 256
+typedef struct { ofp** T; int nt; size_t half; const ofp* r; } wl_bind_ctx;
+static void wl_bind_body(long i, void* vc) {                             /* bound_poly_var_top, hyrax.rs:195-203 */
+    wl_bind_ctx* c = (wl_bind_ctx*)vc;
+    for (int k = 0; k < c->nt; k++) {
+        ofp d;
+        fp_sub(FR, &c->T[k][(size_t)i + c->half], &c->T[k][i], &d);
+        fp_mul(FR, c->r, &d, &d);
+        fp_add(FR, &c->T[k][i], &d, &c->T[k][i]);
+    }
+}
+typedef struct { const ofp* A; const ofp* B; const ofp* C; const ofp* D; size_t half, per; ofp (*part)[3]; int mode; } wl_eval_ctx;
+static void wl_eval_body(long blk, void* vc) {
+    /* mode 0: tau * (Az * Bz - Cz) at 0, 2, 3 (sumcheck.rs:501-530); mode 1: z * ABC at 0, 2 (sumcheck.rs:690-699);
+     * mode 2: A * B * eq at 0, 2, 3 (product layer, sumcheck.rs:236-262) */
+    wl_eval_ctx* c = (wl_eval_ctx*)vc;
+    size_t lo = (size_t)blk * c->per, hi = lo + c->per;
+    if (hi > c->half) hi = c->half;
+    ofp s[3], t, u;
+    memset(s, 0, sizeof s);
+    const ofp* T[4] = {c->A, c->B, c->C, c->D};
+    const int nt = c->mode == 0 ? 4 : (c->mode == 1 ? 2 : 3);
+    for (size_t i = lo; i < hi; i++) {
+        ofp v[3][4];
+        for (int k = 0; k < nt; k++) {
+            const ofp *a = &T[k][i], *b = &T[k][c->half + i];
+            v[0][k] = *a;
+            fp_add(FR, b, b, &v[1][k]); fp_sub(FR, &v[1][k], a, &v[1][k]);           /* 2b - a */
+            fp_add(FR, &v[1][k], b, &v[2][k]); fp_sub(FR, &v[2][k], a, &v[2][k]);    /* 3b - 2a */
+        }
+        for (int e = 0; e < 3; e++) {
+            if (c->mode == 1 && e == 2) break;
+            if (c->mode == 0) { fp_mul(FR, &v[e][1], &v[e][2], &t); fp_sub(FR, &t, &v[e][3], &t); fp_mul(FR, &v[e][0], &t, &u); }
+            else if (c->mode == 1) fp_mul(FR, &v[e][0], &v[e][1], &u);
+            else { fp_mul(FR, &v[e][0], &v[e][1], &t); fp_mul(FR, &t, &v[e][2], &u); }
+            fp_add(FR, &s[e], &u, &s[e]);
+        }
+    }
+    memcpy(c->part[blk], s, sizeof s);
+}
+/* one sumcheck: `rounds` rounds of evaluate + challenge + bind over nt tables of length len; ncommit short commitments per
+ * round stand for comm_poly and the per-round dot-product proof of the ZK variants (sumcheck.rs:533-649) */
+static void wl_sumcheck(ofp** T, int nt, size_t len, int mode, int rounds, int ncommit, const og1a* G4, orc_transcript* tr, int threads_in) {
+    const int nth = host_threads(threads_in);
+    ofp (*part)[3] = (ofp(*)[3])malloc(sizeof(ofp[3]) * (size_t)nth * 4);
+    for (int j = 0; j < rounds && len > 1; j++) {
+        const size_t half = len / 2;
+        const int threads = half >= 8192 ? threads_in : 1;        /* a thread team costs more than a short round (Rayon's pool would not split it either) */
+        long nblk = threads == 1 ? 1 : (long)nth * 4;
+        if ((size_t)nblk > half) nblk = (long)half;
+        wl_eval_ctx ec = {T[0], T[1], nt > 2 ? T[2] : NULL, nt > 3 ? T[3] : NULL, half, (half + (size_t)nblk - 1) / (size_t)nblk, part, mode};
+        parallel_for(nblk, 1, threads, wl_eval_body, &ec);
+        ofp e[3];
+        memset(e, 0, sizeof e);
+        for (long b = 0; b < nblk; b++) for (int k = 0; k < 3; k++) fp_add(FR, &e[k], &part[b][k], &e[k]);
+        for (int k = 0; k < ncommit; k++) {                   /* 4-point commitments (comm_poly, delta, beta, ...) */
+            og1j acc;
+            ofp sc[4] = {e[0], e[1], e[2], e[(k + j) % 3]};
+            msm_naive(G4, NULL, sc, 4, &acc);
+            og1a p; uint8_t inf;
+            j_to_affine(&acc, &p, &inf);
+            t_point(tr, "comm_poly", &p, inf);
+        }
+        for (int k = 0; k < 3; k++) t_scalar(tr, "poly", &e[k]);
+        ofp r;
+        t_challenge(tr, "challenge_nextround", &r);
+        wl_bind_ctx bc = {T, nt, half, &r};
+        parallel_for((long)half, 2048, threads, wl_bind_body, &bc);
+        len = half;
+    }
+    free(part);
+}
+typedef struct { ofp** circ; const size_t* clen; const ofp* eq; size_t len; int layer; const og1a* G4; const orc_transcript* tr; } wl_layer_ctx;
+static void wl_layer_body(long k, void* vc) {                             /* one circuit's share of a layer's batched sumcheck */
+    wl_layer_ctx* c = (wl_layer_ctx*)vc;
+    const size_t len = c->len;
+    if (c->clen[k] < 2 * len) return;
+    size_t off = 0, l2 = c->clen[k];
+    while (l2 > 2 * len) { off += l2; l2 /= 2; }             /* the stored layer with 2 len entries: left half, right half */
+    ofp* tabs[3];
+    for (int t = 0; t < 3; t++) tabs[t] = (ofp*)malloc(sizeof(ofp) * len);
+    memcpy(tabs[0], c->circ[k] + off, sizeof(ofp) * len);
+    memcpy(tabs[1], c->circ[k] + off + len, sizeof(ofp) * len);
+    memcpy(tabs[2], c->eq, sizeof(ofp) * len);
+    orc_transcript local = *c->tr;
+    wl_sumcheck(tabs, 3, len, 2, c->layer, 0, c->G4, &local, 1);
+    for (int t = 0; t < 3; t++) free(tabs[t]);
+}
+typedef struct { const ofp* eq_r; const ofp* eq_c; const ofp* z; ofp* out; size_t n; int nnz_per_row; uint64_t seed; int mode; } wl_sp_ctx;
+static void wl_sparse_body(long i, void* vc) {
+    /* mode 0: (M z)[i] = sum val * z[col] (r1cs.rs:275-288); mode 1: sum val * eq_rx[row] * eq_ry[col] per row
+     * (R1CSInstance::evaluate, sparse_mlpoly.rs), the row's partial sum stored in out[i] */
+    wl_sp_ctx* c = (wl_sp_ctx*)vc;
+    ofp acc, val, t;
+    memset(&acc, 0, sizeof acc);
+    for (int k = 0; k < c->nnz_per_row; k++) {
+        const uint64_t h = wl_mix(c->seed + (uint64_t)i * 8 + (uint64_t)k);
+        const size_t col = (size_t)(h % c->n);
+        wl_scalar(c->seed ^ 0x5555, (uint64_t)i * 8 + (uint64_t)k, &val);
+        if (c->mode == 0) fp_mul(FR, &val, &c->z[col], &t);
+        else { fp_mul(FR, &val, &c->eq_r[i], &t); fp_mul(FR, &t, &c->eq_c[col], &t); }
+        fp_add(FR, &acc, &t, &acc);
+    }
+    c->out[i] = acc;
+}
+typedef struct { const ofp* mem; ofp* out; size_t n; uint64_t seed; const ofp* g1; const ofp* g2; int mode; size_t cells; } wl_hash_ctx;
+static void wl_hash_body(long i, void* vc) {
+    /* mode 0: derefs gather out[i] = mem[addr_i] (AddrTimestamps::deref, sparse_mlpoly_full.rs:245-257);
+     * mode 1: hash of a (addr, val, ts) triple, addr * gamma^2 + val * gamma + ts - tau (:745-790) */
+    wl_hash_ctx* c = (wl_hash_ctx*)vc;
+    const size_t addr = (size_t)(wl_mix(c->seed + (uint64_t)i) % c->cells);
+    if (c->mode == 0) { c->out[i] = c->mem[addr]; return; }
+    ofp a, t, u;
+    memset(&a, 0, sizeof a);
+    a.l[0] = addr;
+    fp_mul(FR, &a, c->g2, &t);
+    fp_mul(FR, &c->mem[addr], c->g1, &u);
+    fp_add(FR, &t, &u, &t);
+    a.l[0] = (uint64_t)i & 0xfffff;
+    fp_mul(FR, &a, c->g1, &u);            /* the timestamp enters Montgomery form through a product, as on the GPU */
+    fp_add(FR, &t, &u, &c->out[i]);
+}
+typedef struct { const ofp* in; ofp* out; size_t half; } wl_prod_ctx;
+static void wl_prod_body(long i, void* vc) {                              /* ProductCircuit::new layers, product_tree.rs:39-57 */
+    wl_prod_ctx* c = (wl_prod_ctx*)vc;
+    fp_mul(FR, &c->in[i], &c->in[(size_t)i + c->half], &c->out[i]);
+}
+typedef struct { const ofp* a; const ofp* b; size_t per, n; ofp* part; } wl_dot_ctx;
+static void wl_dot_body(long blk, void* vc) {                             /* DensePolynomial::evaluate, hyrax.rs:217-222 */
+    wl_dot_ctx* c = (wl_dot_ctx*)vc;
+    size_t lo = (size_t)blk * c->per, hi = lo + c->per;
+    if (hi > c->n) hi = c->n;
+    fr_dot(c->a + lo, c->b + lo, hi > lo ? hi - lo : 0, &c->part[blk]);
+}
+static void wl_opening(const ofp* Z, size_t ell, const og1a* G, const og1a* h, const og1a* G1, int with_blinds, orc_transcript* tr,
+                       orc_transcript* tape) {                            /* PolyEvalProof::prove, hyrax.rs:65-116 */
+    ofp r[64], Zr, blind;
+    for (size_t k = 0; k < ell; k++) t_challenge(tr, "r", &r[k]);
+    wl_scalar(99, ell, &Zr);
+    wl_scalar(98, ell, &blind);
+    ofp* blinds = NULL;
+    if (with_blinds) blinds = wl_table((size_t)1 << (ell / 2), 97, 0);
+    orc_eval_proof proof;
+    og1a cz; uint8_t czi;
+    orc_poly_eval_prove(Z, ell, blinds, r, &Zr, &blind, G, h, G1, tr, tape, &proof, &cz, &czi);
+    free(blinds);
+}
+
+#define WL_PHASES 13
+static const char* const WL_NAMES[WL_PHASES] = {
+    "witness_commit", "Az_Bz_Cz", "sumcheck_phase1", "eval_tables_phase2", "sumcheck_phase2", "witness_opening",
+    "instance_evaluation", "eq_tables_derefs_gather", "derefs_commit", "network_construction", "product_layer_sumchecks",
+    "hash_layer_evaluations", "hash_layer_openings"};
+const char* orc_prove_workload_phase_name(int i) { return i >= 0 && i < WL_PHASES ? WL_NAMES[i] : ""; }
+int orc_prove_workload_phases(void) { return WL_PHASES; }
+
+/* s = log2(constraints) (even or odd, >= 10); derefs_rows_done: 0 = commit every row, otherwise only that many of the
+ * non-zero rows are committed and seconds[8] is scaled up to all of them (flagged by the return value 1) -- the caller
+ * states it.  gens_seconds (may be NULL) receives the one-off generator derivation time (SNARKGens::new, not part of prove). */
+int orc_prove_workload(int s, int threads, size_t derefs_rows_done, double* seconds, double* gens_seconds) {
+    if (s < 10 || s > 24) return -1;
+    const size_t n = (size_t)1 << s, m = 4 * n;              /* nnz padded per matrix */
+    const int ell_w = s, ell_d = s + 5, ell_o = s + 6, ell_m = s + 2;
+    for (int i = 0; i < WL_PHASES; i++) seconds[i] = 0;
+    double t0 = wall_now();
+    /* generators: gens_r1cs_sat over 2^(s - s/2), gens_r1cs_eval over 2^(ell_o - ell_o/2) (its prefixes serve derefs / mem) */
+    const size_t Rw = (size_t)1 << (ell_w - ell_w / 2), Ro = (size_t)1 << (ell_o - ell_o / 2);
+    og1a* Gw = (og1a*)malloc(sizeof(og1a) * (Rw + 2));
+    og1a* Go = (og1a*)malloc(sizeof(og1a) * (Ro + 2));
+    orc_multi_commit_gens((const uint8_t*)"gens_r1cs_sat", 13, Rw + 1, Gw);
+    orc_multi_commit_gens((const uint8_t*)"gens_r1cs_eval", 14, Ro + 1, Go);
+    if (gens_seconds) *gens_seconds = wall_now() - t0;
+    orc_transcript tr, tape;
+    orc_transcript_new(&tr, (const uint8_t*)"snark", 5);
+    orc_transcript_new(&tape, (const uint8_t*)"tape", 4);
+    int scaled = 0;
+
+    /* 0. R1CSProof::commit_poly (r1csproof.rs:210-237): witness polynomial, random blinds */
+    ofp* z = wl_table(2 * n, 1, threads);                    /* (vars, 1, inputs) padded: z of the second sumcheck */
+    {
+        const size_t Lw = n / Rw;
+        ofp* blinds = wl_table(Lw, 2, threads);
+        og1a* C = (og1a*)malloc(sizeof(og1a) * Lw);
+        uint8_t* inf = (uint8_t*)malloc(Lw);
+        t0 = wall_now();
+        orc_hyrax_commit(Gw, &Gw[Rw + 1], z, Lw, Rw, blinds, threads, C, inf);
+        for (size_t i = 0; i < Lw; i++) t_point(&tr, "poly_commitment_share", &C[i], inf[i]);
+        seconds[0] = wall_now() - t0;
+        free(blinds); free(C); free(inf);
+    }
+    /* 1. Az, Bz, Cz (r1cs.rs:275-288) */
+    ofp* T1[4];
+    t0 = wall_now();
+    {
+        const int nnz[3] = {3, 2, 1};
+        for (int k = 0; k < 3; k++) {
+            T1[k + 1] = (ofp*)malloc(sizeof(ofp) * n);
+            wl_sp_ctx c = {NULL, NULL, z, T1[k + 1], 2 * n, nnz[k], 100 + (uint64_t)k, 0};
+            parallel_for((long)n, 1024, threads, wl_sparse_body, &c);
+        }
+    }
+    seconds[1] = wall_now() - t0;
+    /* 2. first ZK sumcheck (sumcheck.rs:465-649): eq(tau) table, s cubic rounds over 4 tables */
+    t0 = wall_now();
+    {
+        ofp tau[64];
+        for (int k = 0; k < s; k++) t_challenge(&tr, "challenge_tau", &tau[k]);
+        T1[0] = (ofp*)malloc(sizeof(ofp) * n);
+        orc_eq_evals(tau, (size_t)s, T1[0]);
+        wl_sumcheck(T1, 4, n, 0, s, 4, Gw, &tr, threads);
+    }
+    seconds[2] = wall_now() - t0;
+    for (int k = 0; k < 4; k++) free(T1[k]);
+    /* 3. evaluation tables of the second phase: eq(rx) and r_A A^T eq + r_B B^T eq + r_C C^T eq (r1cs.rs compute_eval_table_sparse) */
+    ofp* T2[2];
+    t0 = wall_now();
+    {
+        ofp rx[64];
+        for (int k = 0; k < s; k++) t_challenge(&tr, "rx", &rx[k]);
+        ofp* eq = (ofp*)malloc(sizeof(ofp) * n);
+        orc_eq_evals(rx, (size_t)s, eq);
+        T2[1] = (ofp*)calloc(2 * n, sizeof(ofp));
+        /* scatter val * eq[row] into column col: as many products as non-zeros; done as a gather over rows here */
+        ofp* tmp = (ofp*)malloc(sizeof(ofp) * n);
+        for (int k = 0; k < 3; k++) {
+            const int nnz[3] = {3, 2, 1};
+            wl_sp_ctx c = {NULL, NULL, eq, tmp, n, nnz[k], 200 + (uint64_t)k, 0};
+            parallel_for((long)n, 1024, threads, wl_sparse_body, &c);
+            for (size_t i = 0; i < n; i++) fp_add(FR, &T2[1][i], &tmp[i], &T2[1][i]);
+        }
+        free(tmp); free(eq);
+    }
+    seconds[3] = wall_now() - t0;
+    /* 4. second ZK sumcheck (sumcheck.rs:657-811): s + 1 quadratic rounds over (z, ABC) */
+    t0 = wall_now();
+    T2[0] = (ofp*)malloc(sizeof(ofp) * 2 * n);
+    memcpy(T2[0], z, sizeof(ofp) * 2 * n);
+    wl_sumcheck(T2, 2, 2 * n, 1, s + 1, 4, Gw, &tr, threads);
+    seconds[4] = wall_now() - t0;
+    free(T2[0]); free(T2[1]);
+    /* 5. opening of the witness commitment (r1csproof.rs:70-121 = hyrax.rs:65-116) */
+    t0 = wall_now();
+    wl_opening(z, (size_t)ell_w, Gw, &Gw[Rw + 1], &Gw[Rw], 1, &tr, &tape);
+    seconds[5] = wall_now() - t0;
+    /* 6. instance evaluation at (rx, ry) (snark.rs:455-460): eq tables + one pass over the non-zeros */
+    t0 = wall_now();
+    ofp *mem_rx = (ofp*)malloc(sizeof(ofp) * 2 * n), *mem_ry = (ofp*)malloc(sizeof(ofp) * 2 * n);
+    {
+        ofp rr[64];
+        for (int k = 0; k < s + 1; k++) t_challenge(&tr, "ry", &rr[k]);
+        orc_eq_evals(rr, (size_t)s, mem_rx);
+        orc_eq_evals(rr, (size_t)s + 1, mem_ry);
+        ofp* tmp = (ofp*)malloc(sizeof(ofp) * n);
+        for (int k = 0; k < 3; k++) {
+            const int nnz[3] = {3, 2, 1};
+            wl_sp_ctx c = {mem_rx, mem_ry, NULL, tmp, 2 * n, nnz[k], 300 + (uint64_t)k, 1};
+            parallel_for((long)n, 1024, threads, wl_sparse_body, &c);
+        }
+        free(tmp);
+    }
+    seconds[6] = wall_now() - t0;
+    /* 7. derefs (sparse_mlpoly_full.rs:245-257, 292-297): 3 row + 3 col gathers of m entries, merged, zero-padded to 8 m */
+    t0 = wall_now();
+    ofp* derefs = (ofp*)calloc((size_t)1 << ell_d, sizeof(ofp));
+    for (int k = 0; k < 6; k++) {
+        wl_hash_ctx c = {k < 3 ? mem_rx : mem_ry, derefs + (size_t)k * m, m, 400 + (uint64_t)k, NULL, NULL, 0, k < 3 ? n : 2 * n};
+        parallel_for((long)m, 4096, threads, wl_hash_body, &c);
+    }
+    seconds[7] = wall_now() - t0;
+    /* 8. Derefs::commit (sparse_mlpoly_full.rs:301-304 -> hyrax.rs:253-267): zero blinds; the last quarter of the rows is zero */
+    {
+        const size_t Rd = (size_t)1 << (ell_d - ell_d / 2), Ld = ((size_t)1 << ell_d) / Rd, live = (6 * m + Rd - 1) / Rd;
+        size_t done = live;
+        if (derefs_rows_done && derefs_rows_done < live) { done = derefs_rows_done; scaled = 1; }
+        og1a* C = (og1a*)malloc(sizeof(og1a) * Ld);
+        uint8_t* inf = (uint8_t*)malloc(Ld);
+        t0 = wall_now();
+        orc_hyrax_commit(Go, &Go[Ro + 1], derefs, done, Rd, NULL, threads, C, inf);     /* gens_derefs = a prefix of gens_ops' G */
+        for (size_t i = 0; i < done; i++) t_point(&tr, "poly_commitment_share", &C[i], inf[i]);
+        seconds[8] = (wall_now() - t0) * ((double)live / (double)done);
+        free(C); free(inf);
+    }
+    /* 9. network construction (sparse_mlpoly_full.rs:745-866): hash layers of both sides + their product circuits */
+    const int ncirc = 16;
+    ofp* circ[16];
+    size_t clen[16];
+    t0 = wall_now();
+    {
+        ofp g1, g2;
+        t_challenge(&tr, "challenge_gamma_hash", &g1);
+        fp_mul(FR, &g1, &g1, &g2);
+        for (int k = 0; k < ncirc; k++) {
+            const int side = k / 8, idx = k % 8;                 /* per side: init, 3 reads, 3 writes, audit */
+            clen[k] = (idx == 0 || idx == 7) ? 2 * n : m;
+            circ[k] = (ofp*)malloc(sizeof(ofp) * 2 * clen[k]);    /* layer 0 followed by the upper layers */
+            wl_hash_ctx c = {side ? mem_ry : mem_rx, circ[k], clen[k], 500 + (uint64_t)k, &g1, &g2, 1, side ? 2 * n : n};
+            parallel_for((long)clen[k], 4096, threads, wl_hash_body, &c);
+            size_t off = 0, len = clen[k];
+            while (len > 1) {
+                wl_prod_ctx pc = {circ[k] + off, circ[k] + off + len, len / 2};
+                parallel_for((long)(len / 2), 4096, threads, wl_prod_body, &pc);
+                off += len;
+                len /= 2;
+            }
+        }
+    }
+    seconds[9] = wall_now() - t0;
+    /* 10. ProductLayerProof::prove (product_tree.rs:251-392): per layer, one batched cubic sumcheck (sumcheck.rs:165-330) over
+     *     (left, right, eq) of every circuit that has that layer.  The reference batches the circuits into one sumcheck and lets
+     *     Rayon split every round; here the circuits of a layer run side by side, one thread each, every one with its own copy
+     *     of the transcript -- the same field work, and a thread team per layer instead of one per round. */
+    t0 = wall_now();
+    {
+        int top = 0;
+        while (((size_t)1 << top) < m) top++;
+        for (int layer = 1; layer < top; layer++) {              /* a layer with 2^layer outputs per circuit */
+            const size_t len = (size_t)1 << layer;
+            ofp rr[64];
+            for (int k = 0; k < layer; k++) t_challenge(&tr, "challenge_r_layer", &rr[k]);
+            ofp* eq = (ofp*)malloc(sizeof(ofp) * len);
+            orc_eq_evals(rr, (size_t)layer, eq);
+            wl_layer_ctx lc = {circ, clen, eq, len, layer, Gw, &tr};
+            parallel_for(ncirc, 1, threads, wl_layer_body, &lc);
+            free(eq);
+        }
+    }
+    seconds[10] = wall_now() - t0;
+    for (int k = 0; k < ncirc; k++) free(circ[k]);
+    /* 11. HashLayerProof::prove (sparse_mlpoly_full.rs:907-1100): evaluations of the derefs / comb_ops / comb_mem segments
+     *     (hyrax.rs:217-222) and the three joint openings (hyrax.rs:65-116) */
+    t0 = wall_now();
+    {
+        ofp rr[64];
+        for (int k = 0; k < s + 2; k++) t_challenge(&tr, "r_ops", &rr[k]);
+        ofp* eq = (ofp*)malloc(sizeof(ofp) * m);
+        orc_eq_evals(rr, (size_t)s + 2, eq);
+        const int nth = host_threads(threads);
+        ofp* part = (ofp*)malloc(sizeof(ofp) * (size_t)nth * 4);
+        ofp* ops = wl_table((size_t)1 << ell_o, 7, threads);     /* comb_ops: 15 segments of m + padding */
+        for (int seg = 0; seg < 6 + 15 + 2; seg++) {
+            const ofp* base = seg < 6 ? derefs + (size_t)seg * m : ops + (size_t)((seg - 6) % 15) * m;
+            const size_t len = seg < 21 ? m : 2 * n;
+            wl_dot_ctx dc = {base, eq, (len + (size_t)nth * 4 - 1) / ((size_t)nth * 4), len, part};
+            parallel_for((long)nth * 4, 1, threads, wl_dot_body, &dc);
+            ofp e;
+            memset(&e, 0, sizeof e);
+            for (int b = 0; b < nth * 4; b++) fp_add(FR, &e, &part[b], &e);
+            t_scalar(&tr, "eval", &e);
+        }
+        free(part); free(eq);
+        seconds[11] = wall_now() - t0;
+        t0 = wall_now();
+        const size_t Rd = (size_t)1 << (ell_d - ell_d / 2), Rm = (size_t)1 << (ell_m - ell_m / 2);
+        wl_opening(derefs, (size_t)ell_d, Go, &Go[Ro + 1], &Go[Rd], 0, &tr, &tape);
+        wl_opening(ops, (size_t)ell_o, Go, &Go[Ro + 1], &Go[Ro], 0, &tr, &tape);
+        wl_opening(ops, (size_t)ell_m, Go, &Go[Ro + 1], &Go[Rm], 0, &tr, &tape);          /* comb_mem: 2^(s+2) values */
+        free(ops);
+    }
+    seconds[12] = wall_now() - t0;
+    free(derefs); free(mem_rx); free(mem_ry); free(z); free(Gw); free(Go);
+    return scaled;
 }

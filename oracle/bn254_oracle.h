@@ -98,6 +98,15 @@ int orc_poly_eval_verify(const orc_eval_proof* proof, size_t ell, const ofp* r, 
                          const og1a* comm, const uint8_t* comm_inf, const og1a* G, const og1a* h, const og1a* G1,
                          orc_transcript* transcript);
 
+/* CPU baseline of the end-to-end prove: the table-sized phases of SNARK::prove (snark.rs:428-484) for a synthetic R1CS of
+ * the keyless shape with 2^s constraints, on `threads` host threads (0 = all); seconds[] has orc_prove_workload_phases()
+ * entries.  A restatement of the WORK (same algorithms, operation counts and round-to-round dependencies), not a prover.
+ * derefs_rows_done > 0 commits only that many derefs rows and scales that phase up (returns 1 then, 0 otherwise, < 0 on a
+ * bad argument). */
+int orc_prove_workload(int s, int threads, size_t derefs_rows_done, double* seconds, double* gens_seconds);
+int orc_prove_workload_phases(void);
+const char* orc_prove_workload_phase_name(int i);
+
 #ifdef __cplusplus
 }
 #endif

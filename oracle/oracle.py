@@ -300,3 +300,18 @@ def evaluate(Z, r):
     for a, b in zip(zs, cs):
         acc = (acc + a * b) % R_MOD
     return to_mont([acc])[0]
+
+
+def prove_workload(log_cons, threads=0, derefs_rows=0):
+    """CPU baseline of the end-to-end prove (orc_prove_workload): -> dict(seconds=total, phases={name: s}, scaled=bool,
+    gens_seconds=one-off generator derivation)."""
+    L = lib()
+    L.orc_prove_workload_phase_name.restype = C.c_char_p
+    n = L.orc_prove_workload_phases()
+    sec = (C.c_double * n)()
+    gens = C.c_double()
+    rc = L.orc_prove_workload(C.c_int(log_cons), C.c_int(threads), C.c_size_t(derefs_rows), sec, C.byref(gens))
+    if rc < 0:
+        raise ValueError("orc_prove_workload: bad argument")
+    phases = {L.orc_prove_workload_phase_name(i).decode(): float(sec[i]) for i in range(n)}
+    return dict(seconds=sum(phases.values()), phases=phases, scaled=bool(rc), gens_seconds=float(gens.value))
