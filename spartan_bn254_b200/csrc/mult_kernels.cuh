@@ -399,6 +399,183 @@ k_bat_finish(const uint32_t* __restrict__ entries, const Affine* __restrict__ ta
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused rounds ("layout 2").  Ablation of the pipeline above (profiles/r2_ablation_cfg1.txt): of 2.62 ms per cfg1 commit the
+// finish passes take 1.42, the prefix passes 0.77 -- for a sixth of the multiplications: standing alone they are a serial
+// chain of one product per pair behind two loads, bound by latency, not by the multiplier.  Here the prefix pass of round
+// k + 1 rides inside the finish pass of round k: a thread owns ONE ROW and a run of B consecutive pair positions of it, so the
+// two sums that form a pair of the next round come out of the same thread one after the other, and their denominator goes
+// into the next round's running product on the spot (one more product per two additions, in a kernel that is already on
+// the multiplier).  B halves from round to round (32, 16, ..., 1 for six rounds) while the threads stay the same, and the
+// walk alternates direction: a round consumes its running products last-to-first, which is the order the next round's
+// products are built in.  Only round 1 keeps a prefix kernel of its own (its operands are table gathers).
+//   warp w of the grid = (position block w / (rp / 32), rows 32 (w % (rp / 32)) ...); chain of thread = positions pb B ... pb B + B - 1
+//   accumulation step t of a chain <-> position  q0 + t (ascending rounds: 1, 3, 5)  or  q0 + B - 1 - t (descending: 2, 4, 6)
+//   prefix[q rp + r] = product of the chain's denominators BEFORE that pair (exclusive)
+// ------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fq lds_fq(const uint4* a, int i) {
+    const uint4 u = a[2 * i], v = a[2 * i + 1];
+    Fq r;
+    r.l[0] = u.x; r.l[1] = u.y; r.l[2] = u.z; r.l[3] = u.w; r.l[4] = v.x; r.l[5] = v.y; r.l[6] = v.z; r.l[7] = v.w;
+    return r;
+}
+__device__ __forceinline__ void sts_fq(uint4* a, int i, const Fq& v) {
+    a[2 * i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    a[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// other[t] = product of the other threads' totals of this block, *total = the block's total (see k_bat_prefix)
+__device__ __forceinline__ void bat_block_scan(const Fq& run, Fq* __restrict__ other_block, Fq* __restrict__ total, uint4* s_tot,
+                                               uint4* s_exc) {
+    __syncthreads();                                   // the caller may still be reading the shared arrays it aliases
+    sts_fq(s_tot, threadIdx.x, run);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    Fq acc = fq_one();
+#pragma unroll 1
+    for (int i = 0; i < kBaThreads / 32; i++) {
+        const int t = i * 32 + lane;
+        sts_fq(s_exc, t, acc);
+        acc = fp_mul(acc, lds_fq(s_tot, t));
+    }
+    Fq pre = acc, suf = acc;
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        Fq a = shfl_fq(pre, (lane - off) & 31), b = shfl_fq(suf, (lane + off) & 31);
+        if (lane < off) a = fq_one();
+        if (lane + off >= 32) b = fq_one();
+        pre = fp_mul(pre, a);
+        suf = fp_mul(suf, b);
+    }
+    Fq pe = shfl_fq(pre, (lane - 1) & 31), se = shfl_fq(suf, (lane + 1) & 31);
+    if (lane == 0) pe = fq_one();
+    if (lane == 31) se = fq_one();
+    acc = fp_mul(pe, se);
+#pragma unroll 1
+    for (int i = kBaThreads / 32 - 1; i >= 0; i--) {
+        const int t = i * 32 + lane;
+        store_fq(other_block + t, fp_mul(acc, lds_fq(s_exc, t)));
+        acc = fp_mul(acc, lds_fq(s_tot, t));
+    }
+    if (lane == 31) store_fq(total, pre);
+}
+
+struct BatSlot { uint32_t r, pb; bool valid; };
+__device__ __forceinline__ BatSlot bat2_slot(uint32_t rp, uint32_t npb) {
+    const uint32_t w = blockIdx.x * (kBaThreads / 32) + (threadIdx.x >> 5), groups = rp >> 5;
+    BatSlot s;
+    s.pb = w / groups;
+    s.r = (w % groups) * 32 + (threadIdx.x & 31);
+    s.valid = s.pb < npb;
+    return s;
+}
+
+// Round 1's running products: chain position q0 + t, operands entries[(2q) rp + r], entries[(2q + 1) rp + r]
+__global__ void __launch_bounds__(kBaThreads)
+k_bat2_prefix1(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, uint32_t npb, uint32_t rp, int B,
+               Fq* __restrict__ prefix, Fq* __restrict__ other, Fq* __restrict__ block_tot) {
+    __shared__ uint4 s_tot[kBaThreads * 2], s_exc[kBaThreads * 2];
+    const BatSlot sl = bat2_slot(rp, npb);
+    Fq run = fq_one();
+    if (sl.valid) {
+        const uint32_t q0 = sl.pb * (uint32_t)B;
+        size_t iP = (size_t)2 * q0 * rp + sl.r;
+        uint32_t ex = __ldg(entries + iP), ey = __ldg(entries + iP + rp);
+#pragma unroll 1
+        for (int t = 0; t < B; t++) {
+            const size_t g = (size_t)(q0 + t) * rp + sl.r;
+            const uint32_t cx = ex, cy = ey;
+            if (t + 1 < B) {                           // next pair's entries: in flight under this pair's gathers and product
+                iP += (size_t)2 * rp;
+                ex = __ldg(entries + iP);
+                ey = __ldg(entries + iP + rp);
+            }
+            store_fq(prefix + g, run);
+            Fq d;
+            if (bat_denominator<true>(cx, cy, table, nullptr, nullptr, 0, rp, d)) run = fp_mul(run, d);
+        }
+    }
+    bat_block_scan(run, other + (size_t)blockIdx.x * kBaThreads, block_tot + blockIdx.x, s_tot, s_exc);
+}
+
+// One round: the additions of this round's pairs (walking the chain last-to-first) and, when EMIT, the running products of
+// the next round's pairs.  ASC: this round's chain was accumulated in ascending position order.
+template <bool FIRST, bool EMIT, int MINB>
+__global__ void __launch_bounds__(kBaThreads, MINB)
+k_bat2_round(const uint32_t* __restrict__ entries, const Affine* __restrict__ table, const Fq* __restrict__ inx,
+             const Fq* __restrict__ iny, uint32_t npb, uint32_t rp, int B, int asc, const Fq* __restrict__ prefix,
+             const Fq* __restrict__ other, const Fq* __restrict__ block_inv, Fq* __restrict__ outx, Fq* __restrict__ outy,
+             Fq* __restrict__ prefix_next, Fq* __restrict__ other_next, Fq* __restrict__ block_tot_next) {
+    __shared__ uint4 s_a[kBaThreads * 2], s_b[kBaThreads * 2];       // previous sum of the thread (x, y); then the scan's scratch
+    const BatSlot sl = bat2_slot(rp, npb);
+    Fq run2 = fq_one();
+    if (sl.valid) {
+        const uint32_t q0 = sl.pb * (uint32_t)B;
+        const size_t u = (size_t)blockIdx.x * kBaThreads + threadIdx.x;
+        Fq run = fp_mul(load_fq(block_inv + blockIdx.x), load_fq(other + u));      // (own chain total)^-1
+#pragma unroll 1
+        for (int t = B - 1; t >= 0; t--) {
+            const uint32_t q = asc ? q0 + (uint32_t)t : q0 + (uint32_t)(B - 1 - t);
+            const size_t g = (size_t)q * rp + sl.r, iP = 2 * g - sl.r;
+            Affine P, Q;
+            if (FIRST) {
+                const uint32_t ex = __ldg(entries + iP), ey = __ldg(entries + iP + rp);
+                if (ex == kNullEntry) P = Affine::identity();
+                else { P.x = load_fq_tab(&table[ex & 0x7fffffffu].x); P.y = load_fq_tab(&table[ex & 0x7fffffffu].y); }
+                if (ey == kNullEntry) Q = Affine::identity();
+                else { Q.x = load_fq_tab(&table[ey & 0x7fffffffu].x); Q.y = load_fq_tab(&table[ey & 0x7fffffffu].y); }
+                if (ex != kNullEntry && (ex >> 31) && !P.is_identity()) P.y = fp_neg(P.y);
+                if (ey != kNullEntry && (ey >> 31) && !Q.is_identity()) Q.y = fp_neg(Q.y);
+            } else {
+                P.x = load_fq(inx + iP); P.y = load_fq(iny + iP);
+                Q.x = load_fq(inx + iP + rp); Q.y = load_fq(iny + iP + rp);
+            }
+            Fq d;
+            const int kind = ba_classify(P, Q, d);
+            Affine S;
+            if (kind == BA_NONE) {
+                if (P.is_identity()) S = Q;
+                else if (Q.is_identity()) S = P;
+                else S = Affine::identity();
+            } else {
+                Fq inv_d = run;
+                if (t > 0) inv_d = fp_mul(run, load_fq(prefix + g));     // exclusive running product of this chain
+                run = fp_mul(run, d);
+                Fq num;
+                if (kind == BA_ADD) {
+                    num = fp_sub(Q.y, P.y);
+                } else {
+                    const Fq xx = fp_mul(P.x, P.x);
+                    num = fp_add(fp_dbl(xx), xx);
+                }
+                const Fq lambda = fp_mul(num, inv_d);
+                const Fq x3 = fp_sub(fp_sub(fp_mul(lambda, lambda), P.x), Q.x);
+                S.x = x3;
+                S.y = fp_sub(fp_mul(lambda, fp_sub(P.x, x3)), P.y);
+            }
+            store_fq(outx + g, S.x);
+            store_fq(outy + g, S.y);
+            if (EMIT) {
+                if (t & 1) {                                   // first of the two sums of a next-round pair: park it
+                    sts_fq(s_a, threadIdx.x, S.x);
+                    sts_fq(s_b, threadIdx.x, S.y);
+                } else {                                       // second: positions q and q +- 1 -> pair q / 2 of the next round
+                    Affine T;
+                    T.x = lds_fq(s_a, threadIdx.x);
+                    T.y = lds_fq(s_b, threadIdx.x);
+                    // the next round reads its pair as (position 2q', position 2q' + 1): keep that operand order
+                    const bool s_is_low = (q & 1) == 0;
+                    Fq d2;
+                    const int k2 = s_is_low ? ba_classify(S, T, d2) : ba_classify(T, S, d2);
+                    store_fq(prefix_next + (size_t)(q >> 1) * rp + sl.r, run2);
+                    if (k2 != BA_NONE) run2 = fp_mul(run2, d2);
+                }
+            }
+        }
+    }
+    if (EMIT) bat_block_scan(run2, other_next + (size_t)blockIdx.x * kBaThreads, block_tot_next + blockIdx.x, s_a, s_b);
+}
+
 // warp per row: totals[row] = sum of the row's `cnt` points, point i of row r at [i * rp + r] of the x and y arrays.
 // (A block per row with a shared-memory tree -- 9 additions deep instead of 13 -- was measured and is slower, 2.66 against
 // 2.62 ms per cfg1 commit: the kernel's cost is the ~256 XYZZ additions per row, not their depth.)
