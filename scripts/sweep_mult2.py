@@ -43,20 +43,9 @@ def run(tag, n=20):
     return ms
 
 
-ctx.set("mult_layout", 1); run("layout 1: position-major, separate prefix passes")
-ctx.set("mult_layout", 2); run("layout 2: fused rounds, minb=3")
-ctx.set("ba_minb", 4); run("layout 2: fused rounds, minb=4")
-ctx.set("ba_minb", 3)
-for streams, chunk in ((1, 0), (2, 256), (4, 256), (2, 1024)):
-    ctx.set("mult_streams", streams); ctx.set("chunk_rows", chunk)
-    run(f"layout 2 streams={streams} chunk={chunk}")
-ctx.set("mult_streams", 2); ctx.set("chunk_rows", 0)
-for r in (5, 7):
-    ctx.set("mult_rounds", r)
-    run(f"layout 2 rounds={r}")
-ctx.set("mult_rounds", 0)
-for ab, what in ((1, "prefix<1>"), (4, "invert"), (8, "sum_rows"), (16, "round 1"), (32, "rounds 2-6")):
-    ctx.set("ablate", ab)
-    ref = None
-    run(f"layout 2 WITHOUT {what}")
-ctx.set("ablate", 0)
+for rounds in (6, 5, 4, 3):
+    for wpr in (1, 2, 4):
+        ctx.set("mult_rounds", rounds); ctx.set("sum_wpr", wpr)
+        run(f"rounds={rounds} warps per row={wpr}")
+ctx.set("mult_rounds", 0); ctx.set("sum_wpr", 0)
+run("auto")

@@ -579,25 +579,45 @@ k_bat2_round(const uint32_t* __restrict__ entries, const Affine* __restrict__ ta
 // warp per row: totals[row] = sum of the row's `cnt` points, point i of row r at [i * rp + r] of the x and y arrays.
 // (A block per row with a shared-memory tree -- 9 additions deep instead of 13 -- was measured and is slower, 2.66 against
 // 2.62 ms per cfg1 commit: the kernel's cost is the ~256 XYZZ additions per row, not their depth.)
+// WPR warps per row (1, 2 or 4; a block is 4 warps): every lane adds cnt / (32 WPR) points, a shuffle tree adds the lanes,
+// the warps of a row meet in shared memory.  The additions are inlined -- the out-of-line forms keep the accumulator in
+// local memory, which cost 2.68 against 2.56 ms per cfg1 commit.
+template <int WPR>
 __global__ void __launch_bounds__(kMultSumThreads)
 k_mult_sum_rows_t(const Fq* __restrict__ ptsx, const Fq* __restrict__ ptsy, uint32_t cnt, uint32_t rp, int rows,
                   XYZZ* __restrict__ totals) {
-    const int lane = threadIdx.x & 31;
-    const int row = (int)((blockIdx.x * (unsigned)kMultSumThreads + threadIdx.x) >> 5);
-    if (row >= rows) return;
+    __shared__ XYZZ s_w[kMultSumThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = (int)(blockIdx.x * (unsigned)(kMultSumThreads / 32 / WPR)) + warp / WPR;
+    const int part = warp % WPR;
     XYZZ acc = XYZZ::identity();
-    for (uint32_t i = lane; i < cnt; i += 32) {
-        Affine p;
-        p.x = load_fq(ptsx + (size_t)i * rp + row);
-        p.y = load_fq(ptsy + (size_t)i * rp + row);
-        if (!p.is_identity()) xyzz_add_mixed_call(&acc, &p);
+    if (row < rows) {
+#pragma unroll 1
+        for (uint32_t i = (uint32_t)(part * 32 + lane); i < cnt; i += 32 * WPR) {
+            Affine p;
+            p.x = load_fq(ptsx + (size_t)i * rp + row);
+            p.y = load_fq(ptsy + (size_t)i * rp + row);
+            if (p.is_identity()) continue;
+            xyzz_add_mixed<MulInline>(acc, p);
+        }
+#pragma unroll 1
+        for (int stride = 16; stride >= 1; stride >>= 1) {
+            XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
+            if (lane >= stride) o = XYZZ::identity();
+            xyzz_add<MulInline, MulCall>(acc, o);
+        }
     }
-    for (int stride = 16; stride >= 1; stride >>= 1) {
-        XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
-        if (lane >= stride) o = XYZZ::identity();
-        xyzz_add_call(&acc, &o);
+    if (WPR == 1) {
+        if (lane == 0 && row < rows) store_xyzz(totals + row, acc);
+        return;
     }
-    if (lane == 0) store_xyzz(totals + row, acc);
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    if (part == 0 && lane == 0 && row < rows) {
+#pragma unroll 1
+        for (int k = 1; k < WPR; k++) xyzz_add<MulInline, MulCall>(acc, s_w[warp + k]);
+        store_xyzz(totals + row, acc);
+    }
 }
 
 // warp per row: totals[row] = sum of the row's `cnt` affine points.  Lanes add cnt / 32 points each (mixed additions), a

@@ -78,6 +78,7 @@ struct sbn_ctx {
     long ba_prefetch = 0;              // round 1 (measured: loses 5 %): entries read two pairs ahead, table points prefetched into L2 one pair ahead
     long finish_smem_kb = 0;           // dynamic shared memory requested by the finish pass: caps its resident blocks so that a prefix pass of the other stream co-resides
     long prefix_smem_kb = 0;
+    long sum_wpr = 0;                  // warps per row of the final row sums (1, 2, 4); 0 = by the number of points left
     long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
     long small_scalar_path = 1;        // commits without blinds scan their scalars' bit length and use a short window schedule when it is small
     long small_scalar_hits = 0;        // commits that took it
@@ -425,6 +426,9 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
             cudaFuncSetAttribute(k_bat_prefix<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         }
         if (cudaGetLastError() != cudaSuccess) return SBN_ERR_CUDA;
+    } else if (!strcmp(key, "sum_wpr")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return SBN_ERR_ARG;
+        ctx->sum_wpr = value;
     } else if (!strcmp(key, "ablate")) {
         ctx->ablate = value;
     } else if (!strcmp(key, "small_scalar_path")) {
@@ -1122,9 +1126,23 @@ static const Affine* mult_small_table(sbn_ctx* ctx, sbn_bases* b, int bits) {
     return nullptr;
 }
 
+static void launch_sum_rows(sbn_ctx* ctx, int rows, cudaStream_t st, const Fq* px, const Fq* py, uint32_t cnt, uint32_t rp, int nrows,
+                            XYZZ* totals) {
+    (void)nrows;
+    (void)cnt;
+    const int wpr = ctx->sum_wpr > 0 ? (int)ctx->sum_wpr : 1;      // more warps per row only add shuffle-tree levels: 2.55 / 2.61 / 2.73 ms at 1 / 2 / 4
+    const unsigned rows_per_block = (unsigned)(kMultSumThreads / 32 / wpr);
+    const unsigned blocks = ((unsigned)rows + rows_per_block - 1) / rows_per_block;
+    if (wpr == 4) k_mult_sum_rows_t<4><<<blocks, kMultSumThreads, 0, st>>>(px, py, cnt, rp, rows, totals);
+    else if (wpr == 2) k_mult_sum_rows_t<2><<<blocks, kMultSumThreads, 0, st>>>(px, py, cnt, rp, rows, totals);
+    else k_mult_sum_rows_t<1><<<blocks, kMultSumThreads, 0, st>>>(px, py, cnt, rp, rows, totals);
+}
+
 static int mult_rounds_for(uint32_t used) {
     int r = 1;
-    while (r < 10 && (used >> (r + 1)) >= 192) r++;      // leave a few hundred points per row to the XYZZ sum
+    // leave ~400-800 points per row to the XYZZ sum: with its additions inlined the sum kernel is cheap enough that a sixth
+    // round (three more launches and a 26 us inversion for 257 instead of 514 points) no longer pays: 2.55 -> 2.52 ms at cfg1
+    while (r < 10 && (used >> (r + 1)) >= 384) r++;
     return r;
 }
 
@@ -1259,7 +1277,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
                     iny = outy;
                 }
                 if (!(ctx->ablate & 8))
-                    k_mult_sum_rows_t<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, st>>>(
+                    launch_sum_rows(ctx, rows, st, 
                         inx, iny, npb, rp, rows, totals + row0[ci]);
                 ctx->launches++;
                 marks.mark(1, st);
@@ -1302,7 +1320,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
                 ctx->launches += 3;
             }
             if (!(ctx->ablate & 8))
-                k_mult_sum_rows_t<<<(unsigned)((rows * 32 + kMultSumThreads - 1) / kMultSumThreads), kMultSumThreads, 0, st>>>(
+                launch_sum_rows(ctx, rows, st, 
                     inx, iny, stride >> rounds, rp, rows, totals + row0[ci]);
             ctx->launches++;
             marks.mark(1, st);
