@@ -304,6 +304,11 @@ int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats, const sb
                             size_t n_tau, sbn_sumcheck** out);
 int sbn_sumcheck_begin_quad_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats_t, const sbn_fr* coeffs, const sbn_fr* rx,
                                  size_t n_rx, const sbn_fr* z, size_t zlen, sbn_sumcheck** out);
+/* begin_r1cs with z = (vars, tail, 0 ... 0) assembled on the device from the resident witness polynomial (sbn_poly_upload of the
+ * variables, the same handle R1CSProof::commit_poly committed, r1csproof.rs:210-237,255-265): `tail` = the n_tail scalars that
+ * follow the variables (the constant 1 and the public inputs), zlen = 2 * num_vars.  Nothing table-sized crosses the bus. */
+int sbn_sumcheck_begin_r1cs_resident(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_poly* vars, const sbn_fr* tail,
+                                     size_t n_tail, size_t zlen, const sbn_fr* tau, size_t n_tau, sbn_sumcheck** out);
 /* EqPolynomial::evals (hyrax.rs:355-369): the 2^n evaluations of eq(r, .), computed on the device. */
 int sbn_eq_evals(sbn_ctx* ctx, const sbn_fr* r, size_t n, sbn_fr* out);
 

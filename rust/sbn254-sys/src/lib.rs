@@ -76,6 +76,8 @@ extern "C" {
     // the same two set-ups with the tables built in HBM from the resident matrices (r1csproof.rs:268-290, 378-410)
     pub fn sbn_sumcheck_begin_r1cs(ctx: *mut sbn_ctx, mats: *const *const sbn_spmat, z: *const SbnFr, zlen: usize, tau: *const SbnFr,
                                    n_tau: usize, out: *mut *mut sbn_sumcheck) -> c_int;
+    pub fn sbn_sumcheck_begin_r1cs_resident(ctx: *mut sbn_ctx, mats: *const *const sbn_spmat, vars: *const sbn_poly, tail: *const SbnFr,
+                                            n_tail: usize, zlen: usize, tau: *const SbnFr, n_tau: usize, out: *mut *mut sbn_sumcheck) -> c_int;
     pub fn sbn_sumcheck_begin_quad_r1cs(ctx: *mut sbn_ctx, mats_t: *const *const sbn_spmat, coeffs: *const SbnFr, rx: *const SbnFr,
                                         n_rx: usize, z: *const SbnFr, zlen: usize, out: *mut *mut sbn_sumcheck) -> c_int;
     pub fn sbn_sumcheck_round_eval(st: *mut sbn_sumcheck, e0: *mut SbnFr, e2: *mut SbnFr, e3: *mut SbnFr) -> c_int;

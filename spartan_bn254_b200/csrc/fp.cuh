@@ -194,8 +194,68 @@ SBN_HD Fp<F> fp_dbl(const Fp<F>& a) { return fp_add(a, a); }
 // division by 2^32 is a role swap: E' = O + e[1],  O' = E >> 64.
 // Bound: T < a + p <= 3p < 2^256 after every iteration, so neither accumulator overflows.
 // ------------------------------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__) && defined(SBN_HOST_FAST_FP)
+// Host-side product for the library's own host code (transcript challenges, UniPoly arithmetic of the in-library sumcheck
+// loops, point compression): the same CIOS on 4 x 64-bit limbs with unsigned __int128.  The 32-bit form below, with the PTX
+// carry flag emulated through a thread-local, is what the host TESTS compile (they exist to exercise the DEVICE algorithm);
+// it costs ~1 us per product, which 441 sumcheck rounds and 4096 compressed points per proof turn into milliseconds.
+template <class F>
+inline Fp<F> fp_mul_host64(const Fp<F>& a, const Fp<F>& b) {
+    typedef unsigned __int128 u128;
+    uint64_t A[4], B[4], P[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+        B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+        P[i] = (uint64_t)F::P(2 * i) | ((uint64_t)F::P(2 * i + 1) << 32);
+    }
+    // -p^-1 mod 2^64 from the 32-bit constant: one Newton step (x <- x (2 + p x) for the negated inverse)
+    uint64_t inv = (uint64_t)F::INV;
+    inv = inv * (2 + P[0] * inv);
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)A[j] * B[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        const uint64_t m = t[0] * inv;
+        c = (u128)m * P[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)m * P[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    // one conditional subtraction: the result is below 2p for a < 2p (b any 256-bit value), as in the 32-bit form
+    uint64_t r[4], borrow = 0;
+    for (int i = 0; i < 4; i++) {
+        const u128 d = (u128)t[i] - P[i] - borrow;
+        r[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    const bool ge = t[4] != 0 || borrow == 0;
+    Fp<F> out;
+    for (int i = 0; i < 4; i++) {
+        const uint64_t v = ge ? r[i] : t[i];
+        out.l[2 * i] = (uint32_t)v;
+        out.l[2 * i + 1] = (uint32_t)(v >> 32);
+    }
+    return out;
+}
+#endif
+
 template <class F>
 SBN_HD Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
+#if !defined(__CUDA_ARCH__) && defined(SBN_HOST_FAST_FP)
+    return fp_mul_host64(a, b);
+#else
     // Both accumulators start at zero and every word iteration (including the first) has the same
     // shape: with a special-cased first iteration ptxas splits the a*b_i products into
     // IMAD + IMAD.HI + IADD3 instead of IMAD.WIDE.U32.X (IMAD.HI is half rate on sm_100).
@@ -253,6 +313,7 @@ SBN_HD Fp<F> fp_mul(const Fp<F>& a, const Fp<F>& b) {
     r.l[7] = addc(e[7], 0u);
     fp_reduce_once(r);
     return r;
+#endif
 }
 
 template <class F>

@@ -192,14 +192,27 @@ __global__ void k_spmv(SpMat m0, SpMat m1, SpMat m2, Fr c0, Fr c1, Fr c2, int nm
     store_fr(out + i, total);
 }
 
-// out[row] += coeff * sum_k val[k] * vec[idx[k]] for the heavy rows of one matrix: one block per heavy row.
+// out[row] += coeff * sum_k val[k] * vec[idx[k]] for the heavy rows of one matrix.  The constant-1 column of an R1CS transpose
+// holds one entry per constraint (2^20 at keyless scale): one block walking it is 4096 dependent gather + product steps per
+// thread (8 ms, most of the second sumcheck's set-up).  kSpmvSplit blocks per heavy row write partial sums, a second launch
+// adds them up.
+static constexpr int kSpmvSplit = 128;
 __global__ void __launch_bounds__(kDotThreads)
-k_spmv_heavy(SpMat m, const uint32_t* __restrict__ heavy_rows, Fr coeff, int use_coeff, const Fr* __restrict__ vec, Fr* __restrict__ out) {
+k_spmv_heavy_partial(SpMat m, const uint32_t* __restrict__ heavy_rows, const Fr* __restrict__ vec, Fr* __restrict__ part) {
+    __shared__ Fr sm[kDotThreads];
+    const uint32_t row = heavy_rows[blockIdx.y];
+    Fr acc = Fr::zero();
+    for (uint32_t k = m.ptr[row] + blockIdx.x * kDotThreads + threadIdx.x; k < m.ptr[row + 1]; k += kSpmvSplit * kDotThreads)
+        acc = fp_add(acc, fp_mul(load_fr(m.val + k), load_fr(vec + m.idx[k])));
+    acc = block_sum_fr(acc, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(part + (size_t)blockIdx.y * kSpmvSplit + blockIdx.x, acc);
+}
+__global__ void __launch_bounds__(kDotThreads)
+k_spmv_heavy_final(const uint32_t* __restrict__ heavy_rows, const Fr* __restrict__ part, Fr coeff, int use_coeff, Fr* __restrict__ out) {
     __shared__ Fr sm[kDotThreads];
     const uint32_t row = heavy_rows[blockIdx.x];
     Fr acc = Fr::zero();
-    for (uint32_t k = m.ptr[row] + threadIdx.x; k < m.ptr[row + 1]; k += kDotThreads)
-        acc = fp_add(acc, fp_mul(load_fr(m.val + k), load_fr(vec + m.idx[k])));
+    for (int i = threadIdx.x; i < kSpmvSplit; i += kDotThreads) acc = fp_add(acc, load_fr(part + (size_t)blockIdx.x * kSpmvSplit + i));
     acc = block_sum_fr(acc, sm, kDotThreads);
     if (threadIdx.x == 0) {
         if (use_coeff) acc = fp_mul(acc, coeff);

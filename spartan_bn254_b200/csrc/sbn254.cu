@@ -1,5 +1,6 @@
 // libsbn254 C ABI (include/sbn254.h): contexts, resident generator sets, the batched Hyrax commit
 // pipeline and its stream plumbing.  Kernels live in msm_kernels.cuh / opening_kernels.cuh.
+#define SBN_HOST_FAST_FP 1      // host code of this library multiplies on 4 x 64-bit limbs (fp.cuh); the host TESTS do not define it
 #include "../../include/sbn254.h"
 
 #include <cuda_runtime.h>
@@ -66,6 +67,7 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
     DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
     size_t zkeep_len = 0;
@@ -359,7 +361,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -3173,7 +3175,8 @@ extern "C" int sbn_spmat_upload(sbn_ctx* ctx, const uint32_t* ptr, const uint32_
     if (ok && !heavy_rows.empty()) {
         m->nheavy = heavy_rows.size();
         ok = dev_malloc(ctx, &m->heavy, m->nheavy * sizeof(uint32_t)) == cudaSuccess &&
-             cudaMemcpy(m->heavy, heavy_rows.data(), m->nheavy * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+             cudaMemcpy(m->heavy, heavy_rows.data(), m->nheavy * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess &&
+             ensure(ctx, ctx->spmv_part, m->nheavy * (size_t)kSpmvSplit * sizeof(Fr)) == SBN_OK;      // so that spmv_device never allocates
     }
     if (!ok) {
         if (m->heavy) cudaFree(m->heavy);
@@ -3218,8 +3221,11 @@ static void spmv_device(sbn_ctx* ctx, const sbn_spmat* const* mats, size_t nm, c
     ctx->launches++;
     for (size_t m = 0; m < nm; m++)
         if (mats[m]->nheavy) {
-            k_spmv_heavy<<<(unsigned)mats[m]->nheavy, kDotThreads, 0, s>>>(sm[m], mats[m]->heavy, c[m], coeffs ? 1 : 0, dvec, dout);
-            ctx->launches++;
+            k_spmv_heavy_partial<<<dim3(kSpmvSplit, (unsigned)mats[m]->nheavy), kDotThreads, 0, s>>>(sm[m], mats[m]->heavy, dvec,
+                                                                                                      (Fr*)ctx->spmv_part.p);
+            k_spmv_heavy_final<<<(unsigned)mats[m]->nheavy, kDotThreads, 0, s>>>(mats[m]->heavy, (const Fr*)ctx->spmv_part.p, c[m],
+                                                                                 coeffs ? 1 : 0, dout);
+            ctx->launches += 2;
         }
 }
 
@@ -3260,9 +3266,26 @@ static sbn_sumcheck* sumcheck_alloc(sbn_ctx* ctx, int ntables, size_t len) {
     return st;
 }
 
+static int sumcheck_begin_r1cs_impl(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, const sbn_poly* vars,
+                                    const sbn_fr* tail, size_t n_tail, size_t zlen, const sbn_fr* tau, size_t n_tau, sbn_sumcheck** out);
 extern "C" int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, size_t zlen, const sbn_fr* tau,
                                        size_t n_tau, sbn_sumcheck** out) {
-    if (!ctx || !mats || !z || !tau || !out) return SBN_ERR_ARG;
+    if (!z) return SBN_ERR_ARG;
+    return sumcheck_begin_r1cs_impl(ctx, mats, z, nullptr, nullptr, 0, zlen, tau, n_tau, out);
+}
+// The same with z = (vars, tail, 0, ..., 0) assembled ON THE DEVICE from the witness polynomial that sbn_poly_upload already
+// holds (r1csproof.rs:255-265 builds z = [vars, 1, inputs] on the host): the 2^21 x 32 B upload from pageable memory and the
+// host-side assembly of a keyless-scale proof disappear (5-7 ms); `tail` = the n_tail scalars that follow the variables
+// (the constant 1 and the public inputs).
+extern "C" int sbn_sumcheck_begin_r1cs_resident(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_poly* vars, const sbn_fr* tail,
+                                                size_t n_tail, size_t zlen, const sbn_fr* tau, size_t n_tau, sbn_sumcheck** out) {
+    if (!vars || vars->ctx != ctx || (n_tail && !tail)) return SBN_ERR_ARG;
+    if (vars->len + n_tail > zlen) return SBN_ERR_SHAPE;
+    return sumcheck_begin_r1cs_impl(ctx, mats, nullptr, vars, tail, n_tail, zlen, tau, n_tau, out);
+}
+static int sumcheck_begin_r1cs_impl(sbn_ctx* ctx, const sbn_spmat* const* mats, const sbn_fr* z, const sbn_poly* vars,
+                                    const sbn_fr* tail, size_t n_tail, size_t zlen, const sbn_fr* tau, size_t n_tau, sbn_sumcheck** out) {
+    if (!ctx || !mats || !tau || !out) return SBN_ERR_ARG;
     *out = nullptr;
     if (n_tau == 0 || n_tau > 28) return SBN_ERR_SHAPE;
     const size_t len = size_t(1) << n_tau;
@@ -3280,9 +3303,18 @@ extern "C" int sbn_sumcheck_begin_r1cs(sbn_ctx* ctx, const sbn_spmat* const* mat
     if (!st) return SBN_ERR_OOM;
     auto fail = [&](cudaError_t e) { ctx->last_error = std::string("sbn_sumcheck_begin_r1cs: ") + cudaGetErrorString(e); sumcheck_free(st); return SBN_ERR_CUDA; };
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(ctx->zkeep.p, z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+    if (z) {
+        if ((e = cudaMemcpyAsync(ctx->zkeep.p, z, zlen * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+        ctx->h2d += zlen * sizeof(Fr);
+    } else {
+        Fr* dz = (Fr*)ctx->zkeep.p;
+        if ((e = cudaMemcpyAsync(dz, vars->Z, vars->len * sizeof(Fr), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return fail(e);
+        if (n_tail && (e = cudaMemcpyAsync(dz + vars->len, tail, n_tail * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
+        if ((e = cudaMemsetAsync(dz + vars->len + n_tail, 0, (zlen - vars->len - n_tail) * sizeof(Fr), s)) != cudaSuccess) return fail(e);
+        ctx->h2d += n_tail * sizeof(Fr);
+    }
     if ((e = cudaMemcpyAsync(ctx->scratch2.p, tau, n_tau * sizeof(Fr), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e);
-    ctx->h2d += (zlen + n_tau) * sizeof(Fr);
+    ctx->h2d += n_tau * sizeof(Fr);
     eq_evals_device(ctx, (const Fr*)ctx->scratch2.p, n_tau, st->T[0], st->T[1], s);      // T[1] is scratch until A z lands in it
     for (int m = 0; m < 3; m++) spmv_device(ctx, mats + m, 1, nullptr, (const Fr*)ctx->zkeep.p, st->T[1 + m], s);
     if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(e);

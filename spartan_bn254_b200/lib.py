@@ -22,7 +22,7 @@ EXPORTS = [
     "sbn_spmat_upload", "sbn_spmat_destroy", "sbn_spmat_mulvec", "sbn_eq_evals",
     "sbn_spark_evaluate", "sbn_bsumcheck_begin_resident", "sbn_spark_comb_polys", "sbn_poly_triple_dot",
     "sbn_poly_evaluate", "sbn_poly_evaluate_strided", "sbn_addrs_set_timestamps", "sbn_hashlayer_build", "sbn_prodcircuit_download_layer",
-    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_fr_to_canonical_host", "sbn_fr_from_canonical_host", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
+    "sbn_derefs_commit_rows", "sbn_keccak_f1600", "sbn_fr_to_canonical_host", "sbn_fr_from_canonical_host", "sbn_sumcheck_begin_r1cs", "sbn_sumcheck_begin_r1cs_resident", "sbn_sumcheck_begin_quad_r1cs", "sbn_g1_compress", "sbn_merlin_append_points", "sbn_merlin_init", "sbn_merlin_append", "sbn_merlin_append_many", "sbn_merlin_challenge", "sbn_addrs_upload", "sbn_addrs_destroy", "sbn_derefs_commit", "sbn_poly_len", "sbn_poly_download",
     "sbn_prodcircuit_create", "sbn_prodcircuit_evaluate", "sbn_prodcircuit_num_layers", "sbn_prodcircuit_destroy",
     "sbn_bsumcheck_begin", "sbn_bsumcheck_round_eval", "sbn_bsumcheck_bind", "sbn_bsumcheck_end", "sbn_bsumcheck_prove", "sbn_bsumcheck_destroy",
 ]
@@ -239,6 +239,21 @@ class Context:
     def sumcheck_begin_r1cs(self, mats, z, tau):
         """Phase-1 tables eq(tau), A z, B z, C z built on the device from the resident matrices (r1csproof.rs:268-290)."""
         return SumcheckState._resident(self, 4, mats, z, tau, None)
+
+    def sumcheck_begin_r1cs_resident(self, mats, vars_poly, tail, z_len, tau):
+        """sumcheck_begin_r1cs with z = (vars, tail, 0...) assembled on the device from the resident witness polynomial."""
+        st = SumcheckState.__new__(SumcheckState)
+        st.ctx, st.ntables = self, 4
+        tau = _u64(tau, 4)
+        tail = _u64(tail, 4)
+        st.len = 1 << tau.shape[0]
+        hs = (C.c_void_p * 3)(*[m.h for m in mats])
+        h = C.c_void_p()
+        rc = self.lib.sbn_sumcheck_begin_r1cs_resident(self.h, hs, vars_poly.h, _ptr(tail), C.c_size_t(tail.shape[0]), C.c_size_t(z_len),
+                                                       _ptr(tau), C.c_size_t(tau.shape[0]), C.byref(h))
+        self._check(rc, "sbn_sumcheck_begin_r1cs_resident")
+        st.h = h
+        return st
 
     def sumcheck_begin_quad_r1cs(self, mats_t, coeffs, rx, z, z_len=None):
         """Phase-2 tables z and sum_m coeffs[m] M_m^T eq(rx) built on the device (r1csproof.rs:378-410).  z=None with z_len:

@@ -262,14 +262,14 @@ class R1CSProof:
         append_poly_commitment(transcript, b"poly_commitment", comm_vars)
         lap("witness_commit_ms")
         num_vars = vars_m.shape[0]
-        z = np.zeros((2 * num_vars, 4), dtype=np.uint64)
-        z[:num_vars] = vars_m
-        z[num_vars] = fr_from_int(1)
-        z[num_vars + 1: num_vars + 1 + input_m.shape[0]] = input_m
+        # z = [vars, 1, inputs, 0...] (r1csproof.rs:255-265) is assembled on the device from the witness polynomial that
+        # commit_poly left resident; only the tail (1 and the public inputs) crosses the bus
+        z_len = 2 * num_vars
+        tail = np.concatenate([fr_from_int(1).reshape(1, 4), input_m.reshape(-1, 4)])
         num_rounds_x, num_rounds_y = log_2(inst.num_cons), log_2(2 * num_vars)
         tau = transcript.challenge_scalars(b"challenge_tau", num_rounds_x)
         # eq(tau), A z, B z, C z (r1csproof.rs:268-290) are built in HBM from the resident matrices
-        st1 = ctx.sumcheck_begin_r1cs(inst.by_row, z, fr_vec_from_ints(tau))
+        st1 = ctx.sumcheck_begin_r1cs_resident(inst.by_row, poly_vars.resident(ctx), tail, z_len, fr_vec_from_ints(tau))
         lap("sumcheck1_setup(eq(tau), Az, Bz, Cz)_ms")
         sc1, rx, claims1, blind_claim_postsc1 = ZKSumcheckInstanceProof._prove(
             st1, 3, 0, 0, num_rounds_x, gens.gens_sc.gens_1, gens.gens_sc.gens_4, transcript, tape)
@@ -296,7 +296,7 @@ class R1CSProof:
         lap("sigma_protocols_phase1_ms")
         # eq(rx) and r_A A^T eq(rx) + r_B B^T eq(rx) + r_C C^T eq(rx) (r1csproof.rs:378-410) likewise
         st2 = ctx.sumcheck_begin_quad_r1cs(inst.by_col, fr_vec_from_ints([r_A, r_B, r_C]), fr_vec_from_ints(rx), None,
-                                           z_len=z.shape[0])       # z is still resident from phase 1
+                                           z_len=z_len)            # z is still resident from phase 1
         lap("sumcheck2_setup(eq(rx), eval tables)_ms")
         sc2, ry, claims2, blind_claim_postsc2 = ZKSumcheckInstanceProof._prove(
             st2, 2, claim_phase2, blind_claim_phase2, num_rounds_y, gens.gens_sc.gens_1, gens.gens_sc.gens_3, transcript, tape)

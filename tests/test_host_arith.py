@@ -9,11 +9,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["fp_host_test", "ec_host_test"])
-def test_host_emulated_device_arithmetic(orc, tmp_path, name):
+@pytest.mark.parametrize("name,defs", [("fp_host_test", []), ("ec_host_test", []),
+                                       ("fp_host_test", ["-DSBN_HOST_FAST_FP=1"]), ("ec_host_test", ["-DSBN_HOST_FAST_FP=1"])])
+def test_host_emulated_device_arithmetic(orc, tmp_path, name, defs):
+    """Without defines: the 32-bit DEVICE algorithm with the PTX carry flag emulated.  With SBN_HOST_FAST_FP: the 4 x 64-bit
+    product the library's own host code uses (transcript challenges, UniPoly arithmetic, point compression)."""
     exe = str(tmp_path / name)
     build_dir = os.path.join(ROOT, "oracle", "_build")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", name + ".cpp"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17"] + defs + ["-o", exe, os.path.join(ROOT, "tests", "host", name + ".cpp"),
                            "-L" + build_dir, "-loracle", "-Wl,-rpath," + build_dir])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
