@@ -73,6 +73,15 @@ __global__ void k_bind_top_batched(Fr* const* __restrict__ tables, size_t half, 
     store_fr(T + i, fp_add(lo, fp_mul(load_fr(r), fp_sub(hi, lo))));
 }
 
+// The same with the challenge passed by value (the in-library round loop has it on the host: no 32-byte copy per round)
+__global__ void k_bind_top_batched_v(Fr* const* __restrict__ tables, size_t half, const Fr r) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    Fr* T = tables[blockIdx.y];
+    const Fr lo = load_fr(T + i), hi = load_fr(T + half + i);
+    store_fr(T + i, fp_add(lo, fp_mul(r, fp_sub(hi, lo))));
+}
+
 // out[t] = tables[t][0]: the final values of a sumcheck whose tables have been bound down to one entry (sumcheck.rs:309-327)
 __global__ void k_gather_first(Fr* const* __restrict__ tables, int ntables, Fr* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -92,6 +92,7 @@ struct sbn_ctx {
     std::vector<std::pair<size_t, void*>> mem_pool;
     size_t mem_pool_bytes = 0;
     std::unordered_map<void*, size_t> pool_live;   // size class of every buffer handed out by pool_alloc
+    uint8_t *ev_pin = nullptr, *ev_pin_dev = nullptr;   // mapped pinned: the round evaluations of the in-library sumcheck loops
     uint8_t* small_pin = nullptr;      // mapped pinned staging of the short-commitment path (scalars in, points out)
     uint8_t* small_pin_dev = nullptr;
     long small_commit_path = 1;        // 0: short generator sets go through the general pipeline (test hook)
@@ -145,6 +146,7 @@ struct sbn_bases {
         if (_s != SBN_OK) return _s; \
     } while (0)
 
+static constexpr size_t kEvPinBytes = 16384;
 static constexpr size_t kPoolMinBytes = size_t(1) << 20, kPoolMaxBytes = size_t(48) << 30;
 
 static void pool_flush(sbn_ctx* ctx) {
@@ -376,6 +378,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->copy);
     if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
+    if (ctx->ev_pin) cudaFreeHost(ctx->ev_pin);
     delete ctx;
     cudaGetLastError();
     return SBN_OK;
@@ -2627,7 +2630,11 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
     memcpy(cf.data(), coeffs, n * sizeof(Fr));
     Fr e;
     memcpy(e.l, claim, sizeof(Fr));
-    Fr* rdev = st->out + 3 * n;
+    if (3 * n * sizeof(Fr) > kEvPinBytes) return SBN_ERR_SHAPE;
+    if (!ctx->ev_pin) {
+        SBN_CUDA(ctx, cudaHostAlloc((void**)&ctx->ev_pin, kEvPinBytes, cudaHostAllocMapped));
+        SBN_CUDA(ctx, cudaHostGetDevicePointer((void**)&ctx->ev_pin_dev, ctx->ev_pin, 0));
+    }
     auto append_scalar = [&](const Fr& v) {
         const Fr c = fp_from_mont(v);
         sbn::merlin::append_message(tr, (const uint8_t*)"coeff", 5, (const uint8_t*)c.l, 32);
@@ -2635,12 +2642,20 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
     for (size_t j = 0; j < num_rounds; j++) {
         const size_t half = st->len / 2;
         const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
-        k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
-        k_fr_sum<<<(unsigned)(3 * n), kDotThreads, 0, s>>>(st->partial, (int)blocks, st->out, 1);
-        ctx->launches += 2;
+        // The 3 n evaluations land in mapped pinned memory: no copy call per round, and a one-block evaluation (the many short
+        // rounds at the end of every layer) writes them itself instead of through a second launch.
+        Fr* ev_dev = (Fr*)ctx->ev_pin_dev;
+        if (blocks == 1) {
+            k_cubic_eval_batched<<<dim3(1, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, ev_dev);
+            ctx->launches += 1;
+        } else {
+            k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
+            k_fr_sum<<<(unsigned)(3 * n), kDotThreads, 0, s>>>(st->partial, (int)blocks, ev_dev, 1);
+            ctx->launches += 2;
+        }
         SBN_CUDA(ctx, cudaGetLastError());
-        SBN_CUDA(ctx, cudaMemcpyAsync(ev.data(), st->out, 3 * n * sizeof(Fr), cudaMemcpyDeviceToHost, s));
         SBN_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(ev.data(), ctx->ev_pin, 3 * n * sizeof(Fr));
         ctx->d2h += 3 * n * sizeof(Fr);
         Fr comb[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
         for (size_t i = 0; i < n; i++)
@@ -2658,10 +2673,8 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
         uint8_t wide[64];
         sbn::merlin::challenge_bytes(tr, (const uint8_t*)"challenge_nextround", 19, wide, 64);
         const Fr r = FrHost::from_wide(wide);
-        SBN_CUDA(ctx, cudaMemcpyAsync(rdev, &r, sizeof(Fr), cudaMemcpyHostToDevice, s));
-        k_bind_top_batched<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, rdev);
+        k_bind_top_batched_v<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, r);
         ctx->launches += 1;
-        ctx->h2d += sizeof(Fr);
         SBN_CUDA(ctx, cudaGetLastError());
         st->len = half;
         // e = poly(r)
