@@ -514,7 +514,10 @@ def main():
         # the table's own window width; bucket pipeline = one XYZZ mixed addition (10 products) per entry
         per_entry = 6 if mult_bits else FQMUL_PER_MIXED_ADD
         exec_imad_stage = float(prof_rows) * (R + 1) * W * per_entry * IMAD_PER_FQMUL
-        executed = exec_imad_stage / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
+        # An executed fraction exists only where the work per entry is known: the tabulated-sum path with every row on the
+        # full-width schedule.  The bucket pipeline mixes 6-product batched-affine and 10-product XYZZ additions in proportions
+        # the library chooses per chunk, and a commit split into small-scalar runs has no single stage time.
+        executed = exec_imad_stage / (acc_ms * 1e-3) if (acc_ms > 0 and mult_bits and args.scalars != "small") else None
         exec_imad_step = float(L) * (R + 1) * W * per_entry * IMAD_PER_FQMUL
         step_s = ms_max / args.steps * 1e-3
         traffic, traffic_note = stage_traffic(args.workload, mult_bits)
@@ -549,16 +552,16 @@ def main():
                            "k_ba_invert / k_bat_finish per round + k_mult_sum_rows_t)") if mult_bits else
                           ("bucket accumulation stage (k_accumulate; with batched-affine rounds: k_ba_prefix / k_ba_invert / "
                            "k_ba_finish + k_accumulate_pts)"),
-                "achieved": executed / 1e12, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
-                "frac": executed / peak_imad if peak_imad else None,
+                "achieved": executed / 1e12 if executed else None, "peak": peak_imad / 1e12, "unit": "TIMAD/s",
+                "frac": executed / peak_imad if (executed and peak_imad) else None,
                 "frac_note": f"EXECUTED work of the stage: entries x {per_entry} Fq products x 264 IMAD / stage time / peak "
                              f"(entries = rows x (R + 1) x {W} windows of {path_bits} bits)",
                 "executed_imad_per_launch_set": exec_imad_stage,
                 "kernel_ms_per_launch_set": acc_ms, "rows_per_launch_set": prof_rows,
                 "launch_set_note": "median of 4 warm commits of prof_rows rows as ONE chunk on ONE stream, CUDA events inside the "
                                    "library around the stage's launches",
-                "whole_step_executed_frac": exec_imad_step / step_s / peak_imad if peak_imad else None,
-                "algorithmic_vs_formula": formula / peak_imad if peak_imad else None,
+                "whole_step_executed_frac": exec_imad_step / step_s / peak_imad if (executed and peak_imad) else None,
+                "algorithmic_vs_formula": formula / peak_imad if (peak_imad and acc_ms > 0) else None,
                 "algorithmic_vs_formula_note": "SURVEY 8(d)'s accounting (bucket method: W x 10 x 264 IMAD per point at the bucket "
                                                "window width) over the stage time; NOT a utilisation -- the path does less work than "
                                                "the formula assumes (wider window, 6-product additions), so this can exceed 1",
