@@ -293,7 +293,7 @@ def main():
     dCs = [torch.empty((L, 8), dtype=torch.int64, device=dev) for _ in range(2)]
     dinfs = [torch.empty((L,), dtype=torch.uint8, device=dev) for _ in range(2)]
     dC, dinf = dCs[0], dinfs[0]
-    gathers = [[torch.empty_like(dCs[0]) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    gathers = [torch.empty((world * L, 8), dtype=torch.int64, device=dev) for _ in range(2)] if world > 1 else None
     pending = [None, None]
     hC = torch.empty((L, 8), dtype=torch.int64).pin_memory()
     hinf = torch.empty((L,), dtype=torch.uint8).pin_memory()
@@ -307,7 +307,7 @@ def main():
         ctx.hyrax_commit_device(b or bases, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dCs[k].data_ptr(), dinfs[k].data_ptr(),
                                 stream=stream.cuda_stream)
         if world > 1:
-            pending[k] = dist.all_gather(gathers[k], dCs[k], async_op=True)
+            pending[k] = dist.all_gather_into_tensor(gathers[k], dCs[k], async_op=True)     # one NCCL kernel, no per-rank copies
 
     def drain():
         for k in range(2):
@@ -640,12 +640,12 @@ def run_strong(ctx, synth, torch, dist, dev, stream, rank, world, args):
     z = torch.from_numpy(synth.uniform_scalars(77 + rank, Ls * Rs).view(np.int64)).to(dev)
     dCs = torch.empty((Ls, 8), dtype=torch.int64, device=dev)
     dis = torch.empty((Ls,), dtype=torch.uint8, device=dev)
-    gat = [torch.empty_like(dCs) for _ in range(world)] if world > 1 else None
+    gat = torch.empty((world * Ls, 8), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step():
         ctx.hyrax_commit_device(bs, z.data_ptr(), Ls, Rs, 0, dCs.data_ptr(), dis.data_ptr(), stream=stream.cuda_stream)
         if world > 1:
-            dist.all_gather(gat, dCs)
+            dist.all_gather_into_tensor(gat, dCs)
 
     for _ in range(2):
         step()
