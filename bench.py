@@ -62,6 +62,9 @@ def parse():
                     help="budget (MiB) of the digit-multiple table of the commit's generator set (mult_kernels.cuh): the widest "
                          "window whose table fits is tabulated once and kept resident; 0 = bucket pipeline only; the "
                          "library's own default is 6144")
+    ap.add_argument("--caller-streams", type=int, default=2, choices=[1, 2],
+                    help="consecutive (independent) commits of the device-resident leg are issued on this many alternating caller "
+                         "streams: with 2 the tail of one commit runs under the head of the next (sbn_hyrax_commit_device is asynchronous)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true",
                     help="skip the strong-scaling leg (BASELINE configs[2]: 4096 x 8192 derefs-shaped commit divided by rows across the GPUs)")
@@ -298,22 +301,37 @@ def main():
     hC = torch.empty((L, 8), dtype=torch.int64).pin_memory()
     hinf = torch.empty((L,), dtype=torch.uint8).pin_memory()
     stream = torch.cuda.current_stream()
+    # Caller streams of the device-resident leg.  Step i runs on cstreams[i % n] with output buffer i & 1: the commits are
+    # independent, so with two streams the library (two workspace sets, taken in turn) overlaps one commit's tail with the next
+    # one's head.  The timed events sit on `stream`, which every caller stream forks from and joins back into.
+    cstreams = [torch.cuda.Stream(device=dev) for _ in range(args.caller_streams)] if args.caller_streams > 1 else [stream]
+
+    def fork():
+        if len(cstreams) > 1:
+            for cs in cstreams:
+                cs.wait_stream(stream)
 
     def step_device(i, b=None):
         k = i & 1
-        if pending[k] is not None:          # the gather of step i - 2 still reads this output buffer
-            pending[k].wait()
-            pending[k] = None
-        ctx.hyrax_commit_device(b or bases, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dCs[k].data_ptr(), dinfs[k].data_ptr(),
-                                stream=stream.cuda_stream)
-        if world > 1:
-            pending[k] = dist.all_gather_into_tensor(gathers[k], dCs[k], async_op=True)     # one NCCL kernel, no per-rank copies
+        cs = cstreams[i % len(cstreams)]
+        with torch.cuda.stream(cs):
+            if pending[k] is not None:          # the gather of step i - 2 still reads this output buffer
+                pending[k].wait()
+                pending[k] = None
+            ctx.hyrax_commit_device(b or bases, dev_bufs[i % nbuf].data_ptr(), L, R, 0, dCs[k].data_ptr(), dinfs[k].data_ptr(),
+                                    stream=cs.cuda_stream)
+            if world > 1:
+                pending[k] = dist.all_gather_into_tensor(gathers[k], dCs[k], async_op=True)     # one NCCL kernel, no per-rank copies
 
     def drain():
         for k in range(2):
             if pending[k] is not None:
-                pending[k].wait()            # the timed stream waits for the collective: it is inside the timed region
+                with torch.cuda.stream(cstreams[k % len(cstreams)]):
+                    pending[k].wait()        # the caller stream waits for the collective: it is inside the timed region
                 pending[k] = None
+        if len(cstreams) > 1:
+            for cs in cstreams:
+                stream.wait_stream(cs)
 
     def step_e2e(i):
         ctx.hyrax_commit_raw(bases, host_bufs[i % nbuf].data_ptr(), L, R, 0, hC.data_ptr(), hinf.data_ptr())
@@ -330,6 +348,7 @@ def main():
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
+        fork()
         for i in range(steps):
             step_device(warm + i, b)
         drain()
@@ -364,6 +383,7 @@ def main():
     barrier()
     w0 = time.time()
     e0.record(stream)
+    fork()
     for i in range(args.steps):
         step_device(args.warmup + i)
     drain()
@@ -401,6 +421,17 @@ def main():
                   "what": "rows of the last timed commit (device-resident path, this table budget) vs oracle.hyrax_commit, bit-exact affine limbs + infinity flags"}
         if not ok:
             raise SystemExit("bench.py: the timed commit differs from the oracle on sampled rows -- refusing to print a number")
+
+    # ---- the same K commits on ONE caller stream (strict stream order between consecutive commits), for comparison
+    single_stream = None
+    if len(cstreams) > 1:
+        saved = list(cstreams)
+        cstreams[:] = [stream]
+        n1 = max(3, min(args.steps, 100))
+        ms1 = timed_device(n1, args.warmup)
+        cstreams[:] = saved
+        single_stream = {"value": points_per_step * n1 / (ms1 * 1e-3), "unit": UNIT, "ms_per_step": ms1 / n1, "steps": n1,
+                         "note": "consecutive commits on one caller stream: each waits for the previous one's last kernel"}
 
     # ---- stage profile on the library's own stream (CUDA events inside the library): the first `prof_rows` rows as ONE
     #      chunk, so the stages run back to back and each event pair brackets exactly one launch set of that stage
@@ -536,6 +567,10 @@ def main():
                        "table_note": "built once per generator set by the first commit of >= 256 rows, outside the timed region; "
                                      "value_default_budget is the same commit under the library's default 6144 MiB",
                        "gens": args.gens, "scalars": args.scalars, "blinds": "zero (derefs-style, hyrax.rs:301-305)",
+                       "caller_streams": len(cstreams),
+                       "caller_streams_note": "independent commits issued on alternating caller streams; the library takes its two workspace "
+                                              "sets in turn, so one commit's tail overlaps the next one's head (roofline.frac is measured on "
+                                              "ONE commit on ONE stream and does not benefit)",
                        "l2": f"inputs rotated over {nbuf} buffers ({nbuf * L * R * 32 >> 20} MiB > 126 MiB L2)",
                        "points_counted": "L x R scalar-base pairs per GPU per step",
                        "collective": ("NCCL all_gather of the commitment vector per step, issued asynchronously: it runs under the "
@@ -582,6 +617,8 @@ def main():
         }
         if parity is not None:
             line.update(parity)
+        if single_stream is not None:
+            line["value_single_caller_stream"] = single_stream
         if default_budget is not None:
             line["value_default_budget"] = default_budget
         if ref_gens is not None:

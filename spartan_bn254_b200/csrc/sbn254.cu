@@ -67,6 +67,8 @@ struct sbn_ctx {
     cudaStream_t hi = nullptr, lo[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
+    DevBuf mtotals[2];                 // row totals of the tabulated-sum path, one per workspace set
+    uint64_t mult_calls = 0;
     DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
     DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
@@ -363,7 +365,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part, &ctx->mtotals[0], &ctx->mtotals[1]})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1180,8 +1182,14 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
     const size_t chunk_pad = tr ? (chunk + 31) / 32 * 32 : chunk;
     const size_t np1 = chunk_pad * (size_t)stride / 2;
     const size_t ns = std::max<size_t>(1, std::min(ns_max, nchunks));
+    // Two sets of workspaces / streams, taken in turn by consecutive calls: a caller that issues independent commits on two
+    // streams of its own (sbn_hyrax_commit_device is asynchronous) gets the tail of one commit -- the short last rounds, the
+    // row sums, the normalisation: ~0.3 ms of a mostly idle GPU -- underneath the head of the next.  Within one caller stream
+    // nothing changes (stream order).
+    const size_t set = (ns <= 2 && !host_Z) ? (size_t)(ctx->mult_calls++ & 1) : 0;
+    const size_t sb = 2 * set;
     for (size_t k = 0; k < ns; k++) {
-        auto& sl = ctx->slots[k];
+        auto& sl = ctx->slots[sb + k];
         SBN_TRY(ensure(ctx, sl.entries, chunk_pad * (size_t)stride * sizeof(uint32_t)));
         SBN_TRY(ensure(ctx, sl.pts[0], np1 * sizeof(Affine)));
         SBN_TRY(ensure(ctx, sl.pts[1], (np1 / 2 + 1) * sizeof(Affine)));
@@ -1194,11 +1202,11 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
         SBN_TRY(ensure(ctx, sl.winv, 2 * (nthreads / 32 + 1) * sizeof(Fq)));
         if (b->dedup) SBN_TRY(ensure(ctx, sl.zagg, chunk * (size_t)b->n1 * sizeof(Fr)));
     }
-    SBN_TRY(ensure(ctx, ctx->totals, L * sizeof(XYZZ)));
-    XYZZ* totals = (XYZZ*)ctx->totals.p;
+    SBN_TRY(ensure(ctx, ctx->mtotals[set], L * sizeof(XYZZ)));
+    XYZZ* totals = (XYZZ*)ctx->mtotals[set].p;
     size_t ev_idx = 0;
     StageMarks marks{ctx, ev_idx, ev_stage};
-    const size_t sync_base = 3 * nchunks + 8;              // hand-off events live after the profiling events
+    const size_t sync_base = 3 * nchunks + 8 + set * (nchunks + 8);      // hand-off events live after the profiling events, per set
     if (!get_event(ctx, sync_base + nchunks + 4)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
     std::vector<size_t> row0(nchunks, 0);
     for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
@@ -1210,15 +1218,15 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
         return SBN_OK;
     };
     SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
-    for (size_t k = 0; k < ns; k++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[k], ctx->fork, 0));
+    for (size_t k = 0; k < ns; k++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[sb + k], ctx->fork, 0));
     if (host_Z) {
         SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
         SBN_TRY(issue_copy(0));
     }
     for (size_t ci = 0; ci < nchunks; ci++) {
         const int rows = (int)sched[ci];
-        auto& sl = ctx->slots[ci % ns];
-        cudaStream_t st = ctx->lo[ci % ns];
+        auto& sl = ctx->slots[sb + ci % ns];
+        cudaStream_t st = ctx->lo[sb + ci % ns];
         if (host_Z) {
             if (ci + 1 < nchunks) SBN_TRY(issue_copy(ci + 1));
             SBN_CUDA(ctx, cudaStreamWaitEvent(st, get_event(ctx, sync_base + ci), 0));
@@ -1371,7 +1379,7 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
     }
     for (size_t k = 0; k < ns; k++) {
         cudaEvent_t e = get_event(ctx, sync_base + nchunks + k);
-        SBN_CUDA(ctx, cudaEventRecord(e, ctx->lo[k]));
+        SBN_CUDA(ctx, cudaEventRecord(e, ctx->lo[sb + k]));
         SBN_CUDA(ctx, cudaStreamWaitEvent(main, e, 0));
     }
     if (!normalize) return SBN_OK;

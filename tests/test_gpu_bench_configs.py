@@ -137,3 +137,39 @@ def test_mixed_small_and_full_rows(orc, gens_kind):
         bases.close()
     finally:
         ctx.close()
+
+
+def test_independent_commits_on_two_caller_streams(orc):
+    """bench.py's device-resident leg issues consecutive, independent commits on two alternating caller streams; the library
+    takes its two workspace / stream sets in turn so that they overlap.  Eight commits of different inputs in flight must each
+    equal the commit of the same input issued alone, and the oracle on sampled rows."""
+    import torch
+    from spartan_bn254_b200 import Context, synth
+    ctx = Context(0)
+    try:
+        ctx.set("mult_max_mb", 2048)
+        L, R = 512, 128
+        dev = torch.device("cuda", 0)
+        G, h = synth.distinct_generators(ctx, R)
+        bases = ctx.bases(G, h)
+        Zs = [synth.uniform_scalars(40 + i, L * R) for i in range(8)]
+        dZ = [torch.from_numpy(z.view(np.int64)).to(dev) for z in Zs]
+        dC = [torch.empty((L, 8), dtype=torch.int64, device=dev) for _ in range(8)]
+        dinf = [torch.empty((L,), dtype=torch.uint8, device=dev) for _ in range(8)]
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        torch.cuda.synchronize()
+        for i in range(8):
+            ctx.hyrax_commit_device(bases, dZ[i].data_ptr(), L, R, 0, dC[i].data_ptr(), dinf[i].data_ptr(),
+                                    stream=streams[i & 1].cuda_stream)
+        torch.cuda.synchronize()
+        assert bases.mult_table()[0] > 0
+        for i in range(8):
+            C = dC[i].cpu().numpy().view(np.uint64)
+            inf = dinf[i].cpu().numpy()
+            C1, inf1 = _commit_device(ctx, bases, Zs[i], L, R)
+            assert np.array_equal(C, C1) and np.array_equal(inf, inf1), "commit %d in flight differs from the same commit alone" % i
+            if i in (0, 7):
+                _check_rows(orc, G, h, Zs[i], L, R, C, inf, 16)
+        bases.close()
+    finally:
+        ctx.close()
