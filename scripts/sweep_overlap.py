@@ -39,6 +39,27 @@ def run(tag, nstreams, n=40):
     return outs
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "ablate":
+    run("two caller streams, everything", 2)
+    for ab, what in ((1, "prefix<1>"), (2, "prefix rounds >= 2"), (3, "all prefix"), (4, "invert"), (8, "sum_rows"), (16, "finish<1>"),
+                     (32, "finish rounds >= 2"), (15, "all but finish + entries"), (63, "all but entries")):
+        ctx.set("ablate", ab)
+        run(f"two caller streams WITHOUT {what}", 2)
+    ctx.set("ablate", 0)
+    for layout in (2, 1):
+        ctx.set("mult_layout", layout)
+        run(f"two caller streams, layout {layout}", 2)
+    for mb in (4, 3):
+        ctx.set("ba_minb", mb)
+        run(f"two caller streams, minb {mb}", 2)
+    for r in (4, 5, 6):
+        ctx.set("mult_rounds", r)
+        run(f"two caller streams, rounds {r}", 2)
+    ctx.set("mult_rounds", 0)
+    for B in (8, 12, 16, 24):
+        ctx.set("ba_batch", B)
+        run(f"two caller streams, pairs per thread {B}", 2)
+    sys.exit(0)
 one = run("one caller stream", 1)
 two = run("two alternating caller streams", 2)
 # reference results for inputs (n-2) % 6 and (n-1) % 6 on one stream
