@@ -336,6 +336,15 @@ def main():
     def step_e2e(i):
         ctx.hyrax_commit_raw(bases, host_bufs[i % nbuf].data_ptr(), L, R, 0, hC.data_ptr(), hinf.data_ptr())
 
+    # the same call, asynchronous, on two alternating caller streams: H2D of step i + 1 under the kernels of step i
+    hCs = [torch.empty((L, 8), dtype=torch.int64).pin_memory() for _ in range(2)]
+    hinfs = [torch.empty((L,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def step_e2e_async(i):
+        k = i & 1
+        ctx.hyrax_commit_raw_async(bases, host_bufs[i % nbuf].data_ptr(), L, R, 0, hCs[k].data_ptr(), hinfs[k].data_ptr(),
+                                   cstreams[i % len(cstreams)].cuda_stream)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -464,7 +473,19 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return points_per_step * steps / float(tt.item())
 
-    e2e_value = timed_e2e(step_e2e, args.steps)
+    e2e_sync_value = timed_e2e(step_e2e, max(3, min(args.steps, 100)))
+    e2e_value = timed_e2e(step_e2e_async, args.steps) if len(cstreams) > 1 else e2e_sync_value
+    # the last asynchronous commit's commitments, read back on the host, against the device-resident leg's result for the
+    # same input buffer is checked below (e2e_parity)
+    e2e_last = (args.warmup + args.steps - 1)
+    e2e_parity = None
+    if len(cstreams) > 1:
+        kk = e2e_last & 1
+        ctx.hyrax_commit_device(bases, dev_bufs[e2e_last % nbuf].data_ptr(), L, R, 0, dCs[0].data_ptr(), dinfs[0].data_ptr(), stream=0)
+        torch.cuda.synchronize()
+        e2e_parity = bool(torch.equal(dCs[0].cpu(), hCs[kk]) and torch.equal(dinfs[0].cpu(), hinfs[kk]))
+        if not e2e_parity:
+            raise SystemExit("bench.py: the asynchronous host-pointer commit differs from the device-resident one")
     pC = np.empty((L, 8), dtype=np.uint64)
     pinf = np.empty((L,), dtype=np.uint8)
 
@@ -577,7 +598,11 @@ def main():
                                       "next step's commit (two output buffers) and is waited for inside the timed region")
                        if world > 1 else "none (1 GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": L * R * 32, "d2h_bytes_per_step": L * 65,
-                    "host_memory": "pinned", "pageable_value": e2e_pageable,
+                    "host_memory": "pinned",
+                    "call": ("sbn_hyrax_commit_async on two alternating caller streams: the H2D copy of step i + 1 runs under the kernels "
+                             "of step i; every step's H2D and D2H are inside the timed region") if len(cstreams) > 1 else "sbn_hyrax_commit",
+                    "synchronous_value": e2e_sync_value, "results_match_device_leg": e2e_parity,
+                    "pageable_value": e2e_pageable,
                     "pageable_note": "the same call from pageable numpy buffers (a Rust Vec<Scalar>); sbn_host_alloc gives callers pinned memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,

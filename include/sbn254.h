@@ -122,6 +122,15 @@ int sbn_bases_mult_table(const sbn_bases* b, int* window_bits, uint64_t* bytes);
  * (hyrax.rs:301-305).  Outputs are AFFINE (what append_to_transcript needs, hyrax.rs:44-52). */
 int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size_t L_size, size_t R_size,
                      const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);
+/* The same call, asynchronous: the chunked H2D copies of Z, the kernels and the D2H copy of the commitments are ordered on
+ * `stream` (a cudaStream_t, not 0) and the call returns at once; the caller synchronises the stream before reading C_out /
+ * inf_out.  Z, C_out and inf_out should be pinned (sbn_host_alloc) for the copies to be asynchronous.  The library keeps two sets
+ * of staging buffers and workspaces and consecutive calls take them in turn: two commits issued on two streams overlap, the
+ * copy of one under the kernels of the other (a prover that commits several polynomials -- comb_ops and comb_mem at encode time,
+ * sparse_mlpoly_full.rs:183-184 -- issues them back to back).  Generator sets without a digit-multiple table complete before
+ * the call returns. */
+int sbn_hyrax_commit_async(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size_t L_size, size_t R_size,
+                           const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out, void* stream);
 /* Same with every buffer already in device memory of ctx's device (Z, blinds, C_out, inf_out are
  * device pointers); runs asynchronously on `stream` (a cudaStream_t, 0 = the context's stream). */
 int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* bases, const void* dZ, size_t L_size, size_t R_size,

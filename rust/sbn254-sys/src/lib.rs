@@ -33,6 +33,8 @@ extern "C" {
     pub fn sbn_bases_mult_table(b: *const sbn_bases, window_bits: *mut c_int, bytes: *mut u64) -> c_int;
     pub fn sbn_hyrax_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, z: *const SbnFr, l_size: usize, r_size: usize,
                             blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_hyrax_commit_async(ctx: *mut sbn_ctx, b: *const sbn_bases, z: *const SbnFr, l_size: usize, r_size: usize,
+                                  blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8, stream: *mut c_void) -> c_int;
     pub fn sbn_hyrax_commit_multi(ctxs: *const *mut sbn_ctx, bases: *const *const sbn_bases, k: usize, z: *const SbnFr,
                                   l_size: usize, r_size: usize, blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_ctx_memory_stats(ctx: *mut sbn_ctx, out: *mut u64) -> c_int;

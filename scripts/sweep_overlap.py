@@ -60,6 +60,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "ablate":
         ctx.set("ba_batch", B)
         run(f"two caller streams, pairs per thread {B}", 2)
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "smem":
+    run("two caller streams, default", 2)
+    for pk, fk in ((57, 0), (75, 0), (110, 0), (0, 50), (0, 75), (57, 50), (75, 75), (110, 75)):
+        ctx.set("prefix_smem_kb", pk); ctx.set("finish_smem_kb", fk)
+        run(f"two caller streams, prefix smem {pk} KB, finish smem {fk} KB", 2)
+    sys.exit(0)
 one = run("one caller stream", 1)
 two = run("two alternating caller streams", 2)
 # reference results for inputs (n-2) % 6 and (n-1) % 6 on one stream

@@ -68,7 +68,9 @@ struct sbn_ctx {
     cudaEvent_t fork = nullptr, join_hi = nullptr;
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
     DevBuf mtotals[2];                 // row totals of the tabulated-sum path, one per workspace set
-    uint64_t mult_calls = 0;
+    uint64_t mult_calls = 0, host_calls = 0;
+    DevBuf hZ[2], hC[2], hI[2], hB[2];   // staging of sbn_hyrax_commit_async, one set per call in turn
+    int force_set = -1, last_was_mult = 0;
     DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
     DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
     DevBuf zkeep;                      // z of the last sbn_sumcheck_begin_r1cs, reused by _begin_quad_r1cs(z = NULL)
@@ -365,7 +367,8 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part, &ctx->mtotals[0], &ctx->mtotals[1]})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part, &ctx->mtotals[0], &ctx->mtotals[1], &ctx->hZ[0], &ctx->hZ[1], &ctx->hC[0], &ctx->hC[1], &ctx->hI[0], &ctx->hI[1],
+                      &ctx->hB[0], &ctx->hB[1]})
         release(*b);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
@@ -1186,7 +1189,8 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
     // streams of its own (sbn_hyrax_commit_device is asynchronous) gets the tail of one commit -- the short last rounds, the
     // row sums, the normalisation: ~0.3 ms of a mostly idle GPU -- underneath the head of the next.  Within one caller stream
     // nothing changes (stream order).
-    const size_t set = (ns <= 2 && !host_Z) ? (size_t)(ctx->mult_calls++ & 1) : 0;
+    const size_t set = ns > 2 ? 0 : (ctx->force_set >= 0 ? (size_t)ctx->force_set : (host_Z ? 0 : (size_t)(ctx->mult_calls++ & 1)));
+    ctx->last_was_mult = 1;
     const size_t sb = 2 * set;
     for (size_t k = 0; k < ns; k++) {
         auto& sl = ctx->slots[sb + k];
@@ -1580,23 +1584,35 @@ static int small_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_
     return SBN_OK;
 }
 
-extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
-                                sbn_g1a* C_out, uint8_t* inf_out) {
+// Host-pointer commit.  `async_stream` == nullptr: the synchronous call of the ABI (results are in C_out / inf_out on return).
+// Otherwise everything -- the chunked H2D copies, the kernels, the D2H copy of the commitments -- is ordered on the caller's
+// stream and the call returns at once; the staging buffers come in two sets taken in turn, like the workspaces, so that two
+// commits issued on two streams overlap: the copy of one under the kernels of the other.
+static int hyrax_commit_host(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
+                             sbn_g1a* C_out, uint8_t* inf_out, cudaStream_t async_stream) {
     if (!ctx || !b || !Z || !C_out || !inf_out || b->ctx != ctx) return SBN_ERR_ARG;
     SBN_TRY(check_commit_shape(b, L, R));
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_ENTER(ctx);
-    if (b->small && b->n_cols <= kSmallMaxCols && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
+    if (b->small && b->n_cols <= kSmallMaxCols && ctx->small_commit_path && L <= (size_t)kSmallMaxRows) {
+        if (async_stream) SBN_CUDA(ctx, cudaStreamSynchronize(async_stream));      // the short path is synchronous on the context stream
+        return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
+    }
+    const bool async = async_stream != nullptr;
+    const int hset = async ? (int)(ctx->host_calls++ & 1) : 0;
+    cudaStream_t main = async ? async_stream : ctx->compute;
+    DevBuf &bZ = async ? ctx->hZ[hset] : ctx->dZ, &bC = async ? ctx->hC[hset] : ctx->dC, &bI = async ? ctx->hI[hset] : ctx->dinf,
+           &bB = async ? ctx->hB[hset] : ctx->dblinds;
     const size_t chunk = commit_chunk_rows(ctx, L);
     SBN_TRY(ensure_commit_workspace(ctx, b, chunk, L));
-    SBN_TRY(ensure(ctx, ctx->dZ, L * R * sizeof(Fr)));
-    SBN_TRY(ensure(ctx, ctx->dC, L * sizeof(Affine)));
-    SBN_TRY(ensure(ctx, ctx->dinf, L));
+    SBN_TRY(ensure(ctx, bZ, L * R * sizeof(Fr)));
+    SBN_TRY(ensure(ctx, bC, L * sizeof(Affine)));
+    SBN_TRY(ensure(ctx, bI, L));
     Fr* dbl = nullptr;
     if (blinds) {
-        SBN_TRY(ensure(ctx, ctx->dblinds, L * sizeof(Fr)));
-        dbl = (Fr*)ctx->dblinds.p;
-        SBN_CUDA(ctx, cudaMemcpyAsync(dbl, blinds, L * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute));
+        SBN_TRY(ensure(ctx, bB, L * sizeof(Fr)));
+        dbl = (Fr*)bB.p;
+        SBN_CUDA(ctx, cudaMemcpyAsync(dbl, blinds, L * sizeof(Fr), cudaMemcpyHostToDevice, main));
         ctx->h2d += L * sizeof(Fr);
     }
     // Host scalars that look small (a strided sample on the host) are uploaded in one piece, so that the device-side row
@@ -1613,20 +1629,35 @@ extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* 
             any_small = (v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) == 0;
         }
         if (any_small) {
-            SBN_CUDA(ctx, cudaMemcpyAsync(ctx->dZ.p, Z, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute));
+            SBN_CUDA(ctx, cudaMemcpyAsync(bZ.p, Z, n * sizeof(Fr), cudaMemcpyHostToDevice, main));
             ctx->h2d += n * sizeof(Fr);
             host_Z = nullptr;
         }
     }
     std::vector<int> ev_stage;
-    SBN_TRY(run_commit(ctx, b, (const Fr*)ctx->dZ.p, host_Z, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p,
-                       ctx->compute, ev_stage));
-    SBN_CUDA(ctx, cudaMemcpyAsync(C_out, ctx->dC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, ctx->compute));
-    SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, ctx->dinf.p, L, cudaMemcpyDeviceToHost, ctx->compute));
+    ctx->force_set = async ? hset : -1;
+    ctx->last_was_mult = 0;
+    const int rc = run_commit(ctx, b, (const Fr*)bZ.p, host_Z, L, R, dbl, (Affine*)bC.p, (uint8_t*)bI.p, main, ev_stage);
+    ctx->force_set = -1;
+    SBN_TRY(rc);
+    SBN_CUDA(ctx, cudaMemcpyAsync(C_out, bC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, main));
+    SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, bI.p, L, cudaMemcpyDeviceToHost, main));
     ctx->d2h += L * sizeof(Affine) + L;
-    SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    collect_profile(ctx, ev_stage);
+    if (!async || !ctx->last_was_mult) {      // only the tabulated-sum path keeps per-call workspaces: everything else completes here
+        SBN_CUDA(ctx, cudaStreamSynchronize(main));
+        if (!async) collect_profile(ctx, ev_stage);
+    }
     return SBN_OK;
+}
+
+extern "C" int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
+                                sbn_g1a* C_out, uint8_t* inf_out) {
+    return hyrax_commit_host(ctx, b, Z, L, R, blinds, C_out, inf_out, nullptr);
+}
+extern "C" int sbn_hyrax_commit_async(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
+                                      sbn_g1a* C_out, uint8_t* inf_out, void* stream) {
+    if (!stream) return SBN_ERR_ARG;
+    return hyrax_commit_host(ctx, b, Z, L, R, blinds, C_out, inf_out, (cudaStream_t)stream);
 }
 
 // One process, k GPUs: the rows of one commit divided into k contiguous blocks, block i committed by context i (one

@@ -13,7 +13,7 @@ EXPORTS = [
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
     "sbn_ctx_last_commit_profile", "sbn_ctx_memory_stats", "sbn_host_alloc", "sbn_host_free",
     "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
-    "sbn_hyrax_commit", "sbn_hyrax_commit_device", "sbn_hyrax_commit_multi", "sbn_msm", "sbn_commit",
+    "sbn_hyrax_commit", "sbn_hyrax_commit_async", "sbn_hyrax_commit_device", "sbn_hyrax_commit_multi", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
     "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_end_delta", "sbn_bullet_destroy",
@@ -157,6 +157,13 @@ class Context:
                                        C.c_void_p(blinds_ptr) if blinds_ptr else None, C.c_void_p(out_ptr),
                                        C.c_void_p(inf_ptr))
         self._check(st, "sbn_hyrax_commit")
+
+    def hyrax_commit_raw_async(self, bases, Z_ptr, L_size, R_size, blinds_ptr, out_ptr, inf_ptr, stream):
+        """sbn_hyrax_commit_async on raw host pointers (pinned for real asynchrony); the caller synchronises `stream`."""
+        st = self.lib.sbn_hyrax_commit_async(self.h, bases.h, C.c_void_p(Z_ptr), C.c_size_t(L_size), C.c_size_t(R_size),
+                                             C.c_void_p(blinds_ptr) if blinds_ptr else None, C.c_void_p(out_ptr),
+                                             C.c_void_p(inf_ptr), C.c_void_p(stream))
+        self._check(st, "sbn_hyrax_commit_async")
 
     def hyrax_commit_device(self, bases, dZ_ptr, L_size, R_size, dblinds_ptr, dC_ptr, dinf_ptr, stream=0):
         st = self.lib.sbn_hyrax_commit_device(self.h, bases.h, C.c_void_p(dZ_ptr), C.c_size_t(L_size),

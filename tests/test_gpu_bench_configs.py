@@ -173,3 +173,37 @@ def test_independent_commits_on_two_caller_streams(orc):
         bases.close()
     finally:
         ctx.close()
+
+
+def test_async_host_commits_on_two_streams(orc):
+    """sbn_hyrax_commit_async (bench.py's e2e leg): six host-pointer commits from pinned buffers issued on two alternating streams,
+    with and without blinds, over a generator set with a digit-multiple table and over one without (which completes inside the
+    call); every result equals the synchronous sbn_hyrax_commit of the same input."""
+    import torch
+    from spartan_bn254_b200 import Context, synth
+    ctx = Context(0)
+    try:
+        L, R = 512, 128
+        dev = torch.device("cuda", 0)
+        G, h = synth.distinct_generators(ctx, R)
+        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        for table_mb in (2048, 0):
+            ctx.set("mult_max_mb", table_mb)
+            bases = ctx.bases(G, h)
+            Zs = [synth.uniform_scalars(60 + i, L * R) for i in range(6)]
+            bl = synth.uniform_scalars(70, L)
+            pin = [torch.from_numpy(z.view(np.int64)).pin_memory() for z in Zs]
+            pbl = torch.from_numpy(bl.view(np.int64)).pin_memory()
+            outC = [torch.empty((L, 8), dtype=torch.int64).pin_memory() for _ in range(6)]
+            outI = [torch.empty((L,), dtype=torch.uint8).pin_memory() for _ in range(6)]
+            for i in range(6):
+                ctx.hyrax_commit_raw_async(bases, pin[i].data_ptr(), L, R, pbl.data_ptr() if i % 3 == 2 else 0, outC[i].data_ptr(),
+                                           outI[i].data_ptr(), streams[i & 1].cuda_stream)
+            torch.cuda.synchronize()
+            for i in range(6):
+                C, inf = ctx.hyrax_commit(bases, Zs[i], L, R, bl if i % 3 == 2 else None)
+                assert np.array_equal(outC[i].numpy().view(np.uint64), C) and np.array_equal(outI[i].numpy(), inf), (table_mb, i)
+            _check_rows(orc, G, h, Zs[0], L, R, outC[0].numpy().view(np.uint64), outI[0].numpy(), 16)
+            bases.close()
+    finally:
+        ctx.close()
