@@ -39,6 +39,11 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
 struct sbn_ctx {
     int device = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -70,6 +75,7 @@ struct sbn_ctx {
     DevBuf mtotals[2];                 // row totals of the tabulated-sum path, one per workspace set
     uint64_t mult_calls = 0, host_calls = 0;
     DevBuf hZ[2], hC[2], hI[2], hB[2];   // staging of sbn_hyrax_commit_async, one set per call in turn
+    HostBuf stage_pin[2][2];           // pinned ring for pageable host scalars: [workspace set][chunk parity]
     int force_set = -1, last_was_mult = 0;
     DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
     DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
@@ -384,6 +390,7 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamDestroy(ctx->copy);
     if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
     if (ctx->ev_pin) cudaFreeHost(ctx->ev_pin);
+    for (auto& a : ctx->stage_pin) for (auto& r : a) if (r.p) cudaFreeHost(r.p);
     delete ctx;
     cudaGetLastError();
     return SBN_OK;
@@ -1148,6 +1155,20 @@ static void launch_sum_rows(sbn_ctx* ctx, int rows, cudaStream_t st, const Fq* p
     else k_mult_sum_rows_t<1><<<blocks, kMultSumThreads, 0, st>>>(px, py, cnt, rp, rows, totals);
 }
 
+// memcpy of a chunk of scalars on four host threads (one thread moves ~10 GB/s; a 16 MB chunk in ~0.5 ms on four)
+static void host_copy_mt(void* dst, const void* src, size_t bytes) {
+    const int nt = bytes >= (size_t(4) << 20) ? 4 : 1;
+    if (nt == 1) { memcpy(dst, src, bytes); return; }
+    const size_t part = (bytes / nt + 4095) & ~size_t(4095);
+    std::thread th[3];
+    for (int t = 1; t < nt; t++) {
+        const size_t off = std::min(bytes, part * t), len = std::min(bytes - off, part);
+        th[t - 1] = std::thread([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    memcpy(dst, src, std::min(bytes, part));
+    for (int t = 1; t < nt; t++) th[t - 1].join();
+}
+
 static int mult_rounds_for(uint32_t used) {
     int r = 1;
     // leave ~400-800 points per row to the XYZZ sum: with its additions inlined the sum kernel is cheap enough that a sixth
@@ -1214,9 +1235,30 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
     if (!get_event(ctx, sync_base + nchunks + 4)) { ctx->last_error = "cudaEventCreate failed"; return SBN_ERR_CUDA; }
     std::vector<size_t> row0(nchunks, 0);
     for (size_t i = 1; i < nchunks; i++) row0[i] = row0[i - 1] + sched[i - 1];
+    // Pageable host scalars (a Rust Vec<Scalar>; cudaMemcpyAsync stages them through the driver at ~12 GB/s, synchronously) go
+    // through a ring of two pinned buffers per workspace set instead, filled by four host threads: the copy of chunk i + 1 is
+    // then a real asynchronous H2D that runs under the kernels of chunk i.
+    bool pageable = false;
+    if (host_Z) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host_Z) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
     auto issue_copy = [&](size_t ci) -> int {
-        SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0[ci] * R), host_Z + row0[ci] * R, sched[ci] * R * sizeof(Fr),
-                                      cudaMemcpyHostToDevice, ctx->copy));
+        const size_t bytes = sched[ci] * R * sizeof(Fr);
+        const void* src = host_Z + row0[ci] * R;
+        if (pageable) {
+            HostBuf& ring = ctx->stage_pin[set][ci & 1];
+            if (ring.cap < bytes) {
+                if (ring.p) { SBN_CUDA(ctx, cudaDeviceSynchronize()); cudaFreeHost(ring.p); ring.p = nullptr; ring.cap = 0; }
+                SBN_CUDA(ctx, cudaHostAlloc(&ring.p, bytes + bytes / 8, cudaHostAllocDefault));
+                ring.cap = bytes + bytes / 8;
+            }
+            if (ci >= 2) SBN_CUDA(ctx, cudaEventSynchronize(get_event(ctx, sync_base + ci - 2)));   // the H2D out of this slot is done
+            host_copy_mt(ring.p, src, bytes);
+            src = ring.p;
+        }
+        SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0[ci] * R), src, bytes, cudaMemcpyHostToDevice, ctx->copy));
         ctx->h2d += sched[ci] * R * sizeof(Fr);
         SBN_CUDA(ctx, cudaEventRecord(get_event(ctx, sync_base + ci), ctx->copy));
         return SBN_OK;
