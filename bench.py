@@ -10,8 +10,9 @@ commitment vector is all-gathered over NCCL at the end of every step, reference 
 the rows the same way).
 
 The generators' digit-multiple table (mult_kernels.cuh: every d * 2^(kc) * G_j, built once per generator set and kept in
-HBM like the bases themselves) is sized by --table-mb (default 36000 MiB: c = 16 at 1025 generators); --table-mb 0 times
-the bucket pipeline instead.
+HBM like the bases themselves) is sized by --table-mb (default 70000 MiB: c = 17 at 1025 generators, 64.5 GB; 36000 gives
+c = 16 / 34 GB, the library default 6144 c = 13 / 5.4 GB -- reported as value_default_budget); --table-mb 0 times the bucket
+pipeline instead.  The headline table is released before the strong-scaling and prove legs, which run under 36000 MiB.
 
   value  points/s with scalars already resident in HBM (device-pointer C-ABI entry point)
   e2e    the same metric through sbn_hyrax_commit with PINNED HOST buffers: H2D of the scalars and D2H
@@ -58,7 +59,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU commits the workload's rows (default); strong: the workload's rows are divided "
                          "across the GPUs (BASELINE configs[2]: the keyless derefs commitment sharded by rows)")
-    ap.add_argument("--table-mb", type=int, default=36000,
+    ap.add_argument("--table-mb", type=int, default=70000,
                     help="budget (MiB) of the digit-multiple table of the commit's generator set (mult_kernels.cuh): the widest "
                          "window whose table fits is tabulated once and kept resident; 0 = bucket pipeline only; the "
                          "library's own default is 6144")
@@ -494,6 +495,13 @@ def main():
 
     e2e_pageable = timed_e2e(step_pageable, max(3, min(args.steps, 50)))
 
+    # ---- the headline generator set's table (64 GB at the default budget) is released before the other legs build theirs
+    mult_bits, mult_bytes = bases.mult_table()
+    bases_window_bits = bases.window_bits
+    torch.cuda.synchronize()
+    bases.close()
+    other_budget = min(args.table_mb, 36000)     # strong / prove legs: the budget their records were taken with
+
     # ---- the same commit under the LIBRARY's default table budget (6144 MiB: c = 13 at 1025 generators) -- the headline above
     #      uses --table-mb; a deployment that cannot spare that much HBM gets this number
     default_budget = None
@@ -506,7 +514,7 @@ def main():
         default_budget = {"value": points_per_step * nd / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d / nd,
                           "table_budget_mb": 6144, "table_window_bits": bits_d, "table_bytes": bytes_d, "steps": nd}
         bases_d.close()
-        ctx.set("mult_max_mb", args.table_mb)
+    ctx.set("mult_max_mb", other_budget)
 
     # ---- the same commit on the REFERENCE's generator set (MultiCommitGens::new, commitments.rs:31-62): about two thirds of
     #      those generators are the same point, which the library merges (k_aggregate_rows), so the real prover's commits
@@ -552,13 +560,12 @@ def main():
                 prove["cpu_baseline"] = cpu_prove_baseline(prove)
 
     if rank == 0:
-        mult_bits, mult_bytes = bases.mult_table()
-        path_bits = mult_bits or bases.window_bits            # window width of the path that was TIMED
+        path_bits = mult_bits or bases_window_bits            # window width of the path that was TIMED
         W = (254 + path_bits) // path_bits
-        Wb = (254 + bases.window_bits) // bases.window_bits    # the bucket method's window count (SURVEY 8(d) accounting)
+        Wb = (254 + bases_window_bits) // bases_window_bits    # the bucket method's window count (SURVEY 8(d) accounting)
         if args.scalars == "small":     # 21-bit values: only the windows that can hold a non-zero digit count as work
             W = min(W, -(-22 // path_bits))
-            Wb = min(Wb, -(-22 // bases.window_bits))
+            Wb = min(Wb, -(-22 // bases_window_bits))
         # one XYZZ mixed addition per (scalar, window) pair of the BUCKET method = Wb * 10 * 264 IMAD per point
         alg_imad_acc = float(prof_rows) * R * Wb * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         formula = alg_imad_acc / (acc_ms * 1e-3) if acc_ms > 0 else 0.0
@@ -576,15 +583,16 @@ def main():
         hbm_peak, hbm_src = hbm_peak_gbs()
         step_alg = A_ADDS_PER_POINT.get(R, 26.0) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         if args.scalars == "small":
-            step_alg = (Wb + 2.0 * (1 << (bases.window_bits - 1)) / R) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
+            step_alg = (Wb + 2.0 * (1 << (bases_window_bits - 1)) / R) * FQMUL_PER_MIXED_ADD * IMAD_PER_FQMUL
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32x8 Montgomery (integer, IMAD.WIDE carry chains)", "data": "synthetic",
             "config": {"workload": args.workload, "rows_per_gpu": L, "generators": R, "window_bits": path_bits,
                        "path": "tabulated sum over the resident digit-multiple table" if mult_bits else "bucket pipeline",
-                       "bucket_pipeline_window_bits": bases.window_bits,
+                       "bucket_pipeline_window_bits": bases_window_bits,
                        "table_budget_mb": args.table_mb, "table_bytes": mult_bytes, "table_build_s": table_build_s,
+                       "other_legs_table_budget_mb": other_budget,
                        "table_note": "built once per generator set by the first commit of >= 256 rows, outside the timed region; "
                                      "value_default_budget is the same commit under the library's default 6144 MiB",
                        "gens": args.gens, "scalars": args.scalars, "blinds": "zero (derefs-style, hyrax.rs:301-305)",
@@ -729,7 +737,7 @@ def run_strong(ctx, synth, torch, dist, dev, stream, rank, world, args):
     ms = float(tt.item()) / n
     bits, nbytes = bs.mult_table()
     bs.close()
-    ctx.set("mult_max_mb", args.table_mb)
+    ctx.set("mult_max_mb", min(args.table_mb, 36000))
     return {"ms_per_commit": ms, "value": 4096 * Rs / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "rows_per_gpu": Ls,
             "generators": Rs, "scaling": "strong", "steps": n, "table_window_bits": bits, "table_bytes": nbytes,
             "inputs": "2 GiB / n_gpus of uniform scalars per GPU: larger than L2, not rotated",

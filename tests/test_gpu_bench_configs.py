@@ -1,5 +1,5 @@
-"""GPU parity tests AT THE BENCHMARKED CONFIGURATIONS (-m gpu): the exact paths bench.py times -- cfg1 with the 36000 MiB
-table budget (16-bit windows, 34 GB table), the keyless derefs shape 4096 x 8192 with and without a table, the encode-time
+"""GPU parity tests AT THE BENCHMARKED CONFIGURATIONS (-m gpu): the exact paths bench.py times -- cfg1 with the 70000 MiB
+table budget (bench.py's default: 17-bit windows, 64.5 GB table) and with 36000 MiB (16-bit windows, 34 GB), the keyless derefs shape 4096 x 8192 with and without a table, the encode-time
 8192 x 8192 commit of small scalars -- compared with the CPU oracle on >= 64 sampled rows each, through the device-pointer
 C-ABI entry point bench.py calls (sbn_hyrax_commit_device).  Each test owns its context: the tables are tens of GB."""
 import numpy as np
@@ -28,14 +28,14 @@ def _check_rows(orc, G, h, Z, L, R, C, inf, nrows=64, must_include=()):
     return rows
 
 
-@pytest.mark.parametrize("gens_kind", ["distinct", "ref"])
-def test_cfg1_at_bench_table_budget(orc, gens_kind):
-    """bench.py's default: 1024 x 1024, --table-mb 36000 => 16-bit windows."""
+@pytest.mark.parametrize("gens_kind,table_mb,want_bits", [("distinct", 70000, 17), ("distinct", 36000, 16), ("ref", 36000, 16)])
+def test_cfg1_at_bench_table_budget(orc, gens_kind, table_mb, want_bits):
+    """bench.py's default: 1024 x 1024, --table-mb 70000 => 17-bit windows; 36000 => 16-bit windows (round-2 records)."""
     from spartan_bn254_b200 import Context, synth
     from spartan_bn254_b200.hyrax import MultiCommitGens
     ctx = Context(0)
     try:
-        ctx.set("mult_max_mb", 36000)
+        ctx.set("mult_max_mb", table_mb)
         L = R = 1024
         if gens_kind == "distinct":
             G, h = synth.distinct_generators(ctx, R)
@@ -47,8 +47,9 @@ def test_cfg1_at_bench_table_budget(orc, gens_kind):
         Z[5 * R:6 * R] = 0                      # an all-zero row: identity commitment
         C, inf = _commit_device(ctx, bases, Z, L, R)
         bits, nbytes = bases.mult_table()
-        # distinct generators: 16-bit windows (34 GB); the reference set merges to 333 distinct points and affords 17 bits
-        assert bits == 16 if gens_kind == "distinct" else bits >= 16, "the benchmarked path is the 16-bit-window table, got %d" % bits
+        # distinct generators: 17-bit windows (64.5 GB) / 16-bit (34 GB); the reference set merges to 333 distinct points and
+        # affords 17 bits under either budget
+        assert bits == want_bits if gens_kind == "distinct" else bits >= want_bits, "benchmarked window width: want %d, got %d" % (want_bits, bits)
         _check_rows(orc, G, h, Z, L, R, C, inf, 64, must_include=(5,))
         assert inf[5] == 1
         # the same commit through the host-pointer entry point (the e2e leg) and with the row-major layout of round 1
