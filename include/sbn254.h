@@ -124,9 +124,10 @@ int sbn_hyrax_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size
                      const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);
 /* The same call, asynchronous: the chunked H2D copies of Z, the kernels and the D2H copy of the commitments are ordered on
  * `stream` (a cudaStream_t, not 0) and the call returns at once; the caller synchronises the stream before reading C_out /
- * inf_out.  Z, C_out and inf_out should be pinned (sbn_host_alloc) for the copies to be asynchronous.  The library keeps two sets
- * of staging buffers and workspaces and consecutive calls take them in turn: two commits issued on two streams overlap, the
- * copy of one under the kernels of the other (a prover that commits several polynomials -- comb_ops and comb_mem at encode time,
+ * inf_out.  Z, C_out and inf_out should be pinned (sbn_host_alloc) for the copies to be asynchronous.  The library keeps three
+ * sets of staging buffers and two sets of workspaces; consecutive calls take them in turn and every set is handed from one call
+ * to the next by a device-side event, so the calls may sit on any streams: commits issued on two or three streams overlap, the
+ * copy of one under the kernels of the others (a prover that commits several polynomials -- comb_ops and comb_mem at encode time,
  * sparse_mlpoly_full.rs:183-184 -- issues them back to back).  Generator sets without a digit-multiple table complete before
  * the call returns. */
 int sbn_hyrax_commit_async(sbn_ctx* ctx, const sbn_bases* bases, const sbn_fr* Z, size_t L_size, size_t R_size,

@@ -74,7 +74,11 @@ struct sbn_ctx {
     DevBuf totals, dZ, dblinds, dC, dinf, scratch0, scratch1, scratch2;
     DevBuf mtotals[2];                 // row totals of the tabulated-sum path, one per workspace set
     uint64_t mult_calls = 0, host_calls = 0;
-    DevBuf hZ[2], hC[2], hI[2], hB[2];   // staging of sbn_hyrax_commit_async, one set per call in turn
+    DevBuf hZ[3], hC[3], hI[3], hB[3];   // staging of sbn_hyrax_commit_async, one set per call in turn
+    // Completion of the last call that used a workspace set (tabulated-sum path) / a staging set: the next call that takes the
+    // set waits for it on the device, whatever stream the caller put it on (with two alternating caller streams the wait is
+    // already implied by stream order; with three, or with one stream per commit, it is what keeps the sets apart).
+    cudaEvent_t set_done[2] = {nullptr, nullptr}, hset_done[3] = {nullptr, nullptr, nullptr};
     HostBuf stage_pin[2][2];           // pinned ring for pageable host scalars: [workspace set][chunk parity]
     int force_set = -1, last_was_mult = 0;
     DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
@@ -373,9 +377,11 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamSynchronize(ctx->compute);
     cudaStreamSynchronize(ctx->copy);
     for (DevBuf* b : {&ctx->totals, &ctx->dZ, &ctx->dblinds, &ctx->dC, &ctx->dinf, &ctx->scratch0, &ctx->scratch1,
-                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part, &ctx->mtotals[0], &ctx->mtotals[1], &ctx->hZ[0], &ctx->hZ[1], &ctx->hC[0], &ctx->hC[1], &ctx->hI[0], &ctx->hI[1],
-                      &ctx->hB[0], &ctx->hB[1]})
+                      &ctx->scratch2, &ctx->tabpart, &ctx->zkeep, &ctx->scan, &ctx->spmv_part, &ctx->mtotals[0], &ctx->mtotals[1], &ctx->hZ[0], &ctx->hZ[1], &ctx->hZ[2], &ctx->hC[0], &ctx->hC[1], &ctx->hC[2], &ctx->hI[0], &ctx->hI[1],
+                      &ctx->hI[2], &ctx->hB[0], &ctx->hB[1], &ctx->hB[2]})
         release(*b);
+    for (cudaEvent_t e : {ctx->set_done[0], ctx->set_done[1], ctx->hset_done[0], ctx->hset_done[1], ctx->hset_done[2]})
+        if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {ctx->hi, ctx->lo[0], ctx->lo[1], ctx->lo[2], ctx->lo[3]})
         if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     for (auto& sl : ctx->slots)
@@ -1191,7 +1197,10 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
     {
         size_t done = 0;
         const size_t first = ctx->first_chunk_rows > 0 ? std::min<size_t>((size_t)ctx->first_chunk_rows, chunk) : chunk / 4;
-        if ((host_Z || ctx->first_chunk_rows > 0) && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
+        // a short first chunk gets the kernels started under the rest of the copy -- for a BLOCKING call; asynchronous calls
+        // (force_set >= 0) are pipelined against each other by the caller, and equal chunks keep every launch at full size
+        const bool short_first = (host_Z && ctx->force_set < 0) || ctx->first_chunk_rows > 0;
+        if (short_first && L > first && chunk >= 8 && first > 0) { sched.push_back(first); done = first; }
         while (done < L) { size_t cr = std::min(chunk, L - done); sched.push_back(cr); done += cr; }
     }
     const size_t nchunks = sched.size();
@@ -1264,7 +1273,20 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
         return SBN_OK;
     };
     SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
-    for (size_t k = 0; k < ns; k++) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[sb + k], ctx->fork, 0));
+    for (size_t k = 0; k < ns; k++) {
+        SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[sb + k], ctx->fork, 0));
+        // the previous user of this workspace set (both sets when more than two chunks are in flight) may sit on another stream
+        for (size_t q = 0; q < 2; q++)
+            if ((q == set || ns > 2) && ctx->set_done[q]) SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->lo[sb + k], ctx->set_done[q], 0));
+    }
+    auto mark_done = [&]() -> int {
+        for (size_t q = 0; q < 2; q++) {
+            if (q != set && ns <= 2) continue;
+            if (!ctx->set_done[q]) SBN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->set_done[q], cudaEventDisableTiming));
+            SBN_CUDA(ctx, cudaEventRecord(ctx->set_done[q], main));
+        }
+        return SBN_OK;
+    };
     if (host_Z) {
         SBN_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->fork, 0));
         SBN_TRY(issue_copy(0));
@@ -1428,13 +1450,13 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
         SBN_CUDA(ctx, cudaEventRecord(e, ctx->lo[sb + k]));
         SBN_CUDA(ctx, cudaStreamWaitEvent(main, e, 0));
     }
-    if (!normalize) return SBN_OK;
+    if (!normalize) return mark_done();
     marks.mark(-1, main);
     k_normalize<<<(unsigned)((L + 63) / 64), 64, 0, main>>>(totals, (int)L, dC, dinf);
     ctx->launches++;
     marks.mark(3, main);
     SBN_CUDA(ctx, cudaGetLastError());
-    return SBN_OK;
+    return mark_done();
 }
 
 static int run_commit_inner(sbn_ctx* ctx, const sbn_bases* b, const Fr* dZ, const Fr* host_Z, size_t L, size_t R,
@@ -1641,8 +1663,11 @@ static int hyrax_commit_host(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, 
         return small_commit(ctx, b, Z, L, R, blinds, C_out, inf_out);
     }
     const bool async = async_stream != nullptr;
-    const int hset = async ? (int)(ctx->host_calls++ & 1) : 0;
+    // asynchronous calls take the three staging sets and the two workspace sets in turn
+    const int hset = async ? (int)(ctx->host_calls % 3) : 0, wset = async ? (int)(ctx->host_calls & 1) : 0;
+    if (async) ctx->host_calls++;
     cudaStream_t main = async ? async_stream : ctx->compute;
+    if (async && ctx->hset_done[hset]) SBN_CUDA(ctx, cudaStreamWaitEvent(main, ctx->hset_done[hset], 0));
     DevBuf &bZ = async ? ctx->hZ[hset] : ctx->dZ, &bC = async ? ctx->hC[hset] : ctx->dC, &bI = async ? ctx->hI[hset] : ctx->dinf,
            &bB = async ? ctx->hB[hset] : ctx->dblinds;
     const size_t chunk = commit_chunk_rows(ctx, L);
@@ -1677,7 +1702,7 @@ static int hyrax_commit_host(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, 
         }
     }
     std::vector<int> ev_stage;
-    ctx->force_set = async ? hset : -1;
+    ctx->force_set = async ? wset : -1;
     ctx->last_was_mult = 0;
     const int rc = run_commit(ctx, b, (const Fr*)bZ.p, host_Z, L, R, dbl, (Affine*)bC.p, (uint8_t*)bI.p, main, ev_stage);
     ctx->force_set = -1;
@@ -1685,6 +1710,10 @@ static int hyrax_commit_host(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, 
     SBN_CUDA(ctx, cudaMemcpyAsync(C_out, bC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, main));
     SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, bI.p, L, cudaMemcpyDeviceToHost, main));
     ctx->d2h += L * sizeof(Affine) + L;
+    if (async) {
+        if (!ctx->hset_done[hset]) SBN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->hset_done[hset], cudaEventDisableTiming));
+        SBN_CUDA(ctx, cudaEventRecord(ctx->hset_done[hset], main));
+    }
     if (!async || !ctx->last_was_mult) {      // only the tabulated-sum path keeps per-call workspaces: everything else completes here
         SBN_CUDA(ctx, cudaStreamSynchronize(main));
         if (!async) collect_profile(ctx, ev_stage);

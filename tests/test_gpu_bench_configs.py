@@ -140,10 +140,12 @@ def test_mixed_small_and_full_rows(orc, gens_kind):
         ctx.close()
 
 
-def test_independent_commits_on_two_caller_streams(orc):
+@pytest.mark.parametrize("nstreams", [2, 3, 8])
+def test_independent_commits_on_two_caller_streams(orc, nstreams):
     """bench.py's device-resident leg issues consecutive, independent commits on two alternating caller streams; the library
     takes its two workspace / stream sets in turn so that they overlap.  Eight commits of different inputs in flight must each
-    equal the commit of the same input issued alone, and the oracle on sampled rows."""
+    equal the commit of the same input issued alone, and the oracle on sampled rows.  With three streams, or one stream per
+    commit, consecutive users of a workspace set sit on DIFFERENT streams: the library's own completion events keep them apart."""
     import torch
     from spartan_bn254_b200 import Context, synth
     ctx = Context(0)
@@ -157,11 +159,11 @@ def test_independent_commits_on_two_caller_streams(orc):
         dZ = [torch.from_numpy(z.view(np.int64)).to(dev) for z in Zs]
         dC = [torch.empty((L, 8), dtype=torch.int64, device=dev) for _ in range(8)]
         dinf = [torch.empty((L,), dtype=torch.uint8, device=dev) for _ in range(8)]
-        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         torch.cuda.synchronize()
         for i in range(8):
             ctx.hyrax_commit_device(bases, dZ[i].data_ptr(), L, R, 0, dC[i].data_ptr(), dinf[i].data_ptr(),
-                                    stream=streams[i & 1].cuda_stream)
+                                    stream=streams[i % nstreams].cuda_stream)
         torch.cuda.synchronize()
         assert bases.mult_table()[0] > 0
         for i in range(8):
@@ -176,8 +178,10 @@ def test_independent_commits_on_two_caller_streams(orc):
         ctx.close()
 
 
-def test_async_host_commits_on_two_streams(orc):
-    """sbn_hyrax_commit_async (bench.py's e2e leg): six host-pointer commits from pinned buffers issued on two alternating streams,
+@pytest.mark.parametrize("nstreams", [2, 3])
+def test_async_host_commits_on_two_streams(orc, nstreams):
+    """sbn_hyrax_commit_async (bench.py's e2e leg: three streams taken in turn): six host-pointer commits from pinned buffers
+    issued on two alternating streams and on three (three staging sets, two workspace sets, each handed on by an event),
     with and without blinds, over a generator set with a digit-multiple table and over one without (which completes inside the
     call); every result equals the synchronous sbn_hyrax_commit of the same input."""
     import torch
@@ -187,7 +191,7 @@ def test_async_host_commits_on_two_streams(orc):
         L, R = 512, 128
         dev = torch.device("cuda", 0)
         G, h = synth.distinct_generators(ctx, R)
-        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         for table_mb in (2048, 0):
             ctx.set("mult_max_mb", table_mb)
             bases = ctx.bases(G, h)
@@ -199,7 +203,7 @@ def test_async_host_commits_on_two_streams(orc):
             outI = [torch.empty((L,), dtype=torch.uint8).pin_memory() for _ in range(6)]
             for i in range(6):
                 ctx.hyrax_commit_raw_async(bases, pin[i].data_ptr(), L, R, pbl.data_ptr() if i % 3 == 2 else 0, outC[i].data_ptr(),
-                                           outI[i].data_ptr(), streams[i & 1].cuda_stream)
+                                           outI[i].data_ptr(), streams[i % nstreams].cuda_stream)
             torch.cuda.synchronize()
             for i in range(6):
                 C, inf = ctx.hyrax_commit(bases, Zs[i], L, R, bl if i % 3 == 2 else None)
