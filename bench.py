@@ -497,6 +497,23 @@ def main():
         ctx.hyrax_commit_raw(bases, page_bufs[i % nbuf].ctypes.data, L, R, 0, pC.ctypes.data, pinf.ctypes.data)
 
     e2e_pageable = timed_e2e(step_pageable, max(3, min(args.steps, 50)))
+    # pageable inputs AND outputs through the asynchronous call on the same three streams: the host threads that stage call
+    # i + 1's scalars into the pinned ring run while call i's kernels do
+    pCs = [np.empty((L, 8), dtype=np.uint64) for _ in range(NE)]
+    pinfs = [np.empty((L,), dtype=np.uint8) for _ in range(NE)]
+
+    def step_pageable_async(i):
+        k = i % NE
+        ctx.hyrax_commit_raw_async(bases, page_bufs[i % nbuf].ctypes.data, L, R, 0, pCs[k].ctypes.data, pinfs[k].ctypes.data,
+                                   estreams[k].cuda_stream)
+
+    e2e_pageable_async = None
+    if len(cstreams) > 1:
+        e2e_pageable_async = timed_e2e(step_pageable_async, max(3, min(args.steps, 50)))
+        last = args.warmup + max(3, min(args.steps, 50)) - 1
+        step_pageable(last)                                   # the same input through the blocking call, into pC / pinf
+        if not (np.array_equal(pCs[last % NE], pC) and np.array_equal(pinfs[last % NE], pinf)):
+            raise SystemExit("bench.py: the asynchronous pageable commit differs from the blocking one")
 
     # ---- the headline generator set's table (64 GB at the default budget) is released before the other legs build theirs
     mult_bits, mult_bytes = bases.mult_table()
@@ -614,7 +631,7 @@ def main():
                              "library): the H2D copy of step i + 2 runs under the kernels of steps i and i + 1; every step's H2D and "
                              "D2H are inside the timed region") if len(cstreams) > 1 else "sbn_hyrax_commit",
                     "synchronous_value": e2e_sync_value, "results_match_device_leg": e2e_parity,
-                    "pageable_value": e2e_pageable,
+                    "pageable_value": e2e_pageable, "pageable_async_value": e2e_pageable_async,
                     "pageable_note": "the same call from pageable numpy buffers (a Rust Vec<Scalar>); sbn_host_alloc gives callers pinned memory"},
             "gpu_launches": int(launches),
             "clocks": clocks,

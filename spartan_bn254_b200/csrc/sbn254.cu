@@ -42,6 +42,7 @@ struct DevBuf {
 struct HostBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaEvent_t busy = nullptr;      // the last H2D copy that read this buffer (asynchronous calls return before it is done)
 };
 
 struct sbn_ctx {
@@ -80,6 +81,7 @@ struct sbn_ctx {
     // already implied by stream order; with three, or with one stream per commit, it is what keeps the sets apart).
     cudaEvent_t set_done[2] = {nullptr, nullptr}, hset_done[3] = {nullptr, nullptr, nullptr};
     HostBuf stage_pin[2][2];           // pinned ring for pageable host scalars: [workspace set][chunk parity]
+    HostBuf out_pin[3];                // pinned landing buffers for the results of asynchronous calls with pageable outputs
     int force_set = -1, last_was_mult = 0;
     DevBuf spmv_part;                  // partial sums of the heavy rows of a sparse matrix-vector product
     DevBuf scan;                       // two words: largest bit length of a sample / of all scalars (k_max_bits)
@@ -396,7 +398,8 @@ extern "C" int sbn_ctx_destroy(sbn_ctx* ctx) {
     cudaStreamDestroy(ctx->copy);
     if (ctx->small_pin) cudaFreeHost(ctx->small_pin);
     if (ctx->ev_pin) cudaFreeHost(ctx->ev_pin);
-    for (auto& a : ctx->stage_pin) for (auto& r : a) if (r.p) cudaFreeHost(r.p);
+    for (auto& a : ctx->stage_pin) for (auto& r : a) { if (r.p) cudaFreeHost(r.p); if (r.busy) cudaEventDestroy(r.busy); }
+    for (auto& r : ctx->out_pin) if (r.p) cudaFreeHost(r.p);
     delete ctx;
     cudaGetLastError();
     return SBN_OK;
@@ -1263,13 +1266,20 @@ static int mult_commit(sbn_ctx* ctx, const sbn_bases* b, const Affine* mtable, i
                 SBN_CUDA(ctx, cudaHostAlloc(&ring.p, bytes + bytes / 8, cudaHostAllocDefault));
                 ring.cap = bytes + bytes / 8;
             }
-            if (ci >= 2) SBN_CUDA(ctx, cudaEventSynchronize(get_event(ctx, sync_base + ci - 2)));   // the H2D out of this slot is done
+            // the last H2D out of this slot -- two chunks ago in this call, or a chunk of the asynchronous call that had this
+            // workspace set before -- must be done before the host overwrites it
+            if (ring.busy) SBN_CUDA(ctx, cudaEventSynchronize(ring.busy));
             host_copy_mt(ring.p, src, bytes);
             src = ring.p;
         }
         SBN_CUDA(ctx, cudaMemcpyAsync((void*)(dZ + row0[ci] * R), src, bytes, cudaMemcpyHostToDevice, ctx->copy));
         ctx->h2d += sched[ci] * R * sizeof(Fr);
         SBN_CUDA(ctx, cudaEventRecord(get_event(ctx, sync_base + ci), ctx->copy));
+        if (pageable) {
+            HostBuf& ring = ctx->stage_pin[set][ci & 1];
+            if (!ring.busy) SBN_CUDA(ctx, cudaEventCreateWithFlags(&ring.busy, cudaEventDisableTiming));
+            SBN_CUDA(ctx, cudaEventRecord(ring.busy, ctx->copy));
+        }
         return SBN_OK;
     };
     SBN_CUDA(ctx, cudaEventRecord(ctx->fork, main));
@@ -1707,8 +1717,42 @@ static int hyrax_commit_host(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, 
     const int rc = run_commit(ctx, b, (const Fr*)bZ.p, host_Z, L, R, dbl, (Affine*)bC.p, (uint8_t*)bI.p, main, ev_stage);
     ctx->force_set = -1;
     SBN_TRY(rc);
-    SBN_CUDA(ctx, cudaMemcpyAsync(C_out, bC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, main));
-    SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, bI.p, L, cudaMemcpyDeviceToHost, main));
+    // A D2H copy into PAGEABLE memory blocks the host until everything before it on the stream has run -- an asynchronous call
+    // with a Rust Vec as its output would wait for its own commit.  Such outputs land in a pinned buffer of the staging set and
+    // a host function, in stream order, moves them on; the caller's stream synchronisation covers it.
+    bool out_pageable = false;
+    if (async) {
+        cudaPointerAttributes at;
+        for (const void* q : {(const void*)C_out, (const void*)inf_out}) {
+            if (cudaPointerGetAttributes(&at, q) != cudaSuccess) { cudaGetLastError(); out_pageable = true; }
+            else if (at.type == cudaMemoryTypeUnregistered) out_pageable = true;
+        }
+    }
+    if (out_pageable) {
+        HostBuf& oc = ctx->out_pin[hset];
+        const size_t need = L * sizeof(Affine) + L;
+        if (oc.cap < need) {
+            if (oc.p) { SBN_CUDA(ctx, cudaDeviceSynchronize()); cudaFreeHost(oc.p); oc.p = nullptr; oc.cap = 0; }
+            SBN_CUDA(ctx, cudaHostAlloc(&oc.p, need, cudaHostAllocDefault));
+            oc.cap = need;
+        }
+        struct OutJob { const void *s0, *s1; void *d0, *d1; size_t n0, n1; };
+        OutJob* job = new (std::nothrow) OutJob{oc.p, (const char*)oc.p + L * sizeof(Affine), C_out, inf_out, L * sizeof(Affine), L};
+        if (!job) return SBN_ERR_OOM;
+        cudaError_t ce = cudaMemcpyAsync(oc.p, bC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, main);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync((char*)oc.p + L * sizeof(Affine), bI.p, L, cudaMemcpyDeviceToHost, main);
+        if (ce == cudaSuccess)
+            ce = cudaLaunchHostFunc(main, [](void* u) {
+                OutJob* j = (OutJob*)u;
+                memcpy(j->d0, j->s0, j->n0);
+                memcpy(j->d1, j->s1, j->n1);
+                delete j;
+            }, job);
+        if (ce != cudaSuccess) { delete job; SBN_CUDA(ctx, ce); }
+    } else {
+        SBN_CUDA(ctx, cudaMemcpyAsync(C_out, bC.p, L * sizeof(Affine), cudaMemcpyDeviceToHost, main));
+        SBN_CUDA(ctx, cudaMemcpyAsync(inf_out, bI.p, L, cudaMemcpyDeviceToHost, main));
+    }
     ctx->d2h += L * sizeof(Affine) + L;
     if (async) {
         if (!ctx->hset_done[hset]) SBN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->hset_done[hset], cudaEventDisableTiming));

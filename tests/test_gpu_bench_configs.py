@@ -212,3 +212,35 @@ def test_async_host_commits_on_two_streams(orc, nstreams):
             bases.close()
     finally:
         ctx.close()
+
+
+def test_async_host_commits_from_pageable_memory(orc):
+    """sbn_hyrax_commit_async with PAGEABLE inputs and outputs (a Rust Vec<Scalar> / Vec<G1Affine>): the scalars go through
+    the pinned ring of the workspace set, the results through a pinned landing buffer and a stream-ordered host function.
+    Nine commits on three streams, the ring slots and landing buffers reused three times over; every result equals the
+    blocking call's."""
+    import torch
+    from spartan_bn254_b200 import Context, synth
+    ctx = Context(0)
+    try:
+        ctx.set("mult_max_mb", 2048)
+        L, R = 512, 128
+        dev = torch.device("cuda", 0)
+        G, h = synth.distinct_generators(ctx, R)
+        bases = ctx.bases(G, h)
+        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        Zs = [synth.uniform_scalars(80 + i, L * R) for i in range(9)]
+        outC = [np.zeros((L, 8), dtype=np.uint64) for _ in range(9)]
+        outI = [np.full((L,), 7, dtype=np.uint8) for _ in range(9)]
+        for i in range(9):
+            ctx.hyrax_commit_raw_async(bases, Zs[i].ctypes.data, L, R, 0, outC[i].ctypes.data, outI[i].ctypes.data,
+                                       streams[i % 3].cuda_stream)
+        torch.cuda.synchronize()
+        assert bases.mult_table()[0] > 0
+        for i in range(9):
+            C, inf = ctx.hyrax_commit(bases, Zs[i], L, R, None)
+            assert np.array_equal(outC[i], C) and np.array_equal(outI[i], inf), i
+        _check_rows(orc, G, h, Zs[8], L, R, outC[8], outI[8], 16)
+        bases.close()
+    finally:
+        ctx.close()
