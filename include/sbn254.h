@@ -77,6 +77,10 @@ int sbn_ctx_synchronize(sbn_ctx* ctx);
  *   "mult_streams"  chunks in flight, 1..4 (default 2);  "mult_rounds" batched-affine rounds, 0 = auto
  *   "ba_minb"       register target of the finish pass: 3 (80 registers, default) or 4 (64) resident blocks per SM
  *   "ba_prefetch"   round 1 reads its entries two pairs ahead and prefetches the table points into L2 (default 0: loses)
+ *   "bsc_device"    sbn_bsumcheck_prove: 0 (default) the transcript runs on the host between the kernels of a round; 1 the
+ *                   short last rounds of a layer run in ONE block with the Merlin transcript on the device; 2 every round
+ *                   (csrc/transcript_kernels.cuh; identical proofs and transcript states; measured no faster -- a one-warp
+ *                   Keccak + Montgomery step is ~16 us on the GPU)
  *   "finish_smem_kb" / "prefix_smem_kb"  dynamic shared memory requested per block to cap co-residency (default 0)
  *   "l2_fetch"      cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured to change nothing on B200)
  *   "ablate"        PROFILING ONLY: bit mask of skipped launches (1 prefix round 1, 2 prefix rounds >= 2, 4 inversions,

@@ -22,6 +22,7 @@
 #include "small_kernels.cuh"
 #include "mult_kernels.cuh"
 #include "prodtree_kernels.cuh"
+#include "transcript_kernels.cuh"
 #include "host/keccak.hpp"
 #include "host/merlin.hpp"
 
@@ -98,6 +99,7 @@ struct sbn_ctx {
     long prefix_smem_kb = 0;
     long sum_wpr = 0;                  // warps per row of the final row sums (1, 2, 4); 0 = by the number of points left
     long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
+    long bsc_device = 0;               // product-layer sumchecks (transcript_kernels.cuh; measured no faster than the host loop, kept as an option): 1 = the short last rounds of a layer run in one block with the Merlin transcript on the device, the long ones through the host loop; 2 = every round on the device; 0 = host loop only
     long small_scalar_path = 1;        // commits without blinds scan their scalars' bit length and use a short window schedule when it is small
     long small_scalar_hits = 0;        // commits that took it
     long mult_layout = 1;              // 1: position-major lists, separate passes (default); 2: prefix passes fused into the previous round (measured: 2.69 vs 2.65 ms); 0: row-major (round 1)
@@ -462,6 +464,8 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     } else if (!strcmp(key, "mult_layout")) {
         if (value < 0 || value > 2) return SBN_ERR_ARG;
         ctx->mult_layout = value;
+    } else if (!strcmp(key, "bsc_device")) {
+        ctx->bsc_device = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "ba_prefetch")) {
         ctx->ba_prefetch = value ? 1 : 0;
     } else if (!strcmp(key, "l2_fetch")) {      // cudaLimitMaxL2FetchGranularity: the table gathers are random 64 B reads
@@ -2747,6 +2751,55 @@ extern "C" int sbn_bsumcheck_end(sbn_bsumcheck* st, sbn_fr* A_final, sbn_fr* B_f
     return SBN_OK;
 }
 
+// Framing of one sumcheck round's transcript traffic for the device-side transcript (transcript_kernels.cuh): a recording run
+// of exactly the operations csrc/host/merlin.hpp performs for UniPoly::append_to_transcript (unipoly.rs:119-127) followed by
+// challenge_scalar (transcript.rs:56-67), from the cursor (pos, pos_begin), with zeros in place of the coefficient bytes.
+static void bsc_make_frame(int pos, int pos_begin, BscFrame* f) {
+    memset(f, 0, sizeof *f);
+    size_t n = 0, chunk_start = 0;
+    int chunk_pos = pos;
+    auto close_chunk = [&](int fbegin) {
+        const int c = f->nchunks++;
+        f->off[c] = (uint16_t)chunk_start;
+        f->len[c] = (uint16_t)(n - chunk_start);
+        f->pos[c] = (uint16_t)chunk_pos;
+        f->f_begin[c] = (uint16_t)fbegin;
+        chunk_start = n;
+    };
+    auto run_f = [&]() { close_chunk(pos_begin); pos = 0; pos_begin = 0; chunk_pos = 0; };
+    auto absorb = [&](const uint8_t* d, size_t len) {
+        for (size_t i = 0; i < len; i++) {
+            f->stream[n++] = d ? d[i] : 0;
+            if (++pos == sbn::merlin::kRate) run_f();
+        }
+    };
+    auto begin_op = [&](uint8_t flags) {
+        const uint8_t hdr[2] = {(uint8_t)pos_begin, flags};
+        pos_begin = pos + 1;
+        absorb(hdr, 2);
+        if ((flags & (sbn::merlin::FLAG_C | sbn::merlin::FLAG_K)) && pos != 0) run_f();
+    };
+    auto meta_len = [&](uint32_t v) { const uint8_t b[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)}; absorb(b, 4); };
+    auto append_message = [&](const char* label, const char* msg, size_t mlen) -> size_t {
+        begin_op(sbn::merlin::FLAG_M | sbn::merlin::FLAG_A);
+        absorb((const uint8_t*)label, strlen(label));
+        meta_len((uint32_t)mlen);
+        begin_op(sbn::merlin::FLAG_A);
+        const size_t at = n;
+        absorb((const uint8_t*)msg, mlen);
+        return at;
+    };
+    append_message("poly", "UniPoly_begin", 13);
+    for (int k = 0; k < 4; k++) f->coeff_off[k] = (uint16_t)append_message("coeff", nullptr, 32);
+    append_message("poly", "UniPoly_end", 11);
+    begin_op(sbn::merlin::FLAG_M | sbn::merlin::FLAG_A);
+    absorb((const uint8_t*)"challenge_nextround", 19);
+    meta_len(64);
+    begin_op(sbn::merlin::FLAG_I | sbn::merlin::FLAG_A | sbn::merlin::FLAG_C);        // ends in F: the squeeze starts at position 0
+    if (n > chunk_start) close_chunk(0xffff);
+    f->total = (uint16_t)n;
+}
+
 // ---- host-side field helpers of the round loop below (Montgomery Fr; the same fp.cuh code compiled for the host)
 namespace {
 struct FrHost {
@@ -2793,7 +2846,18 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
         const Fr c = fp_from_mont(v);
         sbn::merlin::append_message(tr, (const uint8_t*)"coeff", 5, (const uint8_t*)c.l, 32);
     };
-    for (size_t j = 0; j < num_rounds; j++) {
+    // Rounds whose tables are still long go through the host loop below (evaluation launch, synchronisation, transcript on the
+    // host, bind launch: ~55 us a round, of which the kernels are the larger part); once half a table is kBscTailHalf entries
+    // or fewer, ONE block finishes the layer with the transcript on the device (~20 us a round, no launches).  Measured at
+    // 12 x 2^22 (scripts/exp_bsc.py): a one-warp transcript step costs ~16 us on the GPU (Keccak-f and Montgomery products are
+    // latency chains there), so for the long rounds the device-side transcript (bsc_device = 2) is no faster than the host's.
+    size_t host_rounds = num_rounds;
+    if (ctx->bsc_device && n <= (size_t)kBscTailMaxInst && num_rounds <= 30) {
+        host_rounds = 0;
+        if (ctx->bsc_device == 1)
+            while (host_rounds < num_rounds && ((st->len >> host_rounds) / 2) > (size_t)kBscTailHalf) host_rounds++;
+    }
+    for (size_t j = 0; j < host_rounds; j++) {
         const size_t half = st->len / 2;
         const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
         // The 3 n evaluations land in mapped pinned memory: no copy call per round, and a one-block evaluation (the many short
@@ -2840,6 +2904,81 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
         e = acc;
         memcpy(polys + 4 * j, poly, 4 * sizeof(Fr));
         memcpy(r_out + j, &r, sizeof(Fr));
+    }
+    if (host_rounds < num_rounds) {
+        const size_t j0 = host_rounds, nr = num_rounds - host_rounds;      // rounds j0 .. num_rounds - 1 run on the device
+        // The whole layer on the device: transcript state, claim, coefficients and the framing of a round's transcript traffic
+        // go up once; per round the evaluation, the transcript step (k_bsc_round) and the bind are three launches in stream
+        // order with no host round trip, and once the tables are short ONE block finishes every remaining round
+        // (k_bsc_tail); polynomials, challenges, final values and the transcript state come back in one copy.
+        const size_t nt = (size_t)st->ntables;
+        const size_t sw = (sizeof(BscState) + sizeof(Fr) - 1) / sizeof(Fr);
+        const size_t words = sw + n + 4 * nr + nr + 1 + nt;
+        Fr* buf = nullptr;
+        if (pool_alloc(ctx, &buf, words * sizeof(Fr)) != cudaSuccess) { ctx->last_error = "sbn_bsumcheck_prove: cudaMalloc failed"; return SBN_ERR_OOM; }
+        BscState* dstate = (BscState*)buf;
+        Fr *dcf = buf + sw, *dpolys = dcf + n, *dr = dpolys + 4 * nr, *drcur = dr + nr, *dfin = drcur + 1;
+        std::vector<Fr> up(sw + n);
+        memset(up.data(), 0, sw * sizeof(Fr));
+        BscState* hs = (BscState*)up.data();
+        memcpy(hs->merlin, &tr, sizeof(sbn::merlin::State));
+        hs->claim = e;
+        bsc_make_frame(tr.pos, tr.pos_begin, &hs->frame[0]);
+        bsc_make_frame(64, 0, &hs->frame[1]);
+        memcpy(up.data() + sw, cf.data(), n * sizeof(Fr));
+        auto fail = [&](int code) { cudaStreamSynchronize(s); cudaGetLastError(); pool_release(ctx, buf); return code; };
+        if (cudaMemcpyAsync(buf, up.data(), (sw + n) * sizeof(Fr), cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(SBN_ERR_CUDA);
+        ctx->h2d += (sw + n) * sizeof(Fr);
+        BscConst kc{two_inv, six_inv};
+        bool tail = false;
+        for (size_t j = 0; j < nr; j++) {
+            const size_t half = st->len / 2;
+            if (half <= (size_t)kBscTailHalf) {
+                auto tailk = n <= 16 ? k_bsc_tail<512> : k_bsc_tail<1024>;
+                tailk<<<1, (unsigned)(32 * n), 0, s>>>(dstate, st->d_triples, st->d_tables, st->ntables, (int)n, (int)st->len, j == 0 ? 1 : 0,
+                                                           dcf, kc, dpolys + 4 * j, dr + j, dfin);
+                ctx->launches += 1;
+                st->len = 1;
+                tail = true;
+                break;
+            }
+            const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
+            k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
+            k_bsc_round<<<1, 128, 0, s>>>(dstate, st->partial, (int)blocks, dcf, (int)n, j == 0 ? 1 : 0, kc, dpolys + 4 * j, dr + j, drcur);
+            k_bind_top_batched<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, drcur);
+            ctx->launches += 3;
+            st->len = half;
+        }
+        if (!tail) {
+            k_gather_first<<<(unsigned)((st->ntables + 127) / 128), 128, 0, s>>>(st->d_tables, st->ntables, dfin);
+            ctx->launches += 1;
+        }
+        if (cudaGetLastError() != cudaSuccess) { ctx->last_error = "sbn_bsumcheck_prove: launch failed"; return fail(SBN_ERR_CUDA); }
+        std::vector<Fr> down(words);
+        if (cudaMemcpyAsync(down.data(), buf, words * sizeof(Fr), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            ctx->last_error = std::string("sbn_bsumcheck_prove: ") + cudaGetErrorString(cudaGetLastError());
+            return fail(SBN_ERR_CUDA);
+        }
+        ctx->d2h += words * sizeof(Fr);
+        pool_release(ctx, buf);
+        const BscState* ds = (const BscState*)down.data();
+        memcpy(&tr, ds->merlin, sizeof(sbn::merlin::State));
+        memcpy(claim_out, &ds->claim, sizeof(Fr));
+        memcpy(polys + 4 * j0, down.data() + sw + n, 4 * nr * sizeof(Fr));
+        memcpy(r_out + j0, down.data() + sw + n + 4 * nr, nr * sizeof(Fr));
+        const Fr* fin = down.data() + sw + n + 5 * nr + 1;
+        for (size_t i = 0; i < st->P; i++) {
+            memcpy(A_final + i, &fin[2 * i], sizeof(Fr));
+            memcpy(B_final + i, &fin[2 * i + 1], sizeof(Fr));
+        }
+        memcpy(C_final, &fin[2 * st->P], sizeof(Fr));
+        for (size_t k = 0; k < st->S; k++) {
+            memcpy(A_final + st->P + k, &fin[2 * st->P + 1 + 3 * k], sizeof(Fr));
+            memcpy(B_final + st->P + k, &fin[2 * st->P + 2 + 3 * k], sizeof(Fr));
+            memcpy(C_final + 1 + k, &fin[2 * st->P + 3 + 3 * k], sizeof(Fr));
+        }
+        return SBN_OK;
     }
     memcpy(claim_out, &e, sizeof(Fr));
     // final values: element 0 of every table, gathered by one kernel and one copy

@@ -91,6 +91,39 @@ def test_gpu_prover_matches_oracle(ctx, orc, n, P, S, native):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n,P,S", [(2, 1, 0), (64, 3, 2), (1024, 2, 0), (4096, 1, 2), (1 << 14, 12, 0)])
+def test_device_side_transcript_matches_host_loop(ctx, orc, n, P, S, mode):
+    """sbn_bsumcheck_prove with the Merlin transcript on the device (csrc/transcript_kernels.cuh; sbn_ctx_set "bsc_device":
+    1 = the short last rounds of a layer in one block, 2 = every round) must leave the same proof, the same challenges AND
+    the same transcript state as the host round loop (0, the default): the next layer continues from that state."""
+    import product_model as pm
+    from spartan_bn254_b200.hyrax import fr_vec_from_ints
+    from spartan_bn254_b200.product_tree import ProductCircuit, DotProductCircuit, ProductCircuitEvalProofBatched
+    from spartan_bn254_b200.transcript import Transcript
+    prod, dotp = _instance(300 + n, n, P, S)
+    out = {}
+    try:
+        for m in (0, mode):
+            ctx.set("bsc_device", m)
+            circuits = [ProductCircuit(ctx, fr_vec_from_ints(p)) for p in prod]
+            dcs = [DotProductCircuit(*[fr_vec_from_ints(t) for t in d]) for d in dotp]
+            tr = Transcript(b"prodtest")
+            proof, rand = ProductCircuitEvalProofBatched.prove(ctx, circuits, dcs, tr)
+            out[m] = (rand, [[cp.coeffs_except_linear_term for cp in l.proof.compressed_polys] for l in proof.proof],
+                      [(l.claims_prod_left, l.claims_prod_right) for l in proof.proof], tuple(proof.claims_dotp),
+                      tr.challenge_scalar(b"after"))
+            for c in circuits:
+                c.close()
+    finally:
+        ctx.set("bsc_device", 0)
+    assert out[0] == out[mode]
+    if n <= 4096:
+        want = pm.prove_batched(prod, dotp, orc.Transcript(b"prodtest"))
+        assert out[mode][0] == want["rand"]
+
+
+@pytest.mark.gpu
 def test_gpu_prover_full_size_is_accepted(ctx):
     """2^20-entry circuits (the hash-layer size of a 2^18-constraint instance): acceptance by the verifier, whose work is
     logarithmic, plus the final claims against a GPU-independent evaluation of one input polynomial at rand."""
