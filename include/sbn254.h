@@ -175,7 +175,11 @@ typedef struct sbn_poly sbn_poly;
 int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_poly** out);
 int sbn_poly_destroy(sbn_poly* poly);
 int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* bases, const sbn_poly* poly, size_t L_size, size_t R_size,
-                    const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);                    /* = sbn_hyrax_commit */
+                    const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);
+/* Rows [first_row, first_row + n_rows) of the same commitment (blinds: one per committed row, NULL = zeros): the block one
+ * rank of a row-sharded R1CSProof::commit_poly (r1csproof.rs:210-237) contributes; rows are independent (hyrax.rs:259-265). */
+int sbn_poly_commit_rows(sbn_ctx* ctx, const sbn_bases* bases, const sbn_poly* poly, size_t first_row, size_t n_rows,
+                         size_t R_size, const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out);                    /* = sbn_hyrax_commit */
 int sbn_poly_bound(sbn_ctx* ctx, const sbn_poly* poly, const sbn_fr* L, size_t L_size, size_t R_size, sbn_fr* LZ_out);
 
 /* ---- a14: BulletReductionProof::prove (nizk/bullet.rs:24-126) with a, b (and the generators) resident on device.

@@ -65,6 +65,8 @@ extern "C" {
     pub fn sbn_poly_destroy(p: *mut sbn_poly) -> c_int;
     pub fn sbn_poly_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, p: *const sbn_poly, l_size: usize, r_size: usize,
                            blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
+    pub fn sbn_poly_commit_rows(ctx: *mut sbn_ctx, b: *const sbn_bases, p: *const sbn_poly, first_row: usize, n_rows: usize, r_size: usize,
+                                blinds: *const SbnFr, c_out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_poly_bound(ctx: *mut sbn_ctx, p: *const sbn_poly, l: *const SbnFr, l_size: usize, r_size: usize, lz_out: *mut SbnFr) -> c_int;
     pub fn sbn_poly_evaluate(ctx: *mut sbn_ctx, p: *const sbn_poly, offset: usize, r: *const SbnFr, nr: usize, out: *mut SbnFr) -> c_int;
     pub fn sbn_poly_evaluate_strided(ctx: *mut sbn_ctx, p: *const sbn_poly, offset0: usize, stride: usize, count: usize,

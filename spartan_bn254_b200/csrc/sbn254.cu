@@ -2045,11 +2045,9 @@ extern "C" int sbn_poly_destroy(sbn_poly* p) {
     return SBN_OK;
 }
 
-extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly* poly, size_t L, size_t R, const sbn_fr* blinds,
-                               sbn_g1a* C_out, uint8_t* inf_out) {
-    if (!ctx || !b || !poly || !C_out || !inf_out || b->ctx != ctx || poly->ctx != ctx) return SBN_ERR_ARG;
-    SBN_TRY(check_commit_shape(b, L, R));
-    if (L * R != poly->len) return SBN_ERR_SHAPE;               // hyrax.rs:258
+// rows [first, first + L) of the resident polynomial read as rows of R scalars; blinds: one per committed row
+static int poly_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly* poly, size_t first, size_t L, size_t R, const sbn_fr* blinds,
+                            sbn_g1a* C_out, uint8_t* inf_out) {
     std::lock_guard<std::mutex> g(ctx->mu);
     SBN_ENTER(ctx);
     const size_t chunk = commit_chunk_rows(ctx, L);
@@ -2062,12 +2060,30 @@ extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly*
         dbl = (Fr*)ctx->dblinds.p;
     }
     std::vector<int> ev_stage;
-    SBN_TRY(run_commit(ctx, b, poly->Z, nullptr, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, ctx->compute, ev_stage));
+    SBN_TRY(run_commit(ctx, b, poly->Z + first * R, nullptr, L, R, dbl, (Affine*)ctx->dC.p, (uint8_t*)ctx->dinf.p, ctx->compute, ev_stage));
     SBN_TRY(download(ctx, C_out, ctx->dC.p, L * sizeof(Affine)));
     SBN_TRY(download(ctx, inf_out, ctx->dinf.p, L));
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     collect_profile(ctx, ev_stage);
     return SBN_OK;
+}
+
+extern "C" int sbn_poly_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly* poly, size_t L, size_t R, const sbn_fr* blinds,
+                               sbn_g1a* C_out, uint8_t* inf_out) {
+    if (!ctx || !b || !poly || !C_out || !inf_out || b->ctx != ctx || poly->ctx != ctx) return SBN_ERR_ARG;
+    SBN_TRY(check_commit_shape(b, L, R));
+    if (L * R != poly->len) return SBN_ERR_SHAPE;               // hyrax.rs:258
+    return poly_commit_rows(ctx, b, poly, 0, L, R, blinds, C_out, inf_out);
+}
+
+// A block of rows of the same commitment: rows are independent (hyrax.rs:259-265), so k ranks (one process per GPU, each
+// holding the polynomial) commit k blocks and exchange 65 bytes per row.
+extern "C" int sbn_poly_commit_rows(sbn_ctx* ctx, const sbn_bases* b, const sbn_poly* poly, size_t first_row, size_t n_rows, size_t R,
+                                    const sbn_fr* blinds, sbn_g1a* C_out, uint8_t* inf_out) {
+    if (!ctx || !b || !poly || !C_out || !inf_out || b->ctx != ctx || poly->ctx != ctx) return SBN_ERR_ARG;
+    SBN_TRY(check_commit_shape(b, n_rows, R));
+    if (R == 0 || poly->len % R != 0 || first_row > poly->len / R || n_rows > poly->len / R - first_row) return SBN_ERR_SHAPE;
+    return poly_commit_rows(ctx, b, poly, first_row, n_rows, R, blinds, C_out, inf_out);
 }
 
 extern "C" int sbn_poly_bound(sbn_ctx* ctx, const sbn_poly* poly, const sbn_fr* Lv, size_t L, size_t R, sbn_fr* LZ_out) {

@@ -234,8 +234,10 @@ class DensePolynomial:
             self._poly = (ctx or default_context()).poly_upload(self.Z)
         return self._poly
 
-    def commit_inner(self, blinds, gens):
-        """hyrax.rs:253-281: one batched GPU call instead of the rayon row loop."""
+    def commit_inner(self, blinds, gens, shard=None):
+        """hyrax.rs:253-281: one batched GPU call instead of the rayon row loop.  shard = (rank, world, all_gather): rows are
+        independent (:259-265), so with one process per GPU and the polynomial resident on each, this rank commits its
+        contiguous block of rows (sbn_poly_commit_rows) and the blocks are all-gathered -- 65 bytes per row."""
         blinds = np.ascontiguousarray(blinds, dtype=np.uint64).reshape(-1, 4)
         L_size = blinds.shape[0]
         R_size = self.len // L_size
@@ -244,6 +246,15 @@ class DensePolynomial:
         if gens.n != R_size:
             raise AssertionError("assert_eq!(gens_n.n, self.len())")             # commitments.rs:146
         zero_blinds = not blinds.any()
+        if shard is not None and shard[1] > 1 and getattr(self, "_poly", None) is not None and L_size % shard[1] == 0:
+            from .parallel import shard_rows
+            rank, world, all_gather = shard
+            first, n = shard_rows(L_size, world, rank)
+            C, inf = self._poly.commit_rows(gens.device_bases(), first, n, R_size, None if zero_blinds else blinds[first:first + n])
+            block = np.concatenate([C.view(np.uint8).reshape(n, 64), inf.reshape(n, 1)], axis=1)
+            blocks = all_gather(block)
+            allb = np.concatenate(blocks)
+            return PolyCommitment(np.ascontiguousarray(allb[:, :64]).view(np.uint64).reshape(L_size, 8), np.ascontiguousarray(allb[:, 64]))
         if getattr(self, "_poly", None) is not None:
             C, inf = self._poly.commit(gens.device_bases(), L_size, R_size, None if zero_blinds else blinds)
         else:

@@ -15,7 +15,7 @@ EXPORTS = [
     "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
     "sbn_hyrax_commit", "sbn_hyrax_commit_async", "sbn_hyrax_commit_device", "sbn_hyrax_commit_multi", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
-    "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_bound",
+    "sbn_poly_upload", "sbn_poly_destroy", "sbn_poly_commit", "sbn_poly_commit_rows", "sbn_poly_bound",
     "sbn_bullet_begin", "sbn_bullet_round", "sbn_bullet_fold", "sbn_bullet_end", "sbn_bullet_end_delta", "sbn_bullet_destroy",
     "sbn_sumcheck_begin", "sbn_sumcheck_begin_quad", "sbn_sumcheck_round_eval", "sbn_sumcheck_bind", "sbn_sumcheck_end",
     "sbn_sumcheck_destroy", "sbn_fr_from_canonical", "sbn_fr_to_canonical", "sbn_microbench",
@@ -475,6 +475,16 @@ class Poly:
         st = self.ctx.lib.sbn_poly_commit(self.ctx.h, bases.h, self.h, C.c_size_t(L_size), C.c_size_t(R_size), _ptr(bl),
                                           _ptr(out), _ptr(inf))
         self.ctx._check(st, "sbn_poly_commit")
+        return out, inf
+
+    def commit_rows(self, bases, first_row, n_rows, R_size, blinds=None):
+        """sbn_poly_commit_rows: rows [first_row, first_row + n_rows) of the commitment (blinds: one per committed row)."""
+        bl = None if blinds is None else _u64(blinds, 4)
+        out = np.zeros((n_rows, 8), dtype=np.uint64)
+        inf = np.zeros(n_rows, dtype=np.uint8)
+        st = self.ctx.lib.sbn_poly_commit_rows(self.ctx.h, bases.h, self.h, C.c_size_t(first_row), C.c_size_t(n_rows), C.c_size_t(R_size),
+                                               _ptr(bl), _ptr(out), _ptr(inf))
+        self.ctx._check(st, "sbn_poly_commit_rows")
         return out, inf
 
     def evaluate_strided(self, r, offset0, stride, count):

@@ -236,7 +236,7 @@ class R1CSShape:
 
 class R1CSProof:
     @staticmethod
-    def prove(inst, vars_m, input_m, gens, transcript, tape, timings=None):
+    def prove(inst, vars_m, input_m, gens, transcript, tape, timings=None, shard=None):
         """r1csproof.rs:241-459.  vars_m / input_m: Montgomery uint64[n, 4]; returns (proof, rx, ry) with rx, ry canonical."""
         import time
         ctx = inst.ctx
@@ -258,7 +258,7 @@ class R1CSProof:
         blinds_int = tape.random_vector(b"poly_blinds", L_size)
         blinds_m = fr_vec_from_ints(blinds_int)
         poly_vars.resident(ctx)
-        comm_vars = poly_vars.commit_inner(blinds_m, gens.gens_pc.gens.gens_n)
+        comm_vars = poly_vars.commit_inner(blinds_m, gens.gens_pc.gens.gens_n, shard=shard)
         append_poly_commitment(transcript, b"poly_commitment", comm_vars)
         lap("witness_commit_ms")
         num_vars = vars_m.shape[0]
@@ -388,7 +388,7 @@ class SNARK:
         comm.append_to_transcript(transcript)
         sat_t, eval_t = {}, {}
         t0 = time.perf_counter()
-        sat_proof, rx, ry = R1CSProof.prove(inst, vars_m, input_m, gens.gens_r1cs_sat, transcript, tape, timings=sat_t)
+        sat_proof, rx, ry = R1CSProof.prove(inst, vars_m, input_m, gens.gens_r1cs_sat, transcript, tape, timings=sat_t, shard=shard)
         t1 = time.perf_counter()
         rx_e, ry_e = equalize(rx, ry)
         inst_evals = decomm.multi_evaluate(rx_e, ry_e)                     # inst.evaluate(rx, ry), r1cs.rs:126-129

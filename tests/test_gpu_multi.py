@@ -89,6 +89,20 @@ def _nccl_worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, "C_single.npy"), C1)
         np.save(os.path.join(out_dir, "inf_single.npy"), inf1)
         poly1.close()
+    # R1CSProof::commit_poly sharded the same way (sbn_poly_commit_rows): a resident 64 x 64 witness polynomial with blinds
+    from spartan_bn254_b200.hyrax import DensePolynomial
+    Lw = Rw = 64
+    gw = MultiCommitGens.new(Rw, b"gens_r1cs_sat", ctx)
+    Zw, bw = synth.uniform_scalars(31, Lw * Rw), synth.uniform_scalars(32, Lw)
+    pw = DensePolynomial(Zw)
+    pw.resident(ctx)
+    cw = pw.commit_inner(bw, gw, shard=(rank, world, make_all_gather(dev)))
+    np.save(os.path.join(out_dir, f"W{rank}.npy"), cw.C)
+    np.save(os.path.join(out_dir, f"Winf{rank}.npy"), cw.inf)
+    if rank == 0:
+        c1 = pw.commit_inner(bw, gw)
+        np.save(os.path.join(out_dir, "W_single.npy"), c1.C)
+        np.save(os.path.join(out_dir, "Winf_single.npy"), c1.inf)
     dist.barrier()
     poly.close()
     spark.close()
@@ -109,3 +123,32 @@ def test_nccl_sharded_derefs_commit_matches_one_gpu(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"C{r}.npy"), C1)
         assert np.array_equal(np.load(tmp_path / f"inf{r}.npy"), inf1)
+        assert np.array_equal(np.load(tmp_path / f"W{r}.npy"), np.load(tmp_path / "W_single.npy"))
+        assert np.array_equal(np.load(tmp_path / f"Winf{r}.npy"), np.load(tmp_path / "Winf_single.npy"))
+
+
+def test_poly_commit_rows_blocks_equal_the_whole(orc):
+    """sbn_poly_commit_rows: three uneven row blocks of a resident polynomial (with blinds, and a block long enough for the
+    tabulated-sum path) put side by side equal sbn_poly_commit and the oracle; out-of-range blocks are refused."""
+    from spartan_bn254_b200 import Context, synth
+    from spartan_bn254_b200.lib import Poly, SbnError
+    ctx = Context(0)
+    try:
+        ctx.set("mult_max_mb", 2048)
+        L, R = 700, 64
+        G, h = synth.distinct_generators(ctx, R)
+        bases = ctx.bases(G, h)
+        Z, bl = synth.uniform_scalars(41, L * R), synth.uniform_scalars(42, L)
+        poly = Poly(ctx, Z)
+        C, inf = poly.commit(bases, L, R, bl)
+        parts = [poly.commit_rows(bases, f, n, R, bl[f:f + n]) for f, n in ((0, 300), (300, 1), (301, 399))]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), C)
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), inf)
+        Co, info = orc.hyrax_commit(G, h, Z, L, R, bl, threads=0)
+        assert np.array_equal(C, Co) and np.array_equal(inf, info)
+        with pytest.raises(SbnError):
+            poly.commit_rows(bases, 650, 51, R, None)
+        poly.close()
+        bases.close()
+    finally:
+        ctx.close()
