@@ -340,6 +340,8 @@ void sbn_merlin_init(void* state, const uint8_t* label, size_t label_len);
 void sbn_merlin_append(void* state, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t msg_len);
 void sbn_merlin_append_many(void* state, const uint8_t* label, size_t label_len, const uint8_t* msgs, size_t msg_len, size_t count);
 void sbn_merlin_challenge(void* state, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
+/* n consecutive challenge_scalar calls with one label (transcript.rs:56-73, random.rs:24-31), results in Montgomery form */
+void sbn_merlin_challenge_scalars(void* state, const uint8_t* label, size_t label_len, size_t n, sbn_fr* out);
 /* GroupElement::compress (group.rs:135-140) on the host: n affine Montgomery points -> n x 32 bytes of ark's compressed
  * encoding; and the share loop of PolyCommitment::append_to_transcript (hyrax.rs:46-50): compress + append each point. */
 int sbn_g1_compress(const sbn_g1a* pts, const uint8_t* inf, size_t n, uint8_t* out);

@@ -2011,6 +2011,45 @@ struct sbn_poly {
     size_t len = 0;
 };
 
+// H2D copy of a large host buffer, synchronous.  From pageable memory (a Rust Vec, a numpy array) cudaMemcpy stages through the
+// driver at 4-12 GB/s; here 8 MiB pieces go through two pinned buffers filled by four host threads, so the memcpy of piece
+// i + 1 runs under the DMA of piece i.  Pinned sources take the direct copy.
+static cudaError_t h2d_sync(sbn_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    static constexpr size_t kPiece = size_t(8) << 20;
+    bool pageable = bytes >= 2 * kPiece;
+    if (pageable) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) != cudaSuccess) cudaGetLastError();
+        else pageable = at.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pageable) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    for (int k = 0; k < 2; k++) {
+        HostBuf& ring = ctx->stage_pin[0][k];
+        if (ring.cap < kPiece) {
+            if (ring.p) { cudaDeviceSynchronize(); cudaFreeHost(ring.p); ring.p = nullptr; ring.cap = 0; }
+            cudaError_t e = cudaHostAlloc(&ring.p, kPiece, cudaHostAllocDefault);
+            if (e != cudaSuccess) return e;
+            ring.cap = kPiece;
+        }
+        if (!ring.busy) { cudaError_t e = cudaEventCreateWithFlags(&ring.busy, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    }
+    size_t off = 0;
+    for (int k = 0; off < bytes; k ^= 1) {
+        HostBuf& ring = ctx->stage_pin[0][k];
+        const size_t n = std::min(kPiece, bytes - off);
+        cudaError_t e = cudaEventSynchronize(ring.busy);          // the last DMA out of this buffer (an unrecorded event is complete)
+        if (e != cudaSuccess) return e;
+        host_copy_mt(ring.p, (const char*)src + off, n);
+        if ((e = cudaMemcpyAsync((char*)dst + off, ring.p, n, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ring.busy, st)) != cudaSuccess) return e;
+        off += n;
+    }
+    return cudaStreamSynchronize(st);
+}
+
 extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_poly** out) {
     if (!ctx || !Z || !out) return SBN_ERR_ARG;
     *out = nullptr;
@@ -2022,8 +2061,8 @@ extern "C" int sbn_poly_upload(sbn_ctx* ctx, const sbn_fr* Z, size_t len, sbn_po
     p->ctx = ctx;
     p->len = len;
     if (pool_alloc(ctx, &p->Z, len * sizeof(Fr)) != cudaSuccess) { delete p; ctx->last_error = "sbn_poly_upload: cudaMalloc failed"; return SBN_ERR_OOM; }
-    if (cudaMemcpyAsync(p->Z, Z, len * sizeof(Fr), cudaMemcpyHostToDevice, ctx->compute) != cudaSuccess ||
-        cudaStreamSynchronize(ctx->compute) != cudaSuccess) {
+    if (h2d_sync(ctx, p->Z, Z, len * sizeof(Fr), ctx->compute) != cudaSuccess) {
+        cudaGetLastError();
         pool_release(ctx, p->Z);
         delete p;
         ctx->last_error = "sbn_poly_upload: copy failed";
@@ -2831,6 +2870,18 @@ struct FrHost {
     }
 };
 }  // namespace
+
+// n challenge scalars in one call, in Montgomery form: RandomTape::random_vector (random.rs:24-31) / challenge_vector
+// (transcript.rs:69-73) -- the 1024 row blinds of R1CSProof::commit_poly were 1024 round trips through the binding.
+extern "C" void sbn_merlin_challenge_scalars(void* state, const uint8_t* label, size_t llen, size_t n, sbn_fr* out) {
+    sbn::merlin::State& tr = *(sbn::merlin::State*)state;
+    for (size_t i = 0; i < n; i++) {
+        uint8_t wide[64];
+        sbn::merlin::challenge_bytes(tr, label, llen, wide, 64);
+        const Fr r = FrHost::from_wide(wide);
+        memcpy(out + i, &r, sizeof(Fr));
+    }
+}
 
 // SumcheckInstanceProof::prove_cubic_batched (sumcheck.rs:165-330) for one layer with the round loop inside the library:
 // per round the batched evaluation (:201-271), the combination with `coeffs` (:273-275), UniPoly::from_evals

@@ -255,8 +255,7 @@ class R1CSProof:
         poly_vars = DensePolynomial(vars_m)
         ell = poly_vars.get_num_vars()
         L_size = 1 << (ell // 2)
-        blinds_int = tape.random_vector(b"poly_blinds", L_size)
-        blinds_m = fr_vec_from_ints(blinds_int)
+        blinds_m = tape.random_vector_mont(b"poly_blinds", L_size)
         poly_vars.resident(ctx)
         comm_vars = poly_vars.commit_inner(blinds_m, gens.gens_pc.gens.gens_n, shard=shard)
         append_poly_commitment(transcript, b"poly_commitment", comm_vars)

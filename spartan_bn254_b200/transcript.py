@@ -128,6 +128,18 @@ class Transcript:
     def challenge_scalars(self, label, n):
         return [self.challenge_scalar(label) for _ in range(n)]
 
+    def challenge_scalars_mont(self, label, n):
+        """n challenge scalars as a Montgomery uint64[n, 4] array, in one library call (sbn_merlin_challenge_scalars)."""
+        import numpy as _np
+        out = _np.empty((n, 4), dtype=_np.uint64)
+        f = getattr(self._lib, "sbn_merlin_challenge_scalars", None) if getattr(self, "_lib", None) is not None else None
+        if f is None:
+            from .hyrax import fr_vec_from_ints
+            return fr_vec_from_ints(self.challenge_scalars(label, n))
+        f.restype = None
+        f(self._st, label, _ctypes.c_size_t(len(label)), _ctypes.c_size_t(n), out.ctypes.data_as(_ctypes.c_void_p))
+        return out
+
 
 class PyTranscript(Transcript):
     """The same transcript in pure Python (no library needed)."""
@@ -261,3 +273,7 @@ class RandomTape:
 
     def random_vector(self, label, n):
         return self.tape.challenge_scalars(label, n)
+
+    def random_vector_mont(self, label, n):
+        """random_vector as a Montgomery uint64[n, 4] array (one library call for the whole vector)."""
+        return self.tape.challenge_scalars_mont(label, n)

@@ -107,3 +107,21 @@ def test_host_side_scalar_conversions_and_canonical_append(orc):
     c.append_scalars_canonical(b"a", canon)
     ch = a.challenge_bytes(b"c", 64)
     assert ch == b.challenge_bytes(b"c", 64) == c.challenge_bytes(b"c", 64)
+
+
+def test_challenge_scalars_in_one_call_match_the_loop():
+    """sbn_merlin_challenge_scalars (RandomTape::random_vector, random.rs:24-31, in one library call, Montgomery form out) against
+    n separate challenge_scalar calls on a transcript in the same state -- and the states afterwards."""
+    from spartan_bn254_b200.transcript import Transcript, RandomTape
+    from spartan_bn254_b200.hyrax import fr_vec_to_ints
+    a, b = Transcript(b"t"), Transcript(b"t")
+    if not hasattr(a, "_lib"):
+        pytest.skip("libsbn254 not built")
+    for t in (a, b):
+        t.append_scalar(b"x", 12345)
+    want = a.challenge_scalars(b"poly_blinds", 37)
+    got = fr_vec_to_ints(b.challenge_scalars_mont(b"poly_blinds", 37))
+    assert got == want
+    assert a.challenge_scalar(b"next") == b.challenge_scalar(b"next")
+    ta, tb = RandomTape(b"tape", 7), RandomTape(b"tape", 7)
+    assert fr_vec_to_ints(tb.random_vector_mont(b"v", 5)) == ta.random_vector(b"v", 5)
