@@ -22,7 +22,8 @@ for r in rows[h + 1:]:
     rec = dict(zip(H, r))
     k = int(rec["ID"])
     launches.setdefault(k, {"name": rec["Kernel Name"].split("(")[0]})
-    launches[k][rec["Metric Name"]] = float(rec["Metric Value"].replace(",", ""))
+    mv = rec["Metric Value"].replace(",", "")
+    launches[k][rec["Metric Name"]] = float(mv) if mv not in ("", "n/a") else 0.0
 ids = sorted(launches)
 norm = [i for i in ids if "k_normalize" in launches[i]["name"]]
 end = norm[-1]
