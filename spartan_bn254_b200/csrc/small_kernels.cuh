@@ -94,8 +94,17 @@ k_small_commit(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
 // shared-memory tree over the block's 16 warps -> one partial per 64 scalars; stage 2, one block per row adds the
 // partials.  Critical path ~20 additions; ~7 M products per row.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kTabThreads = 512;
-static constexpr int kTabWinPerThread = 4;                                   // 8 lanes per scalar
+// A shuffle-tree level costs a warp its full issue slots however few lanes carry a value, so the tree work of a block is
+// 5 levels x 14 products x its warps.  With 4 windows per thread (round 1h: 512 threads, 16 warps a block) the trees were
+// three quarters of the kernel's multiplier time: 230-360 us per two-row sum over 8193 generators, whatever the round of the
+// bullet reduction (ncu, scripts/exp_bullet.py).  8 windows per thread: half the warps, the same 64 scalars a block, each
+// thread a chain of 8 inlined mixed additions with the next table point in flight under the current one; two blocks per
+// SM so that the 258 blocks of a two-row sum over 8193 generators are one wave.  (16 windows per thread and 4 warps a block
+// is no faster: 86 k instructions per warp at two warps per scheduler is a latency chain of the same length.)  What is left
+// of a bullet round (0.30 ms, was 0.39) is depth: 8 + 17 dependent point additions at 6-9 us each for a lone warp, a 32 us
+// normalisation and six small launches.
+static constexpr int kTabThreads = 256;
+static constexpr int kTabWinPerThread = 8;                                   // 4 lanes per scalar
 static constexpr int kTabScalarsPerBlock = kTabThreads * kTabWinPerThread / kSmallW;   // 64
 static constexpr int kTabMaxRows = 4;
 
@@ -122,32 +131,34 @@ __device__ __forceinline__ XYZZ tab_block_sum(XYZZ acc, XYZZ* part /* shared, kT
 }
 
 // grid = (ceil((R + 1) / 64), rows).  partial[row * gridDim.x + blockIdx.x] = sum over the block's 64 scalars.
-__global__ void __launch_bounds__(kTabThreads)
+__global__ void __launch_bounds__(kTabThreads, 2)
 k_tab_commit_partial(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n_cols, const Affine* __restrict__ table,
                      XYZZ* __restrict__ partial) {
     __shared__ XYZZ part[kTabThreads / 32];
     const int row = blockIdx.y;
-    constexpr int lanes_per_scalar = kSmallW / kTabWinPerThread;              // 8
+    constexpr int lanes_per_scalar = kSmallW / kTabWinPerThread;              // 4
     const int sidx = blockIdx.x * kTabScalarsPerBlock + threadIdx.x / lanes_per_scalar;
     const int q = threadIdx.x % lanes_per_scalar;                             // windows 4q .. 4q + 3
     XYZZ acc = XYZZ::identity();
     if (sidx < R || (sidx == R && blinds)) {
         const Fr s = fp_from_mont(sidx < R ? load_fr(Z + (size_t)row * R + sidx) : load_fr(blinds + row));
         const int col = sidx < R ? sidx : n_cols - 1;
-        int dig[kTabWinPerThread] = {0, 0, 0, 0};
+        int dig[kTabWinPerThread] = {};
         for_each_digit<kSmallC>(s, [&](int k, uint32_t dm1, bool negative) {
             if ((k / kTabWinPerThread) == q) dig[k % kTabWinPerThread] = negative ? -(int)(dm1 + 1) : (int)(dm1 + 1);
         });
+        Affine cur = Affine::identity();
 #pragma unroll 1
         for (int i = 0; i < kTabWinPerThread; i++) {
             if (dig[i] == 0) continue;
             const int k = q * kTabWinPerThread + i;
             const int d = dig[i] < 0 ? -dig[i] : dig[i];
-            Affine p = load_affine(table + ((size_t)(k * n_cols + col) * kSmallD + (d - 1)));
-            if (p.is_identity()) continue;
-            if (dig[i] < 0) p = affine_neg(p);
-            xyzz_add_mixed_call(&acc, &p);
+            Affine nxt = load_affine(table + ((size_t)(k * n_cols + col) * kSmallD + (d - 1)));      // in flight under the addition below
+            if (!cur.is_identity()) xyzz_add_mixed<MulInline>(acc, cur);
+            if (dig[i] < 0 && !nxt.is_identity()) nxt = affine_neg(nxt);
+            cur = nxt;
         }
+        if (!cur.is_identity()) xyzz_add_mixed<MulInline>(acc, cur);
     }
     const XYZZ v = tab_block_sum(acc, part);
     if (threadIdx.x == 0) store_xyzz(partial + (size_t)row * gridDim.x + blockIdx.x, v);
