@@ -17,7 +17,8 @@ lg = n.bit_length() - 1
 us = synth.uniform_scalars(9, lg); bl = synth.uniform_scalars(10, lg); br = synth.uniform_scalars(11, lg)
 uinv = orc.to_mont([pow(v, -1, R_MOD) for v in orc.from_mont(us)])
 blind = synth.uniform_scalars(12, 1)[0]
-for rep in range(3):
+for rep in range(6):
+    ctx.set("host_normalize", rep & 1)
     t0 = time.perf_counter()
     st = ctx.bullet_begin(bases, None, a_vec, b_vec, blind, q_scalar=q)
     t1 = time.perf_counter()
@@ -27,4 +28,4 @@ for rep in range(3):
         a = time.perf_counter(); st.round(bl[i], br[i]); b = time.perf_counter(); st.fold(us[i], uinv[i]); c = time.perf_counter()
         tr += b - a; tf += c - b; per.append(round(1e6 * (b - a)))
     st.end(); st.close()
-    print(f"n={n} begin {1e3*(t1-t0):.3f} ms rounds {1e3*tr:.3f} ms folds {1e3*tf:.3f} ms per-round us {per}", flush=True)
+    print(f"host_normalize={rep & 1} n={n} begin {1e3*(t1-t0):.3f} ms rounds {1e3*tr:.3f} ms folds {1e3*tf:.3f} ms per-round us {per}", flush=True)

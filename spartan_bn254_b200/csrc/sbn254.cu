@@ -99,6 +99,7 @@ struct sbn_ctx {
     long prefix_smem_kb = 0;
     long sum_wpr = 0;                  // warps per row of the final row sums (1, 2, 4); 0 = by the number of points left
     long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
+    long host_normalize = 1;           // the few points of a short commitment / a bullet round are normalised (XYZZ -> affine) on the host: a 30 us one-warp dependency chain on the device, a few us on a host core
     long bsc_device = 0;               // product-layer sumchecks (transcript_kernels.cuh; measured no faster than the host loop, kept as an option): 1 = the short last rounds of a layer run in one block with the Merlin transcript on the device, the long ones through the host loop; 2 = every round on the device; 0 = host loop only
     long small_scalar_path = 1;        // commits without blinds scan their scalars' bit length and use a short window schedule when it is small
     long small_scalar_hits = 0;        // commits that took it
@@ -464,6 +465,8 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     } else if (!strcmp(key, "mult_layout")) {
         if (value < 0 || value > 2) return SBN_ERR_ARG;
         ctx->mult_layout = value;
+    } else if (!strcmp(key, "host_normalize")) {
+        ctx->host_normalize = value ? 1 : 0;
     } else if (!strcmp(key, "bsc_device")) {
         ctx->bsc_device = value < 0 || value > 2 ? 0 : value;
     } else if (!strcmp(key, "ba_prefetch")) {
@@ -1637,10 +1640,20 @@ extern "C" int sbn_hyrax_commit_device(sbn_ctx* ctx, const sbn_bases* b, const v
 }
 
 // Short generator set, few rows: one launch over the tabulated digit multiples, operands through mapped pinned memory.
+// XYZZ -> affine on the host (the library's host-side field code: 4 x 64-bit limbs, safegcd inverse): for the one to four
+// points of a short commitment or a bullet round, where the device-side normalisation is a 30 us chain on one warp
+static void host_normalize(const XYZZ& v, sbn_g1a* out, uint8_t* inf) {
+    const Affine a = xyzz_to_affine<MulInline>(v);
+    memcpy(out, &a, sizeof(Affine));
+    *inf = v.is_identity() ? 1 : 0;
+}
+
 static int small_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_t L, size_t R, const sbn_fr* blinds,
                         sbn_g1a* C_out, uint8_t* inf_out) {
     const size_t off_blind = (size_t)kSmallMaxRows * kSmallMaxCols * sizeof(Fr), off_out = off_blind + kSmallMaxRows * sizeof(Fr),
-                 off_inf = off_out + kSmallMaxRows * sizeof(Affine), total = off_inf + kSmallMaxRows;
+                 off_inf = off_out + kSmallMaxRows * sizeof(Affine), off_raw = (off_inf + kSmallMaxRows + 15) & ~size_t(15),
+                 total = off_raw + kSmallMaxRows * sizeof(XYZZ);
+    const bool host_norm = ctx->host_normalize != 0;
     if (!ctx->small_pin) {
         SBN_CUDA(ctx, cudaHostAlloc((void**)&ctx->small_pin, total, cudaHostAllocMapped));
         SBN_CUDA(ctx, cudaHostGetDevicePointer((void**)&ctx->small_pin_dev, ctx->small_pin, 0));
@@ -1650,12 +1663,20 @@ static int small_commit(sbn_ctx* ctx, const sbn_bases* b, const sbn_fr* Z, size_
     uint8_t* d = ctx->small_pin_dev;
     k_small_commit<<<(unsigned)L, 32 * ((unsigned)R + 1), 0, ctx->compute>>>((const Fr*)d, blinds ? (const Fr*)(d + off_blind) : nullptr,
                                                                              (int)R, b->n_cols, b->small, (Affine*)(d + off_out),
-                                                                             d + off_inf);
+                                                                             d + off_inf, host_norm ? (XYZZ*)(d + off_raw) : nullptr);
     ctx->launches += 1;
     SBN_CUDA(ctx, cudaGetLastError());
     SBN_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    memcpy(C_out, ctx->small_pin + off_out, L * sizeof(Affine));
-    memcpy(inf_out, ctx->small_pin + off_inf, L);
+    if (host_norm) {
+        for (size_t i = 0; i < L; i++) {
+            XYZZ v;
+            memcpy(&v, ctx->small_pin + off_raw + i * sizeof(XYZZ), sizeof(XYZZ));
+            host_normalize(v, C_out + i, inf_out + i);
+        }
+    } else {
+        memcpy(C_out, ctx->small_pin + off_out, L * sizeof(Affine));
+        memcpy(inf_out, ctx->small_pin + off_inf, L);
+    }
     ctx->h2d += L * R * sizeof(Fr) + (blinds ? L * sizeof(Fr) : 0);
     ctx->d2h += L * (sizeof(Affine) + 1);
     for (int i = 0; i < 4; i++) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
@@ -2266,6 +2287,7 @@ extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn
     SBN_ENTER(ctx);
     cudaStream_t s = ctx->compute;
     const long n2 = (long)(st->n / 2);
+    bool host_norm = false;
     const unsigned dot_blocks = (unsigned)std::min<long>(kBulletDotBlocks, (n2 + kDotThreads - 1) / kDotThreads);
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 2, blind_L, sizeof(Fr), cudaMemcpyHostToDevice, s));
     SBN_CUDA(ctx, cudaMemcpyAsync(st->scal + 3, blind_R, sizeof(Fr), cudaMemcpyHostToDevice, s));
@@ -2281,7 +2303,11 @@ extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn
         ctx->launches++;
         std::vector<int> ev_stage;
         SBN_TRY(ensure_commit_workspace(ctx, st->bases, 2, 2));
-        SBN_TRY(run_commit(ctx, st->bases, st->rows, nullptr, 2, n0 + 1, st->scal + 2, st->outp, st->outinf, s, ev_stage));
+        // the two-row sum over the opening's table leaves its XYZZ totals in ctx->totals; they are normalised on the host
+        const sbn_bases* bb = st->bases;
+        host_norm = ctx->host_normalize && bb->small && ctx->small_commit_path && n0 + 2 <= (size_t)bb->n_cols &&
+                    !(2 >= (size_t)ctx->mult_min_rows && !bb->has_g1 && ctx->mult_max_mb > 0);
+        SBN_TRY(run_commit(ctx, st->bases, st->rows, nullptr, 2, n0 + 1, st->scal + 2, st->outp, st->outinf, s, ev_stage, !host_norm));
     } else {
         const unsigned blocks = (unsigned)((n2 + kSmallThreads - 1) / kSmallThreads);
         // set 0: L = <a_L, G_R>, set 1: R = <a_R, G_L>
@@ -2298,11 +2324,19 @@ extern "C" int sbn_bullet_round(sbn_bullet* st, const sbn_fr* blind_L, const sbn
     SBN_CUDA(ctx, cudaGetLastError());
     sbn_g1a pts[2];
     uint8_t infs[2];
-    SBN_CUDA(ctx, cudaMemcpyAsync(pts, st->outp, 2 * sizeof(Affine), cudaMemcpyDeviceToHost, s));
-    SBN_CUDA(ctx, cudaMemcpyAsync(infs, st->outinf, 2, cudaMemcpyDeviceToHost, s));
-    SBN_CUDA(ctx, cudaStreamSynchronize(s));
+    if (host_norm) {
+        XYZZ tot[2];
+        SBN_CUDA(ctx, cudaMemcpyAsync(tot, ctx->totals.p, 2 * sizeof(XYZZ), cudaMemcpyDeviceToHost, s));
+        SBN_CUDA(ctx, cudaStreamSynchronize(s));
+        for (int i = 0; i < 2; i++) host_normalize(tot[i], &pts[i], &infs[i]);
+        ctx->d2h += 2 * sizeof(XYZZ);
+    } else {
+        SBN_CUDA(ctx, cudaMemcpyAsync(pts, st->outp, 2 * sizeof(Affine), cudaMemcpyDeviceToHost, s));
+        SBN_CUDA(ctx, cudaMemcpyAsync(infs, st->outinf, 2, cudaMemcpyDeviceToHost, s));
+        SBN_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->d2h += 2 * sizeof(Affine) + 2;
+    }
     ctx->h2d += 2 * sizeof(Fr);
-    ctx->d2h += 2 * sizeof(Affine) + 2;
     *L_out = pts[0]; *L_inf = infs[0];
     *R_out = pts[1]; *R_inf = infs[1];
     return SBN_OK;

@@ -42,10 +42,12 @@ __global__ void k_build_small_table(const Affine* __restrict__ orig, int n_cols,
     }
 }
 
-// blockDim.x = 32 * (R + 1).  Z, blinds, out, inf may be mapped host memory.
+// blockDim.x = 32 * (R + 1).  Z, blinds, out, inf, raw may be mapped host memory.  raw != nullptr: the row's sum is handed
+// back as it is (XYZZ) and the caller normalises it -- the inversion is a 30 us dependency chain for a lone warp and a few
+// microseconds for a host core.
 __global__ void __launch_bounds__(32 * kSmallMaxCols)
 k_small_commit(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, int n_cols, const Affine* __restrict__ table,
-               Affine* __restrict__ out, uint8_t* __restrict__ inf) {
+               Affine* __restrict__ out, uint8_t* __restrict__ inf, XYZZ* __restrict__ raw) {
     __shared__ XYZZ part[kSmallMaxCols];
     const int row = blockIdx.x, lane = threadIdx.x & 31, j = threadIdx.x >> 5, nw = blockDim.x >> 5;
     XYZZ acc = XYZZ::identity();
@@ -73,12 +75,15 @@ k_small_commit(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
     __syncthreads();
     if (j != 0) return;
     XYZZ v = lane < nw ? part[lane] : XYZZ::identity();
-    for (int stride = kSmallMaxCols / 2; stride >= 1; stride >>= 1) {
+    int top = 1;                                     // tree levels for nw values only: a level is ~9 us of one warp's latency
+    while (2 * top < nw) top *= 2;
+    for (int stride = nw > 1 ? top : 0; stride >= 1; stride >>= 1) {
         XYZZ o = shfl_xyzz(v, (lane + stride) & 31);
         if (lane >= stride) o = XYZZ::identity();
         xyzz_add_call(&v, &o);
     }
     if (lane == 0) {
+        if (raw) { store_xyzz(raw + row, v); return; }
         const Affine a = xyzz_to_affine<MulInline>(v);
         store_affine(out + row, a);
         inf[row] = v.is_identity() ? 1 : 0;
