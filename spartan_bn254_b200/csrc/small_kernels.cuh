@@ -42,6 +42,72 @@ __global__ void k_build_small_table(const Affine* __restrict__ orig, int n_cols,
     }
 }
 
+// One level of a shuffle tree, with BOTH lanes of a pair at work.  In the plain tree lane i < stride adds the value of lane
+// i + stride while that lane idles, and for a lone warp a point addition is a dependency chain of 14 products (~9 us).  Here
+// the two lanes exchange their values and split the products of add-2008-s between them -- 8 deep instead of 14:
+//   both: U, S of "their" operand and one of ZZ1 ZZ2 / ZZZ1 ZZZ2 | exchange U, S | P^2 on one, R^2 on the other | exchange |
+//   P^3 and ZZ1 ZZ2 P^2 on one, U1 P^2 on the other | exchange | S1 P^3, R (Q - X3) on one, ZZZ1 ZZZ2 P^3 on the other.
+// The sum lands in the lower lane of the pair (lane & stride == 0); the upper lane's value is dead afterwards, as in the
+// plain tree.  The identity, P + P and P - P are resolved after the fact from the operands (rare: table points of distinct
+// generators), so the shuffles stay convergent.  All 32 lanes must call it.
+__device__ __forceinline__ Fq shfl_xor_fq(const Fq& v, int mask) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], mask);
+    return r;
+}
+__device__ __forceinline__ Fq sel_fq(bool c, const Fq& a, const Fq& b) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = c ? a.l[i] : b.l[i];
+    return r;
+}
+__device__ __noinline__ void xyzz_pair_level(XYZZ* accp, int stride) {
+    XYZZ& acc = *accp;
+    const bool hi = ((threadIdx.x & 31) & stride) != 0;
+    XYZZ oth;
+    oth.X = shfl_xor_fq(acc.X, stride); oth.Y = shfl_xor_fq(acc.Y, stride);
+    oth.ZZ = shfl_xor_fq(acc.ZZ, stride); oth.ZZZ = shfl_xor_fq(acc.ZZZ, stride);
+    // (p1, p2) = (lower lane's value, upper lane's value) on both lanes
+    XYZZ p1, p2;
+    p1.X = sel_fq(hi, oth.X, acc.X); p1.Y = sel_fq(hi, oth.Y, acc.Y); p1.ZZ = sel_fq(hi, oth.ZZ, acc.ZZ); p1.ZZZ = sel_fq(hi, oth.ZZZ, acc.ZZZ);
+    p2.X = sel_fq(hi, acc.X, oth.X); p2.Y = sel_fq(hi, acc.Y, oth.Y); p2.ZZ = sel_fq(hi, acc.ZZ, oth.ZZ); p2.ZZZ = sel_fq(hi, acc.ZZZ, oth.ZZZ);
+    // lower lane: U1 = X1 ZZ2, S1 = Y1 ZZZ2, A = ZZ1 ZZ2;  upper lane: U2 = X2 ZZ1, S2 = Y2 ZZZ1, B = ZZZ1 ZZZ2
+    const Fq m1 = fp_mul(sel_fq(hi, p2.X, p1.X), sel_fq(hi, p1.ZZ, p2.ZZ));
+    const Fq m2 = fp_mul(sel_fq(hi, p2.Y, p1.Y), sel_fq(hi, p1.ZZZ, p2.ZZZ));
+    const Fq m3 = fp_mul(sel_fq(hi, p1.ZZZ, p1.ZZ), sel_fq(hi, p2.ZZZ, p2.ZZ));
+    const Fq o1 = shfl_xor_fq(m1, stride), o2 = shfl_xor_fq(m2, stride);
+    const Fq U1 = sel_fq(hi, o1, m1), U2 = sel_fq(hi, m1, o1), S1 = sel_fq(hi, o2, m2), S2 = sel_fq(hi, m2, o2);
+    const Fq P = fp_sub(U2, U1), R = fp_sub(S2, S1);
+    // lower: PP = P^2; upper: RR = R^2
+    const Fq sq_in = sel_fq(hi, R, P);
+    const Fq m4 = fp_mul(sq_in, sq_in);
+    const Fq o4 = shfl_xor_fq(m4, stride);
+    const Fq PP = sel_fq(hi, o4, m4), RR = sel_fq(hi, m4, o4);
+    // lower: PPP = P PP, then ZZ3 = A PP; upper: Q = U1 PP
+    const Fq m5 = fp_mul(sel_fq(hi, U1, P), PP);
+    const Fq o5 = shfl_xor_fq(m5, stride);
+    const Fq PPP = sel_fq(hi, o5, m5), Q = sel_fq(hi, m5, o5);
+    const Fq X3 = fp_sub(fp_sub(RR, PPP), fp_dbl(Q));
+    // lower: ZZ3 = A PP, Y3a = S1 PPP, Y3b = R (Q - X3); upper: ZZZ3 = B PPP (the other two slots idle)
+    const Fq m6 = fp_mul(m3, sel_fq(hi, PPP, PP));              // lower: A PP = ZZ3; upper: B PPP = ZZZ3
+    const Fq zzz3 = shfl_xor_fq(m6, stride);                    // the lower lane receives ZZZ3
+    XYZZ res;
+    res.X = X3;
+    res.Y = fp_sub(fp_mul(R, fp_sub(Q, X3)), fp_mul(S1, PPP));
+    res.ZZ = m6;
+    res.ZZZ = zzz3;
+    if (hi) return;                                             // the pair's sum lives in the lower lane
+    if (p2.is_identity()) return;                               // acc (= p1) stays
+    if (p1.is_identity()) { acc = p2; return; }
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl<MulCall>(p1);
+        else acc = XYZZ::identity();
+        return;
+    }
+    acc = res;
+}
+
 // blockDim.x = 32 * (R + 1).  Z, blinds, out, inf, raw may be mapped host memory.  raw != nullptr: the row's sum is handed
 // back as it is (XYZZ) and the caller normalises it -- the inversion is a 30 us dependency chain for a lone warp and a few
 // microseconds for a host core.
@@ -66,22 +132,14 @@ k_small_commit(const Fr* __restrict__ Z, const Fr* __restrict__ blinds, int R, i
             acc = XYZZ::from_affine(p);
         }
     }
-    for (int stride = 16; stride >= 1; stride >>= 1) {
-        XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
-        if (lane >= stride) o = XYZZ::identity();
-        xyzz_add_call(&acc, &o);
-    }
+    for (int stride = 16; stride >= 1; stride >>= 1) xyzz_pair_level(&acc, stride);
     if (lane == 0) part[j] = acc;
     __syncthreads();
     if (j != 0) return;
     XYZZ v = lane < nw ? part[lane] : XYZZ::identity();
-    int top = 1;                                     // tree levels for nw values only: a level is ~9 us of one warp's latency
+    int top = 1;                                     // tree levels for nw values only: a level is several us of one warp's latency
     while (2 * top < nw) top *= 2;
-    for (int stride = nw > 1 ? top : 0; stride >= 1; stride >>= 1) {
-        XYZZ o = shfl_xyzz(v, (lane + stride) & 31);
-        if (lane >= stride) o = XYZZ::identity();
-        xyzz_add_call(&v, &o);
-    }
+    for (int stride = nw > 1 ? top : 0; stride >= 1; stride >>= 1) xyzz_pair_level(&v, stride);
     if (lane == 0) {
         if (raw) { store_xyzz(raw + row, v); return; }
         const Affine a = xyzz_to_affine<MulInline>(v);
@@ -118,20 +176,12 @@ __device__ __noinline__ void xyzz_add_mixed_call(XYZZ* acc, const Affine* q) { x
 // block tree: every warp's lane-0 value -> value of the whole block in thread 0 (blockDim.x = kTabThreads)
 __device__ __forceinline__ XYZZ tab_block_sum(XYZZ acc, XYZZ* part /* shared, kTabThreads / 32 */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int stride = 16; stride >= 1; stride >>= 1) {
-        XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
-        if (lane >= stride) o = XYZZ::identity();
-        xyzz_add_call(&acc, &o);
-    }
+    for (int stride = 16; stride >= 1; stride >>= 1) xyzz_pair_level(&acc, stride);
     if (lane == 0) part[warp] = acc;
     __syncthreads();
     if (warp != 0) return XYZZ::identity();
     XYZZ v = lane < kTabThreads / 32 ? part[lane] : XYZZ::identity();
-    for (int stride = kTabThreads / 64; stride >= 1; stride >>= 1) {
-        XYZZ o = shfl_xyzz(v, (lane + stride) & 31);
-        if (lane >= stride) o = XYZZ::identity();
-        xyzz_add_call(&v, &o);
-    }
+    for (int stride = kTabThreads / 64; stride >= 1; stride >>= 1) xyzz_pair_level(&v, stride);
     return v;
 }
 
