@@ -600,13 +600,11 @@ k_mult_sum_rows_t(const Fq* __restrict__ ptsx, const Fq* __restrict__ ptsy, uint
             if (p.is_identity()) continue;
             xyzz_add_mixed<MulInline>(acc, p);
         }
-#pragma unroll 1
-        for (int stride = 16; stride >= 1; stride >>= 1) {
-            XYZZ o = shfl_xyzz(acc, (lane + stride) & 31);
-            if (lane >= stride) o = XYZZ::identity();
-            xyzz_add<MulInline, MulCall>(acc, o);
-        }
     }
+    // the shuffle tree runs on every warp of the block (rows past the end hold the identity): both lanes of a pair share the
+    // products of each addition (small_kernels.cuh, xyzz_pair_level)
+#pragma unroll 1
+    for (int stride = 16; stride >= 1; stride >>= 1) xyzz_pair_level(&acc, stride);
     if (WPR == 1) {
         if (lane == 0 && row < rows) store_xyzz(totals + row, acc);
         return;
