@@ -63,7 +63,7 @@ def load_library():
 def _ptr(a):
     if a is None:
         return None
-    return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.ctypes.data)        # three times cheaper than data_as(); the prover makes ~1700 of these per proof
 
 
 def _u64(a, cols):

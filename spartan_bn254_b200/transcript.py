@@ -81,6 +81,7 @@ class Transcript:
     def __init__(self, label, native=True):
         self._lib = _native_merlin()
         self._st = _ctypes.create_string_buffer(208)
+        self._c64 = _ctypes.create_string_buffer(64)          # challenge_scalar's bytes: one buffer, not one per call
         self._lib.sbn_merlin_init(self._st, label, _ctypes.c_size_t(len(label)))
 
     def append_message(self, label, message):
@@ -123,7 +124,8 @@ class Transcript:
                                            inf.ctypes.data_as(_ctypes.c_void_p), _ctypes.c_size_t(xy.shape[0]))
 
     def challenge_scalar(self, label):
-        return int.from_bytes(self.challenge_bytes(label, 64), "little") % R_MOD   # transcript.rs:56-67
+        self._lib.sbn_merlin_challenge(self._st, label, _ctypes.c_size_t(len(label)), self._c64, _ctypes.c_size_t(64))
+        return int.from_bytes(self._c64.raw, "little") % R_MOD                     # transcript.rs:56-67
 
     def challenge_scalars(self, label, n):
         return [self.challenge_scalar(label) for _ in range(n)]
