@@ -116,14 +116,33 @@ __global__ void k_combine(const XYZZ* __restrict__ terms, int groups, int per_gr
 // ---------------------------------------------------------------------------------------------
 // Fr reductions
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fr block_sum_fr(Fr v, Fr* sm, int threads) {
-    for (int stride = threads >> 1; stride >= 1; stride >>= 1) {
-        sm[threadIdx.x] = v;
-        __syncthreads();
-        if (threadIdx.x < stride) v = fp_add(v, sm[threadIdx.x + stride]);
-        __syncthreads();
+// first: the first shuffle distance (16 for a full warp; lanes >= 2 * first must hold zero)
+__device__ __forceinline__ Fr warp_sum_fr(Fr v, int first = 16) {
+#pragma unroll 1
+    for (int off = first; off >= 1; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], off);
+        v = fp_add(v, o);
     }
-    return v;
+    return v;      // lane 0 holds the sum
+}
+
+// Sum over the block; thread 0 holds it.  Shuffle trees inside the warps, one shared-memory hand-over, a shuffle tree over the
+// warps' sums: two barriers instead of the fourteen of a shared-memory tree -- these reductions sit in round-sequential kernels
+// (a sumcheck round evaluation does three of them), where every barrier is latency on the Fiat-Shamir critical path.
+// threads: a multiple of 32, at most 1024; sm: at least threads / 32 elements; callers separate consecutive sums by a barrier.
+__device__ __forceinline__ Fr block_sum_fr(Fr v, Fr* sm, int threads) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = threads >> 5;
+    v = warp_sum_fr(v);
+    if (nw == 1) return v;
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp != 0) return v;
+    v = lane < nw ? sm[lane] : Fr::zero();
+    int first = 1;
+    while (2 * first < nw) first *= 2;
+    return warp_sum_fr(v, first);
 }
 
 static constexpr int kDotThreads = 128;

@@ -111,17 +111,6 @@ __device__ __forceinline__ Fr ld_fr(const Fr* p) {
     return r;
 }
 
-// first: the first shuffle distance (16 for a full warp; lanes >= 2 * first must hold zero)
-__device__ __forceinline__ Fr warp_sum_fr(Fr v, int first = 16) {
-#pragma unroll 1
-    for (int off = first; off >= 1; off >>= 1) {
-        Fr o;
-#pragma unroll
-        for (int k = 0; k < 8; k++) o.l[k] = __shfl_down_sync(0xffffffffu, v.l[k], off);
-        v = fp_add(v, o);
-    }
-    return v;      // lane 0 holds the sum
-}
 
 // One round's transcript step, by one warp.  ev: the round's 3 n evaluations (e0, e2, e3 per instance; shared or global),
 // sh.claim: the running claim (in / out).  The evaluations are combined with the batching coefficients (sumcheck.rs:273-275),
