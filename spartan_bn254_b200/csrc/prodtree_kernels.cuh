@@ -64,6 +64,65 @@ k_cubic_eval_batched(const CubicTriple* __restrict__ triples, size_t half, Fr* _
     if (threadIdx.x == 0) store_fr(out + 2 * gridDim.x + blockIdx.x, e3);
 }
 
+// Round j >= 1 of a batched cubic sumcheck in ONE kernel: the bind of round j - 1 and the evaluation of round j.  A round is
+// Fiat-Shamir-sequential -- evaluation, host (transcript, challenge), bind, next evaluation -- and on that chain every launch
+// costs its launch-to-start latency as well as its run time: with the bind folded into the next evaluation a round is one
+// kernel instead of two.  h = the evaluation's half length; the tables still have 4 h entries (the previous challenge r is
+// pending).  Thread i binds entries i and i + h of every table of its instance,
+//     T'[i] = T[i] + r (T[i + 2h] - T[i]),   T'[i + h] = T[i + h] + r (T[i + 3h] - T[i + h]),
+// stores them in place (a thread writes only what it alone reads; the upper half is never written) and evaluates the cubic on
+// (T'[i], T'[i + h]).  The eq table shared by the parallel instances (inst < P) is read by all of them, so its bound copy
+// goes to the other ping-pong buffer, written by instance 0 only; a sequential instance owns its C table and binds it in place.
+__global__ void __launch_bounds__(kDotThreads)
+k_bind_eval_batched(const CubicTriple* __restrict__ triples, int P, const Fr* __restrict__ eq_in, Fr* __restrict__ eq_out, size_t h,
+                    const Fr r, Fr* __restrict__ partial) {
+    __shared__ Fr sm[kDotThreads];
+    const int inst = blockIdx.y;
+    const CubicTriple t = triples[inst];
+    const bool shared_c = inst < P;
+    Fr* A = const_cast<Fr*>(t.A);
+    Fr* B = const_cast<Fr*>(t.B);
+    const Fr* Cin = shared_c ? eq_in : t.C;
+    Fr* Cout = shared_c ? eq_out : const_cast<Fr*>(t.C);
+    const bool write_c = !shared_c || inst == 0;
+    const size_t hp = 2 * h;
+    Fr e0 = Fr::zero(), e2 = Fr::zero(), e3 = Fr::zero();
+    for (size_t i = (size_t)blockIdx.x * kDotThreads + threadIdx.x; i < h; i += (size_t)gridDim.x * kDotThreads) {
+        // plain loads: these tables are rewritten by this very kernel (by this very thread), not read-only data
+        auto ld = [](const Fr* p) {
+            const uint4* q = reinterpret_cast<const uint4*>(p);
+            const uint4 u = q[0], v = q[1];
+            Fr x;
+            x.l[0] = u.x; x.l[1] = u.y; x.l[2] = u.z; x.l[3] = u.w; x.l[4] = v.x; x.l[5] = v.y; x.l[6] = v.z; x.l[7] = v.w;
+            return x;
+        };
+        auto bound = [&](const Fr* T, size_t k) {
+            const Fr lo = ld(T + k), hi = ld(T + k + hp);
+            return fp_add(lo, fp_mul(r, fp_sub(hi, lo)));
+        };
+        const Fr a0 = bound(A, i), a1 = bound(A, i + h);
+        const Fr b0 = bound(B, i), b1 = bound(B, i + h);
+        const Fr c0 = bound(Cin, i), c1 = bound(Cin, i + h);
+        store_fr(A + i, a0); store_fr(A + i + h, a1);
+        store_fr(B + i, b0); store_fr(B + i + h, b1);
+        if (write_c) { store_fr(Cout + i, c0); store_fr(Cout + i + h, c1); }
+        const Fr a2 = fp_sub(fp_add(a1, a1), a0), b2 = fp_sub(fp_add(b1, b1), b0), c2 = fp_sub(fp_add(c1, c1), c0);
+        const Fr a3 = fp_sub(fp_add(a2, a1), a0), b3 = fp_sub(fp_add(b2, b1), b0), c3 = fp_sub(fp_add(c2, c1), c0);
+        e0 = fp_add(e0, fp_mul(fp_mul(a0, b0), c0));
+        e2 = fp_add(e2, fp_mul(fp_mul(a2, b2), c2));
+        e3 = fp_add(e3, fp_mul(fp_mul(a3, b3), c3));
+    }
+    Fr* out = partial + (size_t)blockIdx.y * 3 * gridDim.x;
+    e0 = block_sum_fr(e0, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + blockIdx.x, e0);
+    __syncthreads();
+    e2 = block_sum_fr(e2, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + gridDim.x + blockIdx.x, e2);
+    __syncthreads();
+    e3 = block_sum_fr(e3, sm, kDotThreads);
+    if (threadIdx.x == 0) store_fr(out + 2 * gridDim.x + blockIdx.x, e3);
+}
+
 // T[i] <- T[i] + r (T[half + i] - T[i]) for every table of the list; blockIdx.y = table.
 __global__ void k_bind_top_batched(Fr* const* __restrict__ tables, size_t half, const Fr* __restrict__ r) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

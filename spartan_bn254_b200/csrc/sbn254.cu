@@ -99,6 +99,7 @@ struct sbn_ctx {
     long prefix_smem_kb = 0;
     long sum_wpr = 0;                  // warps per row of the final row sums (1, 2, 4); 0 = by the number of points left
     long ablate = 0;                   // PROFILING ONLY (results are wrong when non-zero): bit mask of skipped launches of the tabulated-sum path
+    long fused_rounds = 1;             // sbn_bsumcheck_prove: the bind of a round rides in the next round's evaluation kernel (one launch per round on the Fiat-Shamir chain)
     long host_normalize = 1;           // the few points of a short commitment / a bullet round are normalised (XYZZ -> affine) on the host: a 30 us one-warp dependency chain on the device, a few us on a host core
     long bsc_device = 0;               // product-layer sumchecks (transcript_kernels.cuh; measured no faster than the host loop, kept as an option): 1 = the short last rounds of a layer run in one block with the Merlin transcript on the device, the long ones through the host loop; 2 = every round on the device; 0 = host loop only
     long small_scalar_path = 1;        // commits without blinds scan their scalars' bit length and use a short window schedule when it is small
@@ -465,6 +466,8 @@ extern "C" int sbn_ctx_set(sbn_ctx* ctx, const char* key, long value) {
     } else if (!strcmp(key, "mult_layout")) {
         if (value < 0 || value > 2) return SBN_ERR_ARG;
         ctx->mult_layout = value;
+    } else if (!strcmp(key, "fused_rounds")) {
+        ctx->fused_rounds = value ? 1 : 0;
     } else if (!strcmp(key, "host_normalize")) {
         ctx->host_normalize = value ? 1 : 0;
     } else if (!strcmp(key, "bsc_device")) {
@@ -2958,19 +2961,34 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
         if (ctx->bsc_device == 1)
             while (host_rounds < num_rounds && ((st->len >> host_rounds) / 2) > (size_t)kBscTailHalf) host_rounds++;
     }
+    // fused rounds (prodtree_kernels.cuh, k_bind_eval_batched): the bind of a round rides in the next round's evaluation
+    // kernel, so a round is one launch on the Fiat-Shamir chain instead of two; the shared eq table ping-pongs between its two
+    // buffers and the last round's bind is a launch of its own
+    const bool fused = ctx->fused_rounds && host_rounds == num_rounds;
+    bool pending = false;
+    Fr r_prev = Fr::zero();
+    Fr* const eq_baked = st->eq[st->eq_cur];
+    int eq_now = st->eq_cur;
+    // (Measured with timers around the three parts of a round at 12 x 2^22: launches 6 us, host 4 us, waiting for the round's
+    // kernels 54 us, of which their own run time averages 36 -- the long rounds of the upper layers.)
     for (size_t j = 0; j < host_rounds; j++) {
         const size_t half = st->len / 2;
         const unsigned blocks = (unsigned)std::min<size_t>(st->max_blocks, (half + kDotThreads - 1) / kDotThreads);
         // The 3 n evaluations land in mapped pinned memory: no copy call per round, and a one-block evaluation (the many short
         // rounds at the end of every layer) writes them itself instead of through a second launch.
         Fr* ev_dev = (Fr*)ctx->ev_pin_dev;
-        if (blocks == 1) {
-            k_cubic_eval_batched<<<dim3(1, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, ev_dev);
-            ctx->launches += 1;
+        Fr* ev_to = blocks == 1 ? ev_dev : st->partial;
+        if (pending) {
+            k_bind_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, (int)st->P, st->eq[eq_now], st->eq[eq_now ^ 1],
+                                                                                 half, r_prev, ev_to);
+            eq_now ^= 1;
         } else {
-            k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, st->partial);
+            k_cubic_eval_batched<<<dim3(blocks, (unsigned)n), kDotThreads, 0, s>>>(st->d_triples, half, ev_to);
+        }
+        ctx->launches += 1;
+        if (blocks > 1) {
             k_fr_sum<<<(unsigned)(3 * n), kDotThreads, 0, s>>>(st->partial, (int)blocks, ev_dev, 1);
-            ctx->launches += 2;
+            ctx->launches += 1;
         }
         SBN_CUDA(ctx, cudaGetLastError());
         SBN_CUDA(ctx, cudaStreamSynchronize(s));
@@ -2992,9 +3010,19 @@ extern "C" int sbn_bsumcheck_prove(sbn_bsumcheck* st, void* merlin, const sbn_fr
         uint8_t wide[64];
         sbn::merlin::challenge_bytes(tr, (const uint8_t*)"challenge_nextround", 19, wide, 64);
         const Fr r = FrHost::from_wide(wide);
-        k_bind_top_batched_v<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, r);
-        ctx->launches += 1;
-        SBN_CUDA(ctx, cudaGetLastError());
+        if (fused && j + 1 < host_rounds) {
+            pending = true;                       // bound by the next round's kernel
+            r_prev = r;
+        } else {
+            if (eq_now != st->eq_cur) {           // the tables' own eq pointer is the other buffer: bring the 2 * half live entries home
+                SBN_CUDA(ctx, cudaMemcpyAsync(eq_baked, st->eq[eq_now], 2 * half * sizeof(Fr), cudaMemcpyDeviceToDevice, s));
+                eq_now = st->eq_cur;
+            }
+            k_bind_top_batched_v<<<dim3((unsigned)((half + 127) / 128), (unsigned)st->ntables), 128, 0, s>>>(st->d_tables, half, r);
+            ctx->launches += 1;
+            SBN_CUDA(ctx, cudaGetLastError());
+            pending = false;
+        }
         st->len = half;
         // e = poly(r)
         Fr acc = poly[0], power = r;
