@@ -81,6 +81,10 @@ int sbn_ctx_synchronize(sbn_ctx* ctx);
  *                   short last rounds of a layer run in ONE block with the Merlin transcript on the device; 2 every round
  *                   (csrc/transcript_kernels.cuh; identical proofs and transcript states; measured no faster -- a one-warp
  *                   Keccak + Montgomery step is ~16 us on the GPU)
+ *   "fused_rounds"  sbn_bsumcheck_prove: 1 (default) the bind of a round rides in the next round's evaluation kernel (one launch
+ *                   per round on the Fiat-Shamir chain); 0 separate bind launches
+ *   "host_normalize" 1 (default): the one to four points of a short commitment / a bullet round come back as XYZZ and are
+ *                   normalised on the host (a 30 us one-warp inversion chain on the device, a few us on a host core); 0 on the device
  *   "finish_smem_kb" / "prefix_smem_kb"  dynamic shared memory requested per block to cap co-residency (default 0)
  *   "l2_fetch"      cudaLimitMaxL2FetchGranularity (32 / 64 / 128; measured to change nothing on B200)
  *   "ablate"        PROFILING ONLY: bit mask of skipped launches (1 prefix round 1, 2 prefix rounds >= 2, 4 inversions,
