@@ -74,7 +74,19 @@ class GroupElement:
         return (_int(self.xy[:4]) * _RINV_P % P_MOD, _int(self.xy[4:]) * _RINV_P % P_MOD)
 
     def compress(self):
-        """group.rs:135-140: ark compressed SW encoding (x LE, bit7 = y > -y, bit6 = infinity)."""
+        """group.rs:135-140: ark compressed SW encoding (x LE, bit7 = y > -y, bit6 = infinity).  Through the library's host code
+        (sbn_g1_compress) when it is built -- a proof compresses ~400 single points on its Fiat-Shamir path; compress_py is the
+        same in Python integers (and what the tests hold the library's version against)."""
+        lib = _host_lib()
+        if lib is None:
+            return self.compress_py()
+        out = _C.create_string_buffer(32)
+        inf = _C.c_uint8(1 if self.inf else 0)
+        if lib.sbn_g1_compress(_C.c_void_p(self.xy.ctypes.data), _C.byref(inf), _C.c_size_t(1), out) != 0:
+            raise RuntimeError("sbn_g1_compress failed")
+        return out.raw
+
+    def compress_py(self):
         b = bytearray(32)
         a = self.affine_ints()
         if a is None:

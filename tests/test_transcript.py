@@ -72,8 +72,9 @@ def test_native_point_compression_and_append_points(orc):
     out = np.zeros((pts.shape[0], 32), dtype=np.uint8)
     assert lib.sbn_g1_compress(pts.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p), C.c_size_t(pts.shape[0]),
                                out.ctypes.data_as(C.c_void_p)) == 0
-    exp = [GroupElement(p, i or not p.any()).compress() for p, i in zip(pts, inf)]
+    exp = [GroupElement(p, i or not p.any()).compress_py() for p, i in zip(pts, inf)]
     assert [bytes(o) for o in out] == exp
+    assert [GroupElement(p, i or not p.any()).compress() for p, i in zip(pts, inf)] == exp      # the single-point binding
     assert {e[31] >> 7 for e in exp} == {0, 1} and exp[25][31] == 0x40 and exp[26][31] == 0x40
     inf[26] = 1
     a, b, c = Transcript(b"pts"), PyTranscript(b"pts"), orc.Transcript(b"pts")
