@@ -65,3 +65,54 @@ def test_shard_rows_partition():
                 assert f0 + n0 == f1
             assert spans[-1][0] + spans[-1][1] == L
             assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+def _commit_inner_worker(rank, world, port, L, R, out_dir):
+    """DensePolynomial.commit_inner(shard=...) -- the row-sharded R1CSProof::commit_poly -- with the resident polynomial
+    replaced by a stand-in whose commit_rows is the oracle: what runs here is the host logic (block bounds, blinds slice,
+    all-gather of the 65-byte row records over gloo, reassembly)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import torch.distributed as dist
+    import oracle as orc
+    from spartan_bn254_b200 import synth
+    from spartan_bn254_b200.hyrax import DensePolynomial
+    from spartan_bn254_b200.parallel import make_all_gather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G, h = orc.multi_commit_gens(b"gens_r1cs_sat", R)
+    Z = synth.uniform_scalars(21, L * R)
+    blinds = synth.uniform_scalars(22, L)
+
+    class Gens:            # the two things commit_inner asks of a MultiCommitGens
+        n = R
+
+        @staticmethod
+        def device_bases():
+            return None
+
+    class ResidentStandIn:
+        def commit_rows(self, bases, first, n, R_size, bl):
+            return orc.hyrax_commit(G, h, np.ascontiguousarray(Z.reshape(L, R, 4)[first:first + n]).reshape(-1, 4), n, R_size, bl, threads=1)
+
+    poly = DensePolynomial(Z)
+    poly._poly = ResidentStandIn()
+    comm = poly.commit_inner(blinds, Gens, shard=(rank, world, make_all_gather()))
+    np.save(os.path.join(out_dir, f"C{rank}.npy"), comm.C)
+    np.save(os.path.join(out_dir, f"inf{rank}.npy"), comm.inf)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_commit_inner_host_logic(orc, tmp_path):
+    from spartan_bn254_b200 import synth
+    world, L, R = 2, 16, 8
+    mp.spawn(_commit_inner_worker, args=(world, _free_port(), L, R, str(tmp_path)), nprocs=world, join=True)
+    G, h = orc.multi_commit_gens(b"gens_r1cs_sat", R)
+    C, inf = orc.hyrax_commit(G, h, synth.uniform_scalars(21, L * R), L, R, synth.uniform_scalars(22, L))
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"C{r}.npy"), C)
+        assert np.array_equal(np.load(tmp_path / f"inf{r}.npy"), inf)
