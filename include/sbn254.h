@@ -106,6 +106,12 @@ int sbn_ctx_last_commit_profile(sbn_ctx* ctx, float ms[4], int launches[4]);
 /* pinned host memory for callers that want overlapped copies (optional) */
 int sbn_host_alloc(void** out, size_t bytes);
 int sbn_host_free(void* p);
+/* Streams for the asynchronous entry points (sbn_hyrax_commit_async, sbn_hyrax_commit_device), for callers without CUDA bindings
+ * of their own (the Rust shim): a non-blocking stream on ctx's device.  sbn_stream_synchronize does not take the context's
+ * lock, so one thread can wait for a commit while another issues the next one on another stream. */
+int sbn_stream_create(sbn_ctx* ctx, void** stream_out);
+int sbn_stream_synchronize(sbn_ctx* ctx, void* stream);
+int sbn_stream_destroy(sbn_ctx* ctx, void* stream);
 
 /* ---- generators: MultiCommitGens kept resident (commitments.rs:17-27, G_affine + h_affine) ---- */
 /* Uploads n affine generators G and the blinding generator h, and precomputes the fixed-base window

@@ -40,6 +40,9 @@ extern "C" {
     pub fn sbn_ctx_memory_stats(ctx: *mut sbn_ctx, out: *mut u64) -> c_int;
     pub fn sbn_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn sbn_host_free(p: *mut c_void) -> c_int;
+    pub fn sbn_stream_create(ctx: *mut sbn_ctx, stream_out: *mut *mut c_void) -> c_int;
+    pub fn sbn_stream_synchronize(ctx: *mut sbn_ctx, stream: *mut c_void) -> c_int;
+    pub fn sbn_stream_destroy(ctx: *mut sbn_ctx, stream: *mut c_void) -> c_int;
     pub fn sbn_msm(ctx: *mut sbn_ctx, pts: *const SbnG1a, inf: *const u8, s: *const SbnFr, n: usize,
                    out: *mut SbnG1a, inf_out: *mut u8) -> c_int;
     pub fn sbn_commit(ctx: *mut sbn_ctx, b: *const sbn_bases, s: *const SbnFr, n: usize, blind: *const SbnFr,
@@ -307,6 +310,44 @@ impl PinnedScalars {
     pub fn as_slice(&self) -> &[Fr] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
 }
 impl Drop for PinnedScalars { fn drop(&mut self) { unsafe { sbn_host_free(self.ptr as *mut c_void) }; } }
+
+/// A stream of the library's own for the asynchronous commits (no CUDA bindings needed on the Rust side).
+pub struct Stream<'a> { ctx: &'a Context, h: *mut c_void }
+impl<'a> Stream<'a> {
+    pub fn new(ctx: &'a Context) -> Self {
+        let mut h: *mut c_void = std::ptr::null_mut();
+        check(unsafe { sbn_stream_create(ctx.0, &mut h) }, "sbn_stream_create");
+        Stream { ctx, h }
+    }
+    pub fn synchronize(&self) { check(unsafe { sbn_stream_synchronize(self.ctx.0, self.h) }, "sbn_stream_synchronize"); }
+}
+impl<'a> Drop for Stream<'a> { fn drop(&mut self) { unsafe { sbn_stream_destroy(self.ctx.0, self.h) }; } }
+
+/// A commit in flight (`hyrax_commit_async`): the commitments are valid after `wait()`.  Holds its inputs borrowed, so the
+/// scalars cannot be dropped or changed while the copies run.
+pub struct PendingCommit<'a> { stream: &'a Stream<'a>, c: Vec<SbnG1a>, inf: Vec<u8>, _z: &'a [Fr], _b: Option<&'a [Fr]> }
+impl<'a> PendingCommit<'a> {
+    pub fn wait(self) -> Vec<G1Affine> {
+        self.stream.synchronize();
+        self.c.iter().zip(self.inf.iter()).map(|(p, i)| from_abi(p, *i)).collect()
+    }
+}
+
+/// `DensePolynomial::commit_inner` (hyrax.rs:253-281), asynchronous: returns at once; several commits issued on two or three
+/// streams overlap (the copy of one under the kernels of the others).  `z` and `blinds` may be ordinary (pageable) vectors:
+/// the library stages them through pinned buffers and lands the results through a stream-ordered host function.
+pub fn hyrax_commit_async<'a>(ctx: &'a Context, bases: &Bases, z: &'a [Fr], blinds: Option<&'a [Fr]>, l_size: usize,
+                              stream: &'a Stream<'a>) -> PendingCommit<'a> {
+    assert!(l_size > 0 && z.len() % l_size == 0, "assert_eq!(L_size * R_size, self.Z.len())");          // hyrax.rs:258
+    if let Some(b) = blinds { assert_eq!(b.len(), l_size); }
+    let r_size = z.len() / l_size;
+    let mut c = vec![SbnG1a::default(); l_size];
+    let mut inf = vec![0u8; l_size];
+    let bp = blinds.map(|b| b.as_ptr() as *const SbnFr).unwrap_or(std::ptr::null());
+    check(unsafe { sbn_hyrax_commit_async(ctx.0, bases.h, z.as_ptr() as *const SbnFr, l_size, r_size, bp, c.as_mut_ptr(),
+                                          inf.as_mut_ptr(), stream.h) }, "sbn_hyrax_commit_async");
+    PendingCommit { stream, c, inf, _z: z, _b: blinds }
+}
 
 trait IsZeroVartime { fn is_zero_vartime(&self) -> bool; }
 impl IsZeroVartime for Fr { fn is_zero_vartime(&self) -> bool { self.into_bigint().0 == [0u64; 4] } }

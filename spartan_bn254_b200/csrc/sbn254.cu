@@ -551,6 +551,32 @@ extern "C" int sbn_host_alloc(void** out, size_t bytes) {
 }
 extern "C" int sbn_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SBN_OK : SBN_ERR_CUDA; }
 
+// Streams for the asynchronous entry points, for callers without CUDA bindings of their own (the Rust shim): a non-blocking
+// stream on the context's device, its synchronisation and its release.
+extern "C" int sbn_stream_create(sbn_ctx* ctx, void** stream_out) {
+    if (!ctx || !stream_out) return SBN_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_ENTER(ctx);
+    cudaStream_t st = nullptr;
+    SBN_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream_out = (void*)st;
+    return SBN_OK;
+}
+extern "C" int sbn_stream_synchronize(sbn_ctx* ctx, void* stream) {
+    if (!ctx || !stream) return SBN_ERR_ARG;
+    // not under the context's mutex: other threads may issue calls on other streams while this one waits
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return SBN_ERR_CUDA;
+    return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? SBN_OK : SBN_ERR_CUDA;
+}
+extern "C" int sbn_stream_destroy(sbn_ctx* ctx, void* stream) {
+    if (!ctx || !stream) return SBN_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    SBN_ENTER(ctx);
+    SBN_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    SBN_CUDA(ctx, cudaStreamDestroy((cudaStream_t)stream));
+    return SBN_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // window selection: Fq multiplications per row = W * n1 * 10 (mixed adds) + 2 * nb * 14 * 1.3 (reduce)
 // ------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsbn254.so")
 EXPORTS = [
     "sbn_strerror", "sbn_last_cuda_error", "sbn_version",
     "sbn_ctx_create", "sbn_ctx_destroy", "sbn_ctx_synchronize", "sbn_ctx_set", "sbn_ctx_counters",
-    "sbn_ctx_last_commit_profile", "sbn_ctx_memory_stats", "sbn_host_alloc", "sbn_host_free",
+    "sbn_ctx_last_commit_profile", "sbn_ctx_memory_stats", "sbn_host_alloc", "sbn_host_free", "sbn_stream_create", "sbn_stream_synchronize", "sbn_stream_destroy",
     "sbn_bases_create", "sbn_bases_create_ext", "sbn_bases_destroy", "sbn_bases_len", "sbn_bases_window_bits", "sbn_bases_mult_table",
     "sbn_hyrax_commit", "sbn_hyrax_commit_async", "sbn_hyrax_commit_device", "sbn_hyrax_commit_multi", "sbn_msm", "sbn_commit",
     "sbn_g1_scalar_mul_batch", "sbn_g1_scale_points", "sbn_bound",
@@ -157,6 +157,18 @@ class Context:
                                        C.c_void_p(blinds_ptr) if blinds_ptr else None, C.c_void_p(out_ptr),
                                        C.c_void_p(inf_ptr))
         self._check(st, "sbn_hyrax_commit")
+
+    def stream_create(self):
+        """A non-blocking CUDA stream of the library's own (sbn_stream_create): the handle the asynchronous calls take."""
+        h = C.c_void_p()
+        self._check(self.lib.sbn_stream_create(self.h, C.byref(h)), "sbn_stream_create")
+        return h.value
+
+    def stream_synchronize(self, stream):
+        self._check(self.lib.sbn_stream_synchronize(self.h, C.c_void_p(stream)), "sbn_stream_synchronize")
+
+    def stream_destroy(self, stream):
+        self._check(self.lib.sbn_stream_destroy(self.h, C.c_void_p(stream)), "sbn_stream_destroy")
 
     def hyrax_commit_raw_async(self, bases, Z_ptr, L_size, R_size, blinds_ptr, out_ptr, inf_ptr, stream):
         """sbn_hyrax_commit_async on raw host pointers (pinned for real asynchrony); the caller synchronises `stream`."""

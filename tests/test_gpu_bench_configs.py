@@ -228,18 +228,27 @@ def test_async_host_commits_from_pageable_memory(orc):
         dev = torch.device("cuda", 0)
         G, h = synth.distinct_generators(ctx, R)
         bases = ctx.bases(G, h)
-        streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        # streams of the library's own (sbn_stream_create / _synchronize / _destroy: what a Rust caller without CUDA bindings uses)
+        lib_streams = [ctx.stream_create() for _ in range(3)]
+
+        class _S:
+            def __init__(self, h):
+                self.cuda_stream = h
+        streams = [_S(h) for h in lib_streams]
         Zs = [synth.uniform_scalars(80 + i, L * R) for i in range(9)]
         outC = [np.zeros((L, 8), dtype=np.uint64) for _ in range(9)]
         outI = [np.full((L,), 7, dtype=np.uint8) for _ in range(9)]
         for i in range(9):
             ctx.hyrax_commit_raw_async(bases, Zs[i].ctypes.data, L, R, 0, outC[i].ctypes.data, outI[i].ctypes.data,
                                        streams[i % 3].cuda_stream)
-        torch.cuda.synchronize()
+        for h in lib_streams:
+            ctx.stream_synchronize(h)
         assert bases.mult_table()[0] > 0
         for i in range(9):
             C, inf = ctx.hyrax_commit(bases, Zs[i], L, R, None)
             assert np.array_equal(outC[i], C) and np.array_equal(outI[i], inf), i
+        for h in lib_streams:
+            ctx.stream_destroy(h)
         _check_rows(orc, G, h, Zs[8], L, R, outC[8], outI[8], 16)
         bases.close()
     finally:
